@@ -1,0 +1,792 @@
+// C ABI of libc2rt.so (include/c2rt.h): scene validation + upload, frame launches on 1..8 devices,
+// P2P band stores into device 0's frame, host copies, error reporting.  No CPU fallback anywhere:
+// every rendering entry point fails with C2RT_ERR_CUDA if the CUDA runtime cannot run the kernel.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "scene_dev.h"
+
+namespace c2rt {
+cudaError_t upload_scene(const DevScene& s, cudaStream_t st);
+cudaError_t launch_frame(const FrameParams& fp, uint32_t local_tile_rows, cudaStream_t st);
+cudaError_t launch_pixel(const FrameParams& fp, int x, int y, void* d_out, cudaStream_t st);
+cudaError_t launch_deinterleave(const void* src, void* dst, uint32_t row_words, uint32_t height, uint32_t n_ranks,
+                                uint32_t band_rows, uint32_t rows_pad, cudaStream_t st);
+cudaError_t launch_fma_peak(bool fp64, int blocks, int threads, int iters, void* d_out, cudaStream_t st);
+size_t pixel_out_size();
+}  // namespace c2rt
+
+using namespace c2rt;
+
+// must match PixelOut in render_kernel.cu
+struct PixelOutHost {
+    float rgb[3];
+    int node;
+    double dist, p[3], n[3], u, v;
+};
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return fail(C2RT_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+struct DeviceCtx {
+    int dev = -1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    uint64_t uploaded_scene = 0;   // id of the scene currently in this device's constant memory
+    unsigned long long* d_counters = nullptr;
+    uint8_t* d_lut = nullptr;
+    void* d_pixel = nullptr;
+    float* d_rgb = nullptr;
+    uint32_t* d_argb = nullptr;
+    size_t rgb_cap = 0, argb_cap = 0;
+    bool peer_to_root = false;     // can store straight into device 0's frame
+};
+
+struct Context {
+    bool inited = false;
+    int n = 0;
+    DeviceCtx d[C2RT_MAX_GPUS];
+    uint64_t next_scene_id = 1;
+    uint8_t lut[4097];
+};
+
+Context g_ctx;
+std::mutex g_mu;
+
+// color.d:194-207 convertTo8bit_sRGB, quirks kept: 12.02 linear slope, floor instead of round
+uint8_t srgb8(float x) {
+    if (x <= 0) return 0;
+    if (x >= 1) return 255;
+    if (x <= 0.0031308f) x = x * 12.02f;
+    else x = (float)(1.055 * pow((double)x, 1 / 2.4) - 0.055);
+    return (uint8_t)floorf(x * 255.0f);
+}
+
+void destroy_device(DeviceCtx& c) {
+    if (c.dev < 0) return;
+    cudaSetDevice(c.dev);
+    if (c.stream) cudaStreamDestroy(c.stream);
+    if (c.e0) cudaEventDestroy(c.e0);
+    if (c.e1) cudaEventDestroy(c.e1);
+    cudaFree(c.d_counters);
+    cudaFree(c.d_lut);
+    cudaFree(c.d_pixel);
+    cudaFree(c.d_rgb);
+    cudaFree(c.d_argb);
+    c = DeviceCtx();
+}
+
+int init_locked(int n_gpus, const int* ids) {
+    if (n_gpus < 1 || n_gpus > C2RT_MAX_GPUS) return fail(C2RT_ERR_INVALID_ARG, "n_gpus must be in 1..%d", C2RT_MAX_GPUS);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(C2RT_ERR_CUDA, "no CUDA device available (%s); libc2rt has no CPU fallback", cudaGetErrorString(e));
+    for (int i = 0; i < g_ctx.n; i++) destroy_device(g_ctx.d[i]);
+    g_ctx.n = 0;
+    g_ctx.inited = false;
+    for (int i = 0; i < 4097; i++) g_ctx.lut[i] = srgb8((float)i / 4096.f);
+    for (int i = 0; i < n_gpus; i++) {
+        int dev = ids ? ids[i] : i;
+        if (dev < 0 || dev >= count) return fail(C2RT_ERR_INVALID_ARG, "device id %d out of range (have %d)", dev, count);
+        DeviceCtx& c = g_ctx.d[i];
+        c.dev = dev;
+        CU(cudaSetDevice(dev));
+        CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        CU(cudaEventCreate(&c.e0));
+        CU(cudaEventCreate(&c.e1));
+        CU(cudaMalloc(&c.d_counters, 2 * sizeof(unsigned long long)));
+        CU(cudaMemset(c.d_counters, 0, 2 * sizeof(unsigned long long)));
+        CU(cudaMalloc(&c.d_lut, 4097));
+        CU(cudaMemcpy(c.d_lut, g_ctx.lut, 4097, cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&c.d_pixel, pixel_out_size()));
+        g_ctx.n = i + 1;
+    }
+    // peers store their bands straight into the root device's frame when P2P is available
+    for (int i = 1; i < n_gpus; i++) {
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, g_ctx.d[i].dev, g_ctx.d[0].dev);
+        if (can) {
+            cudaSetDevice(g_ctx.d[i].dev);
+            cudaError_t pe = cudaDeviceEnablePeerAccess(g_ctx.d[0].dev, 0);
+            if (pe == cudaSuccess || pe == cudaErrorPeerAccessAlreadyEnabled) g_ctx.d[i].peer_to_root = true;
+            cudaGetLastError();
+        }
+    }
+    cudaSetDevice(g_ctx.d[0].dev);
+    g_ctx.inited = true;
+    return C2RT_OK;
+}
+
+int ensure_init_locked() {
+    if (g_ctx.inited) return C2RT_OK;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(C2RT_ERR_CUDA, "no CUDA device available; libc2rt has no CPU fallback");
+    }
+    return init_locked(1, &dev);
+}
+
+DeviceCtx* find_device(int dev) {
+    for (int i = 0; i < g_ctx.n; i++)
+        if (g_ctx.d[i].dev == dev) return &g_ctx.d[i];
+    return nullptr;
+}
+
+}  // namespace
+
+struct c2rt_scene {
+    uint64_t id;
+    DevScene host;                       // texel pointers patched per device at upload
+    std::vector<float4> texels;          // all bitmaps, float4 per texel
+    std::vector<size_t> tex_offset;      // per texture, in texels (bitmaps only)
+    float4* d_texels[C2RT_MAX_GPUS];     // per context device
+    int n_dev;
+};
+
+namespace {
+
+struct Bound {
+    bool finite;
+    double c[3], r;
+};
+
+Bound bound_of(const c2rt_scene_desc* d, int gi) {
+    Bound b{};
+    const double* p = d->geom_params + 4 * gi;
+    switch (d->geom_type[gi]) {
+        case C2RT_GEOM_SPHERE:
+            b.finite = std::isfinite(p[3]);
+            b.c[0] = p[0]; b.c[1] = p[1]; b.c[2] = p[2];
+            b.r = fabs(p[3]);
+            break;
+        case C2RT_GEOM_CUBE:
+            b.finite = std::isfinite(p[3]);
+            b.c[0] = p[0]; b.c[1] = p[1]; b.c[2] = p[2];
+            b.r = fabs(p[3]) * 0.5 * sqrt(3.0);
+            break;
+        case C2RT_GEOM_CSG_UNION: {
+            Bound l = bound_of(d, d->geom_left[gi]), r = bound_of(d, d->geom_right[gi]);
+            if (!l.finite || !r.finite) { b.finite = false; break; }
+            double dx = r.c[0] - l.c[0], dy = r.c[1] - l.c[1], dz = r.c[2] - l.c[2];
+            double dist = sqrt(dx * dx + dy * dy + dz * dz);
+            if (dist + r.r <= l.r) { b = l; break; }
+            if (dist + l.r <= r.r) { b = r; break; }
+            b.finite = true;
+            b.r = (dist + l.r + r.r) * 0.5;
+            double t = (b.r - l.r) / dist;
+            b.c[0] = l.c[0] + dx * t; b.c[1] = l.c[1] + dy * t; b.c[2] = l.c[2] + dz * t;
+            break;
+        }
+        case C2RT_GEOM_CSG_INTER: {
+            Bound l = bound_of(d, d->geom_left[gi]), r = bound_of(d, d->geom_right[gi]);
+            if (l.finite && r.finite) b = l.r <= r.r ? l : r;
+            else if (l.finite) b = l;
+            else if (r.finite) b = r;
+            else b.finite = false;
+            break;
+        }
+        case C2RT_GEOM_CSG_DIFF:
+            b = bound_of(d, d->geom_left[gi]);
+            break;
+        default:
+            b.finite = false;
+    }
+    if (b.finite && !(std::isfinite(b.c[0]) && std::isfinite(b.c[1]) && std::isfinite(b.c[2]) && std::isfinite(b.r))) b.finite = false;
+    return b;
+}
+
+bool is_identity(const double* m) {
+    for (int i = 0; i < 9; i++)
+        if (m[i] != ((i % 4 == 0) ? 1.0 : 0.0)) return false;
+    return true;
+}
+
+int validate_and_build(const c2rt_scene_desc* d, c2rt_scene* s) {
+    if (!d) return fail(C2RT_ERR_INVALID_ARG, "scene description is null");
+    if (d->struct_size != sizeof(c2rt_scene_desc) || d->abi_version != C2RT_ABI_VERSION)
+        return fail(C2RT_ERR_INVALID_ARG, "scene description ABI mismatch (size %u/%zu, version %u/%d)", d->struct_size,
+                    sizeof(c2rt_scene_desc), d->abi_version, C2RT_ABI_VERSION);
+    if (d->n_nodes > C2RT_MAX_NODES) return fail(C2RT_ERR_LIMIT, "too many nodes (%u > %d)", d->n_nodes, C2RT_MAX_NODES);
+    if (d->n_geoms > C2RT_MAX_GEOMS) return fail(C2RT_ERR_LIMIT, "too many geometries (%u > %d)", d->n_geoms, C2RT_MAX_GEOMS);
+    if (d->n_shaders > C2RT_MAX_SHADERS) return fail(C2RT_ERR_LIMIT, "too many shaders (%u > %d)", d->n_shaders, C2RT_MAX_SHADERS);
+    if (d->n_textures > C2RT_MAX_TEXTURES) return fail(C2RT_ERR_LIMIT, "too many textures (%u > %d)", d->n_textures, C2RT_MAX_TEXTURES);
+    if (d->n_lights > C2RT_MAX_LIGHTS) return fail(C2RT_ERR_LIMIT, "too many lights (%u > %d)", d->n_lights, C2RT_MAX_LIGHTS);
+    if (d->n_nodes && !(d->node_geom && d->node_shader && d->node_transform && d->node_inverse && d->node_inverse_t && d->node_offset))
+        return fail(C2RT_ERR_INVALID_ARG, "node arrays missing");
+    if (d->n_geoms && !(d->geom_type && d->geom_params && d->geom_left && d->geom_right))
+        return fail(C2RT_ERR_INVALID_ARG, "geometry arrays missing");
+    if (d->n_shaders && !(d->shader_type && d->shader_color && d->shader_texture && d->shader_exponent && d->shader_strength))
+        return fail(C2RT_ERR_INVALID_ARG, "shader arrays missing");
+    if (d->n_textures && !(d->tex_type && d->tex_colors && d->tex_params && d->tex_width && d->tex_height && d->tex_texel_offset))
+        return fail(C2RT_ERR_INVALID_ARG, "texture arrays missing");
+    if (d->n_lights && !(d->light_pos && d->light_color && d->light_power)) return fail(C2RT_ERR_INVALID_ARG, "light arrays missing");
+
+    DevScene& h = s->host;
+    memset(&h, 0, sizeof h);
+    h.n_nodes = d->n_nodes; h.n_geoms = d->n_geoms; h.n_shaders = d->n_shaders; h.n_textures = d->n_textures; h.n_lights = d->n_lights;
+
+    for (uint32_t i = 0; i < d->n_geoms; i++) {
+        int t = d->geom_type[i];
+        DevGeom& g = h.geoms[i];
+        g.type = t; g.left = -1; g.right = -1;
+        memcpy(g.p, d->geom_params + 4 * i, 4 * sizeof(double));
+        if (t < C2RT_GEOM_PLANE || t > C2RT_GEOM_CSG_DIFF) return fail(C2RT_ERR_INVALID_ARG, "geometry %u: unknown type %d", i, t);
+        if (t >= C2RT_GEOM_CSG_UNION) {
+            int l = d->geom_left[i], r = d->geom_right[i];
+            if (l < 0 || r < 0 || l >= (int)i || r >= (int)i)
+                return fail(C2RT_ERR_INVALID_ARG, "geometry %u: CSG children must be earlier geometries (left %d, right %d)", i, l, r);
+            if (d->geom_type[l] >= C2RT_GEOM_CSG_UNION || d->geom_type[r] >= C2RT_GEOM_CSG_UNION)
+                return fail(C2RT_ERR_UNSUPPORTED, "geometry %u: nested CSG (a CSG child of a CSG) is not supported by this build", i);
+            g.left = l; g.right = r;
+        }
+    }
+    s->tex_offset.assign(d->n_textures, 0);
+    for (uint32_t i = 0; i < d->n_textures; i++) {
+        DevTex& t = h.textures[i];
+        t.type = d->tex_type[i];
+        if (t.type < C2RT_TEX_CHECKER || t.type > C2RT_TEX_BITMAP) return fail(C2RT_ERR_INVALID_ARG, "texture %u: unknown type %d", i, t.type);
+        memcpy(t.c, d->tex_colors + 18 * i, 18 * sizeof(float));
+        memcpy(t.d, d->tex_params + 6 * i, 6 * sizeof(double));
+        if (t.type == C2RT_TEX_BITMAP) {
+            t.w = d->tex_width[i]; t.h = d->tex_height[i];
+            if (t.w <= 0 || t.h <= 0) return fail(C2RT_ERR_INVALID_ARG, "texture %u: empty bitmap", i);
+            uint64_t off = d->tex_texel_offset[i], n = (uint64_t)t.w * t.h;
+            if (!d->texels || off + n > d->n_texels) return fail(C2RT_ERR_INVALID_ARG, "texture %u: texel range outside `texels`", i);
+            s->tex_offset[i] = s->texels.size();
+            s->texels.resize(s->texels.size() + n);
+            float4* dst = s->texels.data() + s->tex_offset[i];
+            const float* src = d->texels + 3 * off;
+            for (uint64_t k = 0; k < n; k++) dst[k] = make_float4(src[3 * k], src[3 * k + 1], src[3 * k + 2], 0.f);
+        }
+    }
+    for (uint32_t i = 0; i < d->n_shaders; i++) {
+        DevShader& sh = h.shaders[i];
+        sh.type = d->shader_type[i];
+        if (sh.type != C2RT_SHADER_LAMBERT && sh.type != C2RT_SHADER_PHONG) return fail(C2RT_ERR_INVALID_ARG, "shader %u: unknown type %d", i, sh.type);
+        sh.tex = d->shader_texture[i];
+        if (sh.tex >= (int)d->n_textures) return fail(C2RT_ERR_INVALID_ARG, "shader %u: texture index %d out of range", i, sh.tex);
+        if (sh.tex < 0) sh.tex = -1;
+        memcpy(sh.color, d->shader_color + 3 * i, 3 * sizeof(float));
+        sh.exponent = d->shader_exponent[i];
+        sh.strength = d->shader_strength[i];
+    }
+    for (uint32_t i = 0; i < d->n_lights; i++) {
+        DevLight& L = h.lights[i];
+        memcpy(L.pos, d->light_pos + 3 * i, 3 * sizeof(double));
+        // light.d:11-14: Color * float in FP32
+        float pw = d->light_power[i];
+        for (int k = 0; k < 3; k++) L.color[k] = d->light_color[3 * i + k] * pw;
+        float intensity = (L.color[0] + L.color[1] + L.color[2]) / 3;  // color.d:141-144
+        L.lit = intensity != 0;
+    }
+    for (uint32_t i = 0; i < d->n_nodes; i++) {
+        DevNode& nd = h.nodes[i];
+        nd.geom = d->node_geom[i];
+        nd.shader = d->node_shader[i];
+        if (nd.geom < 0 || nd.geom >= (int)d->n_geoms) return fail(C2RT_ERR_INVALID_ARG, "node %u: geometry index %d out of range", i, nd.geom);
+        if (nd.shader < 0 || nd.shader >= (int)d->n_shaders) return fail(C2RT_ERR_INVALID_ARG, "node %u: shader index %d out of range", i, nd.shader);
+        memcpy(nd.M, d->node_transform + 9 * i, 9 * sizeof(double));
+        memcpy(nd.Minv, d->node_inverse + 9 * i, 9 * sizeof(double));
+        memcpy(nd.MinvT, d->node_inverse_t + 9 * i, 9 * sizeof(double));
+        memcpy(nd.off, d->node_offset + 3 * i, 3 * sizeof(double));
+        nd.flags = 0;
+        if (is_identity(nd.M) && is_identity(nd.Minv) && is_identity(nd.MinvT)) nd.flags |= NODE_IDENTITY;
+        Bound b = bound_of(d, nd.geom);
+        if (b.finite) {
+            // world centre = c*M + offset; radius scaled by an upper bound of |M|_2
+            double cx = b.c[0] * nd.M[0] + b.c[1] * nd.M[3] + b.c[2] * nd.M[6] + nd.off[0];
+            double cy = b.c[0] * nd.M[1] + b.c[1] * nd.M[4] + b.c[2] * nd.M[7] + nd.off[1];
+            double cz = b.c[0] * nd.M[2] + b.c[1] * nd.M[5] + b.c[2] * nd.M[8] + nd.off[2];
+            double fro = 0, n1 = 0, ninf = 0;
+            for (int r = 0; r < 3; r++) {
+                double rs = 0, cs = 0;
+                for (int c = 0; c < 3; c++) {
+                    fro += nd.M[3 * r + c] * nd.M[3 * r + c];
+                    rs += fabs(nd.M[3 * r + c]);
+                    cs += fabs(nd.M[3 * c + r]);
+                }
+                ninf = fmax(ninf, rs);
+                n1 = fmax(n1, cs);
+            }
+            double scale = fmin(sqrt(fro), sqrt(n1 * ninf));
+            // inflate: covers the 1e-6 restarts/probes of the CSG walk and rounding in the test itself
+            double r = b.r * scale * (1.0 + 1e-6) + 1e-4 * fmax(1.0, scale);
+            if (std::isfinite(cx) && std::isfinite(cy) && std::isfinite(cz) && std::isfinite(r)) {
+                nd.bc[0] = cx; nd.bc[1] = cy; nd.bc[2] = cz;
+                nd.br = r;
+                nd.br2 = r * r;
+            } else {
+                nd.flags |= NODE_UNBOUNDED;
+            }
+        } else {
+            nd.flags |= NODE_UNBOUNDED;
+        }
+    }
+    return C2RT_OK;
+}
+
+int upload_to_devices(c2rt_scene* s) {
+    s->n_dev = g_ctx.n;
+    for (int i = 0; i < C2RT_MAX_GPUS; i++) s->d_texels[i] = nullptr;
+    if (s->texels.empty()) return C2RT_OK;
+    for (int i = 0; i < g_ctx.n; i++) {
+        CU(cudaSetDevice(g_ctx.d[i].dev));
+        CU(cudaMalloc(&s->d_texels[i], s->texels.size() * sizeof(float4)));
+        CU(cudaMemcpy(s->d_texels[i], s->texels.data(), s->texels.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    }
+    return C2RT_OK;
+}
+
+// make `scene` the one resident in device slot `di`'s constant memory
+int make_resident(c2rt_scene* s, int di, cudaStream_t st) {
+    DeviceCtx& c = g_ctx.d[di];
+    if (c.uploaded_scene == s->id) return C2RT_OK;
+    for (int t = 0; t < s->host.n_textures; t++)
+        s->host.textures[t].texels = (s->host.textures[t].type == C2RT_TEX_BITMAP) ? s->d_texels[di] + s->tex_offset[t] : nullptr;
+    CU(upload_scene(s->host, st));
+    CU(cudaStreamSynchronize(st));  // the source is pageable host memory that the next device patches
+    c.uploaded_scene = s->id;
+    return C2RT_OK;
+}
+
+int check_frame_args(const c2rt_scene* s, const c2rt_camera* cam, const c2rt_settings* set) {
+    if (!s || !cam || !set) return fail(C2RT_ERR_INVALID_ARG, "scene, camera and settings must be non-null");
+    if (set->frame_width == 0 || set->frame_height == 0 || set->frame_width > 65536 || set->frame_height > 65536)
+        return fail(C2RT_ERR_INVALID_ARG, "bad frame size %ux%u", set->frame_width, set->frame_height);
+    if (cam->frame_width == 0 || cam->frame_height == 0) return fail(C2RT_ERR_INVALID_ARG, "camera frame size is zero (setFrameSize not called)");
+    if (set->gi_enabled) return fail(C2RT_ERR_UNSUPPORTED, "GIEnabled (path tracing) is outside the hot-path scope");
+    if (set->prepass_only) return fail(C2RT_ERR_UNSUPPORTED, "prepassOnly is not supported");
+    if (cam->stereo_separation != 0) return fail(C2RT_ERR_UNSUPPORTED, "stereo rendering is outside the hot-path scope");
+    if (cam->dof && cam->num_samples == 0) return fail(C2RT_ERR_INVALID_ARG, "DOF camera with numSamples == 0");
+    return C2RT_OK;
+}
+
+void fill_params(FrameParams& fp, const c2rt_camera* cam, const c2rt_settings* set) {
+    memset(&fp, 0, sizeof fp);
+    for (int k = 0; k < 3; k++) {
+        fp.pos[k] = cam->pos[k];
+        fp.up_left[k] = cam->up_left[k];
+        fp.du[k] = cam->up_right[k] - cam->up_left[k];   // camera.d:141
+        fp.dv[k] = cam->down_left[k] - cam->up_left[k];  // camera.d:142
+        fp.right_dir[k] = cam->right_dir[k];
+        fp.up_dir[k] = cam->up_dir[k];
+        fp.front_dir[k] = cam->front_dir[k];
+        fp.ambient[k] = set->ambient_light[k];
+    }
+    fp.cam_w = (double)cam->frame_width;
+    fp.cam_h = (double)cam->frame_height;
+    fp.focal_plane_dist = cam->focal_plane_dist;
+    fp.disc_multiplier = cam->disc_multiplier;
+    fp.seed = set->rng_seed;
+    fp.W = set->frame_width;
+    fp.H = set->frame_height;
+    fp.aa = set->aa_enabled != 0;
+    fp.dof = cam->dof != 0;
+    fp.num_samples = cam->num_samples;
+    fp.max_trace_depth = set->max_trace_depth;
+    fp.count_rays = set->count_rays != 0;
+    fp.n_ranks = 1;
+    fp.tiles_per_band = 1;
+}
+
+uint32_t local_tile_rows(uint32_t H, uint32_t rank, uint32_t n, uint32_t band_rows) {
+    uint32_t rows = c2rt_band_rows_owned(H, rank, n, band_rows);
+    return (rows + TILE_H - 1) / TILE_H;
+}
+
+}  // namespace
+
+extern "C" {
+
+int c2rt_abi_version(void) { return C2RT_ABI_VERSION; }
+
+const char* c2rt_last_error(void) { return g_err.c_str(); }
+
+int c2rt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int c2rt_init(int n_gpus, const int* device_ids) {
+    std::lock_guard<std::mutex> g(g_mu);
+    return init_locked(n_gpus, device_ids);
+}
+
+void c2rt_shutdown(void) {
+    std::lock_guard<std::mutex> g(g_mu);
+    for (int i = 0; i < g_ctx.n; i++) destroy_device(g_ctx.d[i]);
+    g_ctx.n = 0;
+    g_ctx.inited = false;
+}
+
+uint32_t c2rt_band_rows_owned(uint32_t height, uint32_t rank, uint32_t n_ranks, uint32_t band_rows) {
+    if (n_ranks == 0 || band_rows == 0) return 0;
+    uint32_t rows = 0;
+    for (uint32_t y0 = rank * band_rows; y0 < height; y0 += n_ranks * band_rows) rows += (height - y0 < band_rows) ? height - y0 : band_rows;
+    return rows;
+}
+
+uint32_t c2rt_rng_u31(uint64_t seed, uint32_t px, uint32_t py, uint32_t tap, uint32_t sample, uint32_t draw) {
+    unsigned long long k = seed;
+    k ^= (unsigned long long)px * 0x9E3779B97F4A7C15ull;
+    k = (k ^ (k >> 30)) * 0xBF58476D1CE4E5B9ull;
+    k ^= (unsigned long long)py * 0xC2B2AE3D27D4EB4Full;
+    k = (k ^ (k >> 27)) * 0x94D049BB133111EBull;
+    k ^= ((unsigned long long)tap << 48) ^ ((unsigned long long)sample << 16) ^ (unsigned long long)draw;
+    k = (k ^ (k >> 30)) * 0xBF58476D1CE4E5B9ull;
+    k = (k ^ (k >> 27)) * 0x94D049BB133111EBull;
+    k ^= k >> 31;
+    return (uint32_t)(k >> 33);
+}
+
+void c2rt_srgb_table(uint8_t out[4097]) {
+    for (int i = 0; i < 4097; i++) out[i] = srgb8((float)i / 4096.f);
+}
+
+int c2rt_scene_create(const c2rt_scene_desc* desc, c2rt_scene** out) {
+    if (!out) return fail(C2RT_ERR_INVALID_ARG, "out is null");
+    *out = nullptr;
+    std::lock_guard<std::mutex> g(g_mu);
+    c2rt_scene* s = new c2rt_scene();
+    int rc = validate_and_build(desc, s);
+    if (rc == C2RT_OK) rc = ensure_init_locked();
+    if (rc == C2RT_OK) {
+        s->id = g_ctx.next_scene_id++;
+        rc = upload_to_devices(s);
+    }
+    if (rc != C2RT_OK) {
+        delete s;
+        return rc;
+    }
+    *out = s;
+    return C2RT_OK;
+}
+
+void c2rt_scene_destroy(c2rt_scene* s) {
+    if (!s) return;
+    std::lock_guard<std::mutex> g(g_mu);
+    for (int i = 0; i < s->n_dev && i < g_ctx.n; i++) {
+        if (s->d_texels[i]) {
+            cudaSetDevice(g_ctx.d[i].dev);
+            cudaFree(s->d_texels[i]);
+        }
+        if (g_ctx.d[i].uploaded_scene == s->id) g_ctx.d[i].uploaded_scene = 0;
+    }
+    delete s;
+}
+
+int c2rt_render_device(c2rt_scene* s, const c2rt_camera* cam, const c2rt_settings* set, const c2rt_band* band, float* d_rgb,
+                       uint32_t* d_argb, void* stream, c2rt_stats* stats) {
+    int rc = check_frame_args(s, cam, set);
+    if (rc) return rc;
+    if (!d_rgb) return fail(C2RT_ERR_INVALID_ARG, "d_rgb is null");
+    std::lock_guard<std::mutex> g(g_mu);
+    if (!g_ctx.inited) return fail(C2RT_ERR_NOT_INITIALISED, "c2rt_init has not been called");
+    int dev = -1;
+    CU(cudaGetDevice(&dev));
+    DeviceCtx* c = find_device(dev);
+    if (!c) return fail(C2RT_ERR_INVALID_ARG, "current device %d is not part of the c2rt context", dev);
+    int di = (int)(c - g_ctx.d);
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = make_resident(s, di, st);
+    if (rc) return rc;
+    FrameParams fp;
+    fill_params(fp, cam, set);
+    uint32_t band_rows = TILE_H;
+    if (band) {
+        if (band->n_ranks == 0 || band->rank >= band->n_ranks || band->band_rows == 0 || band->band_rows % TILE_H != 0)
+            return fail(C2RT_ERR_INVALID_ARG, "bad band (rank %u of %u, band_rows %u; band_rows must be a multiple of %d)", band->rank,
+                        band->n_ranks, band->band_rows, TILE_H);
+        fp.rank = band->rank;
+        fp.n_ranks = band->n_ranks;
+        fp.compact = band->compact != 0;
+        band_rows = band->band_rows;
+    }
+    fp.tiles_per_band = band_rows / TILE_H;
+    fp.rgb = d_rgb;
+    fp.argb = d_argb;
+    fp.counters = c->d_counters;
+    fp.lut = c->d_lut;
+    CU(launch_frame(fp, local_tile_rows(fp.H, fp.rank, fp.n_ranks, band_rows), st));
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->n_gpus = 1;
+        stats->launches = 1;
+    }
+    return C2RT_OK;
+}
+
+int c2rt_read_ray_counters(c2rt_scene*, void* stream, uint64_t* primary, uint64_t* shadow) {
+    std::lock_guard<std::mutex> g(g_mu);
+    if (!g_ctx.inited) return fail(C2RT_ERR_NOT_INITIALISED, "c2rt_init has not been called");
+    int dev = -1;
+    CU(cudaGetDevice(&dev));
+    DeviceCtx* c = find_device(dev);
+    if (!c) return fail(C2RT_ERR_INVALID_ARG, "current device %d is not part of the c2rt context", dev);
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long v[2];
+    CU(cudaMemcpyAsync(v, c->d_counters, sizeof v, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemsetAsync(c->d_counters, 0, sizeof v, st));
+    CU(cudaStreamSynchronize(st));
+    if (primary) *primary = v[0];
+    if (shadow) *shadow = v[1];
+    return C2RT_OK;
+}
+
+int c2rt_render(c2rt_scene* s, const c2rt_camera* cam, const c2rt_settings* set, float* rgb, uint32_t* argb, c2rt_stats* stats) {
+    auto t0 = std::chrono::steady_clock::now();
+    int rc = check_frame_args(s, cam, set);
+    if (rc) return rc;
+    if (!rgb) return fail(C2RT_ERR_INVALID_ARG, "rgb is null");
+    std::lock_guard<std::mutex> g(g_mu);
+    rc = ensure_init_locked();
+    if (rc) return rc;
+    if (s->n_dev != g_ctx.n) return fail(C2RT_ERR_INVALID_ARG, "scene was created under a different c2rt_init configuration");
+    const uint32_t W = set->frame_width, H = set->frame_height;
+    const size_t npx = (size_t)W * H;
+    const int n = g_ctx.n;
+    const uint32_t band_rows = TILE_H;
+
+    // root frame
+    DeviceCtx& root = g_ctx.d[0];
+    CU(cudaSetDevice(root.dev));
+    if (root.rgb_cap < npx * 3) {
+        cudaFree(root.d_rgb);
+        root.d_rgb = nullptr; root.rgb_cap = 0;
+        CU(cudaMalloc(&root.d_rgb, npx * 3 * sizeof(float)));
+        root.rgb_cap = npx * 3;
+    }
+    if (argb && root.argb_cap < npx) {
+        cudaFree(root.d_argb);
+        root.d_argb = nullptr; root.argb_cap = 0;
+        CU(cudaMalloc(&root.d_argb, npx * sizeof(uint32_t)));
+        root.argb_cap = npx;
+    }
+    uint32_t launches = 0;
+    for (int i = 0; i < n; i++) {
+        DeviceCtx& c = g_ctx.d[i];
+        CU(cudaSetDevice(c.dev));
+        rc = make_resident(s, i, c.stream);
+        if (rc) return rc;
+        FrameParams fp;
+        fill_params(fp, cam, set);
+        fp.rank = (uint32_t)i;
+        fp.n_ranks = (uint32_t)n;
+        fp.tiles_per_band = band_rows / TILE_H;
+        fp.counters = c.d_counters;
+        fp.lut = c.d_lut;
+        const uint32_t rows_owned = c2rt_band_rows_owned(H, fp.rank, fp.n_ranks, band_rows);
+        if (i == 0 || c.peer_to_root) {
+            // bands land directly in the root frame (peer-mapped stores over NVLink for i > 0)
+            fp.compact = 0;
+            fp.rgb = root.d_rgb;
+            fp.argb = argb ? root.d_argb : nullptr;
+        } else {
+            fp.compact = 1;
+            size_t need = (size_t)rows_owned * W;
+            if (c.rgb_cap < need * 3) {
+                cudaFree(c.d_rgb);
+                c.d_rgb = nullptr; c.rgb_cap = 0;
+                CU(cudaMalloc(&c.d_rgb, need * 3 * sizeof(float)));
+                c.rgb_cap = need * 3;
+            }
+            if (argb && c.argb_cap < need) {
+                cudaFree(c.d_argb);
+                c.d_argb = nullptr; c.argb_cap = 0;
+                CU(cudaMalloc(&c.d_argb, need * sizeof(uint32_t)));
+                c.argb_cap = need;
+            }
+            fp.rgb = c.d_rgb;
+            fp.argb = argb ? c.d_argb : nullptr;
+        }
+        CU(cudaEventRecord(c.e0, c.stream));
+        CU(launch_frame(fp, local_tile_rows(H, fp.rank, fp.n_ranks, band_rows), c.stream));
+        CU(cudaEventRecord(c.e1, c.stream));
+        launches++;
+        if (i > 0 && !c.peer_to_root) {
+            // no P2P mapping: copy each band into the root frame
+            uint32_t local = 0;
+            for (uint32_t y0 = fp.rank * band_rows; y0 < H; y0 += n * band_rows, local += band_rows) {
+                uint32_t rows = (H - y0 < band_rows) ? H - y0 : band_rows;
+                CU(cudaMemcpyPeerAsync(root.d_rgb + (size_t)y0 * W * 3, root.dev, c.d_rgb + (size_t)local * W * 3, c.dev,
+                                       (size_t)rows * W * 3 * sizeof(float), c.stream));
+                if (argb)
+                    CU(cudaMemcpyPeerAsync(root.d_argb + (size_t)y0 * W, root.dev, c.d_argb + (size_t)local * W, c.dev,
+                                           (size_t)rows * W * sizeof(uint32_t), c.stream));
+            }
+        }
+    }
+    double kernel_ms = 0;
+    for (int i = 0; i < n; i++) {
+        DeviceCtx& c = g_ctx.d[i];
+        CU(cudaSetDevice(c.dev));
+        CU(cudaStreamSynchronize(c.stream));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, c.e0, c.e1));
+        if (ms > kernel_ms) kernel_ms = ms;
+    }
+    CU(cudaSetDevice(root.dev));
+    CU(cudaMemcpyAsync(rgb, root.d_rgb, npx * 3 * sizeof(float), cudaMemcpyDeviceToHost, root.stream));
+    if (argb) CU(cudaMemcpyAsync(argb, root.d_argb, npx * sizeof(uint32_t), cudaMemcpyDeviceToHost, root.stream));
+    CU(cudaStreamSynchronize(root.stream));
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->kernel_ms = kernel_ms;
+        stats->n_gpus = (uint32_t)n;
+        stats->launches = launches;
+        if (set->count_rays) {
+            for (int i = 0; i < n; i++) {
+                DeviceCtx& c = g_ctx.d[i];
+                CU(cudaSetDevice(c.dev));
+                unsigned long long v[2];
+                CU(cudaMemcpy(v, c.d_counters, sizeof v, cudaMemcpyDeviceToHost));
+                CU(cudaMemset(c.d_counters, 0, sizeof v));
+                stats->primary_rays += v[0];
+                stats->shadow_rays += v[1];
+            }
+            CU(cudaSetDevice(root.dev));
+        }
+        stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return C2RT_OK;
+}
+
+int c2rt_render_pixel(c2rt_scene* s, const c2rt_camera* cam, const c2rt_settings* set, int x, int y, float rgb[3], c2rt_hit* hit) {
+    int rc = check_frame_args(s, cam, set);
+    if (rc) return rc;
+    if (!rgb) return fail(C2RT_ERR_INVALID_ARG, "rgb is null");
+    if (x < 0 || y < 0 || (uint32_t)x >= set->frame_width || (uint32_t)y >= set->frame_height)
+        return fail(C2RT_ERR_INVALID_ARG, "pixel (%d,%d) outside the %ux%u frame", x, y, set->frame_width, set->frame_height);
+    std::lock_guard<std::mutex> g(g_mu);
+    rc = ensure_init_locked();
+    if (rc) return rc;
+    DeviceCtx& c = g_ctx.d[0];
+    CU(cudaSetDevice(c.dev));
+    rc = make_resident(s, 0, c.stream);
+    if (rc) return rc;
+    FrameParams fp;
+    fill_params(fp, cam, set);
+    fp.counters = c.d_counters;
+    fp.lut = c.d_lut;
+    fp.count_rays = 0;
+    CU(launch_pixel(fp, x, y, c.d_pixel, c.stream));
+    PixelOutHost o;
+    if (pixel_out_size() != sizeof o) return fail(C2RT_ERR_CUDA, "internal: PixelOut layout mismatch");
+    CU(cudaMemcpyAsync(&o, c.d_pixel, sizeof o, cudaMemcpyDeviceToHost, c.stream));
+    CU(cudaStreamSynchronize(c.stream));
+    rgb[0] = o.rgb[0]; rgb[1] = o.rgb[1]; rgb[2] = o.rgb[2];
+    if (hit) {
+        memset(hit, 0, sizeof *hit);
+        hit->node = o.node;
+        hit->dist = o.dist;
+        for (int k = 0; k < 3; k++) { hit->p[k] = o.p[k]; hit->normal[k] = o.n[k]; }
+        hit->u = o.u; hit->v = o.v;
+    }
+    return C2RT_OK;
+}
+
+int c2rt_deinterleave(const void* gathered, void* frame, uint32_t width, uint32_t height, uint32_t elem_words, uint32_t n_ranks,
+                      uint32_t band_rows, uint32_t rows_pad, void* stream) {
+    if (!gathered || !frame || !width || !height || !elem_words || !n_ranks || !band_rows)
+        return fail(C2RT_ERR_INVALID_ARG, "bad deinterleave arguments");
+    CU(launch_deinterleave(gathered, frame, width * elem_words, height, n_ranks, band_rows, rows_pad, (cudaStream_t)stream));
+    return C2RT_OK;
+}
+
+int c2rt_frame_alloc(size_t bytes, void** d_ptr) {
+    if (!d_ptr || !bytes) return fail(C2RT_ERR_INVALID_ARG, "bad frame_alloc arguments");
+    CU(cudaMalloc(d_ptr, bytes));
+    return C2RT_OK;
+}
+int c2rt_frame_free(void* d_ptr) {
+    CU(cudaFree(d_ptr));
+    return C2RT_OK;
+}
+int c2rt_frame_export(void* d_ptr, uint8_t handle[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, d_ptr));
+    memcpy(handle, &h, 64);
+    return C2RT_OK;
+}
+int c2rt_frame_import(const uint8_t handle[64], void** d_ptr) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CU(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return C2RT_OK;
+}
+int c2rt_frame_unimport(void* d_ptr) {
+    CU(cudaIpcCloseMemHandle(d_ptr));
+    return C2RT_OK;
+}
+
+int c2rt_measure_fma_peak(int fp64, double* tflops, double* sm_clock_mhz_est) {
+    if (!tflops) return fail(C2RT_ERR_INVALID_ARG, "tflops is null");
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, dev));
+    void* d_out = nullptr;
+    CU(cudaMalloc(&d_out, 64));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    const int threads = 512, blocks = prop.multiProcessorCount * 4, iters = fp64 ? 2048 : 8192;
+    CU(launch_fma_peak(fp64 != 0, blocks, threads, 64, d_out, 0));  // warm-up
+    CU(cudaDeviceSynchronize());
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        CU(cudaEventRecord(e0, 0));
+        CU(launch_fma_peak(fp64 != 0, blocks, threads, iters, d_out, 0));
+        CU(cudaEventRecord(e1, 0));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        double flops = 2.0 * 64.0 * (double)iters * threads * (double)blocks;
+        double tf = flops / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    *tflops = best;
+    if (sm_clock_mhz_est) {
+        // lanes per SM per clock: 128 FP32, 64 FP64 on sm_100
+        double lanes = fp64 ? 64.0 : 128.0;
+        *sm_clock_mhz_est = best * 1e12 / (2.0 * lanes * prop.multiProcessorCount) / 1e6;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    return C2RT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,89 @@
+// Device-side scene block and per-frame parameter block (plain PODs shared by host and device code).
+//
+// The whole flattened scene lives in constant memory: the reference tests every ray against every
+// node linearly (/root/reference/source/rt/renderer.d:336-338, scene.d:73-75), the node loop is
+// warp-uniform, so every record read is a constant-cache broadcast.  Bitmap texels are the only
+// scene data in global memory (float4 per texel, one 16-byte load each).
+#pragma once
+#include <stdint.h>
+
+#include "../../include/c2rt.h"
+
+namespace c2rt {
+
+enum : int {
+    NODE_IDENTITY = 1,     // transform == identity (offset may be non-zero): skip the six mat-vecs of node.d:27-47
+    NODE_UNBOUNDED = 2,    // no finite bounding sphere (planes)
+};
+
+struct DevNode {
+    double Minv[9];   // Transform.inverseTransform
+    double M[9];      // Transform.transform
+    double MinvT[9];  // Transform.transposedInverse
+    double off[3];    // Transform.offset
+    double bc[3];     // world-space bounding sphere centre
+    double br2;       // squared radius (inflated); unused when NODE_UNBOUNDED
+    double br;        // radius (inflated)
+    int geom, shader, flags, pad;
+};
+
+struct DevGeom {
+    double p[4];      // plane: y, limit | sphere: c.xyz, R | cube: c.xyz, side
+    int type, left, right, pad;
+};
+
+struct DevShader {
+    double exponent;
+    float color[3];
+    float strength;
+    int type, tex;
+};
+
+struct DevTex {
+    double d[6];      // checker: size | procedure2: freqU[3], freqV[3] | bitmap: scaling
+    float c[18];      // checker: color1, color2 | procedure2: colorU[3][3], colorV[3][3]
+    int type, w, h, pad;
+    const float4* texels;  // bitmap only
+};
+
+struct DevLight {
+    double pos[3];
+    float color[3];   // lightColor * lightPower, the FP32 product of light.d:11-14
+    int lit;          // color.intensity() != 0 (shader.d:88,219)
+};
+
+struct DevScene {
+    int n_nodes, n_geoms, n_shaders, n_textures, n_lights, pad0, pad1, pad2;
+    DevNode nodes[C2RT_MAX_NODES];
+    DevGeom geoms[C2RT_MAX_GEOMS];
+    DevShader shaders[C2RT_MAX_SHADERS];
+    DevTex textures[C2RT_MAX_TEXTURES];
+    DevLight lights[C2RT_MAX_LIGHTS];
+};
+
+struct FrameParams {
+    // camera.d:123-147 with the frame invariants (upRight-upLeft, downLeft-upLeft) hoisted
+    double pos[3], up_left[3], du[3], dv[3];
+    double right_dir[3], up_dir[3], front_dir[3];
+    double cam_w, cam_h;              // (double)camera.frameWidth / frameHeight
+    double focal_plane_dist, disc_multiplier;
+    unsigned long long seed;
+    uint32_t W, H;                    // output size
+    int aa, dof;
+    uint32_t num_samples, max_trace_depth;
+    float ambient[3];
+    int count_rays;
+    // interleaved row bands
+    uint32_t rank, n_ranks, tiles_per_band, compact;
+    // outputs
+    float* rgb;
+    uint32_t* argb;
+    unsigned long long* counters;     // [0] primary, [1] shadow
+    const uint8_t* lut;               // 4097-entry sRGB table
+};
+
+constexpr int TILE_W = 16;
+constexpr int TILE_H = 8;
+constexpr int BLOCK_THREADS = TILE_W * TILE_H;
+
+}  // namespace c2rt
