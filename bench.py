@@ -1,0 +1,460 @@
+#!/usr/bin/env python
+"""bench.py — the headline benchmark of BASELINE.json: Mrays/s and frames/s at 1920x1080.
+
+A "step" is ONE FRAME of the workload rendered by the hot path.  At N=1 the workload is
+BASELINE.json configs[1]: data/lecture4-proc-texture.sdl at 1920x1080 (procedural texture + Lambert +
+shadow rays, 5 samples per pixel).  With N>1 ranks (one process per GPU, torchrun) the same frame is
+split into interleaved 8-row bands, each rank renders its bands, and the bands are gathered to rank 0
+(NCCL gather + the library's scatter kernel, or — `--gather p2p` — stores straight into rank 0's
+frame through a CUDA-IPC mapping over NVLink); total work is fixed, so scaling is "strong".
+
+  value      device-resident throughput: inputs (scene, camera) already on the GPU, output left in HBM
+  e2e        the same metric through the public host API (c2rt_render via the host mirror) with HOST
+             buffers: camera/settings go down as launch parameters, the float frame comes back to
+             pinned host memory inside the timed region
+  roofline   FP32 CUDA-core roofline (the path is FMA-bound, not HBM- or tensor-bound: DESIGN.md §4):
+             achieved = algorithmic FLOPs of the frame (counted by the oracle's counting scalar,
+             chess2rt_b200/workloads.json) / mean kernel time (CUDA events)
+  cpu_baseline  the CPU oracle (C++ restatement of the reference: the D reference cannot be built in
+             this image) timed on the box's host cores on the same frame
+`--impl reference` times that CPU implementation alone with the same metric/config.
+`--workload` picks another configuration (c0..c4, chess1080, chess4k); the default is the headline one.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (scene file, width, height, overrides)
+    "c0": ("scenes/lecture4.sdl", 640, 480, {}),
+    "c1": ("scenes/lecture4-proc-texture.sdl", 1920, 1080, {}),
+    "c2": ("scenes/lecture5.sdl", 3840, 2160, {}),
+    "c3": ("scenes/zaphod.sdl", 3840, 2160, {}),
+    "c4": ("scenes/chessboard.sdl", 7680, 4320, {}),
+    "chess1080": ("scenes/chessboard.sdl", 1920, 1080, {}),
+    "chess4k": ("scenes/chessboard.sdl", 3840, 2160, {}),
+    "lecture5_1080": ("scenes/lecture5.sdl", 1920, 1080, {}),
+}
+DEFAULT_WORKLOAD = "c1"
+BAND_ROWS = 8
+RNG_SEED = 0xC2E55
+L2_FLUSH_BYTES = 256 << 20  # > 126 MB L2
+
+
+def load_calibration():
+    p = os.path.join(ROOT, "chess2rt_b200", "workloads.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
+def calibrate(names):
+    """Counts algorithmic FLOPs and rays of each workload with the oracle's counting build (CPU, slow)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_binding import OracleScene
+    cal = load_calibration()
+    for name in names:
+        path, w, h, over = WORKLOADS[name]
+        s = OracleScene(os.path.join(ROOT, path), count_flops=True)
+        s.set_frame_size(w, h)
+        s.override(**over)
+        if name in ("c3", "c4"):
+            # exact counts for 8K / DOF frames take CPU-minutes: count every 16th 8-row band and scale
+            tot = {"flops": 0, "primary": 0, "shadow": 0}
+            rows = 0
+            for y0 in range(0, h, 8 * 16):
+                _, st = s.render_rows(y0, min(h, y0 + 8), seed=RNG_SEED)
+                tot["flops"] += st.flops; tot["primary"] += st.primary_rays; tot["shadow"] += st.shadow_rays
+                rows += min(h, y0 + 8) - y0
+            k = h / rows
+            cal[name] = {"scene": path, "width": w, "height": h, "flops": int(tot["flops"] * k),
+                         "primary_rays": int(tot["primary"] * k), "shadow_rays": int(tot["shadow"] * k),
+                         "exact": False, "how": "every 16th 8-row band counted, scaled by rows"}
+        else:
+            _, st = s.render(seed=RNG_SEED)
+            cal[name] = {"scene": path, "width": w, "height": h, "flops": int(st.flops), "primary_rays": int(st.primary_rays),
+                         "shadow_rays": int(st.shadow_rays), "exact": True, "how": "full frame, oracle counting scalar"}
+        print(name, cal[name], flush=True)
+    json.dump(cal, open(os.path.join(ROOT, "chess2rt_b200", "workloads.json"), "w"), indent=1, sort_keys=True)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_frame_seconds(path, w, h, over, threads, min_seconds=2.0, max_frames=5):
+    """Times the CPU oracle on full frames of the workload (bounded: stops after min_seconds or max_frames)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_binding import OracleScene
+    s = OracleScene(os.path.join(ROOT, path))
+    s.set_frame_size(w, h)
+    s.override(**over)
+    times, rays = [], None
+    t_all = time.perf_counter()
+    while len(times) < max_frames and (time.perf_counter() - t_all < min_seconds or not times):
+        _, st = s.render(threads=threads, seed=RNG_SEED)
+        times.append(st.seconds)
+        rays = st.primary_rays + st.shadow_rays
+    return times, rays
+
+
+def cpu_rows_seconds(path, w, h, over, threads, rows):
+    """Bounded sample for frames too big to render whole on the CPU: `rows` rows spread over the frame."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_binding import OracleScene
+    s = OracleScene(os.path.join(ROOT, path))
+    s.set_frame_size(w, h)
+    s.override(**over)
+    sec, rays, done = 0.0, 0, 0
+    n_win = max(1, rows // 8)
+    for i in range(n_win):
+        y0 = min(h - 8, (h // n_win) * i) // 8 * 8
+        _, st = s.render_rows(y0, min(h, y0 + 8), threads=threads, seed=RNG_SEED)
+        sec += st.seconds; rays += st.primary_rays + st.shadow_rays; done += min(h, y0 + 8) - y0
+    return sec, rays, done
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (the C++ oracle port; the D
+    original needs dmd/ldc2 + dub + gfm + sdlang-d, none present: DESIGN.md) on all host cores."""
+    if rank != 0:
+        return
+    path, w, h, over = WORKLOADS[args.workload]
+    threads = os.cpu_count() or 1
+    big = w * h > 3840 * 2160 or args.workload == "c3"
+    step_s, rays = [], None
+    sample = "full frame per step"
+    for i in range(args.warmup + args.steps):
+        if big:
+            sec, r, done = cpu_rows_seconds(path, w, h, over, threads, rows=64)
+            sec, r = sec * h / done, r * h / done
+            sample = "64 rows (8 windows of 8 rows spread over the frame) per step, scaled to the frame"
+        else:
+            t, r = cpu_frame_seconds(path, w, h, over, threads, min_seconds=0, max_frames=1)
+            sec = t[0]
+        if i >= args.warmup:
+            step_s.append(sec)
+        rays = r
+    ms = 1e3 * sum(step_s) / len(step_s)
+    val = rays / (ms * 1e-3) / 1e6
+    line = {
+        "impl": "reference", "metric": "Mrays/s at %dx%d" % (w, h), "value": val, "unit": "Mrays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "frames_per_s": 1e3 / ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64 geometry / f32 colour", "data": "synthetic (bundled scene file, no external data)",
+        "config": {"workload": "%s: %s at %dx%d" % (args.workload, path, w, h), "rays_per_frame": rays},
+        "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--gather", default="auto", choices=["auto", "nccl", "p2p"])
+    ap.add_argument("--calibrate", nargs="*", default=None, help="(CPU) recount algorithmic FLOPs/rays of the named workloads")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.calibrate is not None:
+        calibrate(args.calibrate or ["c0", "c1", "c2", "chess1080"])
+        return
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import chess2rt_b200 as c2
+    from chess2rt_b200 import api, bands
+
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    c2.init(1, [local_rank])
+
+    path, W, H, over = WORKLOADS[args.workload]
+    scene = c2.HostScene(os.path.join(ROOT, path))
+    scene.set_frame_size(W, H)
+    scene.override(**over)
+    handle = scene.device_scene()
+    cam, st = scene.frame_blocks(seed=RNG_SEED)
+    stream = torch.cuda.current_stream().cuda_stream
+    n_ranks = world
+    band = api.Band(rank, n_ranks, BAND_ROWS, 1 if n_ranks > 1 else 0)
+
+    # ---- output buffers (device resident) ------------------------------------------------------
+    pad = bands.rows_padded(H, n_ranks, BAND_ROWS)
+    gather_mode = "none"
+    frame = None
+    peer_frame_ptr = None
+    if n_ranks == 1:
+        frame = torch.empty((H, W, 3), dtype=torch.float32, device="cuda")
+        out_ptr = frame.data_ptr()
+    else:
+        gather_mode = "nccl" if args.gather in ("auto", "nccl") else "p2p"
+        if gather_mode == "p2p":
+            import ctypes as C
+            handle_bytes = [None]
+            if rank == 0:
+                p = C.c_void_p()
+                api._check(api.lib.c2rt_frame_alloc(H * W * 12, C.byref(p)))
+                hb = (C.c_uint8 * 64)()
+                api._check(api.lib.c2rt_frame_export(p, hb))
+                handle_bytes = [bytes(hb)]
+                peer_frame_ptr = p.value
+            dist.broadcast_object_list(handle_bytes, src=0)
+            if rank != 0:
+                hb = (C.c_uint8 * 64).from_buffer_copy(handle_bytes[0])
+                p = C.c_void_p()
+                api._check(api.lib.c2rt_frame_import(hb, C.byref(p)))
+                peer_frame_ptr = p.value
+            band = api.Band(rank, n_ranks, BAND_ROWS, 0)
+            out_ptr = peer_frame_ptr
+            sync_flag = torch.zeros(1, device="cuda")
+        else:
+            mine = torch.empty((pad, W, 3), dtype=torch.float32, device="cuda")
+            gathered = torch.empty((n_ranks, pad, W, 3), dtype=torch.float32, device="cuda") if rank == 0 else None
+            frame = torch.empty((H, W, 3), dtype=torch.float32, device="cuda") if rank == 0 else None
+            out_ptr = mine.data_ptr()
+    flush_buf = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+    launches = [0]
+
+    def device_step():
+        """one frame: render this rank's bands, gather to rank 0"""
+        c2.render_device(handle, cam, st, out_ptr, None, band if n_ranks > 1 else None, stream)
+        launches[0] += 1
+        if gather_mode == "nccl":
+            dist.gather(mine, list(gathered.unbind(0)) if rank == 0 else None, dst=0)
+            if rank == 0:
+                c2.deinterleave(gathered.data_ptr(), frame.data_ptr(), W, H, 3, n_ranks, BAND_ROWS, pad, stream)
+                launches[0] += 1
+        elif gather_mode == "p2p":
+            dist.all_reduce(sync_flag)  # completion: rank 0 may read the frame once every peer's stores are done
+
+    # ---- sanity: the workload is the calibrated one (ray counts must match the oracle's) ---------
+    cal = load_calibration().get(args.workload)
+    cam_c, st_c = scene.frame_blocks(seed=RNG_SEED, count_rays=True)
+    c2.render_device(handle, cam_c, st_c, out_ptr, None, band if n_ranks > 1 else None, stream)
+    prim, shad = c2.read_ray_counters(handle, stream)
+    counts = torch.tensor([prim, shad], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(counts)
+    prim, shad = int(counts[0]), int(counts[1])
+    if cal and cal.get("exact") and (prim, shad) != (cal["primary_rays"], cal["shadow_rays"]):
+        raise SystemExit(f"ray counts {prim}+{shad} differ from the calibrated workload {cal['primary_rays']}+{cal['shadow_rays']}")
+    rays_per_frame = prim + shad
+    flops_per_frame = cal["flops"] if cal else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up ---------------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        flush_buf.fill_(1)
+        device_step()
+    barrier()
+
+    # ---- timed region: EXACTLY K steps; L2 flushed between steps (untimed) -------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    launches[0] = 0
+    barrier()
+    for e0, ek, e1 in ev:
+        flush_buf.fill_(1)
+        if world > 1:
+            dist.barrier()  # ranks start each frame together, as one frame request would
+        e0.record()
+        c2.render_device(handle, cam, st, out_ptr, None, band if n_ranks > 1 else None, stream)
+        launches[0] += 1
+        ek.record()
+        if gather_mode == "nccl":
+            dist.gather(mine, list(gathered.unbind(0)) if rank == 0 else None, dst=0)
+            if rank == 0:
+                c2.deinterleave(gathered.data_ptr(), frame.data_ptr(), W, H, 3, n_ranks, BAND_ROWS, pad, stream)
+                launches[0] += 1
+        elif gather_mode == "p2p":
+            dist.all_reduce(sync_flag)
+        e1.record()
+    barrier()
+    step_ms = [e0.elapsed_time(e1) for e0, ek, e1 in ev]
+    kern_ms = [e0.elapsed_time(ek) for e0, ek, e1 in ev]
+    t = torch.tensor([sum(step_ms), sum(kern_ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, total_kernel_ms = float(t[0]), float(t[1])
+    n_launches = launches[0]
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e: public host API, HOST buffers, copies inside the timed region ------------------------
+    pinned = torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True) if rank == 0 else None
+    e2e_ms = []
+    if world == 1:
+        out_np = pinned.numpy()
+        for i in range(args.warmup + args.steps):
+            flush_buf.fill_(1)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            scene.render(seed=RNG_SEED, out=out_np)      # c2rt_render: launch params down, kernel, frame D2H, sync
+            t1 = time.perf_counter()
+            if i >= args.warmup:
+                e2e_ms.append((t1 - t0) * 1e3)
+    else:
+        for i in range(args.warmup + args.steps):
+            flush_buf.fill_(1)
+            barrier()
+            t0 = time.perf_counter()
+            cam_i, st_i = scene.frame_blocks(seed=RNG_SEED)  # per-frame host work: Camera.beginFrame + flatten
+            c2.render_device(handle, cam_i, st_i, out_ptr, None, band, stream)
+            if gather_mode == "nccl":
+                dist.gather(mine, list(gathered.unbind(0)) if rank == 0 else None, dst=0)
+                if rank == 0:
+                    c2.deinterleave(gathered.data_ptr(), frame.data_ptr(), W, H, 3, n_ranks, BAND_ROWS, pad, stream)
+                    pinned.copy_(frame, non_blocking=True)
+            else:
+                dist.all_reduce(sync_flag)
+                if rank == 0:
+                    # D2H straight from the IPC-exported frame (no scatter needed in p2p mode)
+                    api._check(api.lib.c2rt_frame_download(pinned.data_ptr(), peer_frame_ptr, H * W * 12, stream))
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            tt = torch.tensor([(t1 - t0) * 1e3], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            if i >= args.warmup:
+                e2e_ms.append(float(tt[0]))
+    e2e_ms_mean = sum(e2e_ms) / len(e2e_ms)
+
+    if rank == 0:
+        ms_per_step = total_ms / args.steps
+        kernel_ms = total_kernel_ms / args.steps
+        value = rays_per_frame / (ms_per_step * 1e-3) / 1e6
+        peak_tf, peak_mhz = c2.measure_fma_peak(False)
+        peak64_tf, _ = c2.measure_fma_peak(True)
+        peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        mp = json.load(open(peaks_file)) if os.path.exists(peaks_file) else {}
+        sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        nominal_tf = 2 * 128 * sms * mp.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(args.workload)
+        roofline = None
+        if flops_per_frame:
+            achieved = flops_per_frame / n_ranks / (kernel_ms * 1e-3) / 1e12  # per GPU: each renders 1/N of the frame
+            roofline = {
+                "bound": "fp32", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                "traffic": traffic, "peak_source": "FFMA micro-benchmark measured in this run (c2rt_measure_fma_peak)",
+                "peak_nominal": nominal_tf, "frac_nominal": achieved / nominal_tf, "fp64_peak_measured": peak64_tf,
+                "algorithmic_flops_per_frame": flops_per_frame, "kernel_ms": kernel_ms,
+                "hbm": {"achieved": W * H * 12 / n_ranks / (kernel_ms * 1e-3) / 1e9, "peak": mp.get("hbm_gbs"), "unit": "GB/s",
+                        "note": "framebuffer bytes written per kernel; far below the HBM roof, the kernel is FMA-bound"},
+            }
+        line = {
+            "metric": "Mrays/s at %dx%d" % (W, H), "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "frames_per_s": 1e3 / ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64 geometry / f32 colour (as the reference)",
+            "data": "synthetic (bundled scene file rendered from a fixed camera; no external data)",
+            "config": {"workload": "%s: %s at %dx%d, AA 5 samples/px, 1 light" % (args.workload, path, W, H),
+                       "rays_per_frame": rays_per_frame, "primary_rays": prim, "shadow_rays": shad,
+                       "l2": "flushed between timed steps (256 MiB fill, untimed); per-step CUDA events summed",
+                       "parallelism": "row bands of %d rows, interleaved over %d GPU(s), gather=%s" % (BAND_ROWS, world, gather_mode)},
+            "roofline": roofline,
+            "e2e": {"value": rays_per_frame / (e2e_ms_mean * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms_mean,
+                    "frames_per_s": 1e3 / e2e_ms_mean, "h2d_bytes_per_step": C_sizeof_frame_blocks(api), "d2h_bytes_per_step": W * H * 12},
+            "gpu_launches": n_launches,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            if W * H <= 3840 * 2160 and args.workload != "c3":
+                times, rays = cpu_frame_seconds(path, W, H, over, threads, min_seconds=3.0, max_frames=5)
+                sec = min(times)
+                sample = "%d full frame(s) of the workload, best of" % len(times)
+            else:
+                s_, rays_, done = cpu_rows_seconds(path, W, H, over, threads, rows=128)
+                sec, rays = s_ * H / done, rays_ * H / done
+                sample = "128 rows (16 windows of 8 rows spread over the frame), scaled to the frame"
+            line["cpu_baseline"] = {"value": rays / sec / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
+                                    "sample": sample, "frames_per_s": 1.0 / sec,
+                                    "note": "C++ restatement of the reference (oracle/), g++ -O2; the D reference cannot be built here"}
+        print(json.dumps(line), flush=True)
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    c2.shutdown()
+
+
+def C_sizeof_frame_blocks(api):
+    import ctypes as C
+    return C.sizeof(api.Camera) + C.sizeof(api.Settings)
+
+
+if __name__ == "__main__":
+    main()

@@ -751,6 +751,12 @@ int c2rt_frame_unimport(void* d_ptr) {
     return C2RT_OK;
 }
 
+int c2rt_frame_download(void* host_dst, const void* d_src, size_t bytes, void* stream) {
+    if (!host_dst || !d_src) return fail(C2RT_ERR_INVALID_ARG, "bad frame_download arguments");
+    CU(cudaMemcpyAsync(host_dst, d_src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return C2RT_OK;
+}
+
 int c2rt_measure_fma_peak(int fp64, double* tflops, double* sm_clock_mhz_est) {
     if (!tflops) return fail(C2RT_ERR_INVALID_ARG, "tflops is null");
     int dev = 0;

@@ -229,6 +229,8 @@ int c2rt_frame_free(void* d_ptr);
 int c2rt_frame_export(void* d_ptr, uint8_t handle[64]);
 int c2rt_frame_import(const uint8_t handle[64], void** d_ptr);
 int c2rt_frame_unimport(void* d_ptr);
+/* asynchronous device->host copy of (part of) such a frame on `stream` (host memory should be pinned) */
+int c2rt_frame_download(void* host_dst, const void* d_src, size_t bytes, void* stream);
 
 /* Micro-benchmarks used by bench.py to measure the roofline denominators on the box:
  * dependent-free FFMA / DFMA throughput in TFLOP/s on the current device. */

@@ -1,0 +1,236 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (libc2rt.so via the host mirror),
+against the CPU oracle on the same inputs.  Bar (BASELINE.json north_star): per-pixel float RGB within
+1e-3 absolute; at most 0.1 % of 8-bit pixels differing by more than 1 LSB.  Integer work (ARGB packing,
+ray counts, band scatter) must be bit-exact."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import chess2rt_b200 as c2
+from chess2rt_b200 import api, bands
+from oracle_binding import OracleScene, pack_rgb32, parity_report
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SC = os.path.join(ROOT, "scenes")
+GOLD = os.path.join(ROOT, "tests", "golden")
+TOL = 1e-3  # float RGB, absolute (north_star)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _ctx():
+    c2.init(1, [0])
+    yield
+    c2.shutdown()
+
+
+def both(path, size=None, seed=0, **over):
+    g, o = c2.HostScene(path), OracleScene(path)
+    for s in (g, o):
+        if size:
+            s.set_frame_size(*size)
+        s.override(**over)
+    return g, o
+
+
+def assert_parity(rgb, ref, argb=None, what=""):
+    rep = parity_report(rgb, ref, argb)
+    assert rep["px_over_1e-3"] == 0, (what, rep)
+    assert rep["frac_over_1lsb"] <= 1e-3, (what, rep)
+    return rep
+
+
+CASES = [
+    ("lecture4.sdl", None, {}),
+    ("lecture4.json", None, {}),
+    ("lecture4-proc-texture.sdl", None, {}),
+    ("lecture5.sdl", None, {}),
+    ("zaphod.sdl", None, {"dof": 0}),          # 645x430: not a multiple of the 16x8 tile nor of 4
+    ("zaphod.sdl", None, {"num_samples": 6}),  # DOF with the pinned generator
+    ("chessboard.sdl", (480, 270), {}),
+    ("../tests/scenes/quirks.sdl", None, {}),
+]
+
+
+@pytest.mark.parametrize("name,size,over", CASES)
+def test_scene_matches_oracle(name, size, over):
+    g, o = both(os.path.join(SC, name), size, **over)
+    rgb, argb, st = g.render(argb=True, seed=11, count_rays=True)
+    ref, ost = o.render(seed=11)
+    assert_parity(rgb, ref, argb, name)
+    # rays the algorithm requires: identical counts (same hit / lit decisions)
+    assert (st.primary_rays, st.shadow_rays) == (ost.primary_rays, ost.shadow_rays)
+    # ARGB plane == Color.toRGB32 of the float plane, bit-exact
+    np.testing.assert_array_equal(argb, pack_rgb32(rgb))
+    assert ost.csg_max_crossings <= 4  # the kernel's per-child crossing capacity
+
+
+def test_golden_fixtures():
+    meta = json.load(open(os.path.join(GOLD, "golden.json")))
+    for name, m in meta.items():
+        g = c2.HostScene(os.path.join(ROOT, m["scene"]))
+        g.set_frame_size(*m["size"])
+        g.override(**m["override"])
+        rgb, _, st = g.render(seed=m["seed"], count_rays=True)
+        assert_parity(rgb, np.load(os.path.join(GOLD, name + ".npy")), what=name)
+        assert (st.primary_rays, st.shadow_rays) == (m["primary_rays"], m["shadow_rays"])
+
+
+def test_config_c1_1080p_full_frame():
+    # BASELINE.json configs[1]: lecture4-proc-texture.sdl at 1920x1080
+    g, o = both(os.path.join(SC, "lecture4-proc-texture.sdl"), (1920, 1080))
+    rgb, argb, st = g.render(argb=True, count_rays=True)
+    ref, ost = o.render()
+    assert_parity(rgb, ref, argb, "C1")
+    assert st.primary_rays == 1920 * 1080 * 5 and st.shadow_rays == ost.shadow_rays
+
+
+def test_config_c2_4k_row_windows():
+    # configs[2]: lecture5.sdl at 3840x2160 — full GPU frame, oracle on row windows spread over the frame
+    g, o = both(os.path.join(SC, "lecture5.sdl"), (3840, 2160))
+    rgb, _, _ = g.render()
+    for y0 in (0, 400, 777, 1200, 1650, 2144):
+        ref, _ = o.render_rows(y0, y0 + 16)
+        assert_parity(rgb[y0:y0 + 16], ref, what=f"C2 rows {y0}")
+
+
+def test_config_c3_zaphod_4k_dof_windows():
+    # configs[3]: zaphod.sdl at 3840x2160 with DOF (25 samples x 5 taps), pinned RNG; no cubemap exists
+    g, o = both(os.path.join(SC, "zaphod.sdl"), (3840, 2160))
+    rgb, _, _ = g.render(seed=99)
+    for y0 in (8, 1080, 2150):
+        ref, _ = o.render_rows(y0, y0 + 4, seed=99)
+        assert_parity(rgb[y0:y0 + 4], ref, what=f"C3 rows {y0}")
+
+
+def test_config_c4_chessboard_8k_windows_and_properties():
+    # configs[4]: synthetic chessboard at 7680x4320 — oracle on row windows + size-independent properties
+    g, o = both(os.path.join(SC, "chessboard.sdl"), (7680, 4320))
+    rgb, argb, st = g.render(argb=True, count_rays=True)
+    for y0 in (0, 1500, 2800, 3600, 4312):
+        ref, _ = o.render_rows(y0, y0 + 8)
+        assert_parity(rgb[y0:y0 + 8], ref, what=f"C4 rows {y0}")
+    assert st.primary_rays == 7680 * 4320 * 5
+    assert st.shadow_rays == st.primary_rays        # every primary ray hits (floor fills the view), one live light
+    np.testing.assert_array_equal(argb, pack_rgb32(rgb))
+    assert np.isfinite(rgb).all() and rgb.min() >= 0
+    # idempotence: the frame is a pure function of (scene, camera, settings)
+    rgb2, _, _ = g.render()
+    np.testing.assert_array_equal(rgb, rgb2)
+
+
+@pytest.mark.parametrize("size", [(1, 1), (3, 2), (17, 9), (16, 8), (33, 41), (130, 7)])
+def test_ragged_and_tiny_frames(size):
+    g, o = both(os.path.join(SC, "lecture5.sdl"), size)
+    rgb, argb, _ = g.render(argb=True)
+    ref, _ = o.render()
+    assert rgb.shape == (size[1], size[0], 3)
+    assert_parity(rgb, ref, argb, str(size))
+
+
+def test_render_pixel_matches_oracle_hit_record():
+    path = os.path.join(ROOT, "tests", "scenes", "quirks.sdl")
+    g, o = both(path)
+    for (x, y) in [(10, 10), (160, 100), (60, 120), (200, 110), (250, 120), (300, 180), (120, 60), (90, 150), (0, 0)]:
+        rgb, hit = g.render_pixel(x, y)
+        ref_rgb, ref_hit = o.render_pixel(x, y)
+        assert hit.node == int(ref_hit[0]), (x, y)
+        np.testing.assert_allclose(rgb, ref_rgb, atol=TOL)
+        if hit.node >= 0:
+            np.testing.assert_allclose(hit.dist, ref_hit[1], rtol=1e-12)
+            np.testing.assert_allclose(list(hit.p), ref_hit[2:5], rtol=1e-11, atol=1e-9)
+            np.testing.assert_allclose(list(hit.normal), ref_hit[5:8], atol=1e-12)
+            np.testing.assert_allclose([hit.u, hit.v], ref_hit[8:10], rtol=1e-10, atol=1e-9)
+
+
+def _render_device_bands(g, n_ranks, band_rows, compact, seed=0):
+    """Emulates n ranks one after another on one GPU through c2rt_render_device (no waiting between kernels)."""
+    import torch
+    w, h = g.frame_size
+    cam, st = g.frame_blocks(seed=seed)
+    handle = g.device_scene()
+    if not compact:
+        frame = torch.zeros((h, w, 3), dtype=torch.float32, device="cuda")
+        argb = torch.zeros((h, w), dtype=torch.int32, device="cuda")
+        for r in range(n_ranks):
+            band = api.Band(r, n_ranks, band_rows, 0)
+            c2.render_device(handle, cam, st, frame.data_ptr(), argb.data_ptr(), band, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        return frame.cpu().numpy(), argb.cpu().numpy().view(np.uint32)
+    pad = bands.rows_padded(h, n_ranks, band_rows)
+    gathered = torch.zeros((n_ranks, pad, w, 3), dtype=torch.float32, device="cuda")
+    gathered_a = torch.zeros((n_ranks, pad, w), dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    for r in range(n_ranks):
+        band = api.Band(r, n_ranks, band_rows, 1)
+        c2.render_device(handle, cam, st, gathered[r].data_ptr(), gathered_a[r].data_ptr(), band, stream)
+    frame = torch.empty((h, w, 3), dtype=torch.float32, device="cuda")
+    argb = torch.empty((h, w), dtype=torch.int32, device="cuda")
+    c2.deinterleave(gathered.data_ptr(), frame.data_ptr(), w, h, 3, n_ranks, band_rows, pad, stream)
+    c2.deinterleave(gathered_a.data_ptr(), argb.data_ptr(), w, h, 1, n_ranks, band_rows, pad, stream)
+    torch.cuda.synchronize()
+    return frame.cpu().numpy(), argb.cpu().numpy().view(np.uint32)
+
+
+@pytest.mark.parametrize("n_ranks,band_rows,compact", [(1, 8, 0), (2, 8, 0), (2, 8, 1), (3, 16, 1), (8, 8, 1), (4, 24, 0)])
+def test_row_bands_reassemble_bit_exactly(n_ranks, band_rows, compact):
+    g = c2.HostScene(os.path.join(SC, "lecture5.sdl"))
+    g.set_frame_size(330, 203)   # ragged in x and y, last band partial
+    full, full_a, _ = g.render(argb=True)
+    rgb, argb = _render_device_bands(g, n_ranks, band_rows, compact)
+    np.testing.assert_array_equal(rgb, full)
+    np.testing.assert_array_equal(argb, full_a)
+
+
+def test_ray_counters_device_path():
+    g, o = both(os.path.join(SC, "lecture5.sdl"), (200, 120))
+    import torch
+    cam, st = g.frame_blocks(count_rays=True)
+    frame = torch.zeros((120, 200, 3), dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    c2.render_device(g.device_scene(), cam, st, frame.data_ptr(), None, None, stream)
+    p, s = c2.read_ray_counters(g.device_scene(), stream)
+    _, ost = o.render()
+    assert (p, s) == (ost.primary_rays, ost.shadow_rays)
+    assert c2.read_ray_counters(g.device_scene(), stream) == (0, 0)
+
+
+def test_unsupported_features_are_errors_not_fallbacks():
+    g = c2.HostScene(os.path.join(SC, "lecture4.sdl"))
+    cam, st = g.frame_blocks()
+    rgb = np.zeros((480, 640, 3), np.float32)
+    st.gi_enabled = 1
+    assert api.lib.c2rt_render(g.device_scene(), C.byref(cam), C.byref(st), rgb.ctypes.data, None, None) == -2
+    st.gi_enabled = 0
+    st.prepass_only = 1
+    assert api.lib.c2rt_render(g.device_scene(), C.byref(cam), C.byref(st), rgb.ctypes.data, None, None) == -2
+    st.prepass_only = 0
+    cam.stereo_separation = 0.5
+    assert api.lib.c2rt_render(g.device_scene(), C.byref(cam), C.byref(st), rgb.ctypes.data, None, None) == -2
+    cam.stereo_separation = 0
+    assert api.lib.c2rt_render(g.device_scene(), C.byref(cam), C.byref(st), None, None, None) == -1
+    assert api.lib.c2rt_render(g.device_scene(), C.byref(cam), C.byref(st), rgb.ctypes.data, None, None) == 0
+
+
+def test_many_scenes_alive_and_scene_switching():
+    paths = ["lecture4.sdl", "lecture5.sdl", "lecture4-proc-texture.sdl"]
+    gs = [c2.HostScene(os.path.join(SC, p)) for p in paths]
+    refs = []
+    for p, g in zip(paths, gs):
+        g.set_frame_size(96, 64)
+        o = OracleScene(os.path.join(SC, p))
+        o.set_frame_size(96, 64)
+        refs.append(o.render()[0])
+    for _ in range(2):
+        for g, ref in zip(gs, refs):
+            assert_parity(g.render()[0], ref)
+
+
+def test_fma_peak_microbenchmarks_are_sane():
+    tf32, mhz = c2.measure_fma_peak(False)
+    tf64, _ = c2.measure_fma_peak(True)
+    assert 40 < tf32 < 90 and 15 < tf64 < 45 and 1000 < mhz < 2100

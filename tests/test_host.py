@@ -1,0 +1,217 @@
+"""Host-side logic without a GPU: the C ABI library loads and exports every symbol of include/c2rt.h,
+the reference-compatible loader + flattener produce the expected structure-of-arrays description,
+load errors mirror the reference's exception behaviour, the render entry points fail LOUDLY (no CPU
+fallback), band arithmetic, and the world_size-2 gather path over gloo."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import chess2rt_b200 as c2
+from chess2rt_b200 import api, bands
+from bmp_kats import KAT1, KAT1_PIXELS, KAT1_SIZE, KAT2, KAT2_PIXELS, KAT2_SIZE
+from oracle_binding import OracleScene, oracle_lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SC = os.path.join(ROOT, "scenes")
+HAS_GPU = c2.device_count() > 0
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "c2rt.h")).read()
+    declared = set(re.findall(r"\b(c2rt_[a-z0-9_]+)\s*\(", header))
+    declared -= {"c2rt_status"}
+    assert declared == set(api.C_ABI_SYMBOLS), declared ^ set(api.C_ABI_SYMBOLS)
+    for name in declared:
+        assert hasattr(api.lib, name), name
+    assert api.lib.c2rt_abi_version() == 1
+    # no torch / C++ types at the boundary: the exported names are unmangled C
+    out = subprocess.run(["nm", "-D", "--defined-only", os.path.join(ROOT, "chess2rt_b200", "libc2rt.so")],
+                         capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    assert declared <= exported
+
+
+def test_struct_layouts_match_header_sizes():
+    # sizes the C compiler gives the ABI structs (x86-64 SysV): guards the ctypes mirrors
+    assert C.sizeof(api.Camera) == 7 * 24 + 4 * 4 + 3 * 8
+    assert C.sizeof(api.Settings) == 56
+    assert C.sizeof(api.Band) == 16
+    assert C.sizeof(api.Stats) == 40
+    assert C.sizeof(api.Hit) == 8 + 8 + 24 + 24 + 16
+    s = c2.HostScene(os.path.join(SC, "lecture4.sdl"))
+    assert s.desc().contents.struct_size == C.sizeof(api.SceneDesc)
+
+
+def test_loader_and_flattener_lecture5():
+    s = c2.HostScene(os.path.join(SC, "lecture5.sdl"))
+    assert s.info() == {"nodes": 6, "geometries": 6, "shaders": 4, "textures": 2, "lights": 1, "aa": 1, "dof": 0,
+                        "num_samples": 25}
+    assert s.frame_size == (640, 480)
+    d = s.desc().contents
+    assert (d.n_nodes, d.n_geoms, d.n_shaders, d.n_textures, d.n_lights) == (6, 6, 4, 2, 1)
+    gt = [d.geom_type[i] for i in range(6)]
+    assert gt == [0, 1, 2, 1, 5, 1]  # plane, sphere, cube, sphere, CsgDiff, sphere
+    assert (d.geom_left[4], d.geom_right[4]) == (2, 3)          # references became indices
+    assert [d.node_geom[i] for i in range(6)] == [0, 1, 4, 5, 5, 5]  # the shared sphere "S" keeps ONE entry
+    assert [d.node_shader[i] for i in range(6)] == [0, 1, 2, 3, 3, 3]
+    np.testing.assert_array_equal([d.node_offset[3 * 3 + k] for k in range(3)], [100, 15, 256])
+    assert [d.node_transform[9 * 3 + k] for k in range(9)] == [1, 0, 0, 0, 1, 0, 0, 0, 1]
+    assert (d.tex_width[0], d.tex_height[0], d.tex_width[1], d.tex_height[1]) == (256, 256, 800, 400)
+    assert d.tex_texel_offset[1] == 256 * 256 and d.n_texels == 256 * 256 + 800 * 400
+    assert abs(d.tex_params[0] - float(np.float32(0.005))) == 0  # float scaling widened exactly
+    assert d.shader_exponent[2] == 60 and d.shader_exponent[3] == 80 and d.shader_strength[2] == 1
+    assert np.isnan(d.geom_params[1])  # Plane.limit stays NaN -> unbounded
+    # texels handed to the backend are bit-identical to the oracle's post-gamma Image!Color
+    o = OracleScene(os.path.join(SC, "lecture5.sdl"))
+    tex0 = o.texture_texels(0)
+    got = np.ctypeslib.as_array(d.texels, shape=(d.n_texels * 3,))[: 256 * 256 * 3].reshape(256, 256, 3)
+    np.testing.assert_array_equal(got, tex0)
+
+
+def test_loader_json_equals_sdl_and_quirks():
+    a = c2.HostScene(os.path.join(SC, "lecture4.sdl"))
+    b = c2.HostScene(os.path.join(SC, "lecture4.json"))
+    ia, ib = a.info(), b.info()
+    assert ia["aa"] == 1 and ib["aa"] == 0
+    ia.pop("aa"), ib.pop("aa")
+    assert ia == ib
+    da, db = a.desc().contents, b.desc().contents
+    assert [da.tex_colors[i] for i in range(6)] == [db.tex_colors[i] for i in range(6)]
+    # Node "rotate" is applied as a second scale (node.d:89-90)
+    q = c2.HostScene(os.path.join(ROOT, "tests", "scenes", "quirks.sdl"))
+    d = q.desc().contents
+    m = [d.node_transform[9 * 7 + k] for k in range(9)]  # "globe": scale 1.2 0.9 1.2 then rotate 1 1.1 1
+    np.testing.assert_allclose(m, [1.2, 0, 0, 0, 0.9 * 1.1, 0, 0, 0, 1.2], rtol=1e-15)
+    inv = [d.node_inverse[9 * 7 + k] for k in range(9)]
+    np.testing.assert_allclose(inv[4], 1 / (0.9 * 1.1), rtol=1e-15)
+    # camera blocks agree with the oracle's Camera.beginFrame
+    cam, st = q.frame_blocks()
+    o = OracleScene(os.path.join(ROOT, "tests", "scenes", "quirks.sdl"))
+    v = o.camera_vectors()
+    got = np.array([list(cam.pos), list(cam.up_left), list(cam.up_right), list(cam.down_left), list(cam.right_dir),
+                    list(cam.up_dir), list(cam.front_dir)])
+    np.testing.assert_array_equal(got, v)
+    assert (st.frame_width, st.frame_height, st.aa_enabled, st.prepass_enabled) == (320, 200, 1, 0)
+
+
+def test_load_errors_mirror_reference(tmp_path):
+    with pytest.raises(c2.C2rtError, match="Scene file not found"):   # scene_loader.d:29-32
+        c2.HostScene(tmp_path / "missing.sdl")
+    p = tmp_path / "x.txt"
+    p.write_text("Scene {}")
+    with pytest.raises(c2.C2rtError, match="unknown file type"):       # scene_loader.d:56-58
+        c2.HostScene(p)
+    p = tmp_path / "bad.sdl"
+    p.write_text("Scene {\n Geometries {\n  Torus \"t\" { R 1 }\n }\n}\n")
+    with pytest.raises(c2.C2rtError, match="Unknown object type"):     # scene_loader.d:189-191
+        c2.HostScene(p)
+    p = tmp_path / "dup.sdl"
+    p.write_text("Scene {\n Geometries {\n  Sphere \"a\" { R 1 }\n  Sphere \"a\" { R 2 }\n }\n}\n")
+    with pytest.raises(c2.C2rtError, match="duplicate name"):          # scene_loader.d:198
+        c2.HostScene(p)
+    p = tmp_path / "brace.sdl"
+    p.write_text("Scene {\n Geometries {\n")
+    with pytest.raises(c2.C2rtError, match="Invalid SDL"):             # scene_loader.d:37-40
+        c2.HostScene(p)
+    p = tmp_path / "bad.json"
+    p.write_text("{ \"Camera\": ")
+    with pytest.raises(c2.C2rtError, match="Invalid JSON"):            # scene_loader.d:33-36
+        c2.HostScene(p)
+
+
+@pytest.mark.parametrize("blob,size,pixels", [(KAT1, KAT1_SIZE, KAT1_PIXELS), (KAT2, KAT2_SIZE, KAT2_PIXELS)])
+def test_host_bmp_decoder_reference_kats(blob, size, pixels):
+    w, h = C.c_uint32(), C.c_uint32()
+    out = np.zeros(16, np.uint32)
+    buf = np.frombuffer(blob, np.uint8)
+    assert api.host_lib.c2rt_host_decode_bmp(buf.ctypes.data, len(blob), C.byref(w), C.byref(h), out.ctypes.data, out.size) == 0
+    assert (w.value, h.value) == size
+    assert [int(v) for v in out[: len(pixels)]] == [p & 0xFFFFFF for p in pixels]  # Color has no alpha
+
+
+def test_validation_errors_come_before_any_device_use(tmp_path):
+    # nested CSG is rejected with C2RT_ERR_UNSUPPORTED by the scene validator (no GPU needed to see it)
+    p = tmp_path / "nested.sdl"
+    p.write_text("""Scene {
+ Geometries {
+  Sphere "a" { R 1 }
+  Cube "b" { side 1 }
+  CsgUnion "u" { left "a"; right "b" }
+  CsgDiff "n" { left "u"; right "a" }
+ }
+ Shaders { Lambert "s" { color 1 1 1 } }
+ Nodes { Node "n" { geometry "n"; shader "s" } }
+}
+""")
+    s = c2.HostScene(p)
+    d = s.desc()
+    handle = C.c_void_p()
+    rc = api.lib.c2rt_scene_create(d, C.byref(handle))
+    assert rc == -2 and b"nested CSG" in api.lib.c2rt_last_error()
+    # ABI mismatch
+    bad = api.SceneDesc()
+    assert api.lib.c2rt_scene_create(C.byref(bad), C.byref(handle)) == -1
+    assert api.lib.c2rt_scene_create(None, C.byref(handle)) == -1
+
+
+@pytest.mark.skipif(HAS_GPU, reason="checks the no-GPU behaviour")
+def test_render_fails_loudly_without_a_gpu():
+    s = c2.HostScene(os.path.join(SC, "lecture4.sdl"))
+    with pytest.raises(c2.C2rtError, match="no CPU fallback"):
+        s.render()
+    with pytest.raises(c2.C2rtError):
+        c2.init(1)
+
+
+def test_pinned_rng_is_shared_between_oracle_and_library():
+    lib = oracle_lib()
+    rng = np.random.default_rng(1)
+    for _ in range(200):
+        seed = int(rng.integers(0, 2**63))
+        px, py, tap, smp, draw = [int(v) for v in rng.integers(0, 8000, 5)]
+        v = c2.rng_u31(seed, px, py, tap, smp, draw)
+        assert v == lib.orc_rng_u31(seed, px, py, tap, smp, draw)
+        assert 0 <= v < 2**31
+    vals = np.array([c2.rng_u31(9, x, y, 0, 0, 0) for x in range(64) for y in range(64)]) / 2147483647.0
+    assert abs(vals.mean() - 0.5) < 0.02 and abs(vals.var() - 1 / 12) < 0.01
+
+
+def test_srgb_table_of_the_library_equals_the_oracle_table():
+    from oracle_binding import srgb_lut
+    np.testing.assert_array_equal(c2.srgb_table(), srgb_lut())
+
+
+@pytest.mark.parametrize("h,n,b", [(1080, 8, 8), (1080, 3, 16), (430, 4, 8), (7, 2, 8), (4320, 8, 8), (100, 1, 8)])
+def test_band_arithmetic(h, n, b):
+    total = 0
+    seen = np.zeros(h, int)
+    for r in range(n):
+        rows = bands.owned_rows(h, r, n, b)
+        assert c2.band_rows_owned(h, r, n, b) == rows.size
+        seen[rows] += 1
+        total += rows.size
+    assert total == h and np.all(seen == 1)
+    assert bands.rows_padded(h, n, b) == max(bands.rows_owned(h, r, n, b) for r in range(n))
+    g = np.zeros((n, bands.rows_padded(h, n, b), 3), np.int64)
+    for r in range(n):
+        rows = bands.owned_rows(h, r, n, b)
+        g[r, : rows.size, 0] = rows
+    np.testing.assert_array_equal(bands.scatter_rows(g, h, n, b)[:, 0], np.arange(h))
+
+
+def test_two_rank_band_gather_over_gloo(tmp_path):
+    """world_size 2 on CPU (gloo): each rank produces its interleaved bands (with the oracle standing in
+    for the kernel), rank 0 gathers + scatters; the assembled frame equals the single-rank frame."""
+    script = os.path.join(ROOT, "tests", "_gloo_band_worker.py")
+    out = tmp_path / "ok.txt"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", script, str(out)]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert out.read_text().strip() == "ok"
