@@ -274,6 +274,7 @@ int validate_and_build(const c2rt_scene_desc* d, c2rt_scene* s) {
         if (t.type < C2RT_TEX_CHECKER || t.type > C2RT_TEX_BITMAP) return fail(C2RT_ERR_INVALID_ARG, "texture %u: unknown type %d", i, t.type);
         memcpy(t.c, d->tex_colors + 18 * i, 18 * sizeof(float));
         memcpy(t.d, d->tex_params + 6 * i, 6 * sizeof(double));
+        if (t.type == C2RT_TEX_CHECKER) t.d[1] = 1.0 / t.d[0];
         if (t.type == C2RT_TEX_BITMAP) {
             t.w = d->tex_width[i]; t.h = d->tex_height[i];
             if (t.w <= 0 || t.h <= 0) return fail(C2RT_ERR_INVALID_ARG, "texture %u: empty bitmap", i);
@@ -338,15 +339,38 @@ int validate_and_build(const c2rt_scene_desc* d, c2rt_scene* s) {
             double scale = fmin(sqrt(fro), sqrt(n1 * ninf));
             // inflate: covers the 1e-6 restarts/probes of the CSG walk and rounding in the test itself
             double r = b.r * scale * (1.0 + 1e-6) + 1e-4 * fmax(1.0, scale);
-            if (std::isfinite(cx) && std::isfinite(cy) && std::isfinite(cz) && std::isfinite(r)) {
-                nd.bc[0] = cx; nd.bc[1] = cy; nd.bc[2] = cz;
-                nd.br = r;
-                nd.br2 = r * r;
+            // the cull runs in FP32: round the centre, grow the radius by the rounding it introduces
+            float fx = (float)cx, fy = (float)cy, fz = (float)cz;
+            double shift = sqrt((cx - fx) * (cx - fx) + (cy - fy) * (cy - fy) + (cz - fz) * (cz - fz));
+            r = (r + shift) * (1.0 + 1e-6);
+            float rf = (float)r;
+            if ((double)rf < r) rf = nextafterf(rf, INFINITY);
+            if (std::isfinite(cx) && std::isfinite(cy) && std::isfinite(cz) && std::isfinite(r) && std::isfinite(rf) &&
+                std::isfinite(rf * rf)) {
+                nd.bcf[0] = fx; nd.bcf[1] = fy; nd.bcf[2] = fz;
+                nd.brf = rf;
+                nd.br2f = nextafterf(rf * rf, INFINITY);
+                nd.bclen = nextafterf(sqrtf(fx * fx + fy * fy + fz * fz), INFINITY);
             } else {
                 nd.flags |= NODE_UNBOUNDED;
             }
         } else {
             nd.flags |= NODE_UNBOUNDED;
+        }
+        // world-space fast path for identity-transform primitives
+        nd.kind = KIND_GENERIC;
+        const DevGeom& g = h.geoms[nd.geom];
+        if ((nd.flags & NODE_IDENTITY) && g.type <= C2RT_GEOM_CUBE) {
+            if (g.type == C2RT_GEOM_PLANE) {
+                if (std::isnan(g.p[1])) {  // bounded planes (limit set) keep the generic path
+                    nd.kind = KIND_PLANE_W;
+                    nd.wp[0] = g.p[0] + nd.off[1];
+                }
+            } else {
+                nd.kind = g.type == C2RT_GEOM_SPHERE ? KIND_SPHERE_W : KIND_CUBE_W;
+                nd.wp[0] = g.p[0] + nd.off[0]; nd.wp[1] = g.p[1] + nd.off[1]; nd.wp[2] = g.p[2] + nd.off[2];
+                nd.wp[3] = g.p[3];
+            }
         }
     }
     return C2RT_OK;
@@ -392,7 +416,7 @@ void fill_params(FrameParams& fp, const c2rt_camera* cam, const c2rt_settings* s
     memset(&fp, 0, sizeof fp);
     for (int k = 0; k < 3; k++) {
         fp.pos[k] = cam->pos[k];
-        fp.up_left[k] = cam->up_left[k];
+        fp.ul_rel[k] = cam->up_left[k] - cam->pos[k];
         fp.du[k] = cam->up_right[k] - cam->up_left[k];   // camera.d:141
         fp.dv[k] = cam->down_left[k] - cam->up_left[k];  // camera.d:142
         fp.right_dir[k] = cam->right_dir[k];
@@ -400,8 +424,8 @@ void fill_params(FrameParams& fp, const c2rt_camera* cam, const c2rt_settings* s
         fp.front_dir[k] = cam->front_dir[k];
         fp.ambient[k] = set->ambient_light[k];
     }
-    fp.cam_w = (double)cam->frame_width;
-    fp.cam_h = (double)cam->frame_height;
+    fp.inv_w = 1.0 / (double)cam->frame_width;
+    fp.inv_h = 1.0 / (double)cam->frame_height;
     fp.focal_plane_dist = cam->focal_plane_dist;
     fp.disc_multiplier = cam->disc_multiplier;
     fp.seed = set->rng_seed;

@@ -26,12 +26,21 @@ namespace c2rt {
 
 __constant__ DevScene c_scene;
 
+// Precision plan: FP64 carries everything a pixel DECISION or a texture coordinate
+// depends on — ray direction, hit distances, hit points, plane/cube uv, checker cells, face-forward
+// sign, CSG crossing order.  FP32 carries what is continuous and ends in an FP32 colour anyway —
+// bounding-sphere culling (conservative margins), normals for lighting, light falloff, cosines, pow,
+// sin after an FP64 range reduction, sphere uv.  Divisions and square roots in FP64 use the
+// MUFU seed + Newton steps below instead of the IEEE library sequences (|rel err| < 4e-16).
+
 struct Ray {
-    double ox, oy, oz, dx, dy, dz;
+    double ox, oy, oz, dx, dy, dz;   // d is unit (to ~1e-16)
+    float fox, foy, foz, fdx, fdy, fdz, olen;  // FP32 shadow of the ray for the conservative cull
 };
 
-// Closest-hit record.  `p` is in the node's object space; normal / uv are derived from
-// (leaf, face, p) only for the winning hit (the reference fills them for every candidate).
+// Closest-hit record.  `p` is in the node's local frame: world space for KIND_*_W nodes, object
+// space for KIND_GENERIC.  Normal / uv are derived from (leaf, face, p) for the winning hit only
+// (the reference fills them for every candidate: geometry.d:49-55,114-123,224-230).
 struct HitRec {
     double dist;
     double px, py, pz;
@@ -46,12 +55,34 @@ struct Col {
 __device__ __forceinline__ Col mkcol(float r, float g, float b) { Col c; c.r = r; c.g = g; c.b = b; return c; }
 
 __device__ __forceinline__ double dot3(double ax, double ay, double az, double bx, double by, double bz) {
-    double s = 0.0;
-    s += ax * bx; s += ay * by; s += az * bz;
-    return s;
+    return fma(az, bz, fma(ay, by, ax * bx));
+}
+__device__ __forceinline__ float dot3f(float ax, float ay, float az, float bx, float by, float bz) {
+    return fmaf(az, bz, fmaf(ay, by, ax * bx));
+}
+// 1/a and 1/sqrt(a) in FP64: hardware seed (MUFU.RCP64H / MUFU.RSQ64H, ~20 bits) + two Newton steps
+__device__ __forceinline__ double rcp64(double a) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double e = fma(-a, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-a, y, 1.0);
+    y = fma(y, e, y);
+    return y;
+}
+__device__ __forceinline__ double rsqrt64(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double h = 0.5 * y;
+    double e = fma(-a * y, y, 1.0);
+    y = fma(h, e, y);
+    h = 0.5 * y;
+    e = fma(-a * y, y, 1.0);
+    y = fma(h, e, y);
+    return y;
 }
 __device__ __forceinline__ void normalize3(double& x, double& y, double& z) {
-    double inv = 1.0 / sqrt(dot3(x, y, z, x, y, z));
+    double inv = rsqrt64(dot3(x, y, z, x, y, z));
     x *= inv; y *= inv; z *= inv;
 }
 // row vector x row-major 3x3 (imported_types.d:13-20)
@@ -60,10 +91,15 @@ __device__ __forceinline__ void mulvm(const double* m, double x, double y, doubl
     ry = x * m[1] + y * m[4] + z * m[7];
     rz = x * m[2] + y * m[5] + z * m[8];
 }
+__device__ __forceinline__ void set_shadow(Ray& r) {
+    r.fox = (float)r.ox; r.foy = (float)r.oy; r.foz = (float)r.oz;
+    r.fdx = (float)r.dx; r.fdy = (float)r.dy; r.fdz = (float)r.dz;
+    r.olen = sqrtf(dot3f(r.fox, r.foy, r.foz, r.fox, r.foy, r.foz));
+}
 
 // ---------------------------------------------------------------- pinned RNG (c2rt.h c2rt_rng_u31)
-__host__ __device__ inline uint32_t rng_u31(unsigned long long seed, uint32_t px, uint32_t py, uint32_t tap,
-                                            uint32_t sample, uint32_t draw) {
+__device__ __forceinline__ uint32_t rng_u31(unsigned long long seed, uint32_t px, uint32_t py, uint32_t tap, uint32_t sample,
+                                            uint32_t draw) {
     unsigned long long k = seed;
     k ^= (unsigned long long)px * 0x9E3779B97F4A7C15ull;
     k = (k ^ (k >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -78,66 +114,71 @@ __host__ __device__ inline uint32_t rng_u31(unsigned long long seed, uint32_t px
 __device__ __forceinline__ double uniform01(const FrameParams& fp, uint32_t px, uint32_t py, uint32_t tap, uint32_t sample,
                                             uint32_t& draw) {
     double r = (double)rng_u31(fp.seed, px, py, tap, sample, draw++);
-    return 0.0 + (r / 2147483647.0) * 1.0;
+    return r * (1.0 / 2147483647.0);
 }
 
 // ---------------------------------------------------------------- camera
+// camera.d:123-174.  fp.up_left is stored relative to the camera position, fp.inv_w/inv_h are the
+// reciprocals of the camera frame size (x / W -> x * (1/W): one rounding apart).
 __device__ __forceinline__ void gen_ray(const FrameParams& fp, double x, double y, uint32_t px, uint32_t py, uint32_t tap,
                                         uint32_t sample, uint32_t& draw, Ray& r) {
-    double sx = x / fp.cam_w, sy = y / fp.cam_h;
-    double tx = fp.up_left[0] + fp.du[0] * sx + fp.dv[0] * sy;
-    double ty = fp.up_left[1] + fp.du[1] * sx + fp.dv[1] * sy;
-    double tz = fp.up_left[2] + fp.du[2] * sx + fp.dv[2] * sy;
+    double sx = x * fp.inv_w, sy = y * fp.inv_h;
+    r.dx = fma(fp.dv[0], sy, fma(fp.du[0], sx, fp.ul_rel[0]));
+    r.dy = fma(fp.dv[1], sy, fma(fp.du[1], sx, fp.ul_rel[1]));
+    r.dz = fma(fp.dv[2], sy, fma(fp.du[2], sx, fp.ul_rel[2]));
     r.ox = fp.pos[0]; r.oy = fp.pos[1]; r.oz = fp.pos[2];
-    r.dx = tx - r.ox; r.dy = ty - r.oy; r.dz = tz - r.oz;
     normalize3(r.dx, r.dy, r.dz);
-    if (!fp.dof) return;
-    double cosTheta = dot3(r.dx, r.dy, r.dz, fp.front_dir[0], fp.front_dir[1], fp.front_dir[2]);
-    double M = fp.focal_plane_dist / cosTheta;
-    double Tx = r.ox + r.dx * M, Ty = r.oy + r.dy * M, Tz = r.oz + r.dz * M;
-    double angle = uniform01(fp, px, py, tap, sample, draw) * 2 * CUDART_PI;
-    double rad = sqrt(uniform01(fp, px, py, tap, sample, draw));
-    double sa, ca;
-    sincos(angle, &sa, &ca);
-    double ddx = sa * rad * fp.disc_multiplier;
-    double ddy = ca * rad * fp.disc_multiplier;
-    r.ox = fp.pos[0] + ddx * fp.right_dir[0] + ddy * fp.up_dir[0];
-    r.oy = fp.pos[1] + ddx * fp.right_dir[1] + ddy * fp.up_dir[1];
-    r.oz = fp.pos[2] + ddx * fp.right_dir[2] + ddy * fp.up_dir[2];
-    r.dx = Tx - r.ox; r.dy = Ty - r.oy; r.dz = Tz - r.oz;
-    normalize3(r.dx, r.dy, r.dz);
+    if (fp.dof) {
+        double cosTheta = dot3(r.dx, r.dy, r.dz, fp.front_dir[0], fp.front_dir[1], fp.front_dir[2]);
+        double M = fp.focal_plane_dist * rcp64(cosTheta);
+        double Tx = r.ox + r.dx * M, Ty = r.oy + r.dy * M, Tz = r.oz + r.dz * M;
+        double angle = uniform01(fp, px, py, tap, sample, draw) * (2 * CUDART_PI);
+        double u2 = uniform01(fp, px, py, tap, sample, draw);
+        double rad = u2 > 0 ? u2 * rsqrt64(u2) : 0.0;
+        double sa, ca;
+        sincos(angle, &sa, &ca);  // lens position: kept in FP64 (it moves the ray origin by up to discMultiplier)
+        double ddx = sa * rad * fp.disc_multiplier;
+        double ddy = ca * rad * fp.disc_multiplier;
+        r.ox = fp.pos[0] + ddx * fp.right_dir[0] + ddy * fp.up_dir[0];
+        r.oy = fp.pos[1] + ddx * fp.right_dir[1] + ddy * fp.up_dir[1];
+        r.oz = fp.pos[2] + ddx * fp.right_dir[2] + ddy * fp.up_dir[2];
+        r.dx = Tx - r.ox; r.dy = Ty - r.oy; r.dz = Tz - r.oz;
+        normalize3(r.dx, r.dy, r.dz);
+    }
+    set_shadow(r);
 }
 
-// ---------------------------------------------------------------- primitives (object space)
+// ---------------------------------------------------------------- primitives
 // Each returns true iff it found a hit with t <= dist, then updates dist and the hit point.
-__device__ __forceinline__ bool isect_plane(const DevGeom& g, const Ray& r, double& dist, double& px, double& py, double& pz) {
-    double y = g.p[0];
-    if ((r.oy > y && r.dy > -1e-9) || (r.oy < y && r.dy < 1e-9)) return false;
-    double mult = (r.oy - y) / -r.dy;
+// (o, d) is the ray in the primitive's frame, p[] the primitive's parameters in that frame.
+__device__ __forceinline__ bool isect_plane(double y, double limit, double ox, double oy, double oz, double dx, double dy, double dz,
+                                            double& dist, double& px, double& py, double& pz) {
+    if ((oy > y && dy > -1e-9) || (oy < y && dy < 1e-9)) return false;
+    double mult = (oy - y) * rcp64(-dy);
     if (mult > dist) return false;
-    double x = r.ox + r.dx * mult, yy = r.oy + r.dy * mult, z = r.oz + r.dz * mult;
-    double limit = g.p[1];  // NaN (unbounded) compares false
-    if (fabs(x) > limit || fabs(z) > limit) return false;
+    double x = fma(dx, mult, ox), yy = fma(dy, mult, oy), z = fma(dz, mult, oz);
+    if (fabs(x) > limit || fabs(z) > limit) return false;  // NaN limit (unbounded) compares false
     dist = mult;
     px = x; py = yy; pz = z;
     return true;
 }
 
-__device__ __forceinline__ bool isect_sphere(const DevGeom& g, const Ray& r, double& dist, double& px, double& py, double& pz) {
-    double hx = r.ox - g.p[0], hy = r.oy - g.p[1], hz = r.oz - g.p[2];
-    double A = dot3(r.dx, r.dy, r.dz, r.dx, r.dy, r.dz);
-    double B = 2 * dot3(hx, hy, hz, r.dx, r.dy, r.dz);
-    double C = dot3(hx, hy, hz, hx, hy, hz) - g.p[3] * g.p[3];
-    double D = B * B - 4 * A * C;
+__device__ __forceinline__ bool isect_sphere(const double* p, double ox, double oy, double oz, double dx, double dy, double dz,
+                                             double& dist, double& px, double& py, double& pz) {
+    double hx = ox - p[0], hy = oy - p[1], hz = oz - p[2];
+    double A = dot3(dx, dy, dz, dx, dy, dz);
+    double B = 2 * dot3(hx, hy, hz, dx, dy, dz);
+    double C = dot3(hx, hy, hz, hx, hy, hz) - p[3] * p[3];
+    double D = fma(B, B, -4 * A * C);
     if (D < 0) return false;
-    double sq = sqrt(D);
-    double x2 = (-B - sq) / (2 * A);
-    double sol = x2;
-    if (sol < 0) sol = (-B + sq) / (2 * A);
+    double sq = D > 0 ? D * rsqrt64(D) : 0.0;
+    double inv2a = rcp64(2 * A);
+    double sol = (-B - sq) * inv2a;
+    if (sol < 0) sol = (-B + sq) * inv2a;
     if (sol < 0) return false;
     if (sol > dist) return false;
     dist = sol;
-    px = r.ox + r.dx * sol; py = r.oy + r.dy * sol; pz = r.oz + r.dz * sol;
+    px = fma(dx, sol, ox); py = fma(dy, sol, oy); pz = fma(dz, sol, oz);
     return true;
 }
 
@@ -146,14 +187,15 @@ __device__ __forceinline__ bool cube_pass(double oa, double ob, double oc, doubl
                                           double cc, double half, double& dist, double& pa, double& pb, double& pc, int& side_out) {
     if (fabs(da) < 1e-9) return false;
     bool found = false;
+    const double inv = rcp64(-da);
 #pragma unroll
     for (int side = -1; side <= 1; side += 2) {
-        double mult = (oa - (ca + side * half)) / -da;
+        double mult = (oa - (ca + side * half)) * inv;
         if (mult < 0) continue;
         if (mult > dist) continue;
-        double qb = ob + db * mult, qc = oc + dc * mult;
+        double qb = fma(db, mult, ob), qc = fma(dc, mult, oc);
         if (qb < cb - half || qb > cb + half || qc < cc - half || qc > cc + half) continue;
-        pa = oa + da * mult; pb = qb; pc = qc;
+        pa = fma(da, mult, oa); pb = qb; pc = qc;
         dist = mult;
         side_out = side > 0;
         found = true;
@@ -161,20 +203,22 @@ __device__ __forceinline__ bool cube_pass(double oa, double ob, double oc, doubl
     return found;
 }
 
-__device__ __forceinline__ bool isect_cube(const DevGeom& g, const Ray& r, double& dist, double& px, double& py, double& pz, int& face) {
-    double half = g.p[3] * 0.5;
+__device__ __forceinline__ bool isect_cube(const double* p, double ox, double oy, double oz, double dx, double dy, double dz,
+                                           double& dist, double& px, double& py, double& pz, int& face) {
+    double half = p[3] * 0.5;
     bool found = false;
     int side;
-    if (cube_pass(r.oy, r.ox, r.oz, r.dy, r.dx, r.dz, g.p[1], g.p[0], g.p[2], half, dist, py, px, pz, side)) { found = true; face = 0 + side; }
-    if (cube_pass(r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, g.p[0], g.p[1], g.p[2], half, dist, px, py, pz, side)) { found = true; face = 2 + side; }
-    if (cube_pass(r.oz, r.ox, r.oy, r.dz, r.dx, r.dy, g.p[2], g.p[0], g.p[1], half, dist, pz, px, py, side)) { found = true; face = 4 + side; }
+    if (cube_pass(oy, ox, oz, dy, dx, dz, p[1], p[0], p[2], half, dist, py, px, pz, side)) { found = true; face = 0 + side; }
+    if (cube_pass(ox, oy, oz, dx, dy, dz, p[0], p[1], p[2], half, dist, px, py, pz, side)) { found = true; face = 2 + side; }
+    if (cube_pass(oz, ox, oy, dz, dx, dy, p[2], p[0], p[1], half, dist, pz, px, py, side)) { found = true; face = 4 + side; }
     return found;
 }
 
-__device__ __forceinline__ bool isect_prim(const DevGeom& g, const Ray& r, double& dist, double& px, double& py, double& pz, int& face) {
-    if (g.type == C2RT_GEOM_PLANE) return isect_plane(g, r, dist, px, py, pz);
-    if (g.type == C2RT_GEOM_SPHERE) return isect_sphere(g, r, dist, px, py, pz);
-    return isect_cube(g, r, dist, px, py, pz, face);
+__device__ __forceinline__ bool isect_prim(const DevGeom& g, double ox, double oy, double oz, double dx, double dy, double dz,
+                                           double& dist, double& px, double& py, double& pz, int& face) {
+    if (g.type == C2RT_GEOM_PLANE) return isect_plane(g.p[0], g.p[1], ox, oy, oz, dx, dy, dz, dist, px, py, pz);
+    if (g.type == C2RT_GEOM_SPHERE) return isect_sphere(g.p, ox, oy, oz, dx, dy, dz, dist, px, py, pz);
+    return isect_cube(g.p, ox, oy, oz, dx, dy, dz, dist, px, py, pz, face);
 }
 
 __device__ __forceinline__ bool prim_inside(const DevGeom& g, double x, double y, double z) {
@@ -209,17 +253,17 @@ struct Crossing {
     int face, leaf;
 };
 
-__device__ int find_all(int gi, Ray r, Crossing* out) {  // geometry.d:271-290
+__device__ __noinline__ int find_all(int gi, double ox, double oy, double oz, double dx, double dy, double dz, Crossing* out) {  // geometry.d:271-290
     const DevGeom& g = c_scene.geoms[gi];
     double cur = 0;
     int n = 0;
     while (n < CSG_MAX_CHILD_CROSSINGS) {
         double dist = 1e99, px, py, pz;
         int face = 0;
-        if (!isect_prim(g, r, dist, px, py, pz, face)) break;
+        if (!isect_prim(g, ox, oy, oz, dx, dy, dz, dist, px, py, pz, face)) break;
         dist += cur;
         cur = dist;
-        r.ox = px + r.dx * 1e-6; r.oy = py + r.dy * 1e-6; r.oz = pz + r.dz * 1e-6;
+        ox = fma(dx, 1e-6, px); oy = fma(dy, 1e-6, py); oz = fma(dz, 1e-6, pz);
         out[n].dist = dist; out[n].px = px; out[n].py = py; out[n].pz = pz;
         out[n].face = face; out[n].leaf = gi;
         n++;
@@ -227,11 +271,12 @@ __device__ int find_all(int gi, Ray r, Crossing* out) {  // geometry.d:271-290
     return n;
 }
 
-__device__ bool isect_csg(int gi, const Ray& r, double& dist, double& px, double& py, double& pz, int& face, int& leaf) {
+__device__ __noinline__ bool isect_csg(int gi, double ox, double oy, double oz, double dx, double dy, double dz, double& dist,
+                                       double& px, double& py, double& pz, int& face, int& leaf) {
     const DevGeom& g = c_scene.geoms[gi];
     Crossing all[2 * CSG_MAX_CHILD_CROSSINGS];
-    int nl = find_all(g.left, r, all);
-    int nr = find_all(g.right, r, all + nl);
+    int nl = find_all(g.left, ox, oy, oz, dx, dy, dz, all);
+    int nr = find_all(g.right, ox, oy, oz, dx, dy, dz, all + nl);
     int n = nl + nr;
     // util/array.d:95-111 shell sort, including the `ref` loop index and the gap sequence
     int inc = n / 2;
@@ -259,8 +304,8 @@ __device__ bool isect_csg(int gi, const Ray& r, double& dist, double& px, double
             face = all[k].face;
             leaf = all[k].leaf;
             if (g.type == C2RT_GEOM_CSG_DIFF) {
-                bool a = geom_inside(g.right, px - r.dx * 1e-6, py - r.dy * 1e-6, pz - r.dz * 1e-6);
-                bool b = geom_inside(g.right, px + r.dx * 1e-6, py + r.dy * 1e-6, pz + r.dz * 1e-6);
+                bool a = geom_inside(g.right, px - dx * 1e-6, py - dy * 1e-6, pz - dz * 1e-6);
+                bool b = geom_inside(g.right, px + dx * 1e-6, py + dy * 1e-6, pz + dz * 1e-6);
                 if (a != b) face |= FACE_FLIP;
             }
             return true;
@@ -270,66 +315,106 @@ __device__ bool isect_csg(int gi, const Ray& r, double& dist, double& px, double
 }
 
 // ---------------------------------------------------------------- node
-// Conservative world-space bounding-sphere rejection (result-identical: it only skips nodes the
-// exact test below would reject).  `tmax` is the current best distance.
-__device__ __forceinline__ bool bound_miss(const DevNode& nd, const Ray& r, double tmax) {
-    if (nd.flags & NODE_UNBOUNDED) return false;
-    double cx = nd.bc[0] - r.ox, cy = nd.bc[1] - r.oy, cz = nd.bc[2] - r.oz;
-    double tca = cx * r.dx + cy * r.dy + cz * r.dz;
-    double c2 = cx * cx + cy * cy + cz * cz;
-    double d2 = c2 - tca * tca;
-    if (d2 > nd.br2) return true;                 // the line misses the sphere
-    if (c2 > nd.br2) {                            // origin outside
-        if (tca < 0) return true;                 // sphere behind the origin
-        if (tca - nd.br > tmax) return true;      // entry beyond the best distance so far
-    }
+// Conservative FP32 bounding-sphere rejection.  Result-identical: it only skips nodes the exact
+// FP64 test would reject.  `margin`/`slack` bound the FP32 rounding of everything in the test
+// (|err(d2)| <= 24 eps S^2, |err(tca)| <= 5 eps S with S = |centre| + |origin|).
+__device__ __forceinline__ bool cull(const DevNode& nd, const Ray& r, float tmaxf) {
+    float cx = nd.bcf[0] - r.fox, cy = nd.bcf[1] - r.foy, cz = nd.bcf[2] - r.foz;
+    float tca = dot3f(cx, cy, cz, r.fdx, r.fdy, r.fdz);
+    float c2 = dot3f(cx, cy, cz, cx, cy, cz);
+    float S = nd.bclen + r.olen;
+    float margin = 4e-6f * S * S;
+    float slack = 1e-6f * S;
+    float d2 = fmaf(-tca, tca, c2);
+    if (d2 > nd.br2f + margin) return true;          // the line misses the sphere
+    if (tca + nd.brf < -slack) return true;          // the sphere is behind the origin
+    if (tca - nd.brf > tmaxf + slack) return true;   // the sphere starts beyond the best distance so far
     return false;
 }
 
-// node.d:23-49.  Returns true and updates `h` iff this node yields a hit with dist <= h.dist.
-__device__ __forceinline__ bool node_intersect(int ni, const Ray& r, HitRec& h) {
+// node.d:23-49 for a transformed node: world ray -> object space, exact FP64 geometry test
+__device__ __noinline__ bool generic_intersect(int ni, const Ray& r, HitRec& h) {
     const DevNode& nd = c_scene.nodes[ni];
-    if (bound_miss(nd, r, h.dist)) return false;
-    Ray rc;
-    double len;
+    double ox, oy, oz, dx, dy, dz, len;
     double tx = r.ox - nd.off[0], ty = r.oy - nd.off[1], tz = r.oz - nd.off[2];
     if (nd.flags & NODE_IDENTITY) {
-        rc.ox = tx; rc.oy = ty; rc.oz = tz;
-        rc.dx = r.dx; rc.dy = r.dy; rc.dz = r.dz;
+        ox = tx; oy = ty; oz = tz;
+        dx = r.dx; dy = r.dy; dz = r.dz;
         len = 1.0;
     } else {
-        mulvm(nd.Minv, tx, ty, tz, rc.ox, rc.oy, rc.oz);
-        mulvm(nd.Minv, r.dx, r.dy, r.dz, rc.dx, rc.dy, rc.dz);
-        len = sqrt(dot3(rc.dx, rc.dy, rc.dz, rc.dx, rc.dy, rc.dz));
-        double inv = 1.0 / len;
-        rc.dx *= inv; rc.dy *= inv; rc.dz *= inv;
+        mulvm(nd.Minv, tx, ty, tz, ox, oy, oz);
+        mulvm(nd.Minv, r.dx, r.dy, r.dz, dx, dy, dz);
+        double l2 = dot3(dx, dy, dz, dx, dy, dz);
+        double inv = rsqrt64(l2);
+        len = l2 * inv;
+        dx *= inv; dy *= inv; dz *= inv;
     }
     double dist = h.dist * len;
     double px, py, pz;
     int face = 0, leaf = nd.geom;
     const DevGeom& g = c_scene.geoms[nd.geom];
     bool hit;
-    if (g.type <= C2RT_GEOM_CUBE) hit = isect_prim(g, rc, dist, px, py, pz, face);
-    else hit = isect_csg(nd.geom, rc, dist, px, py, pz, face, leaf);
+    if (g.type <= C2RT_GEOM_CUBE) hit = isect_prim(g, ox, oy, oz, dx, dy, dz, dist, px, py, pz, face);
+    else hit = isect_csg(nd.geom, ox, oy, oz, dx, dy, dz, dist, px, py, pz, face, leaf);
     if (!hit) return false;
-    h.dist = dist / len;
+    h.dist = (nd.flags & NODE_IDENTITY) ? dist : dist * rcp64(len);
     h.px = px; h.py = py; h.pz = pz;
     h.node = ni; h.leaf = leaf; h.face = face;
     return true;
 }
 
-// scene.d:62-78
-__device__ bool occluded(double fx, double fy, double fz, double tx, double ty, double tz) {
+// Returns true and updates `h` iff node `ni` yields a hit with dist <= h.dist.
+__device__ __forceinline__ bool node_intersect(int ni, const Ray& r, HitRec& h, float tmaxf) {
+    const DevNode& nd = c_scene.nodes[ni];
+    if (!(nd.flags & NODE_UNBOUNDED) && cull(nd, r, tmaxf)) return false;
+    int face = 0;
+    bool hit;
+    if (nd.kind == KIND_PLANE_W) hit = isect_plane(nd.wp[0], CUDART_NAN, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, h.px, h.py, h.pz);
+    else if (nd.kind == KIND_SPHERE_W) hit = isect_sphere(nd.wp, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, h.px, h.py, h.pz);
+    else if (nd.kind == KIND_CUBE_W) hit = isect_cube(nd.wp, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, h.px, h.py, h.pz, face);
+    else return generic_intersect(ni, r, h);
+    if (hit) { h.node = ni; h.leaf = nd.geom; h.face = face; }
+    return hit;
+}
+
+// scene.d:62-78 testVisibility.  (fx,fy,fz) is the shadow-ray origin, D = to - from (unnormalised),
+// len2 = |D|^2.  The FP64 normalisation (scene.d:66-71) is done lazily: most nodes are rejected by a
+// sign test (planes) or the FP32 cull, which only need FP32 directions.
+__device__ bool occluded(double fx, double fy, double fz, double Dx, double Dy, double Dz, double len2) {
     Ray r;
     r.ox = fx; r.oy = fy; r.oz = fz;
-    r.dx = tx - fx; r.dy = ty - fy; r.dz = tz - fz;
-    double maxd = sqrt(dot3(r.dx, r.dy, r.dz, r.dx, r.dy, r.dz));
-    normalize3(r.dx, r.dy, r.dz);
+    const float l2f = (float)len2;
+    const float rsf = rsqrtf(l2f);
+    r.fox = (float)fx; r.foy = (float)fy; r.foz = (float)fz;
+    r.fdx = (float)Dx * rsf; r.fdy = (float)Dy * rsf; r.fdz = (float)Dz * rsf;
+    r.olen = sqrtf(dot3f(r.fox, r.foy, r.foz, r.fox, r.foy, r.foz));
+    const float tmaxf = l2f * rsf * 1.000001f;
+    bool exact = false;
     HitRec h;
-    h.dist = maxd;
     const int n = c_scene.n_nodes;
-    for (int i = 0; i < n; i++)
-        if (node_intersect(i, r, h)) return true;
+    for (int i = 0; i < n; i++) {
+        const DevNode& nd = c_scene.nodes[i];
+        if (nd.kind == KIND_PLANE_W) {
+            // implied by geometry.d:35-36 (dir.y has the sign of D.y): the common "light above the floor" case
+            const double y = nd.wp[0];
+            if ((fy > y && Dy >= 0) || (fy < y && Dy <= 0)) continue;
+        } else if (!(nd.flags & NODE_UNBOUNDED)) {
+            if (cull(nd, r, tmaxf)) continue;
+        }
+        if (!exact) {
+            const double inv = rsqrt64(len2);
+            r.dx = Dx * inv; r.dy = Dy * inv; r.dz = Dz * inv;
+            h.dist = len2 * inv;
+            exact = true;
+        }
+        bool hit;
+        int face = 0;
+        if (nd.kind == KIND_PLANE_W) hit = isect_plane(nd.wp[0], CUDART_NAN, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, h.px, h.py, h.pz);
+        else if (nd.kind == KIND_SPHERE_W) hit = isect_sphere(nd.wp, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, h.px, h.py, h.pz);
+        else if (nd.kind == KIND_CUBE_W) hit = isect_cube(nd.wp, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, h.px, h.py, h.pz, face);
+        else hit = generic_intersect(i, r, h);
+        if (hit) return true;
+    }
     return false;
 }
 
@@ -339,11 +424,21 @@ __device__ __forceinline__ int cast_int_x86(double v) {  // cvttsd2si: out of ra
     return (int)v;
 }
 
+// sin(a) for an FP64 argument: Cody-Waite reduction to [-pi, pi] in FP64, then the FP32 SFU sine
+// (|abs err| < 5e-7).  The reference takes sin in FP64 and narrows to float (texture.d:82-83).
+__device__ __forceinline__ float sin_f64arg(double a) {
+    const double k = rint(a * 0.15915494309189535);  // 1 / 2pi
+    double rr = fma(-k, 6.283185307179586, a);
+    rr = fma(-k, 2.4492935982947064e-16, rr);
+    return __sinf((float)rr);
+}
+
+// (u, v) in FP64 for plane / cube hits; `uf, vf` is the FP32 pair for sphere hits (is_f32)
 __device__ Col sample_texture(int ti, double u, double v) {
     const DevTex& t = c_scene.textures[ti];
     if (t.type == C2RT_TEX_CHECKER) {
-        int x = cast_int_x86(floor(u / t.d[0]));
-        int y = cast_int_x86(floor(v / t.d[0]));
+        int x = cast_int_x86(floor(u * t.d[1]));
+        int y = cast_int_x86(floor(v * t.d[1]));
         int white = (int)((unsigned)x + (unsigned)y) % 2;
         return white ? mkcol(t.c[3], t.c[4], t.c[5]) : mkcol(t.c[0], t.c[1], t.c[2]);
     }
@@ -351,8 +446,8 @@ __device__ Col sample_texture(int ti, double u, double v) {
         Col res = mkcol(0.f, 0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 3; i++) {
-            float su = (float)sin(u * t.d[i]);
-            float sv = (float)sin(v * t.d[3 + i]);
+            float su = sin_f64arg(u * t.d[i]);
+            float sv = sin_f64arg(v * t.d[3 + i]);
             res.r += t.c[3 * i + 0] * su + t.c[9 + 3 * i + 0] * sv;
             res.g += t.c[3 * i + 1] * su + t.c[9 + 3 * i + 1] * sv;
             res.b += t.c[3 * i + 2] * su + t.c[9 + 3 * i + 2] * sv;
@@ -368,8 +463,8 @@ __device__ Col sample_texture(int ti, double u, double v) {
     float y = (float)v * (float)t.h;
     if (!(x >= 0.f) || !(y >= 0.f) || (unsigned)x >= (unsigned)t.w || (unsigned)y >= (unsigned)t.h)
         return mkcol(1.f, 0.f, 0.f);  // NamedColors.red
-    int tx = (int)floorf(x), ty = (int)floorf(y);
-    int txn = (tx + 1) % t.w, tyn = (ty + 1) % t.h;
+    int tx = (int)x, ty = (int)y;
+    int txn = tx + 1 == t.w ? 0 : tx + 1, tyn = ty + 1 == t.h ? 0 : ty + 1;
     float p = x - (float)tx, q = y - (float)ty;
     float4 a = __ldg(&t.texels[(size_t)ty * t.w + tx]);
     float4 b = __ldg(&t.texels[(size_t)ty * t.w + txn]);
@@ -381,110 +476,144 @@ __device__ Col sample_texture(int ti, double u, double v) {
 }
 
 // ---------------------------------------------------------------- hit completion + shading
-// Object-space normal and uv of the winning hit from (leaf, face, p): geometry.d:49-55,114-120,224-230
-__device__ __forceinline__ void finish_hit(const HitRec& h, double& nx, double& ny, double& nz, double& u, double& v, bool need_uv) {
-    const DevGeom& g = c_scene.geoms[h.leaf];
+struct Surface {
+    double px, py, pz;     // world-space hit point
+    double gx, gy, gz;     // world-space geometric normal, NOT normalised: only its sign against the ray is taken in FP64
+    float nx, ny, nz;      // unit world-space normal for lighting
+    double u, v;           // texture coordinates
+};
+
+// Local-frame normal / uv from (leaf, face, p): geometry.d:49-55 (plane), :114-120 (sphere), :224-230 (cube).
+// `c` are the primitive's parameters in the frame of h.p.
+__device__ __forceinline__ void local_surface(int type, const double* c, const HitRec& h, bool need_uv, double& gx, double& gy, double& gz,
+                                              double& u, double& v) {
     u = 0; v = 0;
-    if (g.type == C2RT_GEOM_PLANE) {
-        nx = 0; ny = 1; nz = 0;
+    if (type == C2RT_GEOM_PLANE) {
+        gx = 0; gy = 1; gz = 0;
         u = h.px; v = h.pz;
-    } else if (g.type == C2RT_GEOM_SPHERE) {
-        nx = h.px - g.p[0]; ny = h.py - g.p[1]; nz = h.pz - g.p[2];
-        normalize3(nx, ny, nz);
+    } else if (type == C2RT_GEOM_SPHERE) {
+        gx = h.px - c[0]; gy = h.py - c[1]; gz = h.pz - c[2];
         if (need_uv) {
-            double angle = atan2(h.pz - g.p[2], h.px - g.p[0]);
-            u = (CUDART_PI + angle) / (2 * CUDART_PI);
-            v = 1.0 - (CUDART_PI / 2 + asin((h.py - g.p[1]) / g.p[3])) / CUDART_PI;
+            // sphere uv in FP32 from the FP64 difference vector; the seam is kept inside [-pi, pi]
+            float fx = (float)gx, fy = (float)gy, fz = (float)gz;
+            float angle = atan2f(fz, fx);
+            double ad = fmin(fmax((double)angle, -CUDART_PI), CUDART_PI);
+            u = (CUDART_PI + ad) * (0.5 / CUDART_PI);
+            float as = atan2f(fy, sqrtf(fmaf(fx, fx, fz * fz)));  // asin(dy / R) without the pole singularity
+            v = 1.0 - (CUDART_PI / 2 + (double)as) * (1.0 / CUDART_PI);
         }
     } else {
         int axis = (h.face & 7) >> 1;
         double s = (h.face & 1) ? 1.0 : -1.0;
-        nx = axis == 1 ? s : 0.0;
-        ny = axis == 0 ? s : 0.0;
-        nz = axis == 2 ? s : 0.0;
+        gx = axis == 1 ? s : 0.0;
+        gy = axis == 0 ? s : 0.0;
+        gz = axis == 2 ? s : 0.0;
         // u, v stay in the permuted frame of the pass that produced the hit (quirk)
-        if (axis == 0) { u = h.px - g.p[0]; v = h.pz - g.p[2]; }
-        else if (axis == 1) { u = h.py - g.p[1]; v = h.pz - g.p[2]; }
-        else { u = h.px - g.p[0]; v = h.py - g.p[1]; }
+        if (axis == 0) { u = h.px - c[0]; v = h.pz - c[2]; }
+        else if (axis == 1) { u = h.py - c[1]; v = h.pz - c[2]; }
+        else { u = h.px - c[0]; v = h.py - c[1]; }
     }
-    if (h.face & FACE_FLIP) { nx = -nx; ny = -ny; nz = -nz; }
+    if (h.face & FACE_FLIP) { gx = -gx; gy = -gy; gz = -gz; }
 }
 
-struct WorldHit {
-    double px, py, pz, nx, ny, nz, u, v;
-};
-
-__device__ __forceinline__ void to_world(const HitRec& h, bool need_uv, WorldHit& w) {
+__device__ __forceinline__ void surface_of(const HitRec& h, bool need_uv, Surface& s) {
     const DevNode& nd = c_scene.nodes[h.node];
-    double nx, ny, nz;
-    finish_hit(h, nx, ny, nz, w.u, w.v, need_uv);
-    if (nd.flags & NODE_IDENTITY) {
-        // normalized(n * I): n is unit already for every primitive; keep the renormalisation
-        // only where the reference's differs from a no-op by more than rounding (it does not).
-        w.nx = nx; w.ny = ny; w.nz = nz;
-        w.px = h.px + nd.off[0]; w.py = h.py + nd.off[1]; w.pz = h.pz + nd.off[2];
+    const DevGeom& g = c_scene.geoms[h.leaf];
+    if (nd.kind != KIND_GENERIC) {
+        // world-space fast path: h.p is the world hit point, nd.wp the pre-offset parameters
+        local_surface(g.type, nd.wp, h, need_uv, s.gx, s.gy, s.gz, s.u, s.v);
+        if (nd.kind == KIND_PLANE_W) { s.u = h.px - nd.off[0]; s.v = h.pz - nd.off[2]; }  // uv are object-space (geometry.d:54-55)
+        s.px = h.px; s.py = h.py; s.pz = h.pz;
     } else {
-        mulvm(nd.MinvT, nx, ny, nz, w.nx, w.ny, w.nz);
-        normalize3(w.nx, w.ny, w.nz);
-        double x, y, z;
-        mulvm(nd.M, h.px, h.py, h.pz, x, y, z);
-        w.px = x + nd.off[0]; w.py = y + nd.off[1]; w.pz = z + nd.off[2];
+        double gx, gy, gz;
+        local_surface(g.type, g.p, h, need_uv, gx, gy, gz, s.u, s.v);
+        if (nd.flags & NODE_IDENTITY) {
+            s.gx = gx; s.gy = gy; s.gz = gz;
+            s.px = h.px + nd.off[0]; s.py = h.py + nd.off[1]; s.pz = h.pz + nd.off[2];
+        } else {
+            mulvm(nd.MinvT, gx, gy, gz, s.gx, s.gy, s.gz);   // transform.normal (transform.d:78-81); a positive rescale of g keeps its direction
+            double x, y, z;
+            mulvm(nd.M, h.px, h.py, h.pz, x, y, z);          // transform.point (transform.d:57-63)
+            s.px = x + nd.off[0]; s.py = y + nd.off[1]; s.pz = z + nd.off[2];
+        }
     }
+    float fx = (float)s.gx, fy = (float)s.gy, fz = (float)s.gz;
+    float inv = rsqrtf(dot3f(fx, fy, fz, fx, fy, fz));
+    s.nx = fx * inv; s.ny = fy * inv; s.nz = fz * inv;
 }
 
 __device__ Col shade(const FrameParams& fp, const Ray& ray, const HitRec& h, unsigned& n_shadow) {
     const DevShader& sh = c_scene.shaders[c_scene.nodes[h.node].shader];
-    WorldHit w;
-    to_world(h, sh.tex >= 0, w);
-    // faceforward (imported_types.d:69-73)
-    double Nx = w.nx, Ny = w.ny, Nz = w.nz;
-    if (!(dot3(ray.dx, ray.dy, ray.dz, Nx, Ny, Nz) < 0)) { Nx = -Nx; Ny = -Ny; Nz = -Nz; }
-    Col diffuse = sh.tex >= 0 ? sample_texture(sh.tex, w.u, w.v) : mkcol(sh.color[0], sh.color[1], sh.color[2]);
+    Surface s;
+    surface_of(h, sh.tex >= 0, s);
+    // faceforward (imported_types.d:69-73): the sign decision in FP64, the vector itself in FP32
+    float Nx = s.nx, Ny = s.ny, Nz = s.nz;
+    if (!(dot3(ray.dx, ray.dy, ray.dz, s.gx, s.gy, s.gz) < 0)) { Nx = -Nx; Ny = -Ny; Nz = -Nz; }
+    Col diffuse = sh.tex >= 0 ? sample_texture(sh.tex, s.u, s.v) : mkcol(sh.color[0], sh.color[1], sh.color[2]);
     Col lightContrib = mkcol(fp.ambient[0], fp.ambient[1], fp.ambient[2]);
     Col specular = mkcol(0.f, 0.f, 0.f);
     const bool phong = sh.type == C2RT_SHADER_PHONG;
     const int nl = c_scene.n_lights;
+    // shadow-ray origin p + N * 1e-6 (shader.d:88,219)
+    const double fx = s.px + (double)Nx * 1e-6, fy = s.py + (double)Ny * 1e-6, fz = s.pz + (double)Nz * 1e-6;
     for (int li = 0; li < nl; li++) {
         const DevLight& L = c_scene.lights[li];
         // one sample per PointLight (light.d:56-59): avg / numSamples is a division by 1.0f
         if (!L.lit) continue;
         n_shadow++;
-        if (occluded(w.px + Nx * 1e-6, w.py + Ny * 1e-6, w.pz + Nz * 1e-6, L.pos[0], L.pos[1], L.pos[2])) continue;
-        double lx = L.pos[0] - w.px, ly = L.pos[1] - w.py, lz = L.pos[2] - w.pz;
-        normalize3(lx, ly, lz);
-        double cosTheta = dot3(lx, ly, lz, Nx, Ny, Nz);
-        double ex = w.px - L.pos[0], ey = w.py - L.pos[1], ez = w.pz - L.pos[2];
-        float d2 = (float)dot3(ex, ey, ez, ex, ey, ez);
-        Col base = mkcol(L.color[0] / d2, L.color[1] / d2, L.color[2] / d2);
+        const double Dx = L.pos[0] - fx, Dy = L.pos[1] - fy, Dz = L.pos[2] - fz;
+        const double len2 = dot3(Dx, Dy, Dz, Dx, Dy, Dz);
+        if (occluded(fx, fy, fz, Dx, Dy, Dz, len2)) continue;
+        // lighting in FP32 (the reference narrows every factor to float before it touches a Color: SURVEY.md App. C.1)
+        const float d2 = (float)len2;
+        const float rs = rsqrtf(d2);
+        const float lx = (float)Dx * rs, ly = (float)Dy * rs, lz = (float)Dz * rs;
+        const float inv_d2 = rs * rs;
+        const float cosTheta = dot3f(lx, ly, lz, Nx, Ny, Nz);
+        const float br = L.color[0] * inv_d2, bg = L.color[1] * inv_d2, bb = L.color[2] * inv_d2;
         if (cosTheta > 0) {
-            float c = (float)cosTheta;
-            lightContrib.r += base.r * c; lightContrib.g += base.g * c; lightContrib.b += base.b * c;
+            lightContrib.r = fmaf(br, cosTheta, lightContrib.r);
+            lightContrib.g = fmaf(bg, cosTheta, lightContrib.g);
+            lightContrib.b = fmaf(bb, cosTheta, lightContrib.b);
         }
         if (phong) {
-            // reflect(-lightDir, N) (imported_types.d:62-67)
-            double ix = -lx, iy = -ly, iz = -lz;
-            double k = 2 * dot3(ix, iy, iz, Nx, Ny, Nz);
-            double rx = ix - k * Nx, ry = iy - k * Ny, rz = iz - k * Nz;
-            normalize3(rx, ry, rz);
-            double cosGamma = dot3(rx, ry, rz, -ray.dx, -ray.dy, -ray.dz);
-            if (cosGamma > 0) {
-                float pw = (float)pow(cosGamma, sh.exponent);
-                specular.r += base.r * pw * sh.strength;
-                specular.g += base.g * pw * sh.strength;
-                specular.b += base.b * pw * sh.strength;
+            float pw;
+            if (sh.exponent <= 2048.0) {
+                // reflect(-lightDir, N) . (-ray.dir)  (imported_types.d:62-67, shader.d:235-239)
+                const float k = 2.f * cosTheta;
+                const float rx = fmaf(k, Nx, -lx), ry = fmaf(k, Ny, -ly), rz = fmaf(k, Nz, -lz);
+                const float cosGamma = -dot3f(rx, ry, rz, ray.fdx, ray.fdy, ray.fdz);
+                pw = cosGamma > 0 ? powf(cosGamma, (float)sh.exponent) : 0.f;
+            } else {
+                // very sharp lobes amplify FP32 rounding of cosGamma by `exponent`: keep FP64 here
+                double ldx = Dx, ldy = Dy, ldz = Dz;
+                normalize3(ldx, ldy, ldz);
+                double nx = Nx, ny = Ny, nz = Nz;
+                normalize3(nx, ny, nz);
+                double k = 2 * dot3(ldx, ldy, ldz, nx, ny, nz);
+                double rx = k * nx - ldx, ry = k * ny - ldy, rz = k * nz - ldz;
+                normalize3(rx, ry, rz);
+                double cg = -dot3(rx, ry, rz, ray.dx, ray.dy, ray.dz);
+                pw = cg > 0 ? (float)pow(cg, sh.exponent) : 0.f;
             }
+            const float w = pw * sh.strength;
+            specular.r = fmaf(br, w, specular.r);
+            specular.g = fmaf(bg, w, specular.g);
+            specular.b = fmaf(bb, w, specular.b);
         }
     }
-    return mkcol(diffuse.r * lightContrib.r + specular.r, diffuse.g * lightContrib.g + specular.g,
-                 diffuse.b * lightContrib.b + specular.b);
+    return mkcol(fmaf(diffuse.r, lightContrib.r, specular.r), fmaf(diffuse.g, lightContrib.g, specular.g),
+                 fmaf(diffuse.b, lightContrib.b, specular.b));
 }
 
 __device__ Col trace(const FrameParams& fp, const Ray& ray, unsigned& n_shadow, HitRec* out_hit) {
     HitRec h;
     h.dist = 1e99;
     h.node = -1;
+    float tmaxf = CUDART_INF_F;
     const int n = c_scene.n_nodes;
-    for (int i = 0; i < n; i++) node_intersect(i, ray, h);
+    for (int i = 0; i < n; i++)
+        if (node_intersect(i, ray, h, tmaxf)) tmaxf = (float)h.dist * 1.000001f;
     if (out_hit) *out_hit = h;
     if (h.node < 0) return mkcol(0.f, 0.f, 0.f);  // environment.d:7-10
     return shade(fp, ray, h, n_shadow);
@@ -503,15 +632,15 @@ __device__ Col render_sample(const FrameParams& fp, double x, double y, uint32_t
     Col avg = mkcol(0.f, 0.f, 0.f);
     for (uint32_t i = 0; i < fp.num_samples; i++) {
         draw = 0;
-        double jx = x + uniform01(fp, px, py, tap, i, draw) * 1.0;
-        double jy = y + uniform01(fp, px, py, tap, i, draw) * 1.0;
+        double jx = x + uniform01(fp, px, py, tap, i, draw);
+        double jy = y + uniform01(fp, px, py, tap, i, draw);
         n_primary++;
         gen_ray(fp, jx, jy, px, py, tap, i, draw, r);
         Col c = trace(fp, r, n_shadow, (out_hit && i == 0) ? out_hit : nullptr);
         avg.r += c.r; avg.g += c.g; avg.b += c.b;
     }
-    float n = (float)fp.num_samples;
-    return mkcol(avg.r / n, avg.g / n, avg.b / n);
+    float inv = 1.f / (float)fp.num_samples;
+    return mkcol(avg.r * inv, avg.g * inv, avg.b * inv);
 }
 
 __device__ __forceinline__ uint32_t lut8(const uint8_t* lut, float x) {  // color.d:209-214
@@ -555,7 +684,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) render_frame_kernel(const Frame
                 Col t = render_sample(fp, (double)x + kx[s], (double)y + ky[s], x, y, s + 1, n_primary, n_shadow, nullptr);
                 c.r += t.r; c.g += t.g; c.b += t.b;
             }
-            c.r = c.r / 5.f; c.g = c.g / 5.f; c.b = c.b / 5.f;
+            c.r = c.r / 5.f; c.g = c.g / 5.f; c.b = c.b / 5.f;  // accum / 5 (renderer.d:249)
         }
     }
 
@@ -613,10 +742,12 @@ __global__ void render_pixel_kernel(const FrameParams fp, int x, int y, PixelOut
     out->node = h.node;
     out->dist = h.dist;
     if (h.node >= 0) {
-        WorldHit w;
-        to_world(h, true, w);
+        Surface w;
+        surface_of(h, true, w);
         out->p[0] = w.px; out->p[1] = w.py; out->p[2] = w.pz;
-        out->n[0] = w.nx; out->n[1] = w.ny; out->n[2] = w.nz;
+        double gx = w.gx, gy = w.gy, gz = w.gz;
+        normalize3(gx, gy, gz);
+        out->n[0] = gx; out->n[1] = gy; out->n[2] = gz;
         out->u = w.u; out->v = w.v;
     }
 }

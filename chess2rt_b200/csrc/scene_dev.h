@@ -16,15 +16,22 @@ enum : int {
     NODE_UNBOUNDED = 2,    // no finite bounding sphere (planes)
 };
 
+// Per-node fast paths chosen at scene-create time: identity-transform primitive nodes are tested
+// directly in world space against pre-offset parameters (`wp`).
+enum : int { KIND_PLANE_W = 0, KIND_SPHERE_W = 1, KIND_CUBE_W = 2, KIND_GENERIC = 3 };
+
 struct DevNode {
     double Minv[9];   // Transform.inverseTransform
     double M[9];      // Transform.transform
     double MinvT[9];  // Transform.transposedInverse
     double off[3];    // Transform.offset
-    double bc[3];     // world-space bounding sphere centre
-    double br2;       // squared radius (inflated); unused when NODE_UNBOUNDED
-    double br;        // radius (inflated)
-    int geom, shader, flags, pad;
+    double wp[4];     // KIND_*_W: plane y + off.y | sphere/cube centre + off, R / side
+    float bcf[3];     // world-space bounding sphere centre (FP32 copy for the conservative cull)
+    float brf;        // radius, inflated
+    float br2f;       // radius squared
+    float bclen;      // |centre|, for the cull's rounding-error margin
+    int geom, shader, flags, kind;
+    int pad0, pad1;
 };
 
 struct DevGeom {
@@ -40,7 +47,7 @@ struct DevShader {
 };
 
 struct DevTex {
-    double d[6];      // checker: size | procedure2: freqU[3], freqV[3] | bitmap: scaling
+    double d[6];      // checker: size, 1/size | procedure2: freqU[3], freqV[3] | bitmap: scaling
     float c[18];      // checker: color1, color2 | procedure2: colorU[3][3], colorV[3][3]
     int type, w, h, pad;
     const float4* texels;  // bitmap only
@@ -62,10 +69,11 @@ struct DevScene {
 };
 
 struct FrameParams {
-    // camera.d:123-147 with the frame invariants (upRight-upLeft, downLeft-upLeft) hoisted
-    double pos[3], up_left[3], du[3], dv[3];
+    // camera.d:123-147 with the frame invariants hoisted: ul_rel = upLeft - pos, du = upRight - upLeft,
+    // dv = downLeft - upLeft, inv_w / inv_h = 1 / camera.frameWidth, 1 / camera.frameHeight
+    double pos[3], ul_rel[3], du[3], dv[3];
     double right_dir[3], up_dir[3], front_dir[3];
-    double cam_w, cam_h;              // (double)camera.frameWidth / frameHeight
+    double inv_w, inv_h;
     double focal_plane_dist, disc_multiplier;
     unsigned long long seed;
     uint32_t W, H;                    // output size
