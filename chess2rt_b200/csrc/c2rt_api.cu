@@ -16,7 +16,7 @@
 
 namespace c2rt {
 cudaError_t upload_scene(const DevScene& s, cudaStream_t st);
-cudaError_t launch_frame(const FrameParams& fp, uint32_t local_tile_rows, cudaStream_t st);
+cudaError_t launch_frame(const FrameParams& fp, int mode, uint32_t local_tile_rows, cudaStream_t st);
 cudaError_t launch_pixel(const FrameParams& fp, int x, int y, void* d_out, cudaStream_t st);
 cudaError_t launch_deinterleave(const void* src, void* dst, uint32_t row_words, uint32_t height, uint32_t n_ranks,
                                 uint32_t band_rows, uint32_t rows_pad, cudaStream_t st);
@@ -168,6 +168,7 @@ struct c2rt_scene {
     std::vector<size_t> tex_offset;      // per texture, in texels (bitmaps only)
     float4* d_texels[C2RT_MAX_GPUS];     // per context device
     int n_dev;
+    int mode;                            // kernel specialisation (render_kernel.cu MODE_*)
 };
 
 namespace {
@@ -373,6 +374,11 @@ int validate_and_build(const c2rt_scene_desc* d, c2rt_scene* s) {
             }
         }
     }
+    s->mode = 0;
+    for (uint32_t i = 0; i < d->n_nodes; i++) {
+        if (!(h.nodes[i].flags & NODE_UNBOUNDED)) s->mode |= 1;   // MODE_BOUNDED
+        if (h.nodes[i].kind == KIND_GENERIC) s->mode |= 2;        // MODE_GENERIC
+    }
     return C2RT_OK;
 }
 
@@ -562,7 +568,7 @@ int c2rt_render_device(c2rt_scene* s, const c2rt_camera* cam, const c2rt_setting
     fp.argb = d_argb;
     fp.counters = c->d_counters;
     fp.lut = c->d_lut;
-    CU(launch_frame(fp, local_tile_rows(fp.H, fp.rank, fp.n_ranks, band_rows), st));
+    CU(launch_frame(fp, s->mode, local_tile_rows(fp.H, fp.rank, fp.n_ranks, band_rows), st));
     if (stats) {
         memset(stats, 0, sizeof *stats);
         stats->n_gpus = 1;
@@ -655,7 +661,7 @@ int c2rt_render(c2rt_scene* s, const c2rt_camera* cam, const c2rt_settings* set,
             fp.argb = argb ? c.d_argb : nullptr;
         }
         CU(cudaEventRecord(c.e0, c.stream));
-        CU(launch_frame(fp, local_tile_rows(H, fp.rank, fp.n_ranks, band_rows), c.stream));
+        CU(launch_frame(fp, s->mode, local_tile_rows(H, fp.rank, fp.n_ranks, band_rows), c.stream));
         CU(cudaEventRecord(c.e1, c.stream));
         launches++;
         if (i > 0 && !c.peer_to_root) {

@@ -25,6 +25,13 @@
 namespace c2rt {
 
 __constant__ DevScene c_scene;
+__constant__ double c_tap_x[5] = {0.0, 0.3, 0.6, 0.0, 0.6};  // renderer.d:235-242
+__constant__ double c_tap_y[5] = {0.0, 0.3, 0.0, 0.6, 0.6};
+
+// Kernel specialisations by scene class (chosen at scene-create time, c2rt_api.cu):
+//   MODE_BOUNDED  some node has a finite bounding sphere -> FP32 ray shadow + conservative cull
+//   MODE_GENERIC  some node needs the object-space path (non-identity transform, CSG, bounded plane)
+constexpr int MODE_BOUNDED = 1, MODE_GENERIC = 2;
 
 // Precision plan: FP64 carries everything a pixel DECISION or a texture coordinate
 // depends on — ray direction, hit distances, hit points, plane/cube uv, checker cells, face-forward
@@ -120,6 +127,7 @@ __device__ __forceinline__ double uniform01(const FrameParams& fp, uint32_t px, 
 // ---------------------------------------------------------------- camera
 // camera.d:123-174.  fp.up_left is stored relative to the camera position, fp.inv_w/inv_h are the
 // reciprocals of the camera frame size (x / W -> x * (1/W): one rounding apart).
+template <int MODE>
 __device__ __forceinline__ void gen_ray(const FrameParams& fp, double x, double y, uint32_t px, uint32_t py, uint32_t tap,
                                         uint32_t sample, uint32_t& draw, Ray& r) {
     double sx = x * fp.inv_w, sy = y * fp.inv_h;
@@ -145,7 +153,7 @@ __device__ __forceinline__ void gen_ray(const FrameParams& fp, double x, double 
         r.dx = Tx - r.ox; r.dy = Ty - r.oy; r.dz = Tz - r.oz;
         normalize3(r.dx, r.dy, r.dz);
     }
-    set_shadow(r);
+    if (MODE & MODE_BOUNDED) set_shadow(r);
 }
 
 // ---------------------------------------------------------------- primitives
@@ -364,15 +372,17 @@ __device__ __noinline__ bool generic_intersect(int ni, const Ray& r, HitRec& h) 
 }
 
 // Returns true and updates `h` iff node `ni` yields a hit with dist <= h.dist.
+template <int MODE>
 __device__ __forceinline__ bool node_intersect(int ni, const Ray& r, HitRec& h, float tmaxf) {
     const DevNode& nd = c_scene.nodes[ni];
-    if (!(nd.flags & NODE_UNBOUNDED) && cull(nd, r, tmaxf)) return false;
+    if ((MODE & MODE_BOUNDED) && !(nd.flags & NODE_UNBOUNDED) && cull(nd, r, tmaxf)) return false;
     int face = 0;
     bool hit;
     if (nd.kind == KIND_PLANE_W) hit = isect_plane(nd.wp[0], CUDART_NAN, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, h.px, h.py, h.pz);
     else if (nd.kind == KIND_SPHERE_W) hit = isect_sphere(nd.wp, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, h.px, h.py, h.pz);
     else if (nd.kind == KIND_CUBE_W) hit = isect_cube(nd.wp, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, h.px, h.py, h.pz, face);
-    else return generic_intersect(ni, r, h);
+    else if (MODE & MODE_GENERIC) return generic_intersect(ni, r, h);
+    else return false;
     if (hit) { h.node = ni; h.leaf = nd.geom; h.face = face; }
     return hit;
 }
@@ -380,15 +390,19 @@ __device__ __forceinline__ bool node_intersect(int ni, const Ray& r, HitRec& h, 
 // scene.d:62-78 testVisibility.  (fx,fy,fz) is the shadow-ray origin, D = to - from (unnormalised),
 // len2 = |D|^2.  The FP64 normalisation (scene.d:66-71) is done lazily: most nodes are rejected by a
 // sign test (planes) or the FP32 cull, which only need FP32 directions.
-__device__ bool occluded(double fx, double fy, double fz, double Dx, double Dy, double Dz, double len2) {
+template <int MODE>
+__device__ __forceinline__ bool occluded(double fx, double fy, double fz, double Dx, double Dy, double Dz, double len2) {
     Ray r;
     r.ox = fx; r.oy = fy; r.oz = fz;
-    const float l2f = (float)len2;
-    const float rsf = rsqrtf(l2f);
-    r.fox = (float)fx; r.foy = (float)fy; r.foz = (float)fz;
-    r.fdx = (float)Dx * rsf; r.fdy = (float)Dy * rsf; r.fdz = (float)Dz * rsf;
-    r.olen = sqrtf(dot3f(r.fox, r.foy, r.foz, r.fox, r.foy, r.foz));
-    const float tmaxf = l2f * rsf * 1.000001f;
+    float tmaxf = 0.f;
+    if (MODE & MODE_BOUNDED) {
+        const float l2f = (float)len2;
+        const float rsf = rsqrtf(l2f);
+        r.fox = (float)fx; r.foy = (float)fy; r.foz = (float)fz;
+        r.fdx = (float)Dx * rsf; r.fdy = (float)Dy * rsf; r.fdz = (float)Dz * rsf;
+        r.olen = sqrtf(dot3f(r.fox, r.foy, r.foz, r.fox, r.foy, r.foz));
+        tmaxf = l2f * rsf * 1.000001f;
+    }
     bool exact = false;
     HitRec h;
     const int n = c_scene.n_nodes;
@@ -398,7 +412,7 @@ __device__ bool occluded(double fx, double fy, double fz, double Dx, double Dy, 
             // implied by geometry.d:35-36 (dir.y has the sign of D.y): the common "light above the floor" case
             const double y = nd.wp[0];
             if ((fy > y && Dy >= 0) || (fy < y && Dy <= 0)) continue;
-        } else if (!(nd.flags & NODE_UNBOUNDED)) {
+        } else if ((MODE & MODE_BOUNDED) && !(nd.flags & NODE_UNBOUNDED)) {
             if (cull(nd, r, tmaxf)) continue;
         }
         if (!exact) {
@@ -412,7 +426,8 @@ __device__ bool occluded(double fx, double fy, double fz, double Dx, double Dy, 
         if (nd.kind == KIND_PLANE_W) hit = isect_plane(nd.wp[0], CUDART_NAN, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, h.px, h.py, h.pz);
         else if (nd.kind == KIND_SPHERE_W) hit = isect_sphere(nd.wp, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, h.px, h.py, h.pz);
         else if (nd.kind == KIND_CUBE_W) hit = isect_cube(nd.wp, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, h.px, h.py, h.pz, face);
-        else hit = generic_intersect(i, r, h);
+        else if (MODE & MODE_GENERIC) hit = generic_intersect(i, r, h);
+        else hit = false;
         if (hit) return true;
     }
     return false;
@@ -427,7 +442,8 @@ __device__ __forceinline__ int cast_int_x86(double v) {  // cvttsd2si: out of ra
 // sin(a) for an FP64 argument: Cody-Waite reduction to [-pi, pi] in FP64, then the FP32 SFU sine
 // (|abs err| < 5e-7).  The reference takes sin in FP64 and narrows to float (texture.d:82-83).
 __device__ __forceinline__ float sin_f64arg(double a) {
-    const double k = rint(a * 0.15915494309189535);  // 1 / 2pi
+    const double MAGIC = 6755399441055744.0;                      // 1.5 * 2^52: adding it rounds to the nearest integer
+    const double k = fma(a, 0.15915494309189535, MAGIC) - MAGIC;  // nearest multiple of 2pi
     double rr = fma(-k, 6.283185307179586, a);
     rr = fma(-k, 2.4492935982947064e-16, rr);
     return __sinf((float)rr);
@@ -542,7 +558,8 @@ __device__ __forceinline__ void surface_of(const HitRec& h, bool need_uv, Surfac
     s.nx = fx * inv; s.ny = fy * inv; s.nz = fz * inv;
 }
 
-__device__ Col shade(const FrameParams& fp, const Ray& ray, const HitRec& h, unsigned& n_shadow) {
+template <int MODE>
+__device__ __forceinline__ Col shade(const FrameParams& fp, const Ray& ray, const HitRec& h, unsigned& n_shadow) {
     const DevShader& sh = c_scene.shaders[c_scene.nodes[h.node].shader];
     Surface s;
     surface_of(h, sh.tex >= 0, s);
@@ -563,7 +580,7 @@ __device__ Col shade(const FrameParams& fp, const Ray& ray, const HitRec& h, uns
         n_shadow++;
         const double Dx = L.pos[0] - fx, Dy = L.pos[1] - fy, Dz = L.pos[2] - fz;
         const double len2 = dot3(Dx, Dy, Dz, Dx, Dy, Dz);
-        if (occluded(fx, fy, fz, Dx, Dy, Dz, len2)) continue;
+        if (occluded<MODE>(fx, fy, fz, Dx, Dy, Dz, len2)) continue;
         // lighting in FP32 (the reference narrows every factor to float before it touches a Color: SURVEY.md App. C.1)
         const float d2 = (float)len2;
         const float rs = rsqrtf(d2);
@@ -582,7 +599,7 @@ __device__ Col shade(const FrameParams& fp, const Ray& ray, const HitRec& h, uns
                 // reflect(-lightDir, N) . (-ray.dir)  (imported_types.d:62-67, shader.d:235-239)
                 const float k = 2.f * cosTheta;
                 const float rx = fmaf(k, Nx, -lx), ry = fmaf(k, Ny, -ly), rz = fmaf(k, Nz, -lz);
-                const float cosGamma = -dot3f(rx, ry, rz, ray.fdx, ray.fdy, ray.fdz);
+                const float cosGamma = -dot3f(rx, ry, rz, (float)ray.dx, (float)ray.dy, (float)ray.dz);
                 pw = cosGamma > 0 ? powf(cosGamma, (float)sh.exponent) : 0.f;
             } else {
                 // very sharp lobes amplify FP32 rounding of cosGamma by `exponent`: keep FP64 here
@@ -606,28 +623,32 @@ __device__ Col shade(const FrameParams& fp, const Ray& ray, const HitRec& h, uns
                  fmaf(diffuse.b, lightContrib.b, specular.b));
 }
 
-__device__ Col trace(const FrameParams& fp, const Ray& ray, unsigned& n_shadow, HitRec* out_hit) {
+template <int MODE>
+__device__ __forceinline__ Col trace(const FrameParams& fp, const Ray& ray, unsigned& n_shadow, HitRec* out_hit) {
     HitRec h;
     h.dist = 1e99;
     h.node = -1;
     float tmaxf = CUDART_INF_F;
     const int n = c_scene.n_nodes;
     for (int i = 0; i < n; i++)
-        if (node_intersect(i, ray, h, tmaxf)) tmaxf = (float)h.dist * 1.000001f;
+        if (node_intersect<MODE>(i, ray, h, tmaxf)) {
+            if (MODE & MODE_BOUNDED) tmaxf = (float)h.dist * 1.000001f;
+        }
     if (out_hit) *out_hit = h;
     if (h.node < 0) return mkcol(0.f, 0.f, 0.f);  // environment.d:7-10
-    return shade(fp, ray, h, n_shadow);
+    return shade<MODE>(fp, ray, h, n_shadow);
 }
 
 // renderer.d:254-313 renderSample (default and DOF branches)
-__device__ Col render_sample(const FrameParams& fp, double x, double y, uint32_t px, uint32_t py, uint32_t tap,
-                             unsigned& n_primary, unsigned& n_shadow, HitRec* out_hit) {
+template <int MODE>
+__device__ __forceinline__ Col render_sample(const FrameParams& fp, double x, double y, uint32_t px, uint32_t py, uint32_t tap,
+                                             unsigned& n_primary, unsigned& n_shadow, HitRec* out_hit) {
     Ray r;
     uint32_t draw = 0;
     if (!fp.dof) {
         n_primary++;
-        gen_ray(fp, x, y, px, py, tap, 0, draw, r);
-        return trace(fp, r, n_shadow, out_hit);
+        gen_ray<MODE>(fp, x, y, px, py, tap, 0, draw, r);
+        return trace<MODE>(fp, r, n_shadow, out_hit);
     }
     Col avg = mkcol(0.f, 0.f, 0.f);
     for (uint32_t i = 0; i < fp.num_samples; i++) {
@@ -635,8 +656,8 @@ __device__ Col render_sample(const FrameParams& fp, double x, double y, uint32_t
         double jx = x + uniform01(fp, px, py, tap, i, draw);
         double jy = y + uniform01(fp, px, py, tap, i, draw);
         n_primary++;
-        gen_ray(fp, jx, jy, px, py, tap, i, draw, r);
-        Col c = trace(fp, r, n_shadow, (out_hit && i == 0) ? out_hit : nullptr);
+        gen_ray<MODE>(fp, jx, jy, px, py, tap, i, draw, r);
+        Col c = trace<MODE>(fp, r, n_shadow, (out_hit && i == 0) ? out_hit : nullptr);
         avg.r += c.r; avg.g += c.g; avg.b += c.b;
     }
     float inv = 1.f / (float)fp.num_samples;
@@ -653,7 +674,8 @@ __device__ __forceinline__ uint32_t pack_rgb32(const uint8_t* lut, Col c) {  // 
 }
 
 // ---------------------------------------------------------------- frame kernel
-__global__ void __launch_bounds__(BLOCK_THREADS) render_frame_kernel(const FrameParams fp) {
+template <int MODE, int MIN_BLOCKS>
+__global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS) render_frame_kernel(const FrameParams fp) {
     __shared__ __align__(16) float s_rgb[TILE_H][TILE_W * 3];
 
     // tile -> rows: local tile l of this rank belongs to its band (l / tiles_per_band), which is
@@ -675,17 +697,13 @@ __global__ void __launch_bounds__(BLOCK_THREADS) render_frame_kernel(const Frame
     Col c = mkcol(0.f, 0.f, 0.f);
     if (active) {
         // renderer.d:223-251: tap 0 at the pixel corner, then +(.3,.3) (.6,0) (0,.6) (.6,.6); mean of 5 in FP32
-        c = render_sample(fp, (double)x, (double)y, x, y, 0, n_primary, n_shadow, nullptr);
-        if (fp.aa) {
-            const double kx[4] = {0.3, 0.6, 0.0, 0.6};
-            const double ky[4] = {0.3, 0.0, 0.6, 0.6};
+        const int taps = fp.aa ? 5 : 1;
 #pragma unroll 1
-            for (int s = 0; s < 4; s++) {
-                Col t = render_sample(fp, (double)x + kx[s], (double)y + ky[s], x, y, s + 1, n_primary, n_shadow, nullptr);
-                c.r += t.r; c.g += t.g; c.b += t.b;
-            }
-            c.r = c.r / 5.f; c.g = c.g / 5.f; c.b = c.b / 5.f;  // accum / 5 (renderer.d:249)
+        for (int s = 0; s < taps; s++) {
+            Col t = render_sample<MODE>(fp, (double)x + c_tap_x[s], (double)y + c_tap_y[s], x, y, s, n_primary, n_shadow, nullptr);
+            c.r += t.r; c.g += t.g; c.b += t.b;
         }
+        if (fp.aa) { c.r = c.r / 5.f; c.g = c.g / 5.f; c.b = c.b / 5.f; }  // accum / 5 (renderer.d:249)
     }
 
     // output row of this tile row: full frame or compact (only this rank's rows, in order)
@@ -737,7 +755,7 @@ __global__ void render_pixel_kernel(const FrameParams fp, int x, int y, PixelOut
     HitRec h;
     h.node = -1;
     h.dist = 1e99;
-    Col c = render_sample(fp, (double)x, (double)y, (uint32_t)x, (uint32_t)y, 0, a, b, &h);
+    Col c = render_sample<MODE_BOUNDED | MODE_GENERIC>(fp, (double)x, (double)y, (uint32_t)x, (uint32_t)y, 0, a, b, &h);
     out->rgb[0] = c.r; out->rgb[1] = c.g; out->rgb[2] = c.b;
     out->node = h.node;
     out->dist = h.dist;
@@ -784,10 +802,22 @@ cudaError_t upload_scene(const DevScene& s, cudaStream_t st) {
     return cudaMemcpyToSymbolAsync(c_scene, &s, sizeof(DevScene), 0, cudaMemcpyHostToDevice, st);
 }
 
-cudaError_t launch_frame(const FrameParams& fp, uint32_t local_tile_rows, cudaStream_t st) {
+#ifndef C2RT_MINBLOCKS_SIMPLE
+#define C2RT_MINBLOCKS_SIMPLE 4
+#endif
+#ifndef C2RT_MINBLOCKS_BOUNDED
+#define C2RT_MINBLOCKS_BOUNDED 3
+#endif
+#ifndef C2RT_MINBLOCKS_FULL
+#define C2RT_MINBLOCKS_FULL 3
+#endif
+
+cudaError_t launch_frame(const FrameParams& fp, int mode, uint32_t local_tile_rows, cudaStream_t st) {
     if (local_tile_rows == 0) return cudaSuccess;
     dim3 grid((fp.W + TILE_W - 1) / TILE_W, local_tile_rows);
-    render_frame_kernel<<<grid, BLOCK_THREADS, 0, st>>>(fp);
+    if (mode & MODE_GENERIC) render_frame_kernel<MODE_BOUNDED | MODE_GENERIC, C2RT_MINBLOCKS_FULL><<<grid, BLOCK_THREADS, 0, st>>>(fp);
+    else if (mode & MODE_BOUNDED) render_frame_kernel<MODE_BOUNDED, C2RT_MINBLOCKS_BOUNDED><<<grid, BLOCK_THREADS, 0, st>>>(fp);
+    else render_frame_kernel<0, C2RT_MINBLOCKS_SIMPLE><<<grid, BLOCK_THREADS, 0, st>>>(fp);
     return cudaGetLastError();
 }
 
