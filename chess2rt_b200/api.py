@@ -14,7 +14,7 @@ class C2rtError(RuntimeError):
 
 
 def _load(name):
-    path = os.path.join(_PKG, name)
+    path = os.path.join(os.environ.get("C2RT_LIB_DIR") or _PKG, name)  # C2RT_LIB_DIR: tuning variants (build.build_variant)
     if not os.path.exists(path):
         raise ImportError(
             f"{path} is missing: build it with `python -m chess2rt_b200.build` (or __graft_entry__.build()). "

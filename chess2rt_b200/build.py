@@ -38,6 +38,17 @@ def _nvcc():
     return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 
 
+def build_variant(name, defines):
+    """Tuning aid: a copy of both libraries under build_variants/<name>/ compiled with extra -D flags;
+    select it with C2RT_LIB_DIR=build_variants/<name> (see api.py)."""
+    vdir = os.path.join(ROOT, "build_variants", name)
+    os.makedirs(vdir, exist_ok=True)
+    srcs = [os.path.join(CSRC, f) for f in ("render_kernel.cu", "c2rt_api.cu")]
+    _run([_nvcc()] + list(NVCC_FLAGS) + ["-D" + d for d in defines] + ["-o", os.path.join(vdir, "libc2rt.so")] + srcs)
+    shutil.copy(os.path.join(PKG, "libc2rt_host.so"), os.path.join(vdir, "libc2rt_host.so"))
+    return vdir
+
+
 def build_cuda(force=False, verbose_ptxas=False):
     out = os.path.join(PKG, "libc2rt.so")
     srcs = [os.path.join(CSRC, f) for f in ("render_kernel.cu", "c2rt_api.cu")]

@@ -372,19 +372,27 @@ __device__ __noinline__ bool generic_intersect(int ni, const Ray& r, HitRec& h) 
 }
 
 // Returns true and updates `h` iff node `ni` yields a hit with dist <= h.dist.
+// Exact FP64 test of node `ni` (after the cull).  Returns true and updates `h` iff the node yields a hit
+// with dist <= h.dist.  Spheres and cubes always have a finite bound, so a scene class without
+// MODE_BOUNDED cannot contain KIND_SPHERE_W / KIND_CUBE_W nodes and those branches compile away.
 template <int MODE>
-__device__ __forceinline__ bool node_intersect(int ni, const Ray& r, HitRec& h, float tmaxf) {
-    const DevNode& nd = c_scene.nodes[ni];
-    if ((MODE & MODE_BOUNDED) && !(nd.flags & NODE_UNBOUNDED) && cull(nd, r, tmaxf)) return false;
+__device__ __forceinline__ bool node_exact(int ni, const DevNode& nd, const Ray& r, HitRec& h) {
     int face = 0;
     bool hit;
     if (nd.kind == KIND_PLANE_W) hit = isect_plane(nd.wp[0], CUDART_NAN, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, h.px, h.py, h.pz);
-    else if (nd.kind == KIND_SPHERE_W) hit = isect_sphere(nd.wp, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, h.px, h.py, h.pz);
-    else if (nd.kind == KIND_CUBE_W) hit = isect_cube(nd.wp, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, h.px, h.py, h.pz, face);
+    else if ((MODE & MODE_BOUNDED) && nd.kind == KIND_SPHERE_W) hit = isect_sphere(nd.wp, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, h.px, h.py, h.pz);
+    else if ((MODE & MODE_BOUNDED) && nd.kind == KIND_CUBE_W) hit = isect_cube(nd.wp, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, h.px, h.py, h.pz, face);
     else if (MODE & MODE_GENERIC) return generic_intersect(ni, r, h);
     else return false;
     if (hit) { h.node = ni; h.leaf = nd.geom; h.face = face; }
     return hit;
+}
+
+template <int MODE>
+__device__ __forceinline__ bool node_intersect(int ni, const Ray& r, HitRec& h, float tmaxf) {
+    const DevNode& nd = c_scene.nodes[ni];
+    if ((MODE & MODE_BOUNDED) && !(nd.flags & NODE_UNBOUNDED) && cull(nd, r, tmaxf)) return false;
+    return node_exact<MODE>(ni, nd, r, h);
 }
 
 // scene.d:62-78 testVisibility.  (fx,fy,fz) is the shadow-ray origin, D = to - from (unnormalised),
@@ -421,14 +429,7 @@ __device__ __forceinline__ bool occluded(double fx, double fy, double fz, double
             h.dist = len2 * inv;
             exact = true;
         }
-        bool hit;
-        int face = 0;
-        if (nd.kind == KIND_PLANE_W) hit = isect_plane(nd.wp[0], CUDART_NAN, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, h.px, h.py, h.pz);
-        else if (nd.kind == KIND_SPHERE_W) hit = isect_sphere(nd.wp, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, h.px, h.py, h.pz);
-        else if (nd.kind == KIND_CUBE_W) hit = isect_cube(nd.wp, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, h.px, h.py, h.pz, face);
-        else if (MODE & MODE_GENERIC) hit = generic_intersect(i, r, h);
-        else hit = false;
-        if (hit) return true;
+        if (node_exact<MODE>(i, nd, r, h)) return true;
     }
     return false;
 }
@@ -698,9 +699,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS) render_frame_kernel
     if (active) {
         // renderer.d:223-251: tap 0 at the pixel corner, then +(.3,.3) (.6,0) (0,.6) (.6,.6); mean of 5 in FP32
         const int taps = fp.aa ? 5 : 1;
+        const double xd = (double)x, yd = (double)y;
 #pragma unroll 1
         for (int s = 0; s < taps; s++) {
-            Col t = render_sample<MODE>(fp, (double)x + c_tap_x[s], (double)y + c_tap_y[s], x, y, s, n_primary, n_shadow, nullptr);
+            Col t = render_sample<MODE>(fp, xd + c_tap_x[s], yd + c_tap_y[s], x, y, s, n_primary, n_shadow, nullptr);
             c.r += t.r; c.g += t.g; c.b += t.b;
         }
         if (fp.aa) { c.r = c.r / 5.f; c.g = c.g / 5.f; c.b = c.b / 5.f; }  // accum / 5 (renderer.d:249)
@@ -803,13 +805,13 @@ cudaError_t upload_scene(const DevScene& s, cudaStream_t st) {
 }
 
 #ifndef C2RT_MINBLOCKS_SIMPLE
-#define C2RT_MINBLOCKS_SIMPLE 4
+#define C2RT_MINBLOCKS_SIMPLE 5
 #endif
 #ifndef C2RT_MINBLOCKS_BOUNDED
 #define C2RT_MINBLOCKS_BOUNDED 3
 #endif
 #ifndef C2RT_MINBLOCKS_FULL
-#define C2RT_MINBLOCKS_FULL 3
+#define C2RT_MINBLOCKS_FULL 4
 #endif
 
 cudaError_t launch_frame(const FrameParams& fp, int mode, uint32_t local_tile_rows, cudaStream_t st) {
