@@ -254,72 +254,161 @@ __device__ __forceinline__ bool geom_inside(int gi, double x, double y, double z
 }
 
 // ---------------------------------------------------------------- CSG
-constexpr int CSG_MAX_CHILD_CROSSINGS = 4;
-
-struct Crossing {
-    double dist, px, py, pz;
-    int face, leaf;
+// CsgOp.intersect (geometry.d:292-332) for children that are convex primitives (nesting is rejected at
+// scene-create time).  The reference collects each child's crossings by re-intersecting from
+// p + d*1e-6 (findAllIntersections, geometry.d:271-290), shell-sorts the merged list
+// (util/array.d:95-111) and walks it flipping inside-left / inside-right.  For a convex child that
+// loop can only produce: nothing; the exit (origin inside); or entry + exit (origin outside) — and
+// the distance it records for a child's 2nd crossing is 1e-6 SHORT of the true one, because the
+// restart offset is never added back (geometry.d:283-286).  Both facts are reproduced here from the
+// closed-form entry/exit distances, so the whole walk runs in registers: no restarts, no local arrays.
+struct Crossings {
+    double d0, d1;   // distances as the reference records them (d1 = true exit - 1e-6)
+    int n, f0, f1;   // count (0..2) and cube-face codes
 };
 
-__device__ __noinline__ int find_all(int gi, double ox, double oy, double oz, double dx, double dy, double dz, Crossing* out) {  // geometry.d:271-290
-    const DevGeom& g = c_scene.geoms[gi];
-    double cur = 0;
-    int n = 0;
-    while (n < CSG_MAX_CHILD_CROSSINGS) {
-        double dist = 1e99, px, py, pz;
-        int face = 0;
-        if (!isect_prim(g, ox, oy, oz, dx, dy, dz, dist, px, py, pz, face)) break;
-        dist += cur;
-        cur = dist;
-        ox = fma(dx, 1e-6, px); oy = fma(dy, 1e-6, py); oz = fma(dz, 1e-6, pz);
-        out[n].dist = dist; out[n].px = px; out[n].py = py; out[n].pz = pz;
-        out[n].face = face; out[n].leaf = gi;
-        n++;
+__device__ __forceinline__ Crossings cross_sphere(const double* p, double ox, double oy, double oz, double dx, double dy, double dz) {
+    Crossings c;
+    c.n = 0; c.f0 = 0; c.f1 = 0; c.d0 = 0; c.d1 = 0;
+    double hx = ox - p[0], hy = oy - p[1], hz = oz - p[2];
+    double A = dot3(dx, dy, dz, dx, dy, dz);
+    double B = 2 * dot3(hx, hy, hz, dx, dy, dz);
+    double C = dot3(hx, hy, hz, hx, hy, hz) - p[3] * p[3];
+    double D = fma(B, B, -4 * A * C);
+    if (D < 0) return c;
+    double sq = D > 0 ? D * rsqrt64(D) : 0.0;
+    double inv2a = rcp64(2 * A);
+    double x2 = (-B - sq) * inv2a, x1 = (-B + sq) * inv2a;
+    if (x2 >= 0) {
+        c.d0 = x2;
+        c.n = 1;
+        // restart 1e-6 past the entry: the far root is found iff it is still ahead
+        double rest = x1 - x2 - 1e-6;
+        if (rest >= 0) { c.d1 = x2 + rest; c.n = 2; }
+    } else if (x1 >= 0) {
+        c.d0 = x1;
+        c.n = 1;
     }
-    return n;
+    return c;
 }
 
-__device__ __noinline__ bool isect_csg(int gi, double ox, double oy, double oz, double dx, double dy, double dz, double& dist,
-                                       double& px, double& py, double& pz, int& face, int& leaf) {
+// entry / exit of the axis-aligned cube in the reference's face order (Y, X, Z passes; the later pass wins ties)
+__device__ __forceinline__ Crossings cross_cube(const double* p, double ox, double oy, double oz, double dx, double dy, double dz) {
+    Crossings c;
+    c.n = 0; c.f0 = 0; c.f1 = 0; c.d0 = 0; c.d1 = 0;
+    const double half = p[3] * 0.5;
+    double tin = -1e300, tout = 1e300;
+    int fin = 0, fout = 0;
+    bool miss = false;
+    // pass order of geometry.d:172-191: Y (code 0), X (code 2), Z (code 4)
+    const double o3[3] = {oy, ox, oz}, d3[3] = {dy, dx, dz}, c3[3] = {p[1], p[0], p[2]};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        if (fabs(d3[a]) < 1e-9) {
+            // geometry.d:201-202 skips the pass; the other passes' in-face bounds still reject an origin outside this slab
+            if (o3[a] < c3[a] - half || o3[a] > c3[a] + half) miss = true;
+        } else {
+            const double inv = rcp64(-d3[a]);
+            const double tneg = (o3[a] - (c3[a] - half)) * inv;   // side -1 face
+            const double tpos = (o3[a] - (c3[a] + half)) * inv;   // side +1 face
+            const bool negfirst = tneg < tpos;
+            const double tn = negfirst ? tneg : tpos, tf = negfirst ? tpos : tneg;
+            if (tn >= tin) { tin = tn; fin = 2 * a + (negfirst ? 0 : 1); }
+            if (tf <= tout) { tout = tf; fout = 2 * a + (negfirst ? 1 : 0); }
+        }
+    }
+    if (miss || tin > tout || tout < 0) return c;
+    if (tin >= 0) {
+        c.d0 = tin; c.f0 = fin; c.n = 1;
+        double rest = tout - tin - 1e-6;
+        if (rest >= 0) { c.d1 = tin + rest; c.f1 = fout; c.n = 2; }
+    } else {
+        c.d0 = tout; c.f0 = fout; c.n = 1;
+    }
+    return c;
+}
+
+__device__ __forceinline__ Crossings cross_plane(const double* p, double ox, double oy, double oz, double dx, double dy, double dz) {
+    Crossings c;
+    c.n = 0; c.f0 = 0; c.f1 = 0; c.d0 = 0; c.d1 = 0;
+    double dist = 1e99, px, py, pz;
+    if (isect_plane(p[0], p[1], ox, oy, oz, dx, dy, dz, dist, px, py, pz)) { c.d0 = dist; c.n = 1; }
+    return c;
+}
+
+__device__ __forceinline__ Crossings cross_prim(const DevGeom& g, double ox, double oy, double oz, double dx, double dy, double dz) {
+    if (g.type == C2RT_GEOM_SPHERE) return cross_sphere(g.p, ox, oy, oz, dx, dy, dz);
+    if (g.type == C2RT_GEOM_CUBE) return cross_cube(g.p, ox, oy, oz, dx, dy, dz);
+    return cross_plane(g.p, ox, oy, oz, dx, dy, dz);
+}
+
+// compare-exchange with the strict `>` of IntersectionData.opCmp (intersectable.d:27-32)
+__device__ __forceinline__ void cex(double& ka, int& ia, double& kb, int& ib) {
+    if (ka > kb) {
+        double t = ka; ka = kb; kb = t;
+        int u = ia; ia = ib; ib = u;
+    }
+}
+
+__device__ __forceinline__ bool isect_csg(int gi, double ox, double oy, double oz, double dx, double dy, double dz, double& dist,
+                                          double& px, double& py, double& pz, int& face, int& leaf) {
     const DevGeom& g = c_scene.geoms[gi];
-    Crossing all[2 * CSG_MAX_CHILD_CROSSINGS];
-    int nl = find_all(g.left, ox, oy, oz, dx, dy, dz, all);
-    int nr = find_all(g.right, ox, oy, oz, dx, dy, dz, all + nl);
-    int n = nl + nr;
-    // util/array.d:95-111 shell sort, including the `ref` loop index and the gap sequence
-    int inc = n / 2;
-    while (inc) {
-        for (int key = 0; key < n; key++) {
-            int i = key;
-            Crossing elem = all[i];
-            while (i >= inc && all[i - inc].dist > elem.dist) {
-                all[i] = all[i - inc];
-                i -= inc;
-            }
-            all[i] = elem;
-            key = i;
-        }
-        inc = (inc == 2) ? 1 : (int)(inc * 5.0 / 11);
-    }
-    bool inL = nl & 1, inR = nr & 1;
-    for (int k = 0; k < n; k++) {
-        if (all[k].leaf == g.left) inL = !inL;
-        else inR = !inR;
-        if (csg_bool(g.type, inL, inR)) {
-            if (all[k].dist > dist) return false;
-            dist = all[k].dist;
-            px = all[k].px; py = all[k].py; pz = all[k].pz;
-            face = all[k].face;
-            leaf = all[k].leaf;
-            if (g.type == C2RT_GEOM_CSG_DIFF) {
-                bool a = geom_inside(g.right, px - dx * 1e-6, py - dy * 1e-6, pz - dz * 1e-6);
-                bool b = geom_inside(g.right, px + dx * 1e-6, py + dy * 1e-6, pz + dz * 1e-6);
-                if (a != b) face |= FACE_FLIP;
-            }
-            return true;
+    const Crossings L = cross_prim(c_scene.geoms[g.left], ox, oy, oz, dx, dy, dz);
+    const Crossings R = cross_prim(c_scene.geoms[g.right], ox, oy, oz, dx, dy, dz);
+    const int n = L.n + R.n;
+    if (n == 0) return false;
+    // merged list, left child's crossings first (geometry.d:301-302).  id: bit 1 = right child, bit 0 = second crossing,
+    // bits 2.. = cube face code
+    const double INF = CUDART_INF;
+    double k0 = INF, k1 = INF, k2 = INF, k3 = INF;
+    int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
+    {
+        const int l0 = 0 | (L.f0 << 2), l1 = 1 | (L.f1 << 2), r0 = 2 | (R.f0 << 2), r1 = 3 | (R.f1 << 2);
+        if (L.n == 2) {
+            k0 = L.d0; i0 = l0; k1 = L.d1; i1 = l1;
+            if (R.n >= 1) { k2 = R.d0; i2 = r0; }
+            if (R.n == 2) { k3 = R.d1; i3 = r1; }
+        } else if (L.n == 1) {
+            k0 = L.d0; i0 = l0;
+            if (R.n >= 1) { k1 = R.d0; i1 = r0; }
+            if (R.n == 2) { k2 = R.d1; i2 = r1; }
+        } else {
+            k0 = R.d0; i0 = r0;
+            if (R.n == 2) { k1 = R.d1; i1 = r1; }
         }
     }
-    return false;
+    // util/array.d:95-111 for n <= 4: gap 2 exists only for n == 4 (two compare-exchanges), then the gap-1
+    // insertion pass; padding slots hold +inf and never move
+    if (n == 4) { cex(k0, i0, k2, i2); cex(k1, i1, k3, i3); }
+    cex(k0, i0, k1, i1);
+    cex(k1, i1, k2, i2); cex(k0, i0, k1, i1);
+    cex(k2, i2, k3, i3); cex(k1, i1, k2, i2); cex(k0, i0, k1, i1);
+    bool inL = L.n & 1, inR = R.n & 1;
+    double kd = 0;
+    int id = -1;
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        const double ks = s == 0 ? k0 : s == 1 ? k1 : s == 2 ? k2 : k3;
+        const int is = s == 0 ? i0 : s == 1 ? i1 : s == 2 ? i2 : i3;
+        if (id < 0 && s < n) {
+            if (is & 2) inR = !inR;
+            else inL = !inL;
+            if (csg_bool(g.type, inL, inR)) { kd = ks; id = is; }
+        }
+    }
+    if (id < 0) return false;
+    if (kd > dist) return false;
+    dist = kd;
+    const double tt = (id & 1) ? kd + 1e-6 : kd;   // true parameter of the crossing point
+    px = fma(dx, tt, ox); py = fma(dy, tt, oy); pz = fma(dz, tt, oz);
+    face = id >> 2;
+    leaf = (id & 2) ? g.right : g.left;
+    if (g.type == C2RT_GEOM_CSG_DIFF) {
+        bool a = geom_inside(g.right, px - dx * 1e-6, py - dy * 1e-6, pz - dz * 1e-6);
+        bool b = geom_inside(g.right, px + dx * 1e-6, py + dy * 1e-6, pz + dz * 1e-6);
+        if (a != b) face |= FACE_FLIP;
+    }
+    return true;
 }
 
 // ---------------------------------------------------------------- node
@@ -341,7 +430,7 @@ __device__ __forceinline__ bool cull(const DevNode& nd, const Ray& r, float tmax
 }
 
 // node.d:23-49 for a transformed node: world ray -> object space, exact FP64 geometry test
-__device__ __noinline__ bool generic_intersect(int ni, const Ray& r, HitRec& h) {
+__device__ __forceinline__ bool generic_intersect(int ni, const Ray& r, HitRec& h) {
     const DevNode& nd = c_scene.nodes[ni];
     double ox, oy, oz, dx, dy, dz, len;
     double tx = r.ox - nd.off[0], ty = r.oy - nd.off[1], tz = r.oz - nd.off[2];
