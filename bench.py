@@ -253,23 +253,38 @@ def main():
         frame = torch.empty((H, W, 3), dtype=torch.float32, device="cuda")
         out_ptr = frame.data_ptr()
     else:
-        gather_mode = "nccl" if args.gather in ("auto", "nccl") else "p2p"
+        gather_mode = "nccl" if args.gather == "nccl" else "p2p"
         if gather_mode == "p2p":
+            # rank 0 owns the frame; every other rank maps it (CUDA IPC) and its kernel stores bands into it over NVLink
             import ctypes as C
+            ok = 1
             handle_bytes = [None]
-            if rank == 0:
-                p = C.c_void_p()
-                api._check(api.lib.c2rt_frame_alloc(H * W * 12, C.byref(p)))
-                hb = (C.c_uint8 * 64)()
-                api._check(api.lib.c2rt_frame_export(p, hb))
-                handle_bytes = [bytes(hb)]
-                peer_frame_ptr = p.value
+            try:
+                if rank == 0:
+                    p = C.c_void_p()
+                    api._check(api.lib.c2rt_frame_alloc(H * W * 12, C.byref(p)))
+                    hb = (C.c_uint8 * 64)()
+                    api._check(api.lib.c2rt_frame_export(p, hb))
+                    handle_bytes = [bytes(hb)]
+                    peer_frame_ptr = p.value
+            except Exception:
+                ok = 0
             dist.broadcast_object_list(handle_bytes, src=0)
-            if rank != 0:
-                hb = (C.c_uint8 * 64).from_buffer_copy(handle_bytes[0])
-                p = C.c_void_p()
-                api._check(api.lib.c2rt_frame_import(hb, C.byref(p)))
-                peer_frame_ptr = p.value
+            if rank != 0 and handle_bytes[0] is not None:
+                try:
+                    hb = (C.c_uint8 * 64).from_buffer_copy(handle_bytes[0])
+                    p = C.c_void_p()
+                    api._check(api.lib.c2rt_frame_import(hb, C.byref(p)))
+                    peer_frame_ptr = p.value
+                except Exception:
+                    ok = 0
+            okt = torch.tensor([ok if handle_bytes[0] is not None else 0], device="cuda")
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+            if int(okt[0]) == 0:
+                if args.gather == "p2p":
+                    raise SystemExit("--gather p2p: CUDA IPC mapping of rank 0's frame failed")
+                gather_mode = "nccl"   # auto: fall back to the NCCL gather
+        if gather_mode == "p2p":
             band = api.Band(rank, n_ranks, BAND_ROWS, 0)
             out_ptr = peer_frame_ptr
             sync_flag = torch.zeros(1, device="cuda")
