@@ -3,6 +3,7 @@
 // every rendering entry point fails with C2RT_ERR_CUDA if the CUDA runtime cannot run the kernel.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -55,8 +56,9 @@ int fail(int code, const char* fmt, ...) {
 
 struct DeviceCtx {
     int dev = -1;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaEvent_t chunk_done[8] = {};
     uint64_t uploaded_scene = 0;   // id of the scene currently in this device's constant memory
     unsigned long long* d_counters = nullptr;
     uint8_t* d_lut = nullptr;
@@ -91,6 +93,8 @@ void destroy_device(DeviceCtx& c) {
     if (c.dev < 0) return;
     cudaSetDevice(c.dev);
     if (c.stream) cudaStreamDestroy(c.stream);
+    if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
+    for (auto& e : c.chunk_done) if (e) cudaEventDestroy(e);
     if (c.e0) cudaEventDestroy(c.e0);
     if (c.e1) cudaEventDestroy(c.e1);
     cudaFree(c.d_counters);
@@ -118,6 +122,8 @@ int init_locked(int n_gpus, const int* ids) {
         c.dev = dev;
         CU(cudaSetDevice(dev));
         CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+        for (auto& e : c.chunk_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CU(cudaEventCreate(&c.e0));
         CU(cudaEventCreate(&c.e1));
         CU(cudaMalloc(&c.d_counters, 2 * sizeof(unsigned long long)));
@@ -624,7 +630,41 @@ int c2rt_render(c2rt_scene* s, const c2rt_camera* cam, const c2rt_settings* set,
         root.argb_cap = npx;
     }
     uint32_t launches = 0;
-    for (int i = 0; i < n; i++) {
+    bool copied = false;
+    if (n == 1) {
+        // One device: launch the frame in up to 4 chunks of tile rows and copy each chunk back on a second
+        // stream while the next one renders (the D2H copy of a float frame costs more than rendering it).
+        DeviceCtx& c = root;
+        rc = make_resident(s, 0, c.stream);
+        if (rc) return rc;
+        FrameParams fp;
+        fill_params(fp, cam, set);
+        fp.counters = c.d_counters;
+        fp.lut = c.d_lut;
+        fp.rgb = root.d_rgb;
+        fp.argb = argb ? root.d_argb : nullptr;
+        const uint32_t tile_rows = (H + TILE_H - 1) / TILE_H;
+        const uint32_t n_chunks = tile_rows >= 32 ? 4 : 1;
+        CU(cudaEventRecord(c.e0, c.stream));
+        for (uint32_t k = 0; k < n_chunks; k++) {
+            const uint32_t t0 = tile_rows * k / n_chunks, t1 = tile_rows * (k + 1) / n_chunks;
+            fp.tile_row0 = t0;
+            CU(launch_frame(fp, s->mode, t1 - t0, c.stream));
+            launches++;
+            CU(cudaEventRecord(c.chunk_done[k], c.stream));
+            CU(cudaStreamWaitEvent(c.copy_stream, c.chunk_done[k], 0));
+            const size_t y0 = (size_t)t0 * TILE_H, y1 = std::min<size_t>((size_t)t1 * TILE_H, H);
+            CU(cudaMemcpyAsync(rgb + y0 * W * 3, root.d_rgb + y0 * W * 3, (y1 - y0) * W * 3 * sizeof(float), cudaMemcpyDeviceToHost,
+                               c.copy_stream));
+            if (argb)
+                CU(cudaMemcpyAsync(argb + y0 * W, root.d_argb + y0 * W, (y1 - y0) * W * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                   c.copy_stream));
+        }
+        CU(cudaEventRecord(c.e1, c.stream));
+        CU(cudaStreamSynchronize(c.copy_stream));
+        copied = true;
+    }
+    for (int i = 0; i < n && n > 1; i++) {
         DeviceCtx& c = g_ctx.d[i];
         CU(cudaSetDevice(c.dev));
         rc = make_resident(s, i, c.stream);
@@ -687,9 +727,11 @@ int c2rt_render(c2rt_scene* s, const c2rt_camera* cam, const c2rt_settings* set,
         if (ms > kernel_ms) kernel_ms = ms;
     }
     CU(cudaSetDevice(root.dev));
-    CU(cudaMemcpyAsync(rgb, root.d_rgb, npx * 3 * sizeof(float), cudaMemcpyDeviceToHost, root.stream));
-    if (argb) CU(cudaMemcpyAsync(argb, root.d_argb, npx * sizeof(uint32_t), cudaMemcpyDeviceToHost, root.stream));
-    CU(cudaStreamSynchronize(root.stream));
+    if (!copied) {
+        CU(cudaMemcpyAsync(rgb, root.d_rgb, npx * 3 * sizeof(float), cudaMemcpyDeviceToHost, root.stream));
+        if (argb) CU(cudaMemcpyAsync(argb, root.d_argb, npx * sizeof(uint32_t), cudaMemcpyDeviceToHost, root.stream));
+        CU(cudaStreamSynchronize(root.stream));
+    }
     if (stats) {
         memset(stats, 0, sizeof *stats);
         stats->kernel_ms = kernel_ms;

@@ -770,7 +770,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS) render_frame_kernel
 
     // tile -> rows: local tile l of this rank belongs to its band (l / tiles_per_band), which is
     // global band (band_local * n_ranks + rank)
-    const uint32_t l = blockIdx.y;
+    const uint32_t l = blockIdx.y + fp.tile_row0;
     const uint32_t band_local = l / fp.tiles_per_band;
     const uint32_t within = l - band_local * fp.tiles_per_band;
     const uint32_t tile_row = (band_local * fp.n_ranks + fp.rank) * fp.tiles_per_band + within;

@@ -83,6 +83,7 @@ struct FrameParams {
     int count_rays;
     // interleaved row bands
     uint32_t rank, n_ranks, tiles_per_band, compact;
+    uint32_t tile_row0;               // first local tile row of this launch (frames are launched in chunks to overlap the D2H copy)
     // outputs
     float* rgb;
     uint32_t* argb;
