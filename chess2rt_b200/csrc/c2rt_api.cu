@@ -438,6 +438,9 @@ void fill_params(FrameParams& fp, const c2rt_camera* cam, const c2rt_settings* s
     }
     fp.inv_w = 1.0 / (double)cam->frame_width;
     fp.inv_h = 1.0 / (double)cam->frame_height;
+    static const double kx[5] = {0.0, 0.3, 0.6, 0.0, 0.6}, ky[5] = {0.0, 0.3, 0.0, 0.6, 0.6};
+    for (int t = 0; t < 5; t++)
+        for (int k = 0; k < 3; k++) fp.tap_d[t][k] = fp.du[k] * (kx[t] * fp.inv_w) + fp.dv[k] * (ky[t] * fp.inv_h);
     fp.focal_plane_dist = cam->focal_plane_dist;
     fp.disc_multiplier = cam->disc_multiplier;
     fp.seed = set->rng_seed;

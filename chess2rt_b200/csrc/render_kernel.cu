@@ -127,13 +127,19 @@ __device__ __forceinline__ double uniform01(const FrameParams& fp, uint32_t px, 
 // ---------------------------------------------------------------- camera
 // camera.d:123-174.  fp.up_left is stored relative to the camera position, fp.inv_w/inv_h are the
 // reciprocals of the camera frame size (x / W -> x * (1/W): one rounding apart).
-template <int MODE>
-__device__ __forceinline__ void gen_ray(const FrameParams& fp, double x, double y, uint32_t px, uint32_t py, uint32_t tap,
-                                        uint32_t sample, uint32_t& draw, Ray& r) {
+// Un-normalised direction through screen position (x, y): (upLeft - pos) + du * x/W + dv * y/H
+__device__ __forceinline__ void screen_dir(const FrameParams& fp, double x, double y, double& vx, double& vy, double& vz) {
     double sx = x * fp.inv_w, sy = y * fp.inv_h;
-    r.dx = fma(fp.dv[0], sy, fma(fp.du[0], sx, fp.ul_rel[0]));
-    r.dy = fma(fp.dv[1], sy, fma(fp.du[1], sx, fp.ul_rel[1]));
-    r.dz = fma(fp.dv[2], sy, fma(fp.du[2], sx, fp.ul_rel[2]));
+    vx = fma(fp.dv[0], sy, fma(fp.du[0], sx, fp.ul_rel[0]));
+    vy = fma(fp.dv[1], sy, fma(fp.du[1], sx, fp.ul_rel[1]));
+    vz = fma(fp.dv[2], sy, fma(fp.du[2], sx, fp.ul_rel[2]));
+}
+
+// Completes a camera ray from its un-normalised direction (DOF lens sampling included)
+template <int MODE>
+__device__ __forceinline__ void gen_ray(const FrameParams& fp, double vx, double vy, double vz, uint32_t px, uint32_t py, uint32_t tap,
+                                        uint32_t sample, uint32_t& draw, Ray& r) {
+    r.dx = vx; r.dy = vy; r.dz = vz;
     r.ox = fp.pos[0]; r.oy = fp.pos[1]; r.oz = fp.pos[2];
     normalize3(r.dx, r.dy, r.dz);
     if (fp.dof) {
@@ -468,7 +474,8 @@ template <int MODE>
 __device__ __forceinline__ bool node_exact(int ni, const DevNode& nd, const Ray& r, HitRec& h) {
     int face = 0;
     bool hit;
-    if (nd.kind == KIND_PLANE_W) hit = isect_plane(nd.wp[0], CUDART_NAN, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, h.px, h.py, h.pz);
+    // MODE 0: no bounded and no generic node exists, i.e. every node is a world-space plane
+    if (MODE == 0 || nd.kind == KIND_PLANE_W) hit = isect_plane(nd.wp[0], CUDART_NAN, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, h.px, h.py, h.pz);
     else if ((MODE & MODE_BOUNDED) && nd.kind == KIND_SPHERE_W) hit = isect_sphere(nd.wp, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, h.px, h.py, h.pz);
     else if ((MODE & MODE_BOUNDED) && nd.kind == KIND_CUBE_W) hit = isect_cube(nd.wp, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, h.px, h.py, h.pz, face);
     else if (MODE & MODE_GENERIC) return generic_intersect(ni, r, h);
@@ -505,7 +512,7 @@ __device__ __forceinline__ bool occluded(double fx, double fy, double fz, double
     const int n = c_scene.n_nodes;
     for (int i = 0; i < n; i++) {
         const DevNode& nd = c_scene.nodes[i];
-        if (nd.kind == KIND_PLANE_W) {
+        if (MODE == 0 || nd.kind == KIND_PLANE_W) {
             // implied by geometry.d:35-36 (dir.y has the sign of D.y): the common "light above the floor" case
             const double y = nd.wp[0];
             if ((fy > y && Dy >= 0) || (fy < y && Dy <= 0)) continue;
@@ -643,6 +650,10 @@ __device__ __forceinline__ void surface_of(const HitRec& h, bool need_uv, Surfac
             s.px = x + nd.off[0]; s.py = y + nd.off[1]; s.pz = z + nd.off[2];
         }
     }
+    if (nd.kind == KIND_PLANE_W) {   // (0, 1, 0): nothing to normalise
+        s.nx = 0.f; s.ny = 1.f; s.nz = 0.f;
+        return;
+    }
     float fx = (float)s.gx, fy = (float)s.gy, fz = (float)s.gz;
     float inv = rsqrtf(dot3f(fx, fy, fz, fx, fy, fz));
     s.nx = fx * inv; s.ny = fy * inv; s.nz = fz * inv;
@@ -729,24 +740,27 @@ __device__ __forceinline__ Col trace(const FrameParams& fp, const Ray& ray, unsi
     return shade<MODE>(fp, ray, h, n_shadow);
 }
 
-// renderer.d:254-313 renderSample (default and DOF branches)
+// renderer.d:254-313 renderSample (default and DOF branches).  (bx, by, bz) is the un-normalised
+// direction through the pixel corner; tap k adds the per-frame constant fp.tap_d[k].
 template <int MODE>
-__device__ __forceinline__ Col render_sample(const FrameParams& fp, double x, double y, uint32_t px, uint32_t py, uint32_t tap,
-                                             unsigned& n_primary, unsigned& n_shadow, HitRec* out_hit) {
+__device__ __forceinline__ Col render_sample(const FrameParams& fp, double bx, double by, double bz, double x, double y, uint32_t px,
+                                             uint32_t py, uint32_t tap, unsigned& n_primary, unsigned& n_shadow, HitRec* out_hit) {
     Ray r;
     uint32_t draw = 0;
     if (!fp.dof) {
         n_primary++;
-        gen_ray<MODE>(fp, x, y, px, py, tap, 0, draw, r);
+        gen_ray<MODE>(fp, bx + fp.tap_d[tap][0], by + fp.tap_d[tap][1], bz + fp.tap_d[tap][2], px, py, tap, 0, draw, r);
         return trace<MODE>(fp, r, n_shadow, out_hit);
     }
     Col avg = mkcol(0.f, 0.f, 0.f);
     for (uint32_t i = 0; i < fp.num_samples; i++) {
         draw = 0;
-        double jx = x + uniform01(fp, px, py, tap, i, draw);
-        double jy = y + uniform01(fp, px, py, tap, i, draw);
+        double jx = x + c_tap_x[tap] + uniform01(fp, px, py, tap, i, draw);
+        double jy = y + c_tap_y[tap] + uniform01(fp, px, py, tap, i, draw);
         n_primary++;
-        gen_ray<MODE>(fp, jx, jy, px, py, tap, i, draw, r);
+        double vx, vy, vz;
+        screen_dir(fp, jx, jy, vx, vy, vz);
+        gen_ray<MODE>(fp, vx, vy, vz, px, py, tap, i, draw, r);
         Col c = trace<MODE>(fp, r, n_shadow, (out_hit && i == 0) ? out_hit : nullptr);
         avg.r += c.r; avg.g += c.g; avg.b += c.b;
     }
@@ -789,9 +803,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS) render_frame_kernel
         // renderer.d:223-251: tap 0 at the pixel corner, then +(.3,.3) (.6,0) (0,.6) (.6,.6); mean of 5 in FP32
         const int taps = fp.aa ? 5 : 1;
         const double xd = (double)x, yd = (double)y;
+        double bx, by, bz;
+        screen_dir(fp, xd, yd, bx, by, bz);
 #pragma unroll 1
         for (int s = 0; s < taps; s++) {
-            Col t = render_sample<MODE>(fp, xd + c_tap_x[s], yd + c_tap_y[s], x, y, s, n_primary, n_shadow, nullptr);
+            Col t = render_sample<MODE>(fp, bx, by, bz, xd, yd, x, y, s, n_primary, n_shadow, nullptr);
             c.r += t.r; c.g += t.g; c.b += t.b;
         }
         if (fp.aa) { c.r = c.r / 5.f; c.g = c.g / 5.f; c.b = c.b / 5.f; }  // accum / 5 (renderer.d:249)
@@ -846,7 +862,9 @@ __global__ void render_pixel_kernel(const FrameParams fp, int x, int y, PixelOut
     HitRec h;
     h.node = -1;
     h.dist = 1e99;
-    Col c = render_sample<MODE_BOUNDED | MODE_GENERIC>(fp, (double)x, (double)y, (uint32_t)x, (uint32_t)y, 0, a, b, &h);
+    double bx, by, bz;
+    screen_dir(fp, (double)x, (double)y, bx, by, bz);
+    Col c = render_sample<MODE_BOUNDED | MODE_GENERIC>(fp, bx, by, bz, (double)x, (double)y, (uint32_t)x, (uint32_t)y, 0, a, b, &h);
     out->rgb[0] = c.r; out->rgb[1] = c.g; out->rgb[2] = c.b;
     out->node = h.node;
     out->dist = h.dist;

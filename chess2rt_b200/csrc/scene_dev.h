@@ -74,6 +74,7 @@ struct FrameParams {
     double pos[3], ul_rel[3], du[3], dv[3];
     double right_dir[3], up_dir[3], front_dir[3];
     double inv_w, inv_h;
+    double tap_d[5][3];               // ray-direction offset of AA tap k: du * kx/W + dv * ky/H (renderer.d:235-247)
     double focal_plane_dist, disc_multiplier;
     unsigned long long seed;
     uint32_t W, H;                    // output size
