@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -59,6 +60,7 @@ struct DeviceCtx {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     cudaEvent_t chunk_done[8] = {};
+    std::vector<cudaEvent_t> band_done;
     uint64_t uploaded_scene = 0;   // id of the scene currently in this device's constant memory
     unsigned long long* d_counters = nullptr;
     uint8_t* d_lut = nullptr;
@@ -95,6 +97,7 @@ void destroy_device(DeviceCtx& c) {
     if (c.stream) cudaStreamDestroy(c.stream);
     if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
     for (auto& e : c.chunk_done) if (e) cudaEventDestroy(e);
+    for (auto& e : c.band_done) cudaEventDestroy(e);
     if (c.e0) cudaEventDestroy(c.e0);
     if (c.e1) cudaEventDestroy(c.e1);
     cudaFree(c.d_counters);
@@ -667,7 +670,76 @@ int c2rt_render(c2rt_scene* s, const c2rt_camera* cam, const c2rt_settings* set,
         CU(cudaStreamSynchronize(c.copy_stream));
         copied = true;
     }
-    for (int i = 0; i < n && n > 1; i++) {
+    // N devices.  Default: every device renders its interleaved bands into a compact buffer and copies them to
+    // the caller's HOST frame over its own PCIe link (chunked, overlapped with rendering) — the host copy of a
+    // float frame is the slow part, so N links beat one.  C2RT_GATHER=root keeps the frame on device 0 instead:
+    // peers store their bands straight into it through peer-mapped pointers (NVLink), device 0 copies it back.
+    const char* gather_env = getenv("C2RT_GATHER");
+    const bool direct = n > 1 && !(gather_env && strcmp(gather_env, "root") == 0);
+    for (int i = 0; i < n && direct; i++) {
+        DeviceCtx& c = g_ctx.d[i];
+        CU(cudaSetDevice(c.dev));
+        rc = make_resident(s, i, c.stream);
+        if (rc) return rc;
+        FrameParams fp;
+        fill_params(fp, cam, set);
+        fp.rank = (uint32_t)i;
+        fp.n_ranks = (uint32_t)n;
+        fp.tiles_per_band = 1;
+        fp.compact = 1;
+        fp.counters = c.d_counters;
+        fp.lut = c.d_lut;
+        // ~16 interleaved bands per device: each band is one launch + one contiguous D2H copy
+        uint32_t brows = (H / (uint32_t)(n * 16) + TILE_H - 1) / TILE_H * TILE_H;
+        if (brows < TILE_H) brows = TILE_H;
+        fp.tiles_per_band = brows / TILE_H;
+        const uint32_t rows_owned = c2rt_band_rows_owned(H, fp.rank, fp.n_ranks, brows);
+        const size_t need = (size_t)rows_owned * W;
+        if (c.rgb_cap < need * 3) {
+            cudaFree(c.d_rgb);
+            c.d_rgb = nullptr; c.rgb_cap = 0;
+            CU(cudaMalloc(&c.d_rgb, std::max<size_t>(need, 1) * 3 * sizeof(float)));
+            c.rgb_cap = need * 3;
+        }
+        if (argb && c.argb_cap < need) {
+            cudaFree(c.d_argb);
+            c.d_argb = nullptr; c.argb_cap = 0;
+            CU(cudaMalloc(&c.d_argb, std::max<size_t>(need, 1) * sizeof(uint32_t)));
+            c.argb_cap = need;
+        }
+        fp.rgb = c.d_rgb;
+        fp.argb = argb ? c.d_argb : nullptr;
+        CU(cudaEventRecord(c.e0, c.stream));
+        uint32_t local_row = 0, b = 0;
+        for (uint32_t y0 = (uint32_t)i * brows; y0 < H; y0 += (uint32_t)n * brows, b++) {
+            const uint32_t rows = std::min<uint32_t>(brows, H - y0);
+            if (b >= c.band_done.size()) {
+                cudaEvent_t e;
+                CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                c.band_done.push_back(e);
+            }
+            fp.tile_row0 = b * fp.tiles_per_band;
+            CU(launch_frame(fp, s->mode, (rows + TILE_H - 1) / TILE_H, c.stream));
+            launches++;
+            CU(cudaEventRecord(c.band_done[b], c.stream));
+            CU(cudaStreamWaitEvent(c.copy_stream, c.band_done[b], 0));
+            CU(cudaMemcpyAsync(rgb + (size_t)y0 * W * 3, c.d_rgb + (size_t)local_row * W * 3, (size_t)rows * W * 3 * sizeof(float),
+                               cudaMemcpyDeviceToHost, c.copy_stream));
+            if (argb)
+                CU(cudaMemcpyAsync(argb + (size_t)y0 * W, c.d_argb + (size_t)local_row * W, (size_t)rows * W * sizeof(uint32_t),
+                                   cudaMemcpyDeviceToHost, c.copy_stream));
+            local_row += rows;
+        }
+        CU(cudaEventRecord(c.e1, c.stream));
+    }
+    if (direct) {
+        for (int i = 0; i < n; i++) {
+            CU(cudaSetDevice(g_ctx.d[i].dev));
+            CU(cudaStreamSynchronize(g_ctx.d[i].copy_stream));
+        }
+        copied = true;
+    }
+    for (int i = 0; i < n && n > 1 && !direct; i++) {
         DeviceCtx& c = g_ctx.d[i];
         CU(cudaSetDevice(c.dev));
         rc = make_resident(s, i, c.stream);
