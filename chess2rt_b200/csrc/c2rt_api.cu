@@ -187,46 +187,50 @@ struct Bound {
     double c[3], r;
 };
 
+Bound union_bound(const Bound& l, const Bound& r) {
+    Bound b{};
+    if (!l.finite || !r.finite) { b.finite = false; return b; }
+    double dx = r.c[0] - l.c[0], dy = r.c[1] - l.c[1], dz = r.c[2] - l.c[2];
+    double dist = sqrt(dx * dx + dy * dy + dz * dz);
+    if (dist + r.r <= l.r) return l;
+    if (dist + l.r <= r.r) return r;
+    b.finite = true;
+    b.r = (dist + l.r + r.r) * 0.5;
+    double t = (b.r - l.r) / dist;
+    b.c[0] = l.c[0] + dx * t; b.c[1] = l.c[1] + dy * t; b.c[2] = l.c[2] + dz * t;
+    return b;
+}
+
+// Bounding sphere of everything a geometry can report a hit on.  For a CSG of two primitives the boolean
+// is evaluated faithfully, so diff is bounded by its left child and inter by the smaller child.  Once a
+// child is itself a CSG the reference's walk is quirky (a nested child's crossings toggle the wrong flag,
+// entry-only crossing lists flip the initial parity: tests/scenes/nested.sdl) and a hit may be reported on
+// ANY leaf surface: the bound is then the union over all leaves.
 Bound bound_of(const c2rt_scene_desc* d, int gi) {
     Bound b{};
     const double* p = d->geom_params + 4 * gi;
-    switch (d->geom_type[gi]) {
-        case C2RT_GEOM_SPHERE:
-            b.finite = std::isfinite(p[3]);
-            b.c[0] = p[0]; b.c[1] = p[1]; b.c[2] = p[2];
-            b.r = fabs(p[3]);
-            break;
-        case C2RT_GEOM_CUBE:
-            b.finite = std::isfinite(p[3]);
-            b.c[0] = p[0]; b.c[1] = p[1]; b.c[2] = p[2];
-            b.r = fabs(p[3]) * 0.5 * sqrt(3.0);
-            break;
-        case C2RT_GEOM_CSG_UNION: {
-            Bound l = bound_of(d, d->geom_left[gi]), r = bound_of(d, d->geom_right[gi]);
-            if (!l.finite || !r.finite) { b.finite = false; break; }
-            double dx = r.c[0] - l.c[0], dy = r.c[1] - l.c[1], dz = r.c[2] - l.c[2];
-            double dist = sqrt(dx * dx + dy * dy + dz * dz);
-            if (dist + r.r <= l.r) { b = l; break; }
-            if (dist + l.r <= r.r) { b = r; break; }
-            b.finite = true;
-            b.r = (dist + l.r + r.r) * 0.5;
-            double t = (b.r - l.r) / dist;
-            b.c[0] = l.c[0] + dx * t; b.c[1] = l.c[1] + dy * t; b.c[2] = l.c[2] + dz * t;
-            break;
-        }
-        case C2RT_GEOM_CSG_INTER: {
-            Bound l = bound_of(d, d->geom_left[gi]), r = bound_of(d, d->geom_right[gi]);
+    const int type = d->geom_type[gi];
+    if (type == C2RT_GEOM_SPHERE) {
+        b.finite = std::isfinite(p[3]);
+        b.c[0] = p[0]; b.c[1] = p[1]; b.c[2] = p[2];
+        b.r = fabs(p[3]);
+    } else if (type == C2RT_GEOM_CUBE) {
+        b.finite = std::isfinite(p[3]);
+        b.c[0] = p[0]; b.c[1] = p[1]; b.c[2] = p[2];
+        b.r = fabs(p[3]) * 0.5 * sqrt(3.0);
+    } else if (type >= C2RT_GEOM_CSG_UNION) {
+        const int li = d->geom_left[gi], ri = d->geom_right[gi];
+        Bound l = bound_of(d, li), r = bound_of(d, ri);
+        const bool nested = d->geom_type[li] >= C2RT_GEOM_CSG_UNION || d->geom_type[ri] >= C2RT_GEOM_CSG_UNION;
+        if (nested || type == C2RT_GEOM_CSG_UNION) b = union_bound(l, r);
+        else if (type == C2RT_GEOM_CSG_INTER) {
             if (l.finite && r.finite) b = l.r <= r.r ? l : r;
             else if (l.finite) b = l;
             else if (r.finite) b = r;
             else b.finite = false;
-            break;
-        }
-        case C2RT_GEOM_CSG_DIFF:
-            b = bound_of(d, d->geom_left[gi]);
-            break;
-        default:
-            b.finite = false;
+        } else b = l;  // diff
+    } else {
+        b.finite = false;  // plane
     }
     if (b.finite && !(std::isfinite(b.c[0]) && std::isfinite(b.c[1]) && std::isfinite(b.c[2]) && std::isfinite(b.r))) b.finite = false;
     return b;
@@ -272,9 +276,14 @@ int validate_and_build(const c2rt_scene_desc* d, c2rt_scene* s) {
             int l = d->geom_left[i], r = d->geom_right[i];
             if (l < 0 || r < 0 || l >= (int)i || r >= (int)i)
                 return fail(C2RT_ERR_INVALID_ARG, "geometry %u: CSG children must be earlier geometries (left %d, right %d)", i, l, r);
-            if (d->geom_type[l] >= C2RT_GEOM_CSG_UNION || d->geom_type[r] >= C2RT_GEOM_CSG_UNION)
-                return fail(C2RT_ERR_UNSUPPORTED, "geometry %u: nested CSG (a CSG child of a CSG) is not supported by this build", i);
             g.left = l; g.right = r;
+            const int dl = abs(h.geoms[l].pad), dr = abs(h.geoms[r].pad);
+            g.pad = 1 + (dl > dr ? dl : dr);
+            if (g.pad > 3)
+                return fail(C2RT_ERR_UNSUPPORTED, "geometry %u: CSG nesting deeper than 3 levels is not supported", i);
+            // tuning / testing aid: C2RT_CSG_LITERAL=1 routes every CSG through the literal emulation
+            const char* lit = getenv("C2RT_CSG_LITERAL");
+            if (lit && lit[0] == '1' && g.pad == 1) g.pad = -1;
         }
     }
     s->tex_offset.assign(d->n_textures, 0);
@@ -387,6 +396,8 @@ int validate_and_build(const c2rt_scene_desc* d, c2rt_scene* s) {
     for (uint32_t i = 0; i < d->n_nodes; i++) {
         if (!(h.nodes[i].flags & NODE_UNBOUNDED)) s->mode |= 1;   // MODE_BOUNDED
         if (h.nodes[i].kind == KIND_GENERIC) s->mode |= 2;        // MODE_GENERIC
+        const DevGeom& ng = h.geoms[h.nodes[i].geom];
+        if (ng.type >= C2RT_GEOM_CSG_UNION && ng.pad != 1) s->mode |= 4 | 2 | 1;  // MODE_NESTED (implies the generic, bounded kernel)
     }
     return C2RT_OK;
 }

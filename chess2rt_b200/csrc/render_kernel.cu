@@ -31,7 +31,8 @@ __constant__ double c_tap_y[5] = {0.0, 0.3, 0.0, 0.6, 0.6};
 // Kernel specialisations by scene class (chosen at scene-create time, c2rt_api.cu):
 //   MODE_BOUNDED  some node has a finite bounding sphere -> FP32 ray shadow + conservative cull
 //   MODE_GENERIC  some node needs the object-space path (non-identity transform, CSG, bounded plane)
-constexpr int MODE_BOUNDED = 1, MODE_GENERIC = 2;
+//   MODE_NESTED   some CSG has a CSG child -> literal emulation of the reference's recursive walk
+constexpr int MODE_BOUNDED = 1, MODE_GENERIC = 2, MODE_NESTED = 4;
 
 // Precision plan: FP64 carries everything a pixel DECISION or a texture coordinate
 // depends on — ray direction, hit distances, hit points, plane/cube uv, checker cells, face-forward
@@ -251,12 +252,23 @@ __device__ __forceinline__ bool csg_bool(int type, bool l, bool r) {  // geometr
     return type == C2RT_GEOM_CSG_UNION ? (l || r) : type == C2RT_GEOM_CSG_INTER ? (l && r) : (l && !r);
 }
 
-// CSG children are primitives (nesting is rejected at scene-create time, c2rt_api.cu), so
-// CsgOp.isInside (geometry.d:334-337) needs no recursion.
+// CsgOp.isInside (geometry.d:334-337).  Depth-1 CSGs (primitive children) need no recursion; nested ones
+// are evaluated by a depth-limited template recursion (NESTED_MAX_DEPTH levels, checked at scene create).
+template <int D>
+__device__ __forceinline__ bool geom_inside_d(int gi, double x, double y, double z) {
+    const DevGeom& g = c_scene.geoms[gi];
+    if (g.type <= C2RT_GEOM_CUBE) return prim_inside(g, x, y, z);
+    return csg_bool(g.type, geom_inside_d<D - 1>(g.left, x, y, z), geom_inside_d<D - 1>(g.right, x, y, z));
+}
+template <>
+__device__ __forceinline__ bool geom_inside_d<0>(int gi, double x, double y, double z) {
+    return prim_inside(c_scene.geoms[gi], x, y, z);
+}
 __device__ __forceinline__ bool geom_inside(int gi, double x, double y, double z) {
     const DevGeom& g = c_scene.geoms[gi];
     if (g.type <= C2RT_GEOM_CUBE) return prim_inside(g, x, y, z);
-    return csg_bool(g.type, prim_inside(c_scene.geoms[g.left], x, y, z), prim_inside(c_scene.geoms[g.right], x, y, z));
+    if (g.pad <= 1) return csg_bool(g.type, prim_inside(c_scene.geoms[g.left], x, y, z), prim_inside(c_scene.geoms[g.right], x, y, z));
+    return geom_inside_d<3>(gi, x, y, z);
 }
 
 // ---------------------------------------------------------------- CSG
@@ -417,6 +429,102 @@ __device__ __forceinline__ bool isect_csg(int gi, double ox, double oy, double o
     return true;
 }
 
+// ---------------------------------------------------------------- nested CSG (literal emulation)
+// A CSG whose child is itself a CSG has no closed form: the child can yield many crossings, and the
+// reference's walk has observable quirks there — a nested child's crossings carry the LEAF primitive in
+// `g`, so `current.g is left` is false and they toggle the RIGHT flag (geometry.d:314), and
+// a CSG reports interior boundaries as hits while the boolean stays true (geometry.d:321).  This path
+// therefore replays findAllIntersections / sort / walk literally, recursing through a depth-limited
+// template; it is only compiled into the MODE_NESTED kernel.
+constexpr int NESTED_MAX_CROSSINGS = 8;   // per child
+constexpr int NESTED_MAX_DEPTH = 3;       // CSG levels above the primitives (validated at scene create)
+
+struct LitCrossing {
+    double dist, px, py, pz;
+    int face, leaf;
+};
+
+template <int D>
+__device__ __noinline__ bool isect_geom_lit(int gi, double ox, double oy, double oz, double dx, double dy, double dz, double& dist,
+                                            double& px, double& py, double& pz, int& face, int& leaf);
+
+template <int D>
+__device__ __forceinline__ int find_all_lit(int gi, double ox, double oy, double oz, double dx, double dy, double dz, LitCrossing* out) {
+    double cur = 0;
+    int n = 0;
+    while (n < NESTED_MAX_CROSSINGS) {  // geometry.d:271-290
+        double dist = 1e99, px, py, pz;
+        int face = 0, leaf = gi;
+        if (!isect_geom_lit<D - 1>(gi, ox, oy, oz, dx, dy, dz, dist, px, py, pz, face, leaf)) break;
+        dist += cur;
+        cur = dist;
+        ox = fma(dx, 1e-6, px); oy = fma(dy, 1e-6, py); oz = fma(dz, 1e-6, pz);
+        out[n].dist = dist; out[n].px = px; out[n].py = py; out[n].pz = pz;
+        out[n].face = face; out[n].leaf = leaf;
+        n++;
+    }
+    return n;
+}
+
+template <>
+__device__ __noinline__ bool isect_geom_lit<0>(int gi, double ox, double oy, double oz, double dx, double dy, double dz, double& dist,
+                                               double& px, double& py, double& pz, int& face, int& leaf) {
+    const DevGeom& g = c_scene.geoms[gi];
+    if (g.type > C2RT_GEOM_CUBE) return false;  // deeper than NESTED_MAX_DEPTH: rejected at scene create
+    leaf = gi;
+    face = 0;
+    return isect_prim(g, ox, oy, oz, dx, dy, dz, dist, px, py, pz, face);
+}
+
+template <int D>
+__device__ __noinline__ bool isect_geom_lit(int gi, double ox, double oy, double oz, double dx, double dy, double dz, double& dist,
+                                            double& px, double& py, double& pz, int& face, int& leaf) {
+    const DevGeom& g = c_scene.geoms[gi];
+    if (g.type <= C2RT_GEOM_CUBE) {
+        leaf = gi;
+        face = 0;
+        return isect_prim(g, ox, oy, oz, dx, dy, dz, dist, px, py, pz, face);
+    }
+    LitCrossing all[2 * NESTED_MAX_CROSSINGS];
+    const int nl = find_all_lit<D>(g.left, ox, oy, oz, dx, dy, dz, all);
+    const int nr = find_all_lit<D>(g.right, ox, oy, oz, dx, dy, dz, all + nl);
+    const int n = nl + nr;
+    // util/array.d:95-111 shell sort, including the `ref` loop index and the gap sequence
+    int inc = n / 2;
+    while (inc) {
+        for (int key = 0; key < n; key++) {
+            int i = key;
+            LitCrossing elem = all[i];
+            while (i >= inc && all[i - inc].dist > elem.dist) {
+                all[i] = all[i - inc];
+                i -= inc;
+            }
+            all[i] = elem;
+            key = i;
+        }
+        inc = (inc == 2) ? 1 : (int)(inc * 5.0 / 11);
+    }
+    bool inL = nl & 1, inR = nr & 1;
+    for (int k = 0; k < n; k++) {
+        if (all[k].leaf == g.left) inL = !inL;   // `current.g is left`: only true when the left child is a primitive
+        else inR = !inR;
+        if (csg_bool(g.type, inL, inR)) {
+            if (all[k].dist > dist) return false;
+            dist = all[k].dist;
+            px = all[k].px; py = all[k].py; pz = all[k].pz;
+            face = all[k].face;
+            leaf = all[k].leaf;
+            if (g.type == C2RT_GEOM_CSG_DIFF) {
+                bool a = geom_inside(g.right, px - dx * 1e-6, py - dy * 1e-6, pz - dz * 1e-6);
+                bool b = geom_inside(g.right, px + dx * 1e-6, py + dy * 1e-6, pz + dz * 1e-6);
+                if (a != b) face ^= FACE_FLIP;
+            }
+            return true;
+        }
+    }
+    return false;
+}
+
 // ---------------------------------------------------------------- node
 // Conservative FP32 bounding-sphere rejection.  Result-identical: it only skips nodes the exact
 // FP64 test would reject.  `margin`/`slack` bound the FP32 rounding of everything in the test
@@ -436,6 +544,7 @@ __device__ __forceinline__ bool cull(const DevNode& nd, const Ray& r, float tmax
 }
 
 // node.d:23-49 for a transformed node: world ray -> object space, exact FP64 geometry test
+template <int MODE>
 __device__ __forceinline__ bool generic_intersect(int ni, const Ray& r, HitRec& h) {
     const DevNode& nd = c_scene.nodes[ni];
     double ox, oy, oz, dx, dy, dz, len;
@@ -458,6 +567,7 @@ __device__ __forceinline__ bool generic_intersect(int ni, const Ray& r, HitRec& 
     const DevGeom& g = c_scene.geoms[nd.geom];
     bool hit;
     if (g.type <= C2RT_GEOM_CUBE) hit = isect_prim(g, ox, oy, oz, dx, dy, dz, dist, px, py, pz, face);
+    else if ((MODE & MODE_NESTED) && g.pad != 1) hit = isect_geom_lit<NESTED_MAX_DEPTH>(nd.geom, ox, oy, oz, dx, dy, dz, dist, px, py, pz, face, leaf);
     else hit = isect_csg(nd.geom, ox, oy, oz, dx, dy, dz, dist, px, py, pz, face, leaf);
     if (!hit) return false;
     h.dist = (nd.flags & NODE_IDENTITY) ? dist : dist * rcp64(len);
@@ -478,7 +588,7 @@ __device__ __forceinline__ bool node_exact(int ni, const DevNode& nd, const Ray&
     if (MODE == 0 || nd.kind == KIND_PLANE_W) hit = isect_plane(nd.wp[0], CUDART_NAN, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, h.px, h.py, h.pz);
     else if ((MODE & MODE_BOUNDED) && nd.kind == KIND_SPHERE_W) hit = isect_sphere(nd.wp, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, h.px, h.py, h.pz);
     else if ((MODE & MODE_BOUNDED) && nd.kind == KIND_CUBE_W) hit = isect_cube(nd.wp, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, h.px, h.py, h.pz, face);
-    else if (MODE & MODE_GENERIC) return generic_intersect(ni, r, h);
+    else if (MODE & MODE_GENERIC) return generic_intersect<MODE>(ni, r, h);
     else return false;
     if (hit) { h.node = ni; h.leaf = nd.geom; h.face = face; }
     return hit;
@@ -864,7 +974,7 @@ __global__ void render_pixel_kernel(const FrameParams fp, int x, int y, PixelOut
     h.dist = 1e99;
     double bx, by, bz;
     screen_dir(fp, (double)x, (double)y, bx, by, bz);
-    Col c = render_sample<MODE_BOUNDED | MODE_GENERIC>(fp, bx, by, bz, (double)x, (double)y, (uint32_t)x, (uint32_t)y, 0, a, b, &h);
+    Col c = render_sample<MODE_BOUNDED | MODE_GENERIC | MODE_NESTED>(fp, bx, by, bz, (double)x, (double)y, (uint32_t)x, (uint32_t)y, 0, a, b, &h);
     out->rgb[0] = c.r; out->rgb[1] = c.g; out->rgb[2] = c.b;
     out->node = h.node;
     out->dist = h.dist;
@@ -924,7 +1034,8 @@ cudaError_t upload_scene(const DevScene& s, cudaStream_t st) {
 cudaError_t launch_frame(const FrameParams& fp, int mode, uint32_t local_tile_rows, cudaStream_t st) {
     if (local_tile_rows == 0) return cudaSuccess;
     dim3 grid((fp.W + TILE_W - 1) / TILE_W, local_tile_rows);
-    if (mode & MODE_GENERIC) render_frame_kernel<MODE_BOUNDED | MODE_GENERIC, C2RT_MINBLOCKS_FULL><<<grid, BLOCK_THREADS, 0, st>>>(fp);
+    if (mode & MODE_NESTED) render_frame_kernel<MODE_BOUNDED | MODE_GENERIC | MODE_NESTED, 2><<<grid, BLOCK_THREADS, 0, st>>>(fp);
+    else if (mode & MODE_GENERIC) render_frame_kernel<MODE_BOUNDED | MODE_GENERIC, C2RT_MINBLOCKS_FULL><<<grid, BLOCK_THREADS, 0, st>>>(fp);
     else if (mode & MODE_BOUNDED) render_frame_kernel<MODE_BOUNDED, C2RT_MINBLOCKS_BOUNDED><<<grid, BLOCK_THREADS, 0, st>>>(fp);
     else render_frame_kernel<0, C2RT_MINBLOCKS_SIMPLE><<<grid, BLOCK_THREADS, 0, st>>>(fp);
     return cudaGetLastError();

@@ -36,7 +36,8 @@ struct DevNode {
 
 struct DevGeom {
     double p[4];      // plane: y, limit | sphere: c.xyz, R | cube: c.xyz, side
-    int type, left, right, pad;
+    int type, left, right;
+    int pad;          // CSG depth: 0 primitive, 1 CSG of primitives, >1 nested (or forced literal: -1)
 };
 
 struct DevShader {

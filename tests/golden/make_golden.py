@@ -26,6 +26,7 @@ CASES = [  # name, scene path, (w, h), overrides, seed
     ("zaphod_dof", "scenes/zaphod.sdl", (129, 86), {"num_samples": 5}, 12345),
     ("chessboard", "scenes/chessboard.sdl", (128, 72), {}, 0),
     ("quirks", "tests/scenes/quirks.sdl", (160, 100), {}, 0),
+    ("nested", "tests/scenes/nested.sdl", (160, 100), {}, 0),
 ]
 
 

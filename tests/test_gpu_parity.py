@@ -53,6 +53,7 @@ CASES = [
     ("zaphod.sdl", None, {"num_samples": 6}),  # DOF with the pinned generator
     ("chessboard.sdl", (480, 270), {}),
     ("../tests/scenes/quirks.sdl", None, {}),
+    ("../tests/scenes/nested.sdl", None, {}),   # CSG inside CSG: literal emulation path
 ]
 
 
@@ -66,7 +67,24 @@ def test_scene_matches_oracle(name, size, over):
     assert (st.primary_rays, st.shadow_rays) == (ost.primary_rays, ost.shadow_rays)
     # ARGB plane == Color.toRGB32 of the float plane, bit-exact
     np.testing.assert_array_equal(argb, pack_rgb32(rgb))
-    assert ost.csg_max_crossings <= 4  # the kernel's per-child crossing capacity
+    assert ost.csg_max_crossings <= 8  # the nested-CSG path's per-child crossing capacity
+
+
+@pytest.mark.parametrize("name,size", [("../tests/scenes/quirks.sdl", None), ("chessboard.sdl", (320, 180)), ("lecture5.sdl", (320, 240))])
+def test_closed_form_csg_equals_literal_walk(name, size, monkeypatch):
+    """The register-only closed-form CSG and the literal replay of the reference's restart/sort/walk agree."""
+    g, o = both(os.path.join(SC, name), size)
+    fast, _, st_fast = g.render(count_rays=True)
+    monkeypatch.setenv("C2RT_CSG_LITERAL", "1")   # read at scene-create time
+    lit_scene = c2.HostScene(os.path.join(SC, name))
+    if size:
+        lit_scene.set_frame_size(*size)
+    lit, _, st_lit = lit_scene.render(count_rays=True)
+    ref, ost = o.render()
+    assert_parity(lit, ref, what="literal " + name)
+    assert_parity(fast, ref, what="closed form " + name)
+    assert (st_lit.primary_rays, st_lit.shadow_rays) == (st_fast.primary_rays, st_fast.shadow_rays) == (ost.primary_rays, ost.shadow_rays)
+    assert np.abs(fast - lit).max() < 1e-5
 
 
 def test_golden_fixtures():

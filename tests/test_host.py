@@ -135,24 +135,26 @@ def test_host_bmp_decoder_reference_kats(blob, size, pixels):
 
 
 def test_validation_errors_come_before_any_device_use(tmp_path):
-    # nested CSG is rejected with C2RT_ERR_UNSUPPORTED by the scene validator (no GPU needed to see it)
+    # CSG nesting deeper than 3 levels is rejected with C2RT_ERR_UNSUPPORTED by the scene validator (no GPU needed)
     p = tmp_path / "nested.sdl"
     p.write_text("""Scene {
  Geometries {
   Sphere "a" { R 1 }
   Cube "b" { side 1 }
-  CsgUnion "u" { left "a"; right "b" }
-  CsgDiff "n" { left "u"; right "a" }
+  CsgUnion "u1" { left "a"; right "b" }
+  CsgDiff "u2" { left "u1"; right "a" }
+  CsgInter "u3" { left "u2"; right "b" }
+  CsgUnion "u4" { left "a"; right "u3" }
  }
  Shaders { Lambert "s" { color 1 1 1 } }
- Nodes { Node "n" { geometry "n"; shader "s" } }
+ Nodes { Node "n" { geometry "u4"; shader "s" } }
 }
 """)
     s = c2.HostScene(p)
     d = s.desc()
     handle = C.c_void_p()
     rc = api.lib.c2rt_scene_create(d, C.byref(handle))
-    assert rc == -2 and b"nested CSG" in api.lib.c2rt_last_error()
+    assert rc == -2 and b"nesting deeper" in api.lib.c2rt_last_error()
     # ABI mismatch
     bad = api.SceneDesc()
     assert api.lib.c2rt_scene_create(C.byref(bad), C.byref(handle)) == -1
