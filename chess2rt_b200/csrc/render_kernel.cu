@@ -32,7 +32,8 @@ __constant__ double c_tap_y[5] = {0.0, 0.3, 0.0, 0.6, 0.6};
 //   MODE_BOUNDED  some node has a finite bounding sphere -> FP32 ray shadow + conservative cull
 //   MODE_GENERIC  some node needs the object-space path (non-identity transform, CSG, bounded plane)
 //   MODE_NESTED   some CSG has a CSG child -> literal emulation of the reference's recursive walk
-constexpr int MODE_BOUNDED = 1, MODE_GENERIC = 2, MODE_NESTED = 4;
+//   MODE_CLUSTERS the scene-create partition found runs of nodes worth a common bounding sphere (two-level cull)
+constexpr int MODE_BOUNDED = 1, MODE_GENERIC = 2, MODE_NESTED = 4, MODE_CLUSTERS = 8;
 
 // Precision plan: FP64 carries everything a pixel DECISION or a texture coordinate
 // depends on — ray direction, hit distances, hit points, plane/cube uv, checker cells, face-forward
@@ -99,9 +100,20 @@ __device__ __forceinline__ void mulvm(const double* m, double x, double y, doubl
     ry = x * m[1] + y * m[4] + z * m[7];
     rz = x * m[2] + y * m[5] + z * m[8];
 }
+// double -> float that the register allocator may not rematerialise (F2F runs on the quarter-rate XU pipe;
+// under a register cap ptxas otherwise re-converts at every use inside the node loop)
+__device__ __forceinline__ float cvt_keep(double x) {
+#ifdef C2RT_NO_KEEP
+    return (float)x;
+#else
+    float f;
+    asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(f) : "d"(x));
+    return f;
+#endif
+}
 __device__ __forceinline__ void set_shadow(Ray& r) {
-    r.fox = (float)r.ox; r.foy = (float)r.oy; r.foz = (float)r.oz;
-    r.fdx = (float)r.dx; r.fdy = (float)r.dy; r.fdz = (float)r.dz;
+    r.fox = cvt_keep(r.ox); r.foy = cvt_keep(r.oy); r.foz = cvt_keep(r.oz);
+    r.fdx = cvt_keep(r.dx); r.fdy = cvt_keep(r.dy); r.fdz = cvt_keep(r.dz);
     r.olen = sqrtf(dot3f(r.fox, r.foy, r.foz, r.fox, r.foy, r.foz));
 }
 
@@ -529,18 +541,21 @@ __device__ __noinline__ bool isect_geom_lit(int gi, double ox, double oy, double
 // Conservative FP32 bounding-sphere rejection.  Result-identical: it only skips nodes the exact
 // FP64 test would reject.  `margin`/`slack` bound the FP32 rounding of everything in the test
 // (|err(d2)| <= 24 eps S^2, |err(tca)| <= 5 eps S with S = |centre| + |origin|).
-__device__ __forceinline__ bool cull(const DevNode& nd, const Ray& r, float tmaxf) {
-    float cx = nd.bcf[0] - r.fox, cy = nd.bcf[1] - r.foy, cz = nd.bcf[2] - r.foz;
+__device__ __forceinline__ bool cull_sphere(float bx, float by, float bz, float br, float br2, float bclen, const Ray& r, float tmaxf) {
+    float cx = bx - r.fox, cy = by - r.foy, cz = bz - r.foz;
     float tca = dot3f(cx, cy, cz, r.fdx, r.fdy, r.fdz);
     float c2 = dot3f(cx, cy, cz, cx, cy, cz);
-    float S = nd.bclen + r.olen;
+    float S = bclen + r.olen;
     float margin = 4e-6f * S * S;
     float slack = 1e-6f * S;
     float d2 = fmaf(-tca, tca, c2);
-    if (d2 > nd.br2f + margin) return true;          // the line misses the sphere
-    if (tca + nd.brf < -slack) return true;          // the sphere is behind the origin
-    if (tca - nd.brf > tmaxf + slack) return true;   // the sphere starts beyond the best distance so far
+    if (d2 > br2 + margin) return true;         // the line misses the sphere
+    if (tca + br < -slack) return true;         // the sphere is behind the origin
+    if (tca - br > tmaxf + slack) return true;  // the sphere starts beyond the best distance so far
     return false;
+}
+__device__ __forceinline__ bool cull(const DevNode& nd, const Ray& r, float tmaxf) {
+    return cull_sphere(nd.bcf[0], nd.bcf[1], nd.bcf[2], nd.brf, nd.br2f, nd.bclen, r, tmaxf);
 }
 
 // node.d:23-49 for a transformed node: world ray -> object space, exact FP64 geometry test
@@ -612,30 +627,38 @@ __device__ __forceinline__ bool occluded(double fx, double fy, double fz, double
     if (MODE & MODE_BOUNDED) {
         const float l2f = (float)len2;
         const float rsf = rsqrtf(l2f);
-        r.fox = (float)fx; r.foy = (float)fy; r.foz = (float)fz;
-        r.fdx = (float)Dx * rsf; r.fdy = (float)Dy * rsf; r.fdz = (float)Dz * rsf;
+        r.fox = cvt_keep(fx); r.foy = cvt_keep(fy); r.foz = cvt_keep(fz);
+        r.fdx = cvt_keep(Dx) * rsf; r.fdy = cvt_keep(Dy) * rsf; r.fdz = cvt_keep(Dz) * rsf;
         r.olen = sqrtf(dot3f(r.fox, r.foy, r.foz, r.fox, r.foy, r.foz));
         tmaxf = l2f * rsf * 1.000001f;
     }
     bool exact = false;
     HitRec h;
-    const int n = c_scene.n_nodes;
-    for (int i = 0; i < n; i++) {
-        const DevNode& nd = c_scene.nodes[i];
-        if (MODE == 0 || nd.kind == KIND_PLANE_W) {
-            // implied by geometry.d:35-36 (dir.y has the sign of D.y): the common "light above the floor" case
-            const double y = nd.wp[0];
-            if ((fy > y && Dy >= 0) || (fy < y && Dy <= 0)) continue;
-        } else if ((MODE & MODE_BOUNDED) && !(nd.flags & NODE_UNBOUNDED)) {
-            if (cull(nd, r, tmaxf)) continue;
+    const int ncl = (MODE & MODE_CLUSTERS) ? c_scene.n_clusters : 1;
+    for (int ci = 0; ci < ncl; ci++) {
+        int begin = 0, end = c_scene.n_nodes;
+        if (MODE & MODE_CLUSTERS) {
+            const DevCluster& cl = c_scene.clusters[ci];
+            if (cl.end - cl.begin > 1 && cull_sphere(cl.c[0], cl.c[1], cl.c[2], cl.r, cl.r2, cl.clen, r, tmaxf)) continue;
+            begin = cl.begin; end = cl.end;
         }
-        if (!exact) {
-            const double inv = rsqrt64(len2);
-            r.dx = Dx * inv; r.dy = Dy * inv; r.dz = Dz * inv;
-            h.dist = len2 * inv;
-            exact = true;
+        for (int i = begin; i < end; i++) {
+            const DevNode& nd = c_scene.nodes[i];
+            if (MODE == 0 || nd.kind == KIND_PLANE_W) {
+                // implied by geometry.d:35-36 (dir.y has the sign of D.y): the common "light above the floor" case
+                const double y = nd.wp[0];
+                if ((fy > y && Dy >= 0) || (fy < y && Dy <= 0)) continue;
+            } else if ((MODE & MODE_BOUNDED) && !(nd.flags & NODE_UNBOUNDED)) {
+                if (cull(nd, r, tmaxf)) continue;
+            }
+            if (!exact) {
+                const double inv = rsqrt64(len2);
+                r.dx = Dx * inv; r.dy = Dy * inv; r.dz = Dz * inv;
+                h.dist = len2 * inv;
+                exact = true;
+            }
+            if (node_exact<MODE>(i, nd, r, h)) return true;
         }
-        if (node_exact<MODE>(i, nd, r, h)) return true;
     }
     return false;
 }
@@ -840,11 +863,19 @@ __device__ __forceinline__ Col trace(const FrameParams& fp, const Ray& ray, unsi
     h.dist = 1e99;
     h.node = -1;
     float tmaxf = CUDART_INF_F;
-    const int n = c_scene.n_nodes;
-    for (int i = 0; i < n; i++)
-        if (node_intersect<MODE>(i, ray, h, tmaxf)) {
-            if (MODE & MODE_BOUNDED) tmaxf = (float)h.dist * 1.000001f;
+    const int ncl = (MODE & MODE_CLUSTERS) ? c_scene.n_clusters : 1;
+    for (int ci = 0; ci < ncl; ci++) {
+        int begin = 0, end = c_scene.n_nodes;
+        if (MODE & MODE_CLUSTERS) {
+            const DevCluster& cl = c_scene.clusters[ci];
+            if (cl.end - cl.begin > 1 && cull_sphere(cl.c[0], cl.c[1], cl.c[2], cl.r, cl.r2, cl.clen, ray, tmaxf)) continue;
+            begin = cl.begin; end = cl.end;
         }
+        for (int i = begin; i < end; i++)
+            if (node_intersect<MODE>(i, ray, h, tmaxf)) {
+                if (MODE & MODE_BOUNDED) tmaxf = (float)h.dist * 1.000001f;
+            }
+    }
     if (out_hit) *out_hit = h;
     if (h.node < 0) return mkcol(0.f, 0.f, 0.f);  // environment.d:7-10
     return shade<MODE>(fp, ray, h, n_shadow);
@@ -974,7 +1005,7 @@ __global__ void render_pixel_kernel(const FrameParams fp, int x, int y, PixelOut
     h.dist = 1e99;
     double bx, by, bz;
     screen_dir(fp, (double)x, (double)y, bx, by, bz);
-    Col c = render_sample<MODE_BOUNDED | MODE_GENERIC | MODE_NESTED>(fp, bx, by, bz, (double)x, (double)y, (uint32_t)x, (uint32_t)y, 0, a, b, &h);
+    Col c = render_sample<MODE_BOUNDED | MODE_GENERIC | MODE_NESTED | MODE_CLUSTERS>(fp, bx, by, bz, (double)x, (double)y, (uint32_t)x, (uint32_t)y, 0, a, b, &h);
     out->rgb[0] = c.r; out->rgb[1] = c.g; out->rgb[2] = c.b;
     out->node = h.node;
     out->dist = h.dist;
@@ -1034,7 +1065,10 @@ cudaError_t upload_scene(const DevScene& s, cudaStream_t st) {
 cudaError_t launch_frame(const FrameParams& fp, int mode, uint32_t local_tile_rows, cudaStream_t st) {
     if (local_tile_rows == 0) return cudaSuccess;
     dim3 grid((fp.W + TILE_W - 1) / TILE_W, local_tile_rows);
-    if (mode & MODE_NESTED) render_frame_kernel<MODE_BOUNDED | MODE_GENERIC | MODE_NESTED, 2><<<grid, BLOCK_THREADS, 0, st>>>(fp);
+    if (mode & MODE_NESTED) render_frame_kernel<MODE_BOUNDED | MODE_GENERIC | MODE_NESTED | MODE_CLUSTERS, 2><<<grid, BLOCK_THREADS, 0, st>>>(fp);
+    else if ((mode & MODE_CLUSTERS) && (mode & MODE_GENERIC))
+        render_frame_kernel<MODE_BOUNDED | MODE_GENERIC | MODE_CLUSTERS, C2RT_MINBLOCKS_FULL><<<grid, BLOCK_THREADS, 0, st>>>(fp);
+    else if (mode & MODE_CLUSTERS) render_frame_kernel<MODE_BOUNDED | MODE_CLUSTERS, C2RT_MINBLOCKS_BOUNDED><<<grid, BLOCK_THREADS, 0, st>>>(fp);
     else if (mode & MODE_GENERIC) render_frame_kernel<MODE_BOUNDED | MODE_GENERIC, C2RT_MINBLOCKS_FULL><<<grid, BLOCK_THREADS, 0, st>>>(fp);
     else if (mode & MODE_BOUNDED) render_frame_kernel<MODE_BOUNDED, C2RT_MINBLOCKS_BOUNDED><<<grid, BLOCK_THREADS, 0, st>>>(fp);
     else render_frame_kernel<0, C2RT_MINBLOCKS_SIMPLE><<<grid, BLOCK_THREADS, 0, st>>>(fp);

@@ -60,8 +60,18 @@ struct DevLight {
     int lit;          // color.intensity() != 0 (shader.d:88,219)
 };
 
+// Two-level culling: contiguous runs of node indices (scene order is kept, so the reference's
+// "later node wins an exact tie" rule, geometry.d:43,111,214, is untouched) with a common bounding
+// sphere.  Runs are chosen at scene-create time by a small dynamic programme (c2rt_api.cu).
+struct DevCluster {
+    float c[3];       // bounding sphere of the run's node spheres
+    float r, r2, clen;
+    int begin, end;   // node index range [begin, end); runs of one node carry no sphere of their own
+};
+
 struct DevScene {
-    int n_nodes, n_geoms, n_shaders, n_textures, n_lights, pad0, pad1, pad2;
+    int n_nodes, n_geoms, n_shaders, n_textures, n_lights, n_clusters, pad1, pad2;
+    DevCluster clusters[C2RT_MAX_NODES];
     DevNode nodes[C2RT_MAX_NODES];
     DevGeom geoms[C2RT_MAX_GEOMS];
     DevShader shaders[C2RT_MAX_SHADERS];
