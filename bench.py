@@ -206,6 +206,7 @@ def main():
     ap.add_argument("--gather", default="auto", choices=["auto", "nccl", "p2p"])
     ap.add_argument("--calibrate", nargs="*", default=None, help="(CPU) recount algorithmic FLOPs/rays of the named workloads")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-scaling-target", action="store_true", help="skip the side measurement of the 8K chessboard scene")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -220,7 +221,6 @@ def main():
         run_reference(args, rank, world)
         return
 
-    import numpy as np
     import torch
     import torch.distributed as dist
 
@@ -230,147 +230,178 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     torch.cuda.set_device(local_rank)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         cpu_group = dist.new_group(backend="gloo")  # host-side waits that must not occupy a GPU (see the e2e leg)
     c2.init(1, [local_rank])
-
-    path, W, H, over = WORKLOADS[args.workload]
-    scene = c2.HostScene(os.path.join(ROOT, path))
-    scene.set_frame_size(W, H)
-    scene.override(**over)
-    handle = scene.device_scene()
-    cam, st = scene.frame_blocks(seed=RNG_SEED)
     stream = torch.cuda.current_stream().cuda_stream
-    n_ranks = world
-    band = api.Band(rank, n_ranks, BAND_ROWS, 1 if n_ranks > 1 else 0)
-
-    # ---- output buffers (device resident) ------------------------------------------------------
-    pad = bands.rows_padded(H, n_ranks, BAND_ROWS)
-    gather_mode = "none"
-    frame = None
-    peer_frame_ptr = None
-    if n_ranks == 1:
-        frame = torch.empty((H, W, 3), dtype=torch.float32, device="cuda")
-        out_ptr = frame.data_ptr()
-    else:
-        gather_mode = "nccl" if args.gather == "nccl" else "p2p"
-        if gather_mode == "p2p":
-            # rank 0 owns the frame; every other rank maps it (CUDA IPC) and its kernel stores bands into it over NVLink
-            import ctypes as C
-            ok = 1
-            handle_bytes = [None]
-            try:
-                if rank == 0:
-                    p = C.c_void_p()
-                    api._check(api.lib.c2rt_frame_alloc(H * W * 12, C.byref(p)))
-                    hb = (C.c_uint8 * 64)()
-                    api._check(api.lib.c2rt_frame_export(p, hb))
-                    handle_bytes = [bytes(hb)]
-                    peer_frame_ptr = p.value
-            except Exception:
-                ok = 0
-            dist.broadcast_object_list(handle_bytes, src=0)
-            if rank != 0 and handle_bytes[0] is not None:
-                try:
-                    hb = (C.c_uint8 * 64).from_buffer_copy(handle_bytes[0])
-                    p = C.c_void_p()
-                    api._check(api.lib.c2rt_frame_import(hb, C.byref(p)))
-                    peer_frame_ptr = p.value
-                except Exception:
-                    ok = 0
-            okt = torch.tensor([ok if handle_bytes[0] is not None else 0], device="cuda")
-            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
-            if int(okt[0]) == 0:
-                if args.gather == "p2p":
-                    raise SystemExit("--gather p2p: CUDA IPC mapping of rank 0's frame failed")
-                gather_mode = "nccl"   # auto: fall back to the NCCL gather
-        if gather_mode == "p2p":
-            band = api.Band(rank, n_ranks, BAND_ROWS, 0)
-            out_ptr = peer_frame_ptr
-            sync_flag = torch.zeros(1, device="cuda")
-        else:
-            mine = torch.empty((pad, W, 3), dtype=torch.float32, device="cuda")
-            gathered = torch.empty((n_ranks, pad, W, 3), dtype=torch.float32, device="cuda") if rank == 0 else None
-            frame = torch.empty((H, W, 3), dtype=torch.float32, device="cuda") if rank == 0 else None
-            out_ptr = mine.data_ptr()
     flush_buf = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
-    launches = [0]
-
-    def device_step():
-        """one frame: render this rank's bands, gather to rank 0"""
-        c2.render_device(handle, cam, st, out_ptr, None, band if n_ranks > 1 else None, stream)
-        launches[0] += 1
-        if gather_mode == "nccl":
-            dist.gather(mine, list(gathered.unbind(0)) if rank == 0 else None, dst=0)
-            if rank == 0:
-                c2.deinterleave(gathered.data_ptr(), frame.data_ptr(), W, H, 3, n_ranks, BAND_ROWS, pad, stream)
-                launches[0] += 1
-        elif gather_mode == "p2p":
-            dist.all_reduce(sync_flag)  # completion: rank 0 may read the frame once every peer's stores are done
-
-    # ---- sanity: the workload is the calibrated one (ray counts must match the oracle's) ---------
-    cal = load_calibration().get(args.workload)
-    cam_c, st_c = scene.frame_blocks(seed=RNG_SEED, count_rays=True)
-    c2.render_device(handle, cam_c, st_c, out_ptr, None, band if n_ranks > 1 else None, stream)
-    prim, shad = c2.read_ray_counters(handle, stream)
-    counts = torch.tensor([prim, shad], dtype=torch.int64, device="cuda")
-    if world > 1:
-        dist.all_reduce(counts)
-    prim, shad = int(counts[0]), int(counts[1])
-    if cal and cal.get("exact") and (prim, shad) != (cal["primary_rays"], cal["shadow_rays"]):
-        raise SystemExit(f"ray counts {prim}+{shad} differ from the calibrated workload {cal['primary_rays']}+{cal['shadow_rays']}")
-    rays_per_frame = prim + shad
-    flops_per_frame = cal["flops"] if cal else None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up ---------------------------------------------------------------------------------
-    for _ in range(args.warmup):
-        flush_buf.fill_(1)
-        device_step()
-    barrier()
+    class DeviceRun:
+        """One workload set up for device-resident stepping on this rank: scene upload, band, output buffers, gather."""
 
-    # ---- timed region: EXACTLY K steps; L2 flushed between steps (untimed) -------------------------
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(args.steps)]
-    launches[0] = 0
-    barrier()
-    for e0, ek, e1 in ev:
-        flush_buf.fill_(1)
-        if world > 1:
-            dist.barrier()  # ranks start each frame together, as one frame request would
-        e0.record()
-        c2.render_device(handle, cam, st, out_ptr, None, band if n_ranks > 1 else None, stream)
-        launches[0] += 1
-        ek.record()
-        if gather_mode == "nccl":
-            dist.gather(mine, list(gathered.unbind(0)) if rank == 0 else None, dst=0)
-            if rank == 0:
-                c2.deinterleave(gathered.data_ptr(), frame.data_ptr(), W, H, 3, n_ranks, BAND_ROWS, pad, stream)
-                launches[0] += 1
-        elif gather_mode == "p2p":
-            dist.all_reduce(sync_flag)
-        e1.record()
-    barrier()
-    step_ms = [e0.elapsed_time(e1) for e0, ek, e1 in ev]
-    kern_ms = [e0.elapsed_time(ek) for e0, ek, e1 in ev]
-    t = torch.tensor([sum(step_ms), sum(kern_ms)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, total_kernel_ms = float(t[0]), float(t[1])
-    n_launches = launches[0]
+        def __init__(self, name, gather):
+            import ctypes as C
+            self.name = name
+            self.path, self.W, self.H, self.over = WORKLOADS[name]
+            W, H = self.W, self.H
+            self.scene = c2.HostScene(os.path.join(ROOT, self.path))
+            self.scene.set_frame_size(W, H)
+            self.scene.override(**self.over)
+            self.handle = self.scene.device_scene()
+            self.cam, self.st = self.scene.frame_blocks(seed=RNG_SEED)
+            self.launches = 0
+            self.peer_frame_ptr = None
+            self.frame = None
+            self.pad = bands.rows_padded(H, world, BAND_ROWS)
+            if world == 1:
+                self.mode = "none"
+                self.band = None
+                self.frame = torch.empty((H, W, 3), dtype=torch.float32, device="cuda")
+                self.out_ptr = self.frame.data_ptr()
+                return
+            self.mode = "nccl" if gather == "nccl" else "p2p"
+            if self.mode == "p2p":
+                # rank 0 owns the frame; every other rank maps it (CUDA IPC) and its kernel stores bands into it over NVLink
+                ok = 1
+                handle_bytes = [None]
+                try:
+                    if rank == 0:
+                        p = C.c_void_p()
+                        api._check(api.lib.c2rt_frame_alloc(H * W * 12, C.byref(p)))
+                        hb = (C.c_uint8 * 64)()
+                        api._check(api.lib.c2rt_frame_export(p, hb))
+                        handle_bytes = [bytes(hb)]
+                        self.peer_frame_ptr = p.value
+                except Exception:
+                    ok = 0
+                dist.broadcast_object_list(handle_bytes, src=0)
+                if rank != 0 and handle_bytes[0] is not None:
+                    try:
+                        hb = (C.c_uint8 * 64).from_buffer_copy(handle_bytes[0])
+                        p = C.c_void_p()
+                        api._check(api.lib.c2rt_frame_import(hb, C.byref(p)))
+                        self.peer_frame_ptr = p.value
+                    except Exception:
+                        ok = 0
+                okt = torch.tensor([ok if handle_bytes[0] is not None else 0], device="cuda")
+                dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+                if int(okt[0]) == 0:
+                    if gather == "p2p":
+                        raise SystemExit("--gather p2p: CUDA IPC mapping of rank 0's frame failed")
+                    self.mode = "nccl"   # auto: fall back to the NCCL gather
+            if self.mode == "p2p":
+                self.band = api.Band(rank, world, BAND_ROWS, 0)
+                self.out_ptr = self.peer_frame_ptr
+                self.sync_flag = torch.zeros(1, device="cuda")
+            else:
+                self.band = api.Band(rank, world, BAND_ROWS, 1)
+                self.mine = torch.empty((self.pad, W, 3), dtype=torch.float32, device="cuda")
+                self.gathered = torch.empty((world, self.pad, W, 3), dtype=torch.float32, device="cuda") if rank == 0 else None
+                self.frame = torch.empty((H, W, 3), dtype=torch.float32, device="cuda") if rank == 0 else None
+                self.out_ptr = self.mine.data_ptr()
+
+        def render(self, cam=None, st=None):
+            c2.render_device(self.handle, cam or self.cam, st or self.st, self.out_ptr, None, self.band, stream)
+            self.launches += 1
+
+        def gather(self):
+            if self.mode == "nccl":
+                dist.gather(self.mine, list(self.gathered.unbind(0)) if rank == 0 else None, dst=0)
+                if rank == 0:
+                    c2.deinterleave(self.gathered.data_ptr(), self.frame.data_ptr(), self.W, self.H, 3, world, BAND_ROWS, self.pad, stream)
+                    self.launches += 1
+            elif self.mode == "p2p":
+                dist.all_reduce(self.sync_flag)  # completion: rank 0 may read the frame once every peer's stores have landed
+
+        def count_rays(self):
+            cam_c, st_c = self.scene.frame_blocks(seed=RNG_SEED, count_rays=True)
+            self.render(cam_c, st_c)
+            prim, shad = c2.read_ray_counters(self.handle, stream)
+            counts = torch.tensor([prim, shad], dtype=torch.int64, device="cuda")
+            if world > 1:
+                dist.all_reduce(counts)
+            return int(counts[0]), int(counts[1])
+
+        def time_steps(self, steps, warmup, sampler=None):
+            """EXACTLY `steps` timed frames; L2 flushed between them (untimed); per-step CUDA events; max over ranks."""
+            for _ in range(warmup):
+                flush_buf.fill_(1)
+                self.render()
+                self.gather()
+            barrier()
+            if sampler is not None:
+                sampler.start()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                  for _ in range(steps)]
+            self.launches = 0
+            barrier()
+            for e0, ek, e1 in ev:
+                flush_buf.fill_(1)
+                if world > 1:
+                    dist.barrier()  # ranks start each frame together, as one frame request would
+                e0.record()
+                self.render()
+                ek.record()
+                self.gather()
+                e1.record()
+            barrier()
+            t = torch.tensor([sum(e0.elapsed_time(e1) for e0, ek, e1 in ev), sum(e0.elapsed_time(ek) for e0, ek, e1 in ev)],
+                             dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t[0]) / steps, float(t[1]) / steps, self.launches
+
+        def close(self):
+            import ctypes as C
+            if self.peer_frame_ptr:
+                if rank == 0:
+                    api.lib.c2rt_frame_free(C.c_void_p(self.peer_frame_ptr))
+                else:
+                    api.lib.c2rt_frame_unimport(C.c_void_p(self.peer_frame_ptr))
+            self.scene.close()
+
+    path, W, H, over = WORKLOADS[args.workload]
+    run = DeviceRun(args.workload, args.gather)
+    gather_mode = run.mode
+
+    # ---- sanity: the workload is the calibrated one (ray counts must match the oracle's) ---------
+    cal = load_calibration().get(args.workload)
+    prim, shad = run.count_rays()
+    if cal and cal.get("exact") and (prim, shad) != (cal["primary_rays"], cal["shadow_rays"]):
+        raise SystemExit(f"ray counts {prim}+{shad} differ from the calibrated workload {cal['primary_rays']}+{cal['shadow_rays']}")
+    rays_per_frame = prim + shad
+    flops_per_frame = cal["flops"] if cal else None
+
+    # ---- timed region ------------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_per_step, kernel_ms, n_launches = run.time_steps(args.steps, args.warmup, sampler)
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- the scaling target of BASELINE.json (8K chessboard), measured beside the headline workload ----
+    scaling_target = None
+    if args.workload == DEFAULT_WORKLOAD and not args.no_scaling_target:
+        run4 = DeviceRun("c4", args.gather)
+        p4, s4 = run4.count_rays()
+        ms4, k4, _ = run4.time_steps(max(3, args.steps // 4), 3)
+        cal4 = load_calibration().get("c4") or {}
+        scaling_target = {"workload": "c4: scenes/chessboard.sdl at 7680x4320 (32 CSG pieces, Phong, AA)", "n_gpus": world,
+                          "ms_per_step": ms4, "kernel_ms": k4, "value": (p4 + s4) / (ms4 * 1e-3) / 1e6, "unit": "Mrays/s",
+                          "frames_per_s": 1e3 / ms4, "steps": max(3, args.steps // 4), "gather": run4.mode,
+                          "algorithmic_flops_per_frame": cal4.get("flops"),
+                          "achieved_tflops_per_gpu": (cal4["flops"] / world / (k4 * 1e-3) / 1e12) if cal4.get("flops") else None}
+        run4.close()
 
     # ---- e2e: public host API, HOST buffers, copies inside the timed region ------------------------
     pinned = torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True) if rank == 0 else None
     e2e_ms = []
+    scene = run.scene
     if world == 1:
         out_np = pinned.numpy()
         for i in range(args.warmup + args.steps):
@@ -405,9 +436,9 @@ def main():
     e2e_ms_mean = sum(e2e_ms) / len(e2e_ms)
 
     if rank == 0:
-        ms_per_step = total_ms / args.steps
-        kernel_ms = total_kernel_ms / args.steps
         value = rays_per_frame / (ms_per_step * 1e-3) / 1e6
+        if world > 1:
+            c2.init(1, [local_rank])
         peak_tf, peak_mhz = c2.measure_fma_peak(False)
         peak64_tf, _ = c2.measure_fma_peak(True)
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -420,13 +451,15 @@ def main():
             traffic = json.load(open(tp)).get(args.workload)
         roofline = None
         if flops_per_frame:
-            achieved = flops_per_frame / n_ranks / (kernel_ms * 1e-3) / 1e12  # per GPU: each renders 1/N of the frame
+            achieved = flops_per_frame / world / (kernel_ms * 1e-3) / 1e12  # per GPU: each renders 1/N of the frame
             roofline = {
                 "bound": "fp32", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 "traffic": traffic, "peak_source": "FFMA micro-benchmark measured in this run (c2rt_measure_fma_peak)",
                 "peak_nominal": nominal_tf, "frac_nominal": achieved / nominal_tf, "fp64_peak_measured": peak64_tf,
                 "algorithmic_flops_per_frame": flops_per_frame, "kernel_ms": kernel_ms,
-                "hbm": {"achieved": W * H * 12 / n_ranks / (kernel_ms * 1e-3) / 1e9, "peak": mp.get("hbm_gbs"), "unit": "GB/s",
+                "note": "achieved = algorithmic FLOPs of the reference's arithmetic (oracle counting scalar) / kernel time; "
+                        "culled and simplified work still counts, so frac can exceed 1 on many-node scenes",
+                "hbm": {"achieved": W * H * 12 / world / (kernel_ms * 1e-3) / 1e9, "peak": mp.get("hbm_gbs"), "unit": "GB/s",
                         "note": "framebuffer bytes written per kernel; far below the HBM roof, the kernel is FMA-bound"},
             }
         line = {
@@ -446,6 +479,7 @@ def main():
                             "one process driving %d devices (c2rt_init(%d)), each device copies its own bands to the host" % (world, world))},
             "gpu_launches": n_launches,
             "clocks": clocks,
+            "scaling_target": scaling_target,
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
@@ -463,7 +497,7 @@ def main():
         print(json.dumps(line), flush=True)
 
     if world > 1:
-        dist.barrier()
+        dist.barrier(group=cpu_group)
         dist.destroy_process_group()
     c2.shutdown()
 
