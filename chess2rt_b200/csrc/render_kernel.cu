@@ -642,6 +642,7 @@ __device__ __forceinline__ bool occluded(double fx, double fy, double fz, double
             if (cl.end - cl.begin > 1 && cull_sphere(cl.c[0], cl.c[1], cl.c[2], cl.r, cl.r2, cl.clen, r, tmaxf)) continue;
             begin = cl.begin; end = cl.end;
         }
+#pragma unroll 1
         for (int i = begin; i < end; i++) {
             const DevNode& nd = c_scene.nodes[i];
             if (MODE == 0 || nd.kind == KIND_PLANE_W) {
@@ -871,6 +872,7 @@ __device__ __forceinline__ Col trace(const FrameParams& fp, const Ray& ray, unsi
             if (cl.end - cl.begin > 1 && cull_sphere(cl.c[0], cl.c[1], cl.c[2], cl.r, cl.r2, cl.clen, ray, tmaxf)) continue;
             begin = cl.begin; end = cl.end;
         }
+#pragma unroll 1
         for (int i = begin; i < end; i++)
             if (node_intersect<MODE>(i, ray, h, tmaxf)) {
                 if (MODE & MODE_BOUNDED) tmaxf = (float)h.dist * 1.000001f;
