@@ -985,6 +985,26 @@ int c2rt_frame_download(void* host_dst, const void* d_src, size_t bytes, void* s
     return C2RT_OK;
 }
 
+int c2rt_pin_host_buffer(void* ptr, size_t bytes) {
+    if (!ptr || !bytes) return fail(C2RT_ERR_INVALID_ARG, "bad pin_host_buffer arguments");
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) {
+        cudaGetLastError();
+        return C2RT_OK;
+    }
+    if (e != cudaSuccess) return fail(C2RT_ERR_CUDA, "cudaHostRegister failed: %s", cudaGetErrorString(e));
+    return C2RT_OK;
+}
+int c2rt_unpin_host_buffer(void* ptr) {
+    if (!ptr) return fail(C2RT_ERR_INVALID_ARG, "bad unpin_host_buffer argument");
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(C2RT_ERR_CUDA, "cudaHostUnregister failed: %s", cudaGetErrorString(e));
+    }
+    return C2RT_OK;
+}
+
 int c2rt_measure_fma_peak(int fp64, double* tflops, double* sm_clock_mhz_est) {
     if (!tflops) return fail(C2RT_ERR_INVALID_ARG, "tflops is null");
     int dev = 0;

@@ -62,7 +62,10 @@ int main(int argc, char** argv) {
         if (noAA) scene->settings.AAEnabled = false;
         const uint32_t W = scene->settings.frameWidth, H = scene->settings.frameHeight;
         Image<Color> screen(W, H);
-        Image<uint32_t> argb;
+        Image<uint32_t> argb(W, H);
+        // page-lock the output planes: the per-frame device->host copies then overlap with rendering
+        c2rt_pin_host_buffer(screen.pixels.data(), screen.pixels.size() * sizeof(Color));
+        c2rt_pin_host_buffer(argb.pixels.data(), argb.pixels.size() * sizeof(uint32_t));
         RenderOptions opt;
         opt.rngSeed = seed;
         opt.countRays = true;
@@ -87,6 +90,8 @@ int main(int argc, char** argv) {
             f.write((const char*)bytes.data(), (std::streamsize)bytes.size());
             printf("wrote %s\n", out.c_str());
         }
+        c2rt_unpin_host_buffer(screen.pixels.data());
+        c2rt_unpin_host_buffer(argb.pixels.data());
         if (!pfm.empty()) {  // float RGB, bottom row first (PFM convention), little endian
             std::ofstream f(pfm, std::ios::binary);
             f << "PF\n" << W << " " << H << "\n-1.0\n";

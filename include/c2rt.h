@@ -232,6 +232,12 @@ int c2rt_frame_unimport(void* d_ptr);
 /* asynchronous device->host copy of (part of) such a frame on `stream` (host memory should be pinned) */
 int c2rt_frame_download(void* host_dst, const void* d_src, size_t bytes, void* stream);
 
+/* Page-locks a caller-owned host buffer (e.g. the D host's Image!Color.pixels, which is ordinary GC memory) so
+ * that c2rt_render's device->host copies run asynchronously at full PCIe rate and overlap with rendering.
+ * Optional: without it the copies still work, through the driver's staging path.  Unpin before freeing. */
+int c2rt_pin_host_buffer(void* ptr, size_t bytes);
+int c2rt_unpin_host_buffer(void* ptr);
+
 /* Micro-benchmarks used by bench.py to measure the roofline denominators on the box:
  * dependent-free FFMA / DFMA throughput in TFLOP/s on the current device. */
 int c2rt_measure_fma_peak(int fp64, double* tflops, double* sm_clock_mhz_est);
