@@ -274,7 +274,7 @@ def main():
                 try:
                     if rank == 0:
                         p = C.c_void_p()
-                        api._check(api.lib.c2rt_frame_alloc(H * W * 12, C.byref(p)))
+                        api._check(api.lib.c2rt_frame_alloc(H * W * 12 + 256, C.byref(p)))   # frame + completion flags
                         hb = (C.c_uint8 * 64)()
                         api._check(api.lib.c2rt_frame_export(p, hb))
                         handle_bytes = [bytes(hb)]
@@ -299,7 +299,9 @@ def main():
             if self.mode == "p2p":
                 self.band = api.Band(rank, world, BAND_ROWS, 0)
                 self.out_ptr = self.peer_frame_ptr
-                self.sync_flag = torch.zeros(1, device="cuda")
+                self.flags_ptr = self.peer_frame_ptr + H * W * 12   # uint32 flags[world + 1] behind the frame, in rank 0's memory
+                self.frame_no = 0
+                dist.barrier()   # c2rt_frame_alloc zero-fills: the flags start at 0 before any rank signals
             else:
                 self.band = api.Band(rank, world, BAND_ROWS, 1)
                 self.mine = torch.empty((self.pad, W, 3), dtype=torch.float32, device="cuda")
@@ -318,7 +320,13 @@ def main():
                     c2.deinterleave(self.gathered.data_ptr(), self.frame.data_ptr(), self.W, self.H, 3, world, BAND_ROWS, self.pad, stream)
                     self.launches += 1
             elif self.mode == "p2p":
-                dist.all_reduce(self.sync_flag)  # completion: rank 0 may read the frame once every peer's stores have landed
+                # completion without a collective: peers raise a flag in rank 0's memory after their band stores,
+                # rank 0 waits for all flags on its stream (c2rt_signal / c2rt_wait_signals)
+                self.frame_no += 1
+                if rank == 0:
+                    api._check(api.lib.c2rt_wait_signals(self.flags_ptr, world, self.frame_no, stream))
+                else:
+                    api._check(api.lib.c2rt_signal(self.flags_ptr + 4 * rank, self.frame_no, stream))
 
         def count_rays(self):
             cam_c, st_c = self.scene.frame_blocks(seed=RNG_SEED, count_rays=True)

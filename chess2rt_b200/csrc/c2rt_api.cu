@@ -23,6 +23,8 @@ cudaError_t launch_pixel(const FrameParams& fp, int x, int y, void* d_out, cudaS
 cudaError_t launch_deinterleave(const void* src, void* dst, uint32_t row_words, uint32_t height, uint32_t n_ranks,
                                 uint32_t band_rows, uint32_t rows_pad, cudaStream_t st);
 cudaError_t launch_fma_peak(bool fp64, int blocks, int threads, int iters, void* d_out, cudaStream_t st);
+cudaError_t launch_signal(void* flag, uint32_t value, cudaStream_t st);
+cudaError_t launch_wait_signals(void* flags, uint32_t n_ranks, uint32_t value, cudaStream_t st);
 size_t pixel_out_size();
 }  // namespace c2rt
 
@@ -641,6 +643,7 @@ int c2rt_render_device(c2rt_scene* s, const c2rt_camera* cam, const c2rt_setting
     DeviceCtx* c = find_device(dev);
     if (!c) return fail(C2RT_ERR_INVALID_ARG, "current device %d is not part of the c2rt context", dev);
     int di = (int)(c - g_ctx.d);
+    if (di >= s->n_dev) return fail(C2RT_ERR_INVALID_ARG, "scene was created under a different c2rt_init configuration");
     cudaStream_t st = (cudaStream_t)stream;
     rc = make_resident(s, di, st);
     if (rc) return rc;
@@ -770,8 +773,10 @@ int c2rt_render(c2rt_scene* s, const c2rt_camera* cam, const c2rt_settings* set,
         fp.compact = 1;
         fp.counters = c.d_counters;
         fp.lut = c.d_lut;
-        // ~16 interleaved bands per device: each band is one launch + one contiguous D2H copy
-        uint32_t brows = (H / (uint32_t)(n * 16) + TILE_H - 1) / TILE_H * TILE_H;
+        // 2..16 interleaved bands per device (one band per ~256k pixels): each band is one launch + one contiguous
+        // D2H copy, so small frames must not be cut into many bands (every launch / copy costs a few host microseconds)
+        uint32_t per_dev = (uint32_t)std::min<size_t>(16, std::max<size_t>(2, npx / (size_t)n / 262144));
+        uint32_t brows = (H / ((uint32_t)n * per_dev) + TILE_H - 1) / TILE_H * TILE_H;
         if (brows < TILE_H) brows = TILE_H;
         fp.tiles_per_band = brows / TILE_H;
         const uint32_t rows_owned = c2rt_band_rows_owned(H, fp.rank, fp.n_ranks, brows);
@@ -955,6 +960,7 @@ int c2rt_deinterleave(const void* gathered, void* frame, uint32_t width, uint32_
 int c2rt_frame_alloc(size_t bytes, void** d_ptr) {
     if (!d_ptr || !bytes) return fail(C2RT_ERR_INVALID_ARG, "bad frame_alloc arguments");
     CU(cudaMalloc(d_ptr, bytes));
+    CU(cudaMemset(*d_ptr, 0, bytes));
     return C2RT_OK;
 }
 int c2rt_frame_free(void* d_ptr) {
@@ -982,6 +988,17 @@ int c2rt_frame_unimport(void* d_ptr) {
 int c2rt_frame_download(void* host_dst, const void* d_src, size_t bytes, void* stream) {
     if (!host_dst || !d_src) return fail(C2RT_ERR_INVALID_ARG, "bad frame_download arguments");
     CU(cudaMemcpyAsync(host_dst, d_src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return C2RT_OK;
+}
+
+int c2rt_signal(void* d_flag, uint32_t value, void* stream) {
+    if (!d_flag) return fail(C2RT_ERR_INVALID_ARG, "bad signal arguments");
+    CU(launch_signal(d_flag, value, (cudaStream_t)stream));
+    return C2RT_OK;
+}
+int c2rt_wait_signals(void* d_flags, uint32_t n_ranks, uint32_t value, void* stream) {
+    if (!d_flags || n_ranks < 1 || n_ranks > 32) return fail(C2RT_ERR_INVALID_ARG, "bad wait_signals arguments");
+    CU(launch_wait_signals(d_flags, n_ranks, value, (cudaStream_t)stream));
     return C2RT_OK;
 }
 

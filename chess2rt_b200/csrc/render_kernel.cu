@@ -1034,6 +1034,27 @@ __global__ void deinterleave_kernel(const uint32_t* __restrict__ src, uint32_t* 
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < row_words; i += gridDim.x * blockDim.x) d[i] = s[i];
 }
 
+// frame-complete signalling between ranks (c2rt.h c2rt_signal / c2rt_wait_signals)
+__global__ void signal_kernel(volatile uint32_t* flag, uint32_t value) {
+    __threadfence_system();   // this rank's band stores (previous kernel on the stream) are ordered before the flag
+    *flag = value;
+    __threadfence_system();
+}
+__global__ void wait_signals_kernel(volatile uint32_t* flags, uint32_t n_ranks, uint32_t value) {
+    const uint32_t r = threadIdx.x + 1;
+    if (r < n_ranks) {
+        const long long t0 = clock64();
+        // frame numbers only grow; the signed difference tolerates wrap-around
+        while ((int)(flags[r] - value) < 0) {
+            if (clock64() - t0 > 4000000000ll) {   // ~2 s at 2 GHz: a peer died; do not hang the device
+                atomicAdd((uint32_t*)&flags[n_ranks], 1u);
+                break;
+            }
+        }
+    }
+    __threadfence_system();
+}
+
 // dependent-free FMA streams for the roofline denominators (c2rt.h c2rt_measure_fma_peak)
 template <typename T>
 __global__ void fma_peak_kernel(T* out, int iters, T a, T b) {
@@ -1086,6 +1107,15 @@ cudaError_t launch_deinterleave(const void* src, void* dst, uint32_t row_words, 
                                 uint32_t band_rows, uint32_t rows_pad, cudaStream_t st) {
     dim3 grid((row_words + 1023) / 1024 < 1 ? 1 : (row_words + 1023) / 1024, height);
     deinterleave_kernel<<<grid, 256, 0, st>>>((const uint32_t*)src, (uint32_t*)dst, row_words, height, n_ranks, band_rows, rows_pad);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_signal(void* flag, uint32_t value, cudaStream_t st) {
+    signal_kernel<<<1, 1, 0, st>>>((volatile uint32_t*)flag, value);
+    return cudaGetLastError();
+}
+cudaError_t launch_wait_signals(void* flags, uint32_t n_ranks, uint32_t value, cudaStream_t st) {
+    wait_signals_kernel<<<1, 32, 0, st>>>((volatile uint32_t*)flags, n_ranks, value);
     return cudaGetLastError();
 }
 

@@ -224,13 +224,21 @@ void c2rt_srgb_table(uint8_t out[4097]);
 /* Peer-visible device buffers for the one-process-per-GPU path: rank 0 allocates the frame and
  * exports a 64-byte handle; the other ranks import it and pass the mapped pointer as d_rgb so their
  * kernels store bands directly into rank 0's memory over NVLink. */
-int c2rt_frame_alloc(size_t bytes, void** d_ptr);
+int c2rt_frame_alloc(size_t bytes, void** d_ptr);   /* zero-filled */
 int c2rt_frame_free(void* d_ptr);
 int c2rt_frame_export(void* d_ptr, uint8_t handle[64]);
 int c2rt_frame_import(const uint8_t handle[64], void** d_ptr);
 int c2rt_frame_unimport(void* d_ptr);
 /* asynchronous device->host copy of (part of) such a frame on `stream` (host memory should be pinned) */
 int c2rt_frame_download(void* host_dst, const void* d_src, size_t bytes, void* stream);
+
+/* Frame-complete signalling for the one-process-per-GPU path, without a collective: rank r > 0 enqueues
+ * c2rt_signal(&flags[r], frame_no) after its render kernel (flags live in rank 0's exported allocation, so the store
+ * crosses NVLink after the band stores it follows); rank 0 enqueues c2rt_wait_signals(flags, n_ranks, frame_no) after
+ * its own kernel: a one-warp kernel that polls flags[1..n_ranks-1] until all reached frame_no (it gives up after
+ * ~2 s and bumps flags[n_ranks], which the caller can read back, instead of hanging the device). */
+int c2rt_signal(void* d_flag, uint32_t value, void* stream);
+int c2rt_wait_signals(void* d_flags, uint32_t n_ranks, uint32_t value, void* stream);
 
 /* Page-locks a caller-owned host buffer (e.g. the D host's Image!Color.pixels, which is ordinary GC memory) so
  * that c2rt_render's device->host copies run asynchronously at full PCIe rate and overlap with rendering.
