@@ -505,7 +505,7 @@ int check_frame_args(const c2rt_scene* s, const c2rt_camera* cam, const c2rt_set
     if (cam->frame_width == 0 || cam->frame_height == 0) return fail(C2RT_ERR_INVALID_ARG, "camera frame size is zero (setFrameSize not called)");
     if (set->gi_enabled) return fail(C2RT_ERR_UNSUPPORTED, "GIEnabled (path tracing) is outside the hot-path scope");
     if (set->prepass_only) return fail(C2RT_ERR_UNSUPPORTED, "prepassOnly is not supported");
-    if (cam->stereo_separation != 0) return fail(C2RT_ERR_UNSUPPORTED, "stereo rendering is outside the hot-path scope");
+    if (!std::isfinite(cam->stereo_separation)) return fail(C2RT_ERR_INVALID_ARG, "stereoSeparation is not finite");
     if (cam->dof && cam->num_samples == 0) return fail(C2RT_ERR_INVALID_ARG, "DOF camera with numSamples == 0");
     return C2RT_OK;
 }
@@ -529,6 +529,7 @@ void fill_params(FrameParams& fp, const c2rt_camera* cam, const c2rt_settings* s
         for (int k = 0; k < 3; k++) fp.tap_d[t][k] = fp.du[k] * (kx[t] * fp.inv_w) + fp.dv[k] * (ky[t] * fp.inv_h);
     fp.focal_plane_dist = cam->focal_plane_dist;
     fp.disc_multiplier = cam->disc_multiplier;
+    fp.stereo_sep = cam->stereo_separation;
     fp.seed = set->rng_seed;
     fp.W = set->frame_width;
     fp.H = set->frame_height;

@@ -33,7 +33,8 @@ __constant__ double c_tap_y[5] = {0.0, 0.3, 0.0, 0.6, 0.6};
 //   MODE_GENERIC  some node needs the object-space path (non-identity transform, CSG, bounded plane)
 //   MODE_NESTED   some CSG has a CSG child -> literal emulation of the reference's recursive walk
 //   MODE_CLUSTERS the scene-create partition found runs of nodes worth a common bounding sphere (two-level cull)
-constexpr int MODE_BOUNDED = 1, MODE_GENERIC = 2, MODE_NESTED = 4, MODE_CLUSTERS = 8;
+//   MODE_SAMPLING the CAMERA asks for depth of field and/or stereo: several rays per sample (chosen per frame)
+constexpr int MODE_BOUNDED = 1, MODE_GENERIC = 2, MODE_NESTED = 4, MODE_CLUSTERS = 8, MODE_SAMPLING = 16;
 
 // Precision plan: FP64 carries everything a pixel DECISION or a texture coordinate
 // depends on — ray direction, hit distances, hit points, plane/cube uv, checker cells, face-forward
@@ -149,13 +150,16 @@ __device__ __forceinline__ void screen_dir(const FrameParams& fp, double x, doub
 }
 
 // Completes a camera ray from its un-normalised direction (DOF lens sampling included)
+// `eye`: 0 = Stereo3DOffset.None, -1 = Left, +1 = Right (camera.d:149-152,168-170)
 template <int MODE>
 __device__ __forceinline__ void gen_ray(const FrameParams& fp, double vx, double vy, double vz, uint32_t px, uint32_t py, uint32_t tap,
-                                        uint32_t sample, uint32_t& draw, Ray& r) {
+                                        uint32_t sample, uint32_t& draw, int eye, Ray& r) {
     r.dx = vx; r.dy = vy; r.dz = vz;
     r.ox = fp.pos[0]; r.oy = fp.pos[1]; r.oz = fp.pos[2];
     normalize3(r.dx, r.dy, r.dz);
-    if (fp.dof) {
+    const double sep = eye > 0 ? fp.stereo_sep : -fp.stereo_sep;
+    if ((MODE & MODE_SAMPLING) && eye != 0) { r.ox += fp.right_dir[0] * sep; r.oy += fp.right_dir[1] * sep; r.oz += fp.right_dir[2] * sep; }
+    if ((MODE & MODE_SAMPLING) && fp.dof) {
         double cosTheta = dot3(r.dx, r.dy, r.dz, fp.front_dir[0], fp.front_dir[1], fp.front_dir[2]);
         double M = fp.focal_plane_dist * rcp64(cosTheta);
         double Tx = r.ox + r.dx * M, Ty = r.oy + r.dy * M, Tz = r.oz + r.dz * M;
@@ -169,6 +173,7 @@ __device__ __forceinline__ void gen_ray(const FrameParams& fp, double vx, double
         r.ox = fp.pos[0] + ddx * fp.right_dir[0] + ddy * fp.up_dir[0];
         r.oy = fp.pos[1] + ddx * fp.right_dir[1] + ddy * fp.up_dir[1];
         r.oz = fp.pos[2] + ddx * fp.right_dir[2] + ddy * fp.up_dir[2];
+        if (eye != 0) { r.ox += fp.right_dir[0] * sep; r.oy += fp.right_dir[1] * sep; r.oz += fp.right_dir[2] * sep; }
         r.dx = Tx - r.ox; r.dy = Ty - r.oy; r.dz = Tz - r.oz;
         normalize3(r.dx, r.dy, r.dz);
     }
@@ -885,30 +890,57 @@ __device__ __forceinline__ Col trace(const FrameParams& fp, const Ray& ray, unsi
 
 // renderer.d:254-313 renderSample (default and DOF branches).  (bx, by, bz) is the un-normalised
 // direction through the pixel corner; tap k adds the per-frame constant fp.tap_d[k].
+// color.d:10-15 combineStereo + :76-82 adjustSaturation(0.25): anaglyph of the two eye colours
+__device__ __forceinline__ Col desaturate(Col c) {
+    const float mid = (c.r + c.g + c.b) / 3;
+    return mkcol(c.r * 0.25f + mid * (1 - 0.25f), c.g * 0.25f + mid * (1 - 0.25f), c.b * 0.25f + mid * (1 - 0.25f));
+}
+__device__ __forceinline__ Col combine_stereo(Col left, Col right) {
+    left = desaturate(left);
+    right = desaturate(right);
+    return mkcol(left.r * 1.f + right.r * 0.f, left.g * 0.f + right.g * 1.f, left.b * 0.f + right.b * 1.f);
+}
+
 template <int MODE>
 __device__ __forceinline__ Col render_sample(const FrameParams& fp, double bx, double by, double bz, double x, double y, uint32_t px,
                                              uint32_t py, uint32_t tap, unsigned& n_primary, unsigned& n_shadow, HitRec* out_hit) {
     Ray r;
-    uint32_t draw = 0;
-    if (!fp.dof) {
+    if (!(MODE & MODE_SAMPLING)) {               // renderSampleDefault without stereo (renderer.d:303-306): one ray
+        uint32_t draw = 0;
         n_primary++;
-        gen_ray<MODE>(fp, bx + fp.tap_d[tap][0], by + fp.tap_d[tap][1], bz + fp.tap_d[tap][2], px, py, tap, 0, draw, r);
+        gen_ray<MODE>(fp, bx + fp.tap_d[tap][0], by + fp.tap_d[tap][1], bz + fp.tap_d[tap][2], px, py, tap, 0, draw, 0, r);
         return trace<MODE>(fp, r, n_shadow, out_hit);
     }
+    const bool stereo = fp.stereo_sep != 0;      // renderer.d:276-284,305-312: one ray per eye, then combineStereo
+    const int n_eyes = stereo ? 2 : 1;
+    const uint32_t n_samples = fp.dof ? fp.num_samples : 1u;
     Col avg = mkcol(0.f, 0.f, 0.f);
-    for (uint32_t i = 0; i < fp.num_samples; i++) {
-        draw = 0;
-        double jx = x + c_tap_x[tap] + uniform01(fp, px, py, tap, i, draw);
-        double jy = y + c_tap_y[tap] + uniform01(fp, px, py, tap, i, draw);
-        n_primary++;
-        double vx, vy, vz;
-        screen_dir(fp, jx, jy, vx, vy, vz);
-        gen_ray<MODE>(fp, vx, vy, vz, px, py, tap, i, draw, r);
-        Col c = trace<MODE>(fp, r, n_shadow, (out_hit && i == 0) ? out_hit : nullptr);
+#pragma unroll 1
+    for (uint32_t i = 0; i < n_samples; i++) {
+        uint32_t draw = 0;
+        Col left = mkcol(0.f, 0.f, 0.f), c = left;
+#pragma unroll 1
+        for (int e = 0; e < n_eyes; e++) {
+            double vx, vy, vz;
+            if (fp.dof) {
+                // each call draws its own pixel jitter, then (inside getScreenRay) its own lens sample
+                double jx = x + c_tap_x[tap] + uniform01(fp, px, py, tap, i, draw);
+                double jy = y + c_tap_y[tap] + uniform01(fp, px, py, tap, i, draw);
+                screen_dir(fp, jx, jy, vx, vy, vz);
+            } else {
+                vx = bx + fp.tap_d[tap][0]; vy = by + fp.tap_d[tap][1]; vz = bz + fp.tap_d[tap][2];
+            }
+            n_primary++;
+            gen_ray<MODE>(fp, vx, vy, vz, px, py, tap, i, draw, stereo ? (e ? +1 : -1) : 0, r);
+            c = trace<MODE>(fp, r, n_shadow, (out_hit && i == 0 && e == 0) ? out_hit : nullptr);
+            if (e == 0) left = c;
+        }
+        if (stereo) c = combine_stereo(left, c);
+        if (!fp.dof) return c;
         avg.r += c.r; avg.g += c.g; avg.b += c.b;
     }
-    float inv = 1.f / (float)fp.num_samples;
-    return mkcol(avg.r * inv, avg.g * inv, avg.b * inv);
+    float n = (float)fp.num_samples;
+    return mkcol(avg.r / n, avg.g / n, avg.b / n);
 }
 
 __device__ __forceinline__ uint32_t lut8(const uint8_t* lut, float x) {  // color.d:209-214
@@ -1007,7 +1039,7 @@ __global__ void render_pixel_kernel(const FrameParams fp, int x, int y, PixelOut
     h.dist = 1e99;
     double bx, by, bz;
     screen_dir(fp, (double)x, (double)y, bx, by, bz);
-    Col c = render_sample<MODE_BOUNDED | MODE_GENERIC | MODE_NESTED | MODE_CLUSTERS>(fp, bx, by, bz, (double)x, (double)y, (uint32_t)x, (uint32_t)y, 0, a, b, &h);
+    Col c = render_sample<MODE_BOUNDED | MODE_GENERIC | MODE_NESTED | MODE_CLUSTERS | MODE_SAMPLING>(fp, bx, by, bz, (double)x, (double)y, (uint32_t)x, (uint32_t)y, 0, a, b, &h);
     out->rgb[0] = c.r; out->rgb[1] = c.g; out->rgb[2] = c.b;
     out->node = h.node;
     out->dist = h.dist;
@@ -1088,11 +1120,15 @@ cudaError_t upload_scene(const DevScene& s, cudaStream_t st) {
 cudaError_t launch_frame(const FrameParams& fp, int mode, uint32_t local_tile_rows, cudaStream_t st) {
     if (local_tile_rows == 0) return cudaSuccess;
     dim3 grid((fp.W + TILE_W - 1) / TILE_W, local_tile_rows);
-    if (mode & MODE_NESTED) render_frame_kernel<MODE_BOUNDED | MODE_GENERIC | MODE_NESTED | MODE_CLUSTERS, 2><<<grid, BLOCK_THREADS, 0, st>>>(fp);
-    else if ((mode & MODE_CLUSTERS) && (mode & MODE_GENERIC))
-        render_frame_kernel<MODE_BOUNDED | MODE_GENERIC | MODE_CLUSTERS, C2RT_MINBLOCKS_FULL><<<grid, BLOCK_THREADS, 0, st>>>(fp);
+    constexpr int FULL = MODE_BOUNDED | MODE_GENERIC, ALL = FULL | MODE_NESTED | MODE_CLUSTERS;
+    if (fp.dof || fp.stereo_sep != 0) {
+        // DOF / stereo frames: two general kernels only (the per-sample loop dominates, the scene class matters less)
+        if (mode & (MODE_NESTED | MODE_CLUSTERS)) render_frame_kernel<ALL | MODE_SAMPLING, 2><<<grid, BLOCK_THREADS, 0, st>>>(fp);
+        else render_frame_kernel<FULL | MODE_SAMPLING, C2RT_MINBLOCKS_FULL><<<grid, BLOCK_THREADS, 0, st>>>(fp);
+    } else if (mode & MODE_NESTED) render_frame_kernel<ALL, 2><<<grid, BLOCK_THREADS, 0, st>>>(fp);
+    else if ((mode & MODE_CLUSTERS) && (mode & MODE_GENERIC)) render_frame_kernel<FULL | MODE_CLUSTERS, C2RT_MINBLOCKS_FULL><<<grid, BLOCK_THREADS, 0, st>>>(fp);
     else if (mode & MODE_CLUSTERS) render_frame_kernel<MODE_BOUNDED | MODE_CLUSTERS, C2RT_MINBLOCKS_BOUNDED><<<grid, BLOCK_THREADS, 0, st>>>(fp);
-    else if (mode & MODE_GENERIC) render_frame_kernel<MODE_BOUNDED | MODE_GENERIC, C2RT_MINBLOCKS_FULL><<<grid, BLOCK_THREADS, 0, st>>>(fp);
+    else if (mode & MODE_GENERIC) render_frame_kernel<FULL, C2RT_MINBLOCKS_FULL><<<grid, BLOCK_THREADS, 0, st>>>(fp);
     else if (mode & MODE_BOUNDED) render_frame_kernel<MODE_BOUNDED, C2RT_MINBLOCKS_BOUNDED><<<grid, BLOCK_THREADS, 0, st>>>(fp);
     else render_frame_kernel<0, C2RT_MINBLOCKS_SIMPLE><<<grid, BLOCK_THREADS, 0, st>>>(fp);
     return cudaGetLastError();

@@ -87,6 +87,7 @@ struct FrameParams {
     double inv_w, inv_h;
     double tap_d[5][3];               // ray-direction offset of AA tap k: du * kx/W + dv * ky/H (renderer.d:235-247)
     double focal_plane_dist, disc_multiplier;
+    double stereo_sep;                // camera.stereoSeparation (0 = off)
     unsigned long long seed;
     uint32_t W, H;                    // output size
     int aa, dof;

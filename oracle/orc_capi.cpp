@@ -37,11 +37,6 @@ orc_scene* orc_scene_load(const char* path) {
             g_err = "GIEnabled scenes are outside the hot-path scope";
             return nullptr;
         }
-        if (h->scene->camera.stereoSeparation != 0) {
-            delete h;
-            g_err = "stereo rendering is outside the hot-path scope";
-            return nullptr;
-        }
         return h;
     } catch (const std::exception& e) {
         g_err = e.what();

@@ -73,17 +73,33 @@ struct Renderer {
     Color renderSample(real x, real y, int dx, int dy, uint32_t tap) const {  // renderer.d:254-313
         RngState& rs = tl_rng();
         rs.tap = tap;
+        const bool stereo = scene.camera.stereoSeparation != 0;
         if (scene.camera.dof) {
             Color average = Color::fromFloats(0, 0, 0);
             for (size_t i = 0; i < scene.camera.numSamples; i++) {
                 rs.sample = (uint32_t)i;
                 rs.draw = 0;
-                real jx = x + uniform01() * mk_real((double)dx);
-                real jy = y + uniform01() * mk_real((double)dy);
-                tl_stats().primary++;
-                average += trace(scene.camera.getScreenRay(jx, jy));
+                if (!stereo) {
+                    real jx = x + uniform01() * mk_real((double)dx);
+                    real jy = y + uniform01() * mk_real((double)dy);
+                    tl_stats().primary++;
+                    average += trace(scene.camera.getScreenRay(jx, jy));
+                } else {  // renderer.d:280-283: each eye draws its own jitter and lens sample
+                    real lx = x + uniform01() * mk_real((double)dx);
+                    real ly = y + uniform01() * mk_real((double)dy);
+                    Color left = trace(scene.camera.getScreenRay(lx, ly, -1));
+                    real rx = x + uniform01() * mk_real((double)dx);
+                    real ry = y + uniform01() * mk_real((double)dy);
+                    Color right = trace(scene.camera.getScreenRay(rx, ry, +1));
+                    tl_stats().primary += 2;
+                    average += combineStereo(left, right);
+                }
             }
             return average / mk_colf((float)scene.camera.numSamples);
+        }
+        if (stereo) {  // renderer.d:307-312
+            tl_stats().primary += 2;
+            return combineStereo(trace(scene.camera.getScreenRay(x, y, -1)), trace(scene.camera.getScreenRay(x, y, +1)));
         }
         tl_stats().primary++;
         return trace(scene.camera.getScreenRay(x, y));

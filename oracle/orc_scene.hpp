@@ -38,7 +38,20 @@ struct Color {
     Color operator*(colf f) const { return Color(r * f, g * f, b * f); }                // color.d:128-132
     Color operator/(colf f) const { return Color(r / f, g / f, b / f); }
     colf intensity() const { return (r + g + b) / mk_colf(3.f); }                       // color.d:141-144
+    void adjustSaturation(colf amount) {                                                // color.d:76-82
+        colf mid = intensity();
+        r = r * amount + mid * (mk_colf(1.f) - amount);
+        g = g * amount + mid * (mk_colf(1.f) - amount);
+        b = b * amount + mid * (mk_colf(1.f) - amount);
+    }
 };
+
+// color.d:10-15: anaglyph combination of the left / right eye colours
+inline Color combineStereo(Color left, Color right) {
+    left.adjustSaturation(mk_colf(0.25f));
+    right.adjustSaturation(mk_colf(0.25f));
+    return left * Color::fromFloats(1, 0, 0) + right * Color::fromFloats(0, 1, 1);
+}
 
 // color.d:194-229: 8-bit sRGB packing through the 4097-entry table, quirks included
 // (12.02 linear slope, floor instead of round).
@@ -565,15 +578,19 @@ struct Camera {
     }
     static Vec3 v(const double a[3]) { return Vec3(mk_real(a[0]), mk_real(a[1]), mk_real(a[2])); }
 
-    Ray getScreenRay(real x, real y) const {  // camera.d:123-174 (Stereo3DOffset.None branch)
+    // camera.d:123-174.  eye: 0 = Stereo3DOffset.None, -1 = Left, +1 = Right
+    Ray getScreenRay(real x, real y, int eye = 0) const {
         Ray result;
         Vec3 P = v(pos), UL = v(upLeft), UR = v(upRight), DL = v(downLeft);
         result.orig = P;
         Vec3 target = UL + (UR - UL) * (x / mk_real((double)frameWidth)) + (DL - UL) * (y / mk_real((double)frameHeight));
         result.dir = target - P;
         normalize(result.dir);
+        Vec3 right = v(rightDir);
+        const real sep = mk_real(eye > 0 ? +stereoSeparation : -stereoSeparation);
+        if (eye != 0) result.orig = result.orig + right * sep;   // camera.d:149-152
         if (!dof) return result;
-        Vec3 front = v(frontDir), right = v(rightDir), up = v(upDir);
+        Vec3 front = v(frontDir), up = v(upDir);
         real cosTheta = dot(result.dir, front);
         real M = mk_real(focalPlaneDist) / cosTheta;
         Vec3 T = result.orig + result.dir * M;
@@ -582,6 +599,7 @@ struct Camera {
         dx *= mk_real(discMultiplier);
         dy *= mk_real(discMultiplier);
         result.orig = P + dx * right + dy * up;
+        if (eye != 0) result.orig = result.orig + right * sep;   // camera.d:168-170
         result.dir = T - result.orig;
         normalize(result.dir);
         return result;

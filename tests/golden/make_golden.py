@@ -27,6 +27,8 @@ CASES = [  # name, scene path, (w, h), overrides, seed
     ("chessboard", "scenes/chessboard.sdl", (128, 72), {}, 0),
     ("quirks", "tests/scenes/quirks.sdl", (160, 100), {}, 0),
     ("nested", "tests/scenes/nested.sdl", (160, 100), {}, 0),
+    ("stereo", "tests/scenes/stereo.sdl", (128, 96), {}, 0),
+    ("stereo_dof", "tests/scenes/stereo_dof.sdl", (129, 86), {}, 77),
 ]
 
 

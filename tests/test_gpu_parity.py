@@ -54,6 +54,8 @@ CASES = [
     ("chessboard.sdl", (480, 270), {}),
     ("../tests/scenes/quirks.sdl", None, {}),
     ("../tests/scenes/nested.sdl", None, {}),   # CSG inside CSG: literal emulation path
+    ("../tests/scenes/stereo.sdl", None, {}),       # anaglyph stereo: two eyes per sample, combineStereo
+    ("../tests/scenes/stereo_dof.sdl", None, {}),   # stereo + DOF: each eye draws its own jitter and lens sample
 ]
 
 
@@ -227,9 +229,6 @@ def test_unsupported_features_are_errors_not_fallbacks():
     st.prepass_only = 1
     assert api.lib.c2rt_render(g.device_scene(), C.byref(cam), C.byref(st), rgb.ctypes.data, None, None) == -2
     st.prepass_only = 0
-    cam.stereo_separation = 0.5
-    assert api.lib.c2rt_render(g.device_scene(), C.byref(cam), C.byref(st), rgb.ctypes.data, None, None) == -2
-    cam.stereo_separation = 0
     assert api.lib.c2rt_render(g.device_scene(), C.byref(cam), C.byref(st), None, None, None) == -1
     assert api.lib.c2rt_render(g.device_scene(), C.byref(cam), C.byref(st), rgb.ctypes.data, None, None) == 0
 
