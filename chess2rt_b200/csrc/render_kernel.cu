@@ -1108,13 +1108,16 @@ cudaError_t upload_scene(const DevScene& s, cudaStream_t st) {
 }
 
 #ifndef C2RT_MINBLOCKS_SIMPLE
-#define C2RT_MINBLOCKS_SIMPLE 5
+#define C2RT_MINBLOCKS_SIMPLE 6
 #endif
 #ifndef C2RT_MINBLOCKS_BOUNDED
-#define C2RT_MINBLOCKS_BOUNDED 3
+#define C2RT_MINBLOCKS_BOUNDED 4
+#endif
+#ifndef C2RT_MINBLOCKS_SAMPLING
+#define C2RT_MINBLOCKS_SAMPLING 4
 #endif
 #ifndef C2RT_MINBLOCKS_FULL
-#define C2RT_MINBLOCKS_FULL 4
+#define C2RT_MINBLOCKS_FULL 5
 #endif
 
 cudaError_t launch_frame(const FrameParams& fp, int mode, uint32_t local_tile_rows, cudaStream_t st) {
@@ -1124,7 +1127,7 @@ cudaError_t launch_frame(const FrameParams& fp, int mode, uint32_t local_tile_ro
     if (fp.dof || fp.stereo_sep != 0) {
         // DOF / stereo frames: two general kernels only (the per-sample loop dominates, the scene class matters less)
         if (mode & (MODE_NESTED | MODE_CLUSTERS)) render_frame_kernel<ALL | MODE_SAMPLING, 2><<<grid, BLOCK_THREADS, 0, st>>>(fp);
-        else render_frame_kernel<FULL | MODE_SAMPLING, C2RT_MINBLOCKS_FULL><<<grid, BLOCK_THREADS, 0, st>>>(fp);
+        else render_frame_kernel<FULL | MODE_SAMPLING, C2RT_MINBLOCKS_SAMPLING><<<grid, BLOCK_THREADS, 0, st>>>(fp);
     } else if (mode & MODE_NESTED) render_frame_kernel<ALL, 2><<<grid, BLOCK_THREADS, 0, st>>>(fp);
     else if ((mode & MODE_CLUSTERS) && (mode & MODE_GENERIC)) render_frame_kernel<FULL | MODE_CLUSTERS, C2RT_MINBLOCKS_FULL><<<grid, BLOCK_THREADS, 0, st>>>(fp);
     else if (mode & MODE_CLUSTERS) render_frame_kernel<MODE_BOUNDED | MODE_CLUSTERS, C2RT_MINBLOCKS_BOUNDED><<<grid, BLOCK_THREADS, 0, st>>>(fp);
