@@ -604,10 +604,11 @@ template <int MODE>
 __device__ __forceinline__ bool node_exact(int ni, const DevNode& nd, const Ray& r, HitRec& h) {
     int face = 0;
     bool hit;
+    double px, py, pz;   // world-space kinds: the hit point is o + d * dist, recomputed for the winning hit only (surface_of)
     // MODE 0: no bounded and no generic node exists, i.e. every node is a world-space plane
-    if (MODE == 0 || nd.kind == KIND_PLANE_W) hit = isect_plane(nd.wp[0], CUDART_NAN, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, h.px, h.py, h.pz);
-    else if ((MODE & MODE_BOUNDED) && nd.kind == KIND_SPHERE_W) hit = isect_sphere(nd.wp, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, h.px, h.py, h.pz);
-    else if ((MODE & MODE_BOUNDED) && nd.kind == KIND_CUBE_W) hit = isect_cube(nd.wp, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, h.px, h.py, h.pz, face);
+    if (MODE == 0 || nd.kind == KIND_PLANE_W) hit = isect_plane(nd.wp[0], CUDART_NAN, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, px, py, pz);
+    else if ((MODE & MODE_BOUNDED) && nd.kind == KIND_SPHERE_W) hit = isect_sphere(nd.wp, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, px, py, pz);
+    else if ((MODE & MODE_BOUNDED) && nd.kind == KIND_CUBE_W) hit = isect_cube(nd.wp, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, px, py, pz, face);
     else if (MODE & MODE_GENERIC) return generic_intersect<MODE>(ni, r, h);
     else return false;
     if (hit) { h.node = ni; h.leaf = nd.geom; h.face = face; }
@@ -768,11 +769,14 @@ __device__ __forceinline__ void local_surface(int type, const double* c, const H
     if (h.face & FACE_FLIP) { gx = -gx; gy = -gy; gz = -gz; }
 }
 
-__device__ __forceinline__ void surface_of(const HitRec& h, bool need_uv, Surface& s) {
-    const DevNode& nd = c_scene.nodes[h.node];
-    const DevGeom& g = c_scene.geoms[h.leaf];
+// `ray` == nullptr: hin.p is already complete (debug pixel pick)
+__device__ __forceinline__ void surface_of(const HitRec& hin, const Ray* ray, bool need_uv, Surface& s) {
+    const DevNode& nd = c_scene.nodes[hin.node];
+    const DevGeom& g = c_scene.geoms[hin.leaf];
+    HitRec h = hin;
     if (nd.kind != KIND_GENERIC) {
-        // world-space fast path: h.p is the world hit point, nd.wp the pre-offset parameters
+        // world-space fast path: the hit point is o + d * dist (exactly what the intersector computed), nd.wp the pre-offset parameters
+        if (ray) { h.px = fma(ray->dx, h.dist, ray->ox); h.py = fma(ray->dy, h.dist, ray->oy); h.pz = fma(ray->dz, h.dist, ray->oz); }
         local_surface(g.type, nd.wp, h, need_uv, s.gx, s.gy, s.gz, s.u, s.v);
         if (nd.kind == KIND_PLANE_W) { s.u = h.px - nd.off[0]; s.v = h.pz - nd.off[2]; }  // uv are object-space (geometry.d:54-55)
         s.px = h.px; s.py = h.py; s.pz = h.pz;
@@ -802,7 +806,7 @@ template <int MODE>
 __device__ __forceinline__ Col shade(const FrameParams& fp, const Ray& ray, const HitRec& h, unsigned& n_shadow) {
     const DevShader& sh = c_scene.shaders[c_scene.nodes[h.node].shader];
     Surface s;
-    surface_of(h, sh.tex >= 0, s);
+    surface_of(h, &ray, sh.tex >= 0, s);
     // faceforward (imported_types.d:69-73): the sign decision in FP64, the vector itself in FP32
     float Nx = s.nx, Ny = s.ny, Nz = s.nz;
     if (!(dot3(ray.dx, ray.dy, ray.dz, s.gx, s.gy, s.gz) < 0)) { Nx = -Nx; Ny = -Ny; Nz = -Nz; }
@@ -883,7 +887,12 @@ __device__ __forceinline__ Col trace(const FrameParams& fp, const Ray& ray, unsi
                 if (MODE & MODE_BOUNDED) tmaxf = (float)h.dist * 1.000001f;
             }
     }
-    if (out_hit) *out_hit = h;
+    if (out_hit) {
+        *out_hit = h;
+        if (h.node >= 0 && c_scene.nodes[h.node].kind != KIND_GENERIC) {
+            out_hit->px = fma(ray.dx, h.dist, ray.ox); out_hit->py = fma(ray.dy, h.dist, ray.oy); out_hit->pz = fma(ray.dz, h.dist, ray.oz);
+        }
+    }
     if (h.node < 0) return mkcol(0.f, 0.f, 0.f);  // environment.d:7-10
     return shade<MODE>(fp, ray, h, n_shadow);
 }
@@ -1045,7 +1054,7 @@ __global__ void render_pixel_kernel(const FrameParams fp, int x, int y, PixelOut
     out->dist = h.dist;
     if (h.node >= 0) {
         Surface w;
-        surface_of(h, true, w);
+        surface_of(h, nullptr, true, w);
         out->p[0] = w.px; out->p[1] = w.py; out->p[2] = w.pz;
         double gx = w.gx, gy = w.gy, gz = w.gz;
         normalize3(gx, gy, gz);
