@@ -172,9 +172,10 @@ int orc_render_pixel(orc_scene* s, int x, int y, int rng_mode, uint64_t seed, fl
                 rs.mode = rng_mode; rs.seed = seed; rs.px = x; rs.py = y; rs.tap = 0; rs.sample = 0; rs.draw = 0;
                 real jx = mk_real((double)x) + uniform01() * mk_real(1.0);
                 real jy = mk_real((double)y) + uniform01() * mk_real(1.0);
-                ray = sc.camera.getScreenRay(jx, jy);
+                ray = sc.camera.getScreenRay(jx, jy, sc.camera.stereoSeparation != 0 ? -1 : 0);
             } else {
-                ray = sc.camera.getScreenRay(mk_real((double)x), mk_real((double)y));
+                // with stereo on, the record is the LEFT eye's (the first ray traced: renderer.d:309-311)
+                ray = sc.camera.getScreenRay(mk_real((double)x), mk_real((double)y), sc.camera.stereoSeparation != 0 ? -1 : 0);
             }
             IntersectionData data;
             data.dist = mk_real(1e99);
