@@ -310,23 +310,26 @@ def main():
                 self.out_ptr = self.mine.data_ptr()
 
         def render(self, cam=None, st=None):
-            c2.render_device(self.handle, cam or self.cam, st or self.st, self.out_ptr, None, self.band, stream)
+            c2.render_device(self.handle, cam or self.cam, st or self.st, self.out_ptr, None, self.band,
+                             torch.cuda.current_stream().cuda_stream)
             self.launches += 1
 
         def gather(self):
             if self.mode == "nccl":
                 dist.gather(self.mine, list(self.gathered.unbind(0)) if rank == 0 else None, dst=0)
                 if rank == 0:
-                    c2.deinterleave(self.gathered.data_ptr(), self.frame.data_ptr(), self.W, self.H, 3, world, BAND_ROWS, self.pad, stream)
+                    c2.deinterleave(self.gathered.data_ptr(), self.frame.data_ptr(), self.W, self.H, 3, world, BAND_ROWS, self.pad,
+                                    torch.cuda.current_stream().cuda_stream)
                     self.launches += 1
             elif self.mode == "p2p":
                 # completion without a collective: peers raise a flag in rank 0's memory after their band stores,
                 # rank 0 waits for all flags on its stream (c2rt_signal / c2rt_wait_signals)
-                self.frame_no += 1
+                # (counting mode, value 0: the same two launches can be replayed from a CUDA graph)
+                cur = torch.cuda.current_stream().cuda_stream
                 if rank == 0:
-                    api._check(api.lib.c2rt_wait_signals(self.flags_ptr, world, self.frame_no, stream))
+                    api._check(api.lib.c2rt_wait_signals(self.flags_ptr, world, 0, cur))
                 else:
-                    api._check(api.lib.c2rt_signal(self.flags_ptr + 4 * rank, self.frame_no, stream))
+                    api._check(api.lib.c2rt_signal(self.flags_ptr + 4 * rank, 0, cur))
 
         def count_rays(self):
             cam_c, st_c = self.scene.frame_blocks(seed=RNG_SEED, count_rays=True)
@@ -337,34 +340,71 @@ def main():
                 dist.all_reduce(counts)
             return int(counts[0]), int(counts[1])
 
-        def time_steps(self, steps, warmup, sampler=None):
-            """EXACTLY `steps` timed frames; L2 flushed between them (untimed); per-step CUDA events; max over ranks."""
+        def capture(self):
+            """One frame (render + completion signal) as a CUDA graph: a single launch per step instead of several
+            calls through ctypes.  Not used with the NCCL gather."""
+            if self.mode == "nccl":
+                return None
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self.render()          # scene block resident, kernels loaded: nothing but launches is left to capture
+                self.gather()
+            torch.cuda.current_stream().wait_stream(side)
+            barrier()
+            n0 = self.launches
+            with torch.cuda.graph(g, stream=side):
+                self.render()
+                self.gather()
+            self.launches_per_step = self.launches - n0
+            return g
+
+        def time_steps(self, steps, warmup, sampler=None, use_graph=True):
+            """EXACTLY `steps` timed frames; L2 flushed between them (untimed); per-step CUDA events; max over ranks.
+            Returns (ms per step, ms per render kernel, launches).  The step is replayed from a CUDA graph when
+            possible; the kernel-only time comes from a second pass with an event right after the render kernel."""
             for _ in range(warmup):
                 flush_buf.fill_(1)
                 self.render()
                 self.gather()
             barrier()
+            graph = self.capture() if (use_graph and world > 1) else None   # one GPU: a single kernel launch, nothing to batch
+            barrier()
             if sampler is not None:
                 sampler.start()
-            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-                  for _ in range(steps)]
-            self.launches = 0
-            barrier()
-            for e0, ek, e1 in ev:
-                flush_buf.fill_(1)
+
+            def run(use):
+                ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                      for _ in range(steps)]
+                self.launches = 0
+                barrier()
+                for e0, ek, e1 in ev:
+                    flush_buf.fill_(1)
+                    if world > 1:
+                        dist.barrier()  # ranks start each frame together, as one frame request would
+                    e0.record()
+                    if use is not None:
+                        use.replay()
+                        ek.record()
+                    else:
+                        self.render()
+                        ek.record()
+                        self.gather()
+                    e1.record()
+                barrier()
+                t = torch.tensor([sum(e0.elapsed_time(e1) for e0, ek, e1 in ev), sum(e0.elapsed_time(ek) for e0, ek, e1 in ev)],
+                                 dtype=torch.float64, device="cuda")
                 if world > 1:
-                    dist.barrier()  # ranks start each frame together, as one frame request would
-                e0.record()
-                self.render()
-                ek.record()
-                self.gather()
-                e1.record()
-            barrier()
-            t = torch.tensor([sum(e0.elapsed_time(e1) for e0, ek, e1 in ev), sum(e0.elapsed_time(ek) for e0, ek, e1 in ev)],
-                             dtype=torch.float64, device="cuda")
-            if world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t[0]) / steps, float(t[1]) / steps, self.launches
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                return float(t[0]) / steps, float(t[1]) / steps
+
+            ms_plain, kernel_ms = run(None)
+            n_launches = self.launches
+            if graph is None:
+                return ms_plain, kernel_ms, n_launches, "direct launches"
+            ms_graph, _ = run(graph)
+            return ms_graph, kernel_ms, steps * self.launches_per_step, "CUDA graph replay (1 graph launch per step)"
 
         def close(self):
             import ctypes as C
@@ -389,7 +429,7 @@ def main():
 
     # ---- timed region ------------------------------------------------------------------------------
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    ms_per_step, kernel_ms, n_launches = run.time_steps(args.steps, args.warmup, sampler)
+    ms_per_step, kernel_ms, n_launches, launch_how = run.time_steps(args.steps, args.warmup, sampler)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- the scaling target of BASELINE.json (8K chessboard), measured beside the headline workload ----
@@ -397,7 +437,7 @@ def main():
     if args.workload == DEFAULT_WORKLOAD and not args.no_scaling_target:
         run4 = DeviceRun("c4", args.gather)
         p4, s4 = run4.count_rays()
-        ms4, k4, _ = run4.time_steps(max(3, args.steps // 4), 3)
+        ms4, k4, _, _ = run4.time_steps(max(3, args.steps // 4), 3)
         cal4 = load_calibration().get("c4") or {}
         scaling_target = {"workload": "c4: scenes/chessboard.sdl at 7680x4320 (32 CSG pieces, Phong, AA)", "n_gpus": world,
                           "ms_per_step": ms4, "kernel_ms": k4, "value": (p4 + s4) / (ms4 * 1e-3) / 1e6, "unit": "Mrays/s",
@@ -478,7 +518,8 @@ def main():
             "config": {"workload": "%s: %s at %dx%d, AA 5 samples/px, 1 light" % (args.workload, path, W, H),
                        "rays_per_frame": rays_per_frame, "primary_rays": prim, "shadow_rays": shad,
                        "l2": "flushed between timed steps (256 MiB fill, untimed); per-step CUDA events summed",
-                       "parallelism": "row bands of %d rows, interleaved over %d GPU(s), gather=%s" % (BAND_ROWS, world, gather_mode)},
+                       "parallelism": "row bands of %d rows, interleaved over %d GPU(s), gather=%s" % (BAND_ROWS, world, gather_mode),
+                       "launch": launch_how},
             "roofline": roofline,
             "e2e": {"value": rays_per_frame / (e2e_ms_mean * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms_mean,
                     "frames_per_s": 1e3 / e2e_ms_mean, "h2d_bytes_per_step": C_sizeof_frame_blocks(api) * world, "d2h_bytes_per_step": W * H * 12,

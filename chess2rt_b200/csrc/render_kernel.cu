@@ -1078,15 +1078,20 @@ __global__ void deinterleave_kernel(const uint32_t* __restrict__ src, uint32_t* 
 // frame-complete signalling between ranks (c2rt.h c2rt_signal / c2rt_wait_signals)
 __global__ void signal_kernel(volatile uint32_t* flag, uint32_t value) {
     __threadfence_system();   // this rank's band stores (previous kernel on the stream) are ordered before the flag
-    *flag = value;
+    if (value) *flag = value;
+    else atomicAdd_system((uint32_t*)flag, 1u);   // counting mode: replayable from a CUDA graph
     __threadfence_system();
 }
 __global__ void wait_signals_kernel(volatile uint32_t* flags, uint32_t n_ranks, uint32_t value) {
+    __shared__ uint32_t s_expected;
+    if (threadIdx.x == 0) s_expected = value ? value : ++*(uint32_t*)&flags[n_ranks + 1];   // counting mode: own frame counter
+    __syncthreads();
+    const uint32_t expected = s_expected;
     const uint32_t r = threadIdx.x + 1;
     if (r < n_ranks) {
         const long long t0 = clock64();
         // frame numbers only grow; the signed difference tolerates wrap-around
-        while ((int)(flags[r] - value) < 0) {
+        while ((int)(flags[r] - expected) < 0) {
             if (clock64() - t0 > 4000000000ll) {   // ~2 s at 2 GHz: a peer died; do not hang the device
                 atomicAdd((uint32_t*)&flags[n_ranks], 1u);
                 break;

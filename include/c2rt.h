@@ -236,7 +236,9 @@ int c2rt_frame_download(void* host_dst, const void* d_src, size_t bytes, void* s
  * c2rt_signal(&flags[r], frame_no) after its render kernel (flags live in rank 0's exported allocation, so the store
  * crosses NVLink after the band stores it follows); rank 0 enqueues c2rt_wait_signals(flags, n_ranks, frame_no) after
  * its own kernel: a one-warp kernel that polls flags[1..n_ranks-1] until all reached frame_no (it gives up after
- * ~2 s and bumps flags[n_ranks], which the caller can read back, instead of hanging the device). */
+ * ~2 s and bumps flags[n_ranks], which the caller can read back, instead of hanging the device).
+ * value == 0 selects the counting mode, which can be captured once into a CUDA graph and replayed: c2rt_signal
+ * increments its flag, c2rt_wait_signals waits for its own call count (kept in flags[n_ranks + 1]). */
 int c2rt_signal(void* d_flag, uint32_t value, void* stream);
 int c2rt_wait_signals(void* d_flags, uint32_t n_ranks, uint32_t value, void* stream);
 
