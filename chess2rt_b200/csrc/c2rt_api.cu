@@ -445,20 +445,26 @@ int validate_and_build(const c2rt_scene_desc* d, c2rt_scene* s) {
         } else {
             nd.flags |= NODE_UNBOUNDED;
         }
-        // world-space fast path for identity-transform primitives
+        // world-space fast path for identity-transform primitives, and for unbounded planes under a positive
+        // diagonal scale (Node "scale", zaphod.sdl): such a plane is the world plane y = y0 * sy + off.y, its
+        // object-space uv (geometry.d:54-55) are the world offsets times 1/sx, 1/sz
         nd.kind = KIND_GENERIC;
         const DevGeom& g = h.geoms[nd.geom];
-        if ((nd.flags & NODE_IDENTITY) && g.type <= C2RT_GEOM_CUBE) {
-            if (g.type == C2RT_GEOM_PLANE) {
-                if (std::isnan(g.p[1])) {  // bounded planes (limit set) keep the generic path
-                    nd.kind = KIND_PLANE_W;
-                    nd.wp[0] = g.p[0] + nd.off[1];
-                }
-            } else {
-                nd.kind = g.type == C2RT_GEOM_SPHERE ? KIND_SPHERE_W : KIND_CUBE_W;
-                nd.wp[0] = g.p[0] + nd.off[0]; nd.wp[1] = g.p[1] + nd.off[1]; nd.wp[2] = g.p[2] + nd.off[2];
-                nd.wp[3] = g.p[3];
+        nd.wp[1] = 1.0; nd.wp[2] = 1.0;
+        if (g.type == C2RT_GEOM_PLANE && std::isnan(g.p[1])) {   // bounded planes (limit set) keep the generic path
+            bool diag = nd.M[0] > 0 && nd.M[4] > 0 && nd.M[8] > 0;
+            for (int k = 0; k < 9; k++)
+                if (k % 4 != 0 && (nd.M[k] != 0.0 || nd.Minv[k] != 0.0)) diag = false;
+            if (diag) {
+                nd.kind = KIND_PLANE_W;
+                nd.wp[0] = g.p[0] * nd.M[4] + nd.off[1];
+                nd.wp[1] = nd.Minv[0];
+                nd.wp[2] = nd.Minv[8];
             }
+        } else if ((nd.flags & NODE_IDENTITY) && (g.type == C2RT_GEOM_SPHERE || g.type == C2RT_GEOM_CUBE)) {
+            nd.kind = g.type == C2RT_GEOM_SPHERE ? KIND_SPHERE_W : KIND_CUBE_W;
+            nd.wp[0] = g.p[0] + nd.off[0]; nd.wp[1] = g.p[1] + nd.off[1]; nd.wp[2] = g.p[2] + nd.off[2];
+            nd.wp[3] = g.p[3];
         }
     }
     build_clusters(h);

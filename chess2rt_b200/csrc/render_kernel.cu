@@ -778,7 +778,10 @@ __device__ __forceinline__ void surface_of(const HitRec& hin, const Ray* ray, bo
         // world-space fast path: the hit point is o + d * dist (exactly what the intersector computed), nd.wp the pre-offset parameters
         if (ray) { h.px = fma(ray->dx, h.dist, ray->ox); h.py = fma(ray->dy, h.dist, ray->oy); h.pz = fma(ray->dz, h.dist, ray->oz); }
         local_surface(g.type, nd.wp, h, need_uv, s.gx, s.gy, s.gz, s.u, s.v);
-        if (nd.kind == KIND_PLANE_W) { s.u = h.px - nd.off[0]; s.v = h.pz - nd.off[2]; }  // uv are object-space (geometry.d:54-55)
+        if (nd.kind == KIND_PLANE_W) {  // uv are object-space (geometry.d:54-55): undo the offset and the diagonal scale
+            s.u = (h.px - nd.off[0]) * nd.wp[1];
+            s.v = (h.pz - nd.off[2]) * nd.wp[2];
+        }
         s.px = h.px; s.py = h.py; s.pz = h.pz;
     } else {
         double gx, gy, gz;
