@@ -590,16 +590,17 @@ uint32_t c2rt_band_rows_owned(uint32_t height, uint32_t rank, uint32_t n_ranks, 
 }
 
 uint32_t c2rt_rng_u31(uint64_t seed, uint32_t px, uint32_t py, uint32_t tap, uint32_t sample, uint32_t draw) {
-    unsigned long long k = seed;
-    k ^= (unsigned long long)px * 0x9E3779B97F4A7C15ull;
-    k = (k ^ (k >> 30)) * 0xBF58476D1CE4E5B9ull;
-    k ^= (unsigned long long)py * 0xC2B2AE3D27D4EB4Full;
-    k = (k ^ (k >> 27)) * 0x94D049BB133111EBull;
-    k ^= ((unsigned long long)tap << 48) ^ ((unsigned long long)sample << 16) ^ (unsigned long long)draw;
-    k = (k ^ (k >> 30)) * 0xBF58476D1CE4E5B9ull;
-    k = (k ^ (k >> 27)) * 0x94D049BB133111EBull;
-    k ^= k >> 31;
-    return (uint32_t)(k >> 33);
+    // counter-based: four rounds of the 32-bit "lowbias32" finaliser over (seed, pixel) / (tap, sample) / draw.
+    // The pixel and sample rounds do not depend on `draw`, so a compiler hoists them out of the draw sequence.
+    uint32_t h = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B9u) ^ (px * 0x85EBCA6Bu);
+    h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+    h ^= py * 0xC2B2AE35u;
+    h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+    h ^= tap * 0x27D4EB2Fu + sample * 0x165667B1u;
+    h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+    h += draw * 0x9E3779B9u;
+    h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+    return h >> 1;
 }
 
 void c2rt_srgb_table(uint8_t out[4097]) {

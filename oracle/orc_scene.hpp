@@ -506,17 +506,17 @@ inline RngState& tl_rng() {
     return s;
 }
 inline uint32_t rng_u31(uint64_t seed, uint32_t px, uint32_t py, uint32_t tap, uint32_t sample, uint32_t draw) {
-    // splitmix64-style finaliser over a packed key; 31 output bits like rand() with RAND_MAX = 2^31-1
-    uint64_t k = seed;
-    k ^= (uint64_t)px * 0x9E3779B97F4A7C15ull;
-    k = (k ^ (k >> 30)) * 0xBF58476D1CE4E5B9ull;
-    k ^= (uint64_t)py * 0xC2B2AE3D27D4EB4Full;
-    k = (k ^ (k >> 27)) * 0x94D049BB133111EBull;
-    k ^= ((uint64_t)tap << 48) ^ ((uint64_t)sample << 16) ^ (uint64_t)draw;
-    k = (k ^ (k >> 30)) * 0xBF58476D1CE4E5B9ull;
-    k = (k ^ (k >> 27)) * 0x94D049BB133111EBull;
-    k ^= k >> 31;
-    return (uint32_t)(k >> 33);
+    // counter-based: four rounds of the 32-bit "lowbias32" finaliser over (seed, pixel) / (tap, sample) / draw.
+    // The pixel and sample rounds do not depend on `draw`, so a compiler hoists them out of the draw sequence.
+    uint32_t h = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B9u) ^ (px * 0x85EBCA6Bu);
+    h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+    h ^= py * 0xC2B2AE35u;
+    h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+    h ^= tap * 0x27D4EB2Fu + sample * 0x165667B1u;
+    h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+    h += draw * 0x9E3779B9u;
+    h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+    return h >> 1;
 }
 inline real uniform01() {  // util/random.d:19-28 with a=0, b=1:  0 + (r / RAND_MAX) * 1
     RngState& s = tl_rng();
