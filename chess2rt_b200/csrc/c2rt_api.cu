@@ -510,7 +510,6 @@ int check_frame_args(const c2rt_scene* s, const c2rt_camera* cam, const c2rt_set
         return fail(C2RT_ERR_INVALID_ARG, "bad frame size %ux%u", set->frame_width, set->frame_height);
     if (cam->frame_width == 0 || cam->frame_height == 0) return fail(C2RT_ERR_INVALID_ARG, "camera frame size is zero (setFrameSize not called)");
     if (set->gi_enabled) return fail(C2RT_ERR_UNSUPPORTED, "GIEnabled (path tracing) is outside the hot-path scope");
-    if (set->prepass_only) return fail(C2RT_ERR_UNSUPPORTED, "prepassOnly is not supported");
     if (!std::isfinite(cam->stereo_separation)) return fail(C2RT_ERR_INVALID_ARG, "stereoSeparation is not finite");
     if (cam->dof && cam->num_samples == 0) return fail(C2RT_ERR_INVALID_ARG, "DOF camera with numSamples == 0");
     return C2RT_OK;
@@ -544,6 +543,7 @@ void fill_params(FrameParams& fp, const c2rt_camera* cam, const c2rt_settings* s
     fp.num_samples = cam->num_samples;
     fp.max_trace_depth = set->max_trace_depth;
     fp.count_rays = set->count_rays != 0;
+    fp.prepass_bucket = set->prepass_only ? (set->bucket_size ? set->bucket_size : 48u) : 0u;
     fp.n_ranks = 1;
     fp.tiles_per_band = 1;
 }
@@ -644,6 +644,7 @@ int c2rt_render_device(c2rt_scene* s, const c2rt_camera* cam, const c2rt_setting
     int rc = check_frame_args(s, cam, set);
     if (rc) return rc;
     if (!d_rgb) return fail(C2RT_ERR_INVALID_ARG, "d_rgb is null");
+    if (set->prepass_only && !set->prepass_enabled) return C2RT_OK;  // renderer.d:110,129-130: nothing is drawn
     std::lock_guard<std::mutex> g(g_mu);
     if (!g_ctx.inited) return fail(C2RT_ERR_NOT_INITIALISED, "c2rt_init has not been called");
     int dev = -1;
@@ -703,6 +704,10 @@ int c2rt_render(c2rt_scene* s, const c2rt_camera* cam, const c2rt_settings* set,
     int rc = check_frame_args(s, cam, set);
     if (rc) return rc;
     if (!rgb) return fail(C2RT_ERR_INVALID_ARG, "rgb is null");
+    if (set->prepass_only && !set->prepass_enabled) {  // renderer.d:110,129-130: nothing is drawn, the image keeps its contents
+        if (stats) memset(stats, 0, sizeof *stats);
+        return C2RT_OK;
+    }
     std::lock_guard<std::mutex> g(g_mu);
     rc = ensure_init_locked();
     if (rc) return rc;

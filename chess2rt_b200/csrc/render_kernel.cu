@@ -916,7 +916,7 @@ __device__ __forceinline__ Col combine_stereo(Col left, Col right) {
 
 template <int MODE>
 __device__ __forceinline__ Col render_sample(const FrameParams& fp, double bx, double by, double bz, double x, double y, uint32_t px,
-                                             uint32_t py, uint32_t tap, unsigned& n_primary, unsigned& n_shadow, HitRec* out_hit) {
+                                             uint32_t py, uint32_t tap, double jw, double jh, unsigned& n_primary, unsigned& n_shadow, HitRec* out_hit) {
     Ray r;
     if (!(MODE & MODE_SAMPLING)) {               // renderSampleDefault without stereo (renderer.d:303-306): one ray
         uint32_t draw = 0;
@@ -937,8 +937,8 @@ __device__ __forceinline__ Col render_sample(const FrameParams& fp, double bx, d
             double vx, vy, vz;
             if (fp.dof) {
                 // each call draws its own pixel jitter, then (inside getScreenRay) its own lens sample
-                double jx = x + c_tap_x[tap] + uniform01(fp, px, py, tap, i, draw);
-                double jy = y + c_tap_y[tap] + uniform01(fp, px, py, tap, i, draw);
+                double jx = x + c_tap_x[tap] + uniform01(fp, px, py, tap, i, draw) * jw;   // x + uniform * dx (renderer.d:277)
+                double jy = y + c_tap_y[tap] + uniform01(fp, px, py, tap, i, draw) * jh;
                 screen_dir(fp, jx, jy, vx, vy, vz);
             } else {
                 vx = bx + fp.tap_d[tap][0]; vy = by + fp.tap_d[tap][1]; vz = bz + fp.tap_d[tap][2];
@@ -989,16 +989,30 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS) render_frame_kernel
     Col c = mkcol(0.f, 0.f, 0.f);
     if (active) {
         // renderer.d:223-251: tap 0 at the pixel corner, then +(.3,.3) (.6,0) (0,.6) (.6,.6); mean of 5 in FP32
-        const int taps = fp.aa ? 5 : 1;
-        const double xd = (double)x, yd = (double)y;
+        int taps = fp.aa ? 5 : 1;
+        uint32_t sx = x, sy = y;
+        double jw = 1.0, jh = 1.0;
+        if ((MODE & MODE_SAMPLING) && fp.prepass_bucket) {   // preview frames run on the general (sampling) kernels only
+            // prepassOnly (renderer.d:110-130): one sample at the corner of the pixel's 16x16 block (blocks are laid out
+            // inside each bucket, clipped to it), jitter extent = block size, the colour replicated over the block
+            const uint32_t B = fp.prepass_bucket;
+            const uint32_t bx0 = x / B * B, by0 = y / B * B;
+            const uint32_t rw = min(B, fp.W - bx0), rh = min(B, fp.H - by0);
+            const uint32_t dxl = (x - bx0) / 16 * 16, dyl = (y - by0) / 16 * 16;
+            sx = bx0 + dxl; sy = by0 + dyl;
+            jw = (double)(min(rw, dxl + 16) - dxl);
+            jh = (double)(min(rh, dyl + 16) - dyl);
+            taps = 1;
+        }
+        const double xd = (double)sx, yd = (double)sy;
         double bx, by, bz;
         screen_dir(fp, xd, yd, bx, by, bz);
 #pragma unroll 1
         for (int s = 0; s < taps; s++) {
-            Col t = render_sample<MODE>(fp, bx, by, bz, xd, yd, x, y, s, n_primary, n_shadow, nullptr);
+            Col t = render_sample<MODE>(fp, bx, by, bz, xd, yd, sx, sy, s, jw, jh, n_primary, n_shadow, nullptr);
             c.r += t.r; c.g += t.g; c.b += t.b;
         }
-        if (fp.aa) { c.r = c.r / 5.f; c.g = c.g / 5.f; c.b = c.b / 5.f; }  // accum / 5 (renderer.d:249)
+        if (taps == 5) { c.r = c.r / 5.f; c.g = c.g / 5.f; c.b = c.b / 5.f; }  // accum / 5 (renderer.d:249)
     }
 
     // output row of this tile row: full frame or compact (only this rank's rows, in order)
@@ -1052,7 +1066,7 @@ __global__ void render_pixel_kernel(const FrameParams fp, int x, int y, PixelOut
     h.dist = 1e99;
     double bx, by, bz;
     screen_dir(fp, (double)x, (double)y, bx, by, bz);
-    Col c = render_sample<MODE_BOUNDED | MODE_GENERIC | MODE_NESTED | MODE_CLUSTERS | MODE_SAMPLING>(fp, bx, by, bz, (double)x, (double)y, (uint32_t)x, (uint32_t)y, 0, a, b, &h);
+    Col c = render_sample<MODE_BOUNDED | MODE_GENERIC | MODE_NESTED | MODE_CLUSTERS | MODE_SAMPLING>(fp, bx, by, bz, (double)x, (double)y, (uint32_t)x, (uint32_t)y, 0, 1.0, 1.0, a, b, &h);
     out->rgb[0] = c.r; out->rgb[1] = c.g; out->rgb[2] = c.b;
     out->node = h.node;
     out->dist = h.dist;
@@ -1142,8 +1156,8 @@ cudaError_t launch_frame(const FrameParams& fp, int mode, uint32_t local_tile_ro
     if (local_tile_rows == 0) return cudaSuccess;
     dim3 grid((fp.W + TILE_W - 1) / TILE_W, local_tile_rows);
     constexpr int FULL = MODE_BOUNDED | MODE_GENERIC, ALL = FULL | MODE_NESTED | MODE_CLUSTERS;
-    if (fp.dof || fp.stereo_sep != 0) {
-        // DOF / stereo frames: two general kernels only (the per-sample loop dominates, the scene class matters less)
+    if (fp.dof || fp.stereo_sep != 0 || fp.prepass_bucket) {
+        // DOF / stereo / prepass-only frames: two general kernels only (the per-sample loop dominates, the scene class matters less)
         if (mode & (MODE_NESTED | MODE_CLUSTERS)) render_frame_kernel<ALL | MODE_SAMPLING, 2><<<grid, BLOCK_THREADS, 0, st>>>(fp);
         else render_frame_kernel<FULL | MODE_SAMPLING, C2RT_MINBLOCKS_SAMPLING><<<grid, BLOCK_THREADS, 0, st>>>(fp);
     } else if (mode & MODE_NESTED) render_frame_kernel<ALL, 2><<<grid, BLOCK_THREADS, 0, st>>>(fp);

@@ -94,6 +94,7 @@ struct FrameParams {
     uint32_t num_samples, max_trace_depth;
     float ambient[3];
     int count_rays;
+    uint32_t prepass_bucket;          // > 0: prepassOnly frame (16x16-block preview inside buckets of this size)
     // interleaved row bands
     uint32_t rank, n_ranks, tiles_per_band, compact;
     uint32_t tile_row0;               // first local tile row of this launch (frames are launched in chunks to overlap the D2H copy)

@@ -222,6 +222,7 @@ c2rt_settings flattenSettings(const GlobalSettings& s, uint64_t rngSeed, bool co
     o.ambient_light[2] = s.ambientLightColor.b;
     o.rng_seed = rngSeed;
     o.count_rays = countRays;
+    o.bucket_size = s.bucketSize;
     return o;
 }
 

@@ -173,7 +173,7 @@ struct Renderer {
                     int ey = std::min(rh, dy + 16);
                     for (int dx = 0; dx < rw; dx += 16) {
                         int ex = std::min(rw, dx + 16);
-                        Color c = renderPixelNoAA(r.x0 + dx, r.y0 + dy, ex - dx, ey - dy, /*tap=*/7);
+                        Color c = renderPixelNoAA(r.x0 + dx, r.y0 + dy, ex - dx, ey - dy);
                         for (int yy = r.y0 + dy; yy < r.y0 + ey; yy++)
                             for (int xx = r.x0 + dx; xx < r.x0 + ex; xx++) setPx(xx, yy, c);
                     }

@@ -226,11 +226,35 @@ def test_unsupported_features_are_errors_not_fallbacks():
     st.gi_enabled = 1
     assert api.lib.c2rt_render(g.device_scene(), C.byref(cam), C.byref(st), rgb.ctypes.data, None, None) == -2
     st.gi_enabled = 0
-    st.prepass_only = 1
-    assert api.lib.c2rt_render(g.device_scene(), C.byref(cam), C.byref(st), rgb.ctypes.data, None, None) == -2
-    st.prepass_only = 0
     assert api.lib.c2rt_render(g.device_scene(), C.byref(cam), C.byref(st), None, None, None) == -1
     assert api.lib.c2rt_render(g.device_scene(), C.byref(cam), C.byref(st), rgb.ctypes.data, None, None) == 0
+
+
+@pytest.mark.parametrize("scene,size,extra", [("lecture5.sdl", (200, 150), ""), ("lecture5.sdl", (97, 61), "bucketSize 40"),
+                                              ("zaphod.sdl", (130, 70), "")])
+def test_prepass_only_preview(scene, size, extra, tmp_path):
+    """prepassOnly (renderer.d:110-130): one sample per 16x16 block laid out inside each bucket, replicated."""
+    txt = open(os.path.join(SC, scene)).read()
+    txt = txt.replace('"floor.bmp"', '"%s/floor.bmp"' % SC).replace('"world.bmp"', '"%s/world.bmp"' % SC)
+    txt = txt.replace('"texture/zaphod.bmp"', '"%s/texture/zaphod.bmp"' % SC)
+    txt = txt.replace("prepassOnly         false", "").replace("prepassEnabled      false", "")
+    txt = txt.replace("GlobalSettings {", "GlobalSettings {\n    prepassOnly true\n    prepassEnabled true\n    %s\n" % extra, 1)
+    p = tmp_path / "prepass.sdl"
+    p.write_text(txt)
+    g, o = both(p, size)
+    rgb, argb, _ = g.render(argb=True, seed=5)
+    ref, _ = o.render(seed=5)
+    assert_parity(rgb, ref, argb, "prepassOnly " + scene)
+    # blocks really are constant
+    assert np.array_equal(rgb[0:8, 0:16], np.broadcast_to(rgb[0, 0], (8, 16, 3)))
+    # prepassOnly without prepassEnabled draws nothing: the caller's buffer keeps its contents
+    p2 = tmp_path / "nothing.sdl"
+    p2.write_text(txt.replace("prepassEnabled true", "prepassEnabled false"))
+    g2 = c2.HostScene(p2)
+    g2.set_frame_size(*size)
+    buf = np.full((size[1], size[0], 3), 7.0, np.float32)
+    g2.render(out=buf)
+    assert (buf == 7.0).all()
 
 
 def test_many_scenes_alive_and_scene_switching():
