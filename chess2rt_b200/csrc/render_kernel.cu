@@ -7,16 +7,20 @@
 //   isect_plane        rt/geometry.d:30-59
 //   isect_sphere       rt/geometry.d:92-125
 //   isect_cube         rt/geometry.d:172-235
-//   isect_csg          rt/geometry.d:271-332, :382-397; util/array.d:95-111 (shell sort)
+//   isect_csg          rt/geometry.d:271-332, :382-397; util/array.d:95-111 (shell sort) — closed form, primitive children
+//   isect_geom_lit     the same walk replayed literally for CSG nested inside CSG
 //   geom_inside        rt/geometry.d:25-28,127-130,165-170,334-337
-//   node_intersect     rt/node.d:23-49 + rt/transform.d:57-86
+//   node_intersect / generic_intersect   rt/node.d:23-49 + rt/transform.d:57-86
+//   cull_sphere        (no counterpart: conservative FP32 bounding-sphere rejection, one and two level)
 //   occluded           rt/scene.d:62-78 testVisibility
 //   sample_texture     rt/texture.d:36-54,77-86,116-126 + rt/bitmap.d:48-63
 //   shade              rt/shader.d:67-105 (Lambert), :197-250 (Phong)
 //   trace              rt/renderer.d:325-376 (+ rt/environment.d:7-10)
-//   render_pixel_body  rt/renderer.d:223-313 (renderPixelNoAA / renderPixelAA / renderSample*)
+//   render_sample      rt/renderer.d:254-313 (renderSampleDefault / renderSampleDof, stereo via color.d:10-15)
+//   render_frame_kernel rt/renderer.d:83-251 (renderRT: 1-spp + AA passes fused per pixel; prepassOnly preview)
+//   render_pixel_kernel rt/renderer.d:46-57 (renderPixel)
 //   pack_rgb32         rt/color.d:154-162,209-214
-// Geometry runs in FP64 and colour in FP32, as in the reference.
+// Decisions and coordinates run in FP64, colours in FP32 (precision plan below).
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
@@ -687,7 +691,7 @@ __device__ __forceinline__ float sin_f64arg(double a) {
     return __sinf((float)rr);
 }
 
-// (u, v) in FP64 for plane / cube hits; `uf, vf` is the FP32 pair for sphere hits (is_f32)
+// Texture lookup at (u, v): texture.d:36-54 (Checker), :77-86 (Procedure2), :116-126 + bitmap.d:48-63 (bitmap, bilinear)
 __device__ Col sample_texture(int ti, double u, double v) {
     const DevTex& t = c_scene.textures[ti];
     if (t.type == C2RT_TEX_CHECKER) {
