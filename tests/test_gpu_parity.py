@@ -257,6 +257,42 @@ def test_prepass_only_preview(scene, size, extra, tmp_path):
     assert (buf == 7.0).all()
 
 
+def test_degenerate_scenes(tmp_path):
+    """Empty node list, no lights, only a dark light, camera inside a CSG solid: still the oracle's image."""
+    cases = {
+        "empty": 'Scene { GlobalSettings { frameWidth 40; frameHeight 24 }\n Camera { pos 0 10 0; fov 90 } }',
+        "nolights": 'Scene { GlobalSettings { frameWidth 40; frameHeight 24; ambientLightColor 0.3 0.2 0.1 }\n Camera { pos 0 50 -80; pitch -20; fov 80 }\n'
+                    ' Geometries { Plane "f" { y 0 }; Sphere "s" { center 0 20 0; R 20 } }\n Shaders { Lambert "a" { color 1 0.5 0.25 } }\n'
+                    ' Nodes { Node "n0" { geometry "f"; shader "a" }; Node "n1" { geometry "s"; shader "a" } } }',
+        "darklight": 'Scene { GlobalSettings { frameWidth 40; frameHeight 24; ambientLightColor 0.1 0.1 0.1 }\n Camera { pos 0 50 -80; pitch -20; fov 80 }\n'
+                     ' Lights { PointLight "l" { pos 0 100 0; color 1 1 1; power 0 } }\n'
+                     ' Geometries { Plane "f" { y 0 } }\n Shaders { Phong "a" { color 1 0.5 0.25; exponent 10 } }\n Nodes { Node "n0" { geometry "f"; shader "a" } } }',
+        "inside": 'Scene { GlobalSettings { frameWidth 48; frameHeight 32; ambientLightColor 0.05 0.05 0.05 }\n Camera { pos 0 0 0; yaw 20; pitch 10; fov 100 }\n'
+                  ' Lights { PointLight "l" { pos 5 6 -4; color 1 1 1; power 900 } }\n'
+                  ' Geometries { Cube "c" { side 60 }; Sphere "s" { R 36 }; CsgInter "i" { left "c"; right "s" }; CsgDiff "d" { left "s"; right "c" } }\n'
+                  ' Shaders { Phong "a" { color 0.6 0.7 0.8; exponent 20 }; Lambert "b" { color 0.9 0.3 0.3 } }\n'
+                  ' Nodes { Node "n0" { geometry "i"; shader "a" }; Node "n1" { geometry "d"; shader "b"; scale 1.5 1.5 1.5 } } }',
+    }
+    for name, txt in cases.items():
+        p = tmp_path / (name + ".sdl")
+        p.write_text(txt)
+        g, o = both(p)
+        rgb, argb, st = g.render(argb=True, count_rays=True)
+        ref, ost = o.render()
+        assert_parity(rgb, ref, argb, name)
+        assert (st.primary_rays, st.shadow_rays) == (ost.primary_rays, ost.shadow_rays), name
+    assert np.all(c2.HostScene(tmp_path / "empty.sdl").render()[0] == 0)
+
+
+def test_capacity_limits_are_errors(tmp_path):
+    nodes = "".join('Node "n%d" { geometry "s"; shader "a"; translate %d 0 0 }; ' % (i, 3 * i) for i in range(65))
+    p = tmp_path / "many.sdl"
+    p.write_text('Scene { Camera { pos 0 0 -50; fov 60 }\n Geometries { Sphere "s" { R 1 } }\n Shaders { Lambert "a" { color 1 1 1 } }\n Nodes { %s } }' % nodes)
+    g = c2.HostScene(p)
+    with pytest.raises(c2.C2rtError, match="too many nodes"):
+        g.render()
+
+
 def test_many_scenes_alive_and_scene_switching():
     paths = ["lecture4.sdl", "lecture5.sdl", "lecture4-proc-texture.sdl"]
     gs = [c2.HostScene(os.path.join(SC, p)) for p in paths]
