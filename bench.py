@@ -406,6 +406,29 @@ def main():
             ms_graph, _ = run(graph)
             return ms_graph, kernel_ms, steps * self.launches_per_step, "CUDA graph replay (1 graph launch per step)"
 
+        def verify(self):
+            """(untimed) rank 0: the frame assembled from all ranks' bands equals, bit for bit, the same frame rendered by
+            rank 0 alone."""
+            if world == 1:
+                return None
+            self.render()
+            self.gather()
+            barrier()
+            if rank != 0:
+                return None
+            W, H = self.W, self.H
+            alone = torch.empty((H, W, 3), dtype=torch.float32, device="cuda")
+            c2.render_device(self.handle, self.cam, self.st, alone.data_ptr(), None, None, torch.cuda.current_stream().cuda_stream)
+            if self.mode == "p2p":
+                got = torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True)
+                api._check(api.lib.c2rt_frame_download(got.data_ptr(), self.peer_frame_ptr, H * W * 12, torch.cuda.current_stream().cuda_stream))
+                torch.cuda.synchronize()
+                same = bool(torch.equal(got, alone.cpu()))
+            else:
+                torch.cuda.synchronize()
+                same = bool(torch.equal(self.frame, alone))
+            return "bit-identical to the frame rendered by rank 0 alone" if same else "MISMATCH"
+
         def close(self):
             import ctypes as C
             if self.peer_frame_ptr:
@@ -433,6 +456,12 @@ def main():
         sampler.start()   # sampled from before the warm-up to the end of the e2e leg (a 1080p frame takes 0.16 ms:
                           # the timed loops alone are shorter than one nvidia-smi period)
     ms_per_step, kernel_ms, n_launches, launch_how = run.time_steps(args.steps, args.warmup, None)
+
+    frame_check = run.verify()
+    if world > 1:
+        dist.barrier()
+    if frame_check == "MISMATCH":
+        raise SystemExit("multi-GPU frame differs from the single-GPU frame")
 
     # ---- the scaling target of BASELINE.json (8K chessboard), measured beside the headline workload ----
     scaling_target = None
@@ -532,6 +561,7 @@ def main():
             "gpu_launches": n_launches,
             "clocks": clocks,
             "scaling_target": scaling_target,
+            "multi_gpu_frame_check": frame_check,
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
