@@ -363,6 +363,8 @@ int validate_and_build(const c2rt_scene_desc* d, c2rt_scene* s) {
         memcpy(t.c, d->tex_colors + 18 * i, 18 * sizeof(float));
         memcpy(t.d, d->tex_params + 6 * i, 6 * sizeof(double));
         if (t.type == C2RT_TEX_CHECKER) t.d[1] = 1.0 / t.d[0];
+        if (t.type == C2RT_TEX_PROCEDURE2)   // frequencies in revolutions per unit (render_kernel.cu sin_rev)
+            for (int k = 0; k < 6; k++) t.d[k] /= 6.283185307179586476925;
         if (t.type == C2RT_TEX_BITMAP) {
             t.w = d->tex_width[i]; t.h = d->tex_height[i];
             if (t.w <= 0 || t.h <= 0) return fail(C2RT_ERR_INVALID_ARG, "texture %u: empty bitmap", i);
@@ -476,6 +478,25 @@ int validate_and_build(const c2rt_scene_desc* d, c2rt_scene* s) {
         if (h.nodes[i].kind == KIND_GENERIC) s->mode |= 2;        // MODE_GENERIC
         const DevGeom& ng = h.geoms[h.nodes[i].geom];
         if (ng.type >= C2RT_GEOM_CSG_UNION && ng.pad != 1) s->mode |= 4 | 2 | 1;  // MODE_NESTED (implies the generic, bounded kernel)
+    }
+    // MODE_SOLO: exactly one node, a world-space plane, and exactly one light.  The node's shader and that shader's
+    // texture are swapped into record 0 so the kernel addresses every scene constant statically.
+    const char* no_solo = getenv("C2RT_NO_SOLO");   // test hook: keep such scenes on the general plane-only kernel
+    if (s->mode == 0 && h.n_nodes == 1 && h.n_lights == 1 && h.nodes[0].kind == KIND_PLANE_W && !(no_solo && no_solo[0] == '1')) {
+        const int si = h.nodes[0].shader;
+        std::swap(h.shaders[0], h.shaders[si]);
+        h.nodes[0].shader = 0;
+        const int ti = h.shaders[0].tex;
+        if (ti >= 0) {
+            std::swap(h.textures[0], h.textures[ti]);
+            std::swap(s->tex_offset[0], s->tex_offset[ti]);
+            for (int k = 0; k < h.n_shaders; k++) {
+                if (h.shaders[k].tex == 0) h.shaders[k].tex = ti;
+                else if (h.shaders[k].tex == ti) h.shaders[k].tex = 0;
+            }
+        }
+        s->mode = MODE_SOLO | ((h.shaders[0].tex >= 0 ? 1 + h.textures[0].type : 0) << MODE_TEX_SHIFT) |
+                  (h.shaders[0].type == C2RT_SHADER_PHONG ? MODE_PHONG : 0);
     }
     return C2RT_OK;
 }

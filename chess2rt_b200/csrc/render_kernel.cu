@@ -32,14 +32,6 @@ __constant__ DevScene c_scene;
 __constant__ double c_tap_x[5] = {0.0, 0.3, 0.6, 0.0, 0.6};  // renderer.d:235-242
 __constant__ double c_tap_y[5] = {0.0, 0.3, 0.0, 0.6, 0.6};
 
-// Kernel specialisations by scene class (chosen at scene-create time, c2rt_api.cu):
-//   MODE_BOUNDED  some node has a finite bounding sphere -> FP32 ray shadow + conservative cull
-//   MODE_GENERIC  some node needs the object-space path (non-identity transform, CSG, bounded plane)
-//   MODE_NESTED   some CSG has a CSG child -> literal emulation of the reference's recursive walk
-//   MODE_CLUSTERS the scene-create partition found runs of nodes worth a common bounding sphere (two-level cull)
-//   MODE_SAMPLING the CAMERA asks for depth of field and/or stereo: several rays per sample (chosen per frame)
-constexpr int MODE_BOUNDED = 1, MODE_GENERIC = 2, MODE_NESTED = 4, MODE_CLUSTERS = 8, MODE_SAMPLING = 16;
-
 // Precision plan: FP64 carries everything a pixel DECISION or a texture coordinate
 // depends on — ray direction, hit distances, hit points, plane/cube uv, checker cells, face-forward
 // sign, CSG crossing order.  FP32 carries what is continuous and ends in an FP32 colour anyway —
@@ -610,8 +602,8 @@ __device__ __forceinline__ bool node_exact(int ni, const DevNode& nd, const Ray&
     int face = 0;
     bool hit;
     double px, py, pz;   // world-space kinds: the hit point is o + d * dist, recomputed for the winning hit only (surface_of)
-    // MODE 0: no bounded and no generic node exists, i.e. every node is a world-space plane
-    if (MODE == 0 || nd.kind == KIND_PLANE_W) hit = isect_plane(nd.wp[0], CUDART_NAN, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, px, py, pz);
+    // plane-only scene classes: no bounded and no generic node exists, i.e. every node is a world-space plane
+    if (plane_only(MODE) || nd.kind == KIND_PLANE_W) hit = isect_plane(nd.wp[0], CUDART_NAN, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, px, py, pz);
     else if ((MODE & MODE_BOUNDED) && nd.kind == KIND_SPHERE_W) hit = isect_sphere(nd.wp, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, px, py, pz);
     else if ((MODE & MODE_BOUNDED) && nd.kind == KIND_CUBE_W) hit = isect_cube(nd.wp, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, px, py, pz, face);
     else if (MODE & MODE_GENERIC) return generic_intersect<MODE>(ni, r, h);
@@ -647,7 +639,7 @@ __device__ __forceinline__ bool occluded(double fx, double fy, double fz, double
     HitRec h;
     const int ncl = (MODE & MODE_CLUSTERS) ? c_scene.n_clusters : 1;
     for (int ci = 0; ci < ncl; ci++) {
-        int begin = 0, end = c_scene.n_nodes;
+        int begin = 0, end = (MODE & MODE_SOLO) ? 1 : c_scene.n_nodes;
         if (MODE & MODE_CLUSTERS) {
             const DevCluster& cl = c_scene.clusters[ci];
             if (cl.end - cl.begin > 1 && cull_sphere(cl.c[0], cl.c[1], cl.c[2], cl.r, cl.r2, cl.clen, r, tmaxf)) continue;
@@ -655,8 +647,8 @@ __device__ __forceinline__ bool occluded(double fx, double fy, double fz, double
         }
 #pragma unroll 1
         for (int i = begin; i < end; i++) {
-            const DevNode& nd = c_scene.nodes[i];
-            if (MODE == 0 || nd.kind == KIND_PLANE_W) {
+            const DevNode& nd = c_scene.nodes[(MODE & MODE_SOLO) ? 0 : i];
+            if (plane_only(MODE) || nd.kind == KIND_PLANE_W) {
                 // implied by geometry.d:35-36 (dir.y has the sign of D.y): the common "light above the floor" case
                 const double y = nd.wp[0];
                 if ((fy > y && Dy >= 0) || (fy < y && Dy <= 0)) continue;
@@ -681,31 +673,40 @@ __device__ __forceinline__ int cast_int_x86(double v) {  // cvttsd2si: out of ra
     return (int)v;
 }
 
-// sin(a) for an FP64 argument: Cody-Waite reduction to [-pi, pi] in FP64, then the FP32 SFU sine
-// (|abs err| < 5e-7).  The reference takes sin in FP64 and narrows to float (texture.d:82-83).
-__device__ __forceinline__ float sin_f64arg(double a) {
-    const double MAGIC = 6755399441055744.0;                      // 1.5 * 2^52: adding it rounds to the nearest integer
-    const double k = fma(a, 0.15915494309189535, MAGIC) - MAGIC;  // nearest multiple of 2pi
-    double rr = fma(-k, 6.283185307179586, a);
-    rr = fma(-k, 2.4492935982947064e-16, rr);
-    return __sinf((float)rr);
+// sin(2 pi u f) for FP64 u and f = frequency / 2 pi (folded at scene create): the product is reduced to a
+// fraction of a revolution in FP64 — fma(u, f, MAGIC) rounds u f to the nearest integer k, a second fma
+// gives u f - k with a single rounding — then the FP32 SFU sine (|abs err| < 2e-6).  The reference takes
+// sin(u * frequency) in FP64 and narrows to float (texture.d:82-83).  The fraction is biased by +1 into
+// [0.5, 1.5] so its FP64 -> FP32 conversion can be a truncating bit shuffle on the ALU pipe: F2F shares the
+// quarter-rate XU pipe with MUFU.SIN, which this texture keeps busy.
+__device__ __forceinline__ float sin_rev(double u, double f) {
+    const double MAGIC = 6755399441055744.0;                      // 1.5 * 2^52
+    const double k1 = fma(u, f, MAGIC) - (MAGIC + 1.0);           // nearest integer - 1, exact
+    const double fr = fma(u, f, -k1);
+    const unsigned hi = (unsigned)__double2hiint(fr), lo = (unsigned)__double2loint(fr);
+    const float x = __uint_as_float(__funnelshift_l(lo, hi - 0x38000000u, 3));   // exponent rebias 1023 -> 127, top 23 mantissa bits
+    return __sinf(x * 6.2831853f);
 }
 
 // Texture lookup at (u, v): texture.d:36-54 (Checker), :77-86 (Procedure2), :116-126 + bitmap.d:48-63 (bitmap, bilinear)
-__device__ Col sample_texture(int ti, double u, double v) {
-    const DevTex& t = c_scene.textures[ti];
-    if (t.type == C2RT_TEX_CHECKER) {
+// MODE_SOLO: the texture is record 0 and its kind is a template constant
+template <int MODE>
+__device__ __forceinline__ Col sample_texture(int ti, double u, double v) {
+    constexpr bool SOLO = (MODE & MODE_SOLO) != 0;
+    const DevTex& t = c_scene.textures[SOLO ? 0 : ti];
+    const int type = SOLO ? ((MODE & MODE_TEX_MASK) >> MODE_TEX_SHIFT) - 1 : t.type;
+    if (type == C2RT_TEX_CHECKER) {
         int x = cast_int_x86(floor(u * t.d[1]));
         int y = cast_int_x86(floor(v * t.d[1]));
         int white = (int)((unsigned)x + (unsigned)y) % 2;
         return white ? mkcol(t.c[3], t.c[4], t.c[5]) : mkcol(t.c[0], t.c[1], t.c[2]);
     }
-    if (t.type == C2RT_TEX_PROCEDURE2) {
+    if (type == C2RT_TEX_PROCEDURE2) {
         Col res = mkcol(0.f, 0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 3; i++) {
-            float su = sin_f64arg(u * t.d[i]);
-            float sv = sin_f64arg(v * t.d[3 + i]);
+            float su = sin_rev(u, t.d[i]);
+            float sv = sin_rev(v, t.d[3 + i]);
             res.r += t.c[3 * i + 0] * su + t.c[9 + 3 * i + 0] * sv;
             res.g += t.c[3 * i + 1] * su + t.c[9 + 3 * i + 1] * sv;
             res.b += t.c[3 * i + 2] * su + t.c[9 + 3 * i + 2] * sv;
@@ -775,10 +776,20 @@ __device__ __forceinline__ void local_surface(int type, const double* c, const H
 }
 
 // `ray` == nullptr: hin.p is already complete (debug pixel pick)
+template <int MODE>
 __device__ __forceinline__ void surface_of(const HitRec& hin, const Ray* ray, bool need_uv, Surface& s) {
-    const DevNode& nd = c_scene.nodes[hin.node];
-    const DevGeom& g = c_scene.geoms[hin.leaf];
+    const DevNode& nd = c_scene.nodes[(MODE & MODE_SOLO) ? 0 : hin.node];
     HitRec h = hin;
+    if (plane_only(MODE)) {   // every node is a world-space plane: normal (0, 1, 0), uv = object-space x, z (geometry.d:49-55)
+        if (ray) { h.px = fma(ray->dx, h.dist, ray->ox); h.py = fma(ray->dy, h.dist, ray->oy); h.pz = fma(ray->dz, h.dist, ray->oz); }
+        s.gx = 0; s.gy = 1; s.gz = 0;
+        s.u = (h.px - nd.off[0]) * nd.wp[1];
+        s.v = (h.pz - nd.off[2]) * nd.wp[2];
+        s.px = h.px; s.py = h.py; s.pz = h.pz;
+        s.nx = 0.f; s.ny = 1.f; s.nz = 0.f;
+        return;
+    }
+    const DevGeom& g = c_scene.geoms[hin.leaf];
     if (nd.kind != KIND_GENERIC) {
         // world-space fast path: the hit point is o + d * dist (exactly what the intersector computed), nd.wp the pre-offset parameters
         if (ray) { h.px = fma(ray->dx, h.dist, ray->ox); h.py = fma(ray->dy, h.dist, ray->oy); h.pz = fma(ray->dz, h.dist, ray->oz); }
@@ -812,21 +823,28 @@ __device__ __forceinline__ void surface_of(const HitRec& hin, const Ray* ray, bo
 
 template <int MODE>
 __device__ __forceinline__ Col shade(const FrameParams& fp, const Ray& ray, const HitRec& h, unsigned& n_shadow) {
-    const DevShader& sh = c_scene.shaders[c_scene.nodes[h.node].shader];
+    constexpr bool SOLO = (MODE & MODE_SOLO) != 0;
+    const DevShader& sh = c_scene.shaders[SOLO ? 0 : c_scene.nodes[h.node].shader];
+    const bool has_tex = SOLO ? (MODE & MODE_TEX_MASK) != 0 : sh.tex >= 0;
     Surface s;
-    surface_of(h, &ray, sh.tex >= 0, s);
+    surface_of<MODE>(h, &ray, has_tex, s);
     // faceforward (imported_types.d:69-73): the sign decision in FP64, the vector itself in FP32
     float Nx = s.nx, Ny = s.ny, Nz = s.nz;
-    if (!(dot3(ray.dx, ray.dy, ray.dz, s.gx, s.gy, s.gz) < 0)) { Nx = -Nx; Ny = -Ny; Nz = -Nz; }
-    Col diffuse = sh.tex >= 0 ? sample_texture(sh.tex, s.u, s.v) : mkcol(sh.color[0], sh.color[1], sh.color[2]);
+    // (plane-only scene classes: the geometric normal is (0, 1, 0), the dot product is ray.dy)
+    const bool facing = plane_only(MODE) ? ray.dy < 0 : dot3(ray.dx, ray.dy, ray.dz, s.gx, s.gy, s.gz) < 0;
+    if (!facing) { Nx = -Nx; Ny = -Ny; Nz = -Nz; }
+    Col diffuse = has_tex ? sample_texture<MODE>(sh.tex, s.u, s.v) : mkcol(sh.color[0], sh.color[1], sh.color[2]);
     Col lightContrib = mkcol(fp.ambient[0], fp.ambient[1], fp.ambient[2]);
     Col specular = mkcol(0.f, 0.f, 0.f);
-    const bool phong = sh.type == C2RT_SHADER_PHONG;
-    const int nl = c_scene.n_lights;
+    const bool phong = SOLO ? (MODE & MODE_PHONG) != 0 : sh.type == C2RT_SHADER_PHONG;
+    const int nl = SOLO ? 1 : c_scene.n_lights;
     // shadow-ray origin p + N * 1e-6 (shader.d:88,219)
-    const double fx = s.px + (double)Nx * 1e-6, fy = s.py + (double)Ny * 1e-6, fz = s.pz + (double)Nz * 1e-6;
+    // (plane-only scene classes: N = (0, +-1, 0), the x and z terms add an exact zero)
+    const double fx = plane_only(MODE) ? s.px : s.px + (double)Nx * 1e-6;
+    const double fy = plane_only(MODE) ? s.py + (facing ? 1e-6 : -1e-6) : s.py + (double)Ny * 1e-6;
+    const double fz = plane_only(MODE) ? s.pz : s.pz + (double)Nz * 1e-6;
     for (int li = 0; li < nl; li++) {
-        const DevLight& L = c_scene.lights[li];
+        const DevLight& L = c_scene.lights[SOLO ? 0 : li];
         // one sample per PointLight (light.d:56-59): avg / numSamples is a division by 1.0f
         if (!L.lit) continue;
         n_shadow++;
@@ -838,7 +856,7 @@ __device__ __forceinline__ Col shade(const FrameParams& fp, const Ray& ray, cons
         const float rs = rsqrtf(d2);
         const float lx = (float)Dx * rs, ly = (float)Dy * rs, lz = (float)Dz * rs;
         const float inv_d2 = rs * rs;
-        const float cosTheta = dot3f(lx, ly, lz, Nx, Ny, Nz);
+        const float cosTheta = plane_only(MODE) ? (facing ? ly : -ly) : dot3f(lx, ly, lz, Nx, Ny, Nz);
         const float br = L.color[0] * inv_d2, bg = L.color[1] * inv_d2, bb = L.color[2] * inv_d2;
         if (cosTheta > 0) {
             lightContrib.r = fmaf(br, cosTheta, lightContrib.r);
@@ -882,7 +900,8 @@ __device__ __forceinline__ Col trace(const FrameParams& fp, const Ray& ray, unsi
     h.node = -1;
     float tmaxf = CUDART_INF_F;
     const int ncl = (MODE & MODE_CLUSTERS) ? c_scene.n_clusters : 1;
-    for (int ci = 0; ci < ncl; ci++) {
+    if (MODE & MODE_SOLO) node_intersect<MODE>(0, ray, h, tmaxf);
+    else for (int ci = 0; ci < ncl; ci++) {
         int begin = 0, end = c_scene.n_nodes;
         if (MODE & MODE_CLUSTERS) {
             const DevCluster& cl = c_scene.clusters[ci];
@@ -1076,7 +1095,7 @@ __global__ void render_pixel_kernel(const FrameParams fp, int x, int y, PixelOut
     out->dist = h.dist;
     if (h.node >= 0) {
         Surface w;
-        surface_of(h, nullptr, true, w);
+        surface_of<MODE_BOUNDED | MODE_GENERIC>(h, nullptr, true, w);
         out->p[0] = w.px; out->p[1] = w.py; out->p[2] = w.pz;
         double gx = w.gx, gy = w.gy, gz = w.gz;
         normalize3(gx, gy, gz);
@@ -1155,12 +1174,38 @@ cudaError_t upload_scene(const DevScene& s, cudaStream_t st) {
 #ifndef C2RT_MINBLOCKS_FULL
 #define C2RT_MINBLOCKS_FULL 5
 #endif
+#ifndef C2RT_MINBLOCKS_SOLO
+#define C2RT_MINBLOCKS_SOLO 7
+#endif
+#ifndef C2RT_MINBLOCKS_SOLO_SAMPLING
+#define C2RT_MINBLOCKS_SOLO_SAMPLING 6
+#endif
+
+// MODE_SOLO scene classes: texture kind x shader kind, each with and without the DOF / stereo sampling loop
+template <int TEXK, int PH>
+static void launch_solo(const FrameParams& fp, bool sampling, dim3 grid, cudaStream_t st) {
+    constexpr int M = MODE_SOLO | (TEXK << MODE_TEX_SHIFT) | (PH ? MODE_PHONG : 0);
+    if (sampling) render_frame_kernel<M | MODE_SAMPLING, C2RT_MINBLOCKS_SOLO_SAMPLING><<<grid, BLOCK_THREADS, 0, st>>>(fp);
+    else render_frame_kernel<M, C2RT_MINBLOCKS_SOLO><<<grid, BLOCK_THREADS, 0, st>>>(fp);
+}
 
 cudaError_t launch_frame(const FrameParams& fp, int mode, uint32_t local_tile_rows, cudaStream_t st) {
     if (local_tile_rows == 0) return cudaSuccess;
     dim3 grid((fp.W + TILE_W - 1) / TILE_W, local_tile_rows);
     constexpr int FULL = MODE_BOUNDED | MODE_GENERIC, ALL = FULL | MODE_NESTED | MODE_CLUSTERS;
-    if (fp.dof || fp.stereo_sep != 0 || fp.prepass_bucket) {
+    const bool sampling = fp.dof || fp.stereo_sep != 0 || fp.prepass_bucket;
+    if (mode & MODE_SOLO) {
+        switch (((mode & MODE_TEX_MASK) >> MODE_TEX_SHIFT) | ((mode & MODE_PHONG) ? 4 : 0)) {
+            case 0: launch_solo<0, 0>(fp, sampling, grid, st); break;
+            case 1: launch_solo<1, 0>(fp, sampling, grid, st); break;
+            case 2: launch_solo<2, 0>(fp, sampling, grid, st); break;
+            case 3: launch_solo<3, 0>(fp, sampling, grid, st); break;
+            case 4: launch_solo<0, 1>(fp, sampling, grid, st); break;
+            case 5: launch_solo<1, 1>(fp, sampling, grid, st); break;
+            case 6: launch_solo<2, 1>(fp, sampling, grid, st); break;
+            default: launch_solo<3, 1>(fp, sampling, grid, st); break;
+        }
+    } else if (sampling) {
         // DOF / stereo / prepass-only frames: two general kernels only (the per-sample loop dominates, the scene class matters less)
         if (mode & (MODE_NESTED | MODE_CLUSTERS)) render_frame_kernel<ALL | MODE_SAMPLING, 2><<<grid, BLOCK_THREADS, 0, st>>>(fp);
         else render_frame_kernel<FULL | MODE_SAMPLING, C2RT_MINBLOCKS_SAMPLING><<<grid, BLOCK_THREADS, 0, st>>>(fp);

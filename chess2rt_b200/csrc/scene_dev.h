@@ -48,7 +48,7 @@ struct DevShader {
 };
 
 struct DevTex {
-    double d[6];      // checker: size, 1/size | procedure2: freqU[3], freqV[3] | bitmap: scaling
+    double d[6];      // checker: size, 1/size | procedure2: freqU[3] / 2pi, freqV[3] / 2pi | bitmap: scaling
     float c[18];      // checker: color1, color2 | procedure2: colorU[3][3], colorV[3][3]
     int type, w, h, pad;
     const float4* texels;  // bitmap only
@@ -104,6 +104,24 @@ struct FrameParams {
     unsigned long long* counters;     // [0] primary, [1] shadow
     const uint8_t* lut;               // 4097-entry sRGB table
 };
+
+// Kernel specialisations by scene class (chosen at scene-create time, c2rt_api.cu):
+//   MODE_BOUNDED  some node has a finite bounding sphere -> FP32 ray shadow + conservative cull
+//   MODE_GENERIC  some node needs the object-space path (non-identity transform, CSG, bounded plane)
+//   MODE_NESTED   some CSG has a CSG child -> literal emulation of the reference's recursive walk
+//   MODE_CLUSTERS the scene-create partition found runs of nodes worth a common bounding sphere (two-level cull)
+//   MODE_SAMPLING the CAMERA asks for depth of field and/or stereo: several rays per sample (chosen per frame)
+//   MODE_SOLO     one world-space plane node and one light (lecture4*, zaphod): node / shader / texture / light records
+//                 sit at index 0 (c2rt_api.cu moves them there), so every scene constant is read through a static
+//                 c[3][imm] operand instead of an indexed LDC, no loop survives, and the texture kind
+//                 (MODE_TEX_SHIFT: 0 none, 1 + C2RT_TEX_*) and shader kind (MODE_PHONG) are compile-time
+constexpr int MODE_BOUNDED = 1, MODE_GENERIC = 2, MODE_NESTED = 4, MODE_CLUSTERS = 8, MODE_SAMPLING = 16;
+constexpr int MODE_SOLO = 32, MODE_TEX_SHIFT = 6, MODE_TEX_MASK = 3 << MODE_TEX_SHIFT, MODE_PHONG = 256;
+// every node is a world-space plane (KIND_PLANE_W): no bounded and no generic node exists
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+constexpr bool plane_only(int mode) { return (mode & (MODE_BOUNDED | MODE_GENERIC | MODE_NESTED | MODE_CLUSTERS)) == 0; }
 
 constexpr int TILE_W = 16;
 constexpr int TILE_H = 8;

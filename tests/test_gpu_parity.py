@@ -89,6 +89,62 @@ def test_closed_form_csg_equals_literal_walk(name, size, monkeypatch):
     assert np.abs(fast - lit).max() < 1e-5
 
 
+SOLO_SCENE = """Scene {{
+  GlobalSettings {{ frameWidth 322; frameHeight 203; ambientLightColor 0.03 0.02 0.04; prepassEnabled false }}
+  Camera {{ pos 3 {camy} -20; yaw 12; pitch {pitch}; roll 4; fov 80{cam_extra} }}
+  Lights {{ PointLight "l" {{ pos -40 {lighty} 90; color 1 0.9 0.8; power 30000 }} }}
+  Geometries {{ Plane "floor" {{ y 1.5 }} }}
+  Textures {{
+    Checker "decoy" {{ color1 1 0 0; color2 0 1 0; size 2 }}
+    BitmapTexture "decoy2" {{ file "{root}/scenes/world.bmp" }}
+    Checker "chk" {{ color1 0.1 0.2 0.1; color2 0.9 0.6 0.2; size 7 }}
+    Procedure2 "proc" {{
+      freqU 0.3 0.11 0.05
+      freqV 0.07 0.4 0.13
+      colorU {{ color 0.4 0.1 0.2; color 0.2 0.3 0.1; color 0.1 0.2 0.4 }}
+      colorV {{ color 0.1 0.3 0.3; color 0.3 0.1 0.1; color 0.2 0.2 0.2 }}
+    }}
+    BitmapTexture "bmp" {{ file "{root}/scenes/floor.bmp"; scaling 0.02; assumedGamma 1.8 }}
+  }}
+  Shaders {{
+    Lambert "decoy_shader" {{ color 0 0 1; texture "decoy" }}
+    Phong "decoy_shader2" {{ color 0 1 1; exponent 5 }}
+    {shader} "s" {{ color 0.7 0.5 0.3{tex}{shader_extra} }}
+  }}
+  Nodes {{ Node "n" {{ geometry "floor"; shader "s"{node_extra} }} }}
+}}
+"""
+
+
+@pytest.mark.parametrize("shader", ["Lambert", "Phong"])
+@pytest.mark.parametrize("tex", [None, "chk", "proc", "bmp"])
+@pytest.mark.parametrize("variant", ["plain", "below_scaled", "dof"])
+def test_solo_scene_class_kernels(shader, tex, variant, tmp_path, monkeypatch):
+    """One plane + one light scenes run on the MODE_SOLO kernels (scene constants at static addresses, texture and shader
+    kind compiled in; the node's shader / texture are moved to record 0 at scene create).  Each of the 8 kinds, with and
+    without the sampling loop, against the oracle and against the general plane-only kernel (C2RT_NO_SOLO=1)."""
+    text = SOLO_SCENE.format(
+        root=ROOT, shader=shader, tex=f'; texture "{tex}"' if tex else "",
+        shader_extra="; exponent 24; strength 0.8" if shader == "Phong" else "",
+        camy=-60 if variant == "below_scaled" else 45, pitch=25 if variant == "below_scaled" else -22,
+        lighty=-80 if variant == "below_scaled" else 70,    # camera and light under the plane: the face-forward flip
+        node_extra="; scale 3 2 0.5; translate 4 1 -6" if variant == "below_scaled" else "",
+        cam_extra="; dof true; numSamples 3; focalPlaneDist 60; fNumber 4" if variant == "dof" else "")
+    path = tmp_path / "solo.sdl"
+    path.write_text(text)
+    g, o = both(str(path))
+    rgb, argb, st = g.render(argb=True, seed=5, count_rays=True)
+    ref, ost = o.render(seed=5)
+    assert ref.max() > 0.05
+    assert_parity(rgb, ref, argb, f"solo {shader} {tex} {variant}")
+    assert (st.primary_rays, st.shadow_rays) == (ost.primary_rays, ost.shadow_rays)
+    monkeypatch.setenv("C2RT_NO_SOLO", "1")   # read at scene-create time
+    general = c2.HostScene(str(path))
+    rgb2, _, st2 = general.render(seed=5, count_rays=True)
+    assert (st2.primary_rays, st2.shadow_rays) == (st.primary_rays, st.shadow_rays)
+    assert np.abs(rgb - rgb2).max() < 1e-5
+
+
 def test_golden_fixtures():
     meta = json.load(open(os.path.join(GOLD, "golden.json")))
     for name, m in meta.items():
