@@ -38,7 +38,8 @@ class Settings(C.Structure):
     _fields_ = [("frame_width", C.c_uint32), ("frame_height", C.c_uint32), ("aa_enabled", C.c_int32),
                 ("gi_enabled", C.c_int32), ("prepass_enabled", C.c_int32), ("prepass_only", C.c_int32),
                 ("max_trace_depth", C.c_uint32), ("ambient_light", C.c_float * 3), ("rng_seed", C.c_uint64),
-                ("count_rays", C.c_int32), ("bucket_size", C.c_uint32)]
+                ("count_rays", C.c_int32), ("bucket_size", C.c_uint32),
+                ("paths_per_pixel", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class Band(C.Structure):

@@ -396,6 +396,7 @@ int validate_and_build(const c2rt_scene_desc* d, c2rt_scene* s) {
         for (int k = 0; k < 3; k++) L.color[k] = d->light_color[3 * i + k] * pw;
         float intensity = (L.color[0] + L.color[1] + L.color[2]) / 3;  // color.d:141-144
         L.lit = intensity != 0;
+        for (int k = 0; k < 3; k++) L.posf[k] = (float)L.pos[k];
     }
     for (uint32_t i = 0; i < d->n_nodes; i++) {
         DevNode& nd = h.nodes[i];
@@ -530,7 +531,11 @@ int check_frame_args(const c2rt_scene* s, const c2rt_camera* cam, const c2rt_set
     if (set->frame_width == 0 || set->frame_height == 0 || set->frame_width > 65536 || set->frame_height > 65536)
         return fail(C2RT_ERR_INVALID_ARG, "bad frame size %ux%u", set->frame_width, set->frame_height);
     if (cam->frame_width == 0 || cam->frame_height == 0) return fail(C2RT_ERR_INVALID_ARG, "camera frame size is zero (setFrameSize not called)");
-    if (set->gi_enabled) return fail(C2RT_ERR_UNSUPPORTED, "GIEnabled (path tracing) is outside the hot-path scope");
+    if (set->gi_enabled && !cam->dof)   // renderer.d:256-263: the DOF branch is tested first and ignores GIEnabled
+        for (int i = 0; i < s->host.n_nodes; i++)
+            if (s->host.shaders[s->host.nodes[i].shader].type == C2RT_SHADER_PHONG)
+                return fail(C2RT_ERR_UNSUPPORTED, "GIEnabled with a Phong-shaded node: Phong.spawnRay / eval are assert(0) in the reference "
+                                                  "(shader.d:252-262), it halts as soon as a path reaches that node");
     if (!std::isfinite(cam->stereo_separation)) return fail(C2RT_ERR_INVALID_ARG, "stereoSeparation is not finite");
     if (cam->dof && cam->num_samples == 0) return fail(C2RT_ERR_INVALID_ARG, "DOF camera with numSamples == 0");
     return C2RT_OK;
@@ -564,6 +569,10 @@ void fill_params(FrameParams& fp, const c2rt_camera* cam, const c2rt_settings* s
     fp.num_samples = cam->num_samples;
     fp.max_trace_depth = set->max_trace_depth;
     fp.count_rays = set->count_rays != 0;
+    // GI frame (renderer.d:289-301,378-463): every path returns exactly black — PointLight.solidAngle is 0 (light.d:72-75) so
+    // resultDirect is 0, lights cannot be hit, misses read the black environment — and the pixel is the mean of pathsPerPixel zeros
+    fp.gi = set->gi_enabled && !cam->dof;
+    fp.gi_fill = set->paths_per_pixel ? 0.f : nanf("");
     fp.prepass_bucket = set->prepass_only ? (set->bucket_size ? set->bucket_size : 48u) : 0u;
     fp.n_ranks = 1;
     fp.tiles_per_band = 1;
@@ -953,6 +962,8 @@ int c2rt_render_pixel(c2rt_scene* s, const c2rt_camera* cam, const c2rt_settings
     int rc = check_frame_args(s, cam, set);
     if (rc) return rc;
     if (!rgb) return fail(C2RT_ERR_INVALID_ARG, "rgb is null");
+    if (set->gi_enabled && !cam->dof)
+        return fail(C2RT_ERR_UNSUPPORTED, "pixel pick on a GI frame: the reference's lastTracingResult is the last random path segment");
     if (x < 0 || y < 0 || (uint32_t)x >= set->frame_width || (uint32_t)y >= set->frame_height)
         return fail(C2RT_ERR_INVALID_ARG, "pixel (%d,%d) outside the %ux%u frame", x, y, set->frame_width, set->frame_height);
     std::lock_guard<std::mutex> g(g_mu);

@@ -40,7 +40,8 @@ __constant__ double c_tap_y[5] = {0.0, 0.3, 0.0, 0.6, 0.6};
 // MUFU seed + Newton steps below instead of the IEEE library sequences (|rel err| < 4e-16).
 
 struct Ray {
-    double ox, oy, oz, dx, dy, dz;   // d is unit (to ~1e-16)
+    double ox, oy, oz, dx, dy, dz;   // d is unit (to ~1e-16) — except camera rays of the plane-only scene classes, see l2
+    double l2;                       // plane-only scene classes: camera rays keep the UN-normalised direction, l2 = |d|^2 (gen_ray)
     float fox, foy, foz, fdx, fdy, fdz, olen;  // FP32 shadow of the ray for the conservative cull
 };
 
@@ -131,8 +132,39 @@ __device__ __forceinline__ uint32_t rng_u31(unsigned long long seed, uint32_t px
 }
 __device__ __forceinline__ double uniform01(const FrameParams& fp, uint32_t px, uint32_t py, uint32_t tap, uint32_t sample,
                                             uint32_t& draw) {
-    double r = (double)rng_u31(fp.seed, px, py, tap, sample, draw++);
+    // u31 -> double through the 2^52 mantissa trick (one DADD; I2F.F64 would go through the quarter-rate XU pipe)
+    const double r = __hiloint2double(0x43300000, (int)rng_u31(fp.seed, px, py, tap, sample, draw++)) - 4503599627370496.0;
     return r * (1.0 / 2147483647.0);
+}
+
+// sin(2 pi u), cos(2 pi u) for u in [0, 1] in FP64 (|err| < 3e-16): quadrant by the 2^52 rounding trick, then the
+// classic degree-13 / degree-14 minimax kernels on |t| <= pi/4.  Replaces sincos(u * 2 pi) of camera.d:260-263, whose
+// library form spends most of its ~75 instructions on argument ranges a unit-interval input cannot reach.
+__device__ __forceinline__ void sincos_rev(double u, double& s, double& c) {
+    const double MAGIC = 6755399441055744.0;            // 1.5 * 2^52
+    const double qm = fma(u, 4.0, MAGIC);               // nearest integer to 4u in the low mantissa bits
+    const int q = __double2loint(qm);
+    const double r = fma(qm - MAGIC, -0.25, u);         // exact: u - q/4 in [-1/8, 1/8]
+    const double t = r * 6.283185307179586476925;
+    const double z = t * t;
+    double ps = 1.58969099521155010221e-10;
+    ps = fma(ps, z, -2.50507602534068634195e-08);
+    ps = fma(ps, z, 2.75573137070700676789e-06);
+    ps = fma(ps, z, -1.98412698298579493134e-04);
+    ps = fma(ps, z, 8.33333333332248946124e-03);
+    ps = fma(ps, z, -1.66666666666666324348e-01);
+    const double st = fma(t * z, ps, t);
+    double pc = -1.13596475577881948265e-11;
+    pc = fma(pc, z, 2.08757232129817482790e-09);
+    pc = fma(pc, z, -2.75573143513906633035e-07);
+    pc = fma(pc, z, 2.48015872894767294178e-05);
+    pc = fma(pc, z, -1.38888888888741095749e-03);
+    pc = fma(pc, z, 4.16666666666666019037e-02);
+    const double ct = fma(z * z, pc, fma(z, -0.5, 1.0));
+    // quadrant q mod 4: (s, c), (c, -s), (-s, -c), (-c, s)
+    const double a = (q & 1) ? ct : st, b = (q & 1) ? st : ct;
+    s = (q & 2) ? -a : a;
+    c = ((q + 1) & 2) ? -b : b;
 }
 
 // ---------------------------------------------------------------- camera
@@ -151,20 +183,25 @@ __device__ __forceinline__ void screen_dir(const FrameParams& fp, double x, doub
 template <int MODE>
 __device__ __forceinline__ void gen_ray(const FrameParams& fp, double vx, double vy, double vz, uint32_t px, uint32_t py, uint32_t tap,
                                         uint32_t sample, uint32_t& draw, int eye, Ray& r) {
+    // Plane-only scene classes keep camera rays UN-normalised: a plane hit o + d t and the closest-hit order do not
+    // depend on |d| (all planes see the same parametrisation), the 1e-9 grazing thresholds of geometry.d:35-36 are
+    // applied to d.y^2 / |d|^2 (isect_plane_u), and the DOF focal point o + d (f / (d . front)) is the same point for
+    // any positive rescale of d.  This drops both FP64 normalisations (camera.d:144,172) from the ray.
+    constexpr bool UNNORM = plane_only(MODE);
     r.dx = vx; r.dy = vy; r.dz = vz;
     r.ox = fp.pos[0]; r.oy = fp.pos[1]; r.oz = fp.pos[2];
-    normalize3(r.dx, r.dy, r.dz);
+    if (!UNNORM) normalize3(r.dx, r.dy, r.dz);
     const double sep = eye > 0 ? fp.stereo_sep : -fp.stereo_sep;
     if ((MODE & MODE_SAMPLING) && eye != 0) { r.ox += fp.right_dir[0] * sep; r.oy += fp.right_dir[1] * sep; r.oz += fp.right_dir[2] * sep; }
     if ((MODE & MODE_SAMPLING) && fp.dof) {
         double cosTheta = dot3(r.dx, r.dy, r.dz, fp.front_dir[0], fp.front_dir[1], fp.front_dir[2]);
         double M = fp.focal_plane_dist * rcp64(cosTheta);
         double Tx = r.ox + r.dx * M, Ty = r.oy + r.dy * M, Tz = r.oz + r.dz * M;
-        double angle = uniform01(fp, px, py, tap, sample, draw) * (2 * CUDART_PI);
+        double u1 = uniform01(fp, px, py, tap, sample, draw);   // angle = u1 * 2 pi (camera.d:260)
         double u2 = uniform01(fp, px, py, tap, sample, draw);
         double rad = u2 > 0 ? u2 * rsqrt64(u2) : 0.0;
         double sa, ca;
-        sincos(angle, &sa, &ca);  // lens position: kept in FP64 (it moves the ray origin by up to discMultiplier)
+        sincos_rev(u1, sa, ca);  // lens position: kept in FP64 (it moves the ray origin by up to discMultiplier)
         double ddx = sa * rad * fp.disc_multiplier;
         double ddy = ca * rad * fp.disc_multiplier;
         r.ox = fp.pos[0] + ddx * fp.right_dir[0] + ddy * fp.up_dir[0];
@@ -172,8 +209,9 @@ __device__ __forceinline__ void gen_ray(const FrameParams& fp, double vx, double
         r.oz = fp.pos[2] + ddx * fp.right_dir[2] + ddy * fp.up_dir[2];
         if (eye != 0) { r.ox += fp.right_dir[0] * sep; r.oy += fp.right_dir[1] * sep; r.oz += fp.right_dir[2] * sep; }
         r.dx = Tx - r.ox; r.dy = Ty - r.oy; r.dz = Tz - r.oz;
-        normalize3(r.dx, r.dy, r.dz);
+        if (!UNNORM) normalize3(r.dx, r.dy, r.dz);
     }
+    if (UNNORM) r.l2 = dot3(r.dx, r.dy, r.dz, r.dx, r.dy, r.dz);
     if (MODE & MODE_BOUNDED) set_shadow(r);
 }
 
@@ -189,6 +227,19 @@ __device__ __forceinline__ bool isect_plane(double y, double limit, double ox, d
     if (fabs(x) > limit || fabs(z) > limit) return false;  // NaN limit (unbounded) compares false
     dist = mult;
     px = x; py = yy; pz = z;
+    return true;
+}
+
+// Unbounded plane against a ray whose direction d is NOT normalised (l2 = |d|^2); `dist` and the returned parameter are in
+// units of |d|.  geometry.d:35-36 rejects dir.y > -1e-9 (origin above) / dir.y < 1e-9 (below) on the unit direction:
+// here d.y has the wrong sign, or d.y^2 < 1e-18 |d|^2.
+__device__ __forceinline__ bool isect_plane_u(double y, double ox, double oy, double oz, double dx, double dy, double dz, double l2,
+                                              double& dist) {
+    const bool grazing = dy * dy < 1e-18 * l2;
+    if ((oy > y && (dy >= 0 || grazing)) || (oy < y && (dy <= 0 || grazing))) return false;
+    double mult = (oy - y) * rcp64(-dy);
+    if (mult > dist) return false;
+    dist = mult;
     return true;
 }
 
@@ -597,13 +648,15 @@ __device__ __forceinline__ bool generic_intersect(int ni, const Ray& r, HitRec& 
 // Exact FP64 test of node `ni` (after the cull).  Returns true and updates `h` iff the node yields a hit
 // with dist <= h.dist.  Spheres and cubes always have a finite bound, so a scene class without
 // MODE_BOUNDED cannot contain KIND_SPHERE_W / KIND_CUBE_W nodes and those branches compile away.
-template <int MODE>
+// CAMERA_RAY: `r` comes from gen_ray (un-normalised in the plane-only scene classes); shadow rays are always unit
+template <int MODE, bool CAMERA_RAY>
 __device__ __forceinline__ bool node_exact(int ni, const DevNode& nd, const Ray& r, HitRec& h) {
     int face = 0;
     bool hit;
     double px, py, pz;   // world-space kinds: the hit point is o + d * dist, recomputed for the winning hit only (surface_of)
     // plane-only scene classes: no bounded and no generic node exists, i.e. every node is a world-space plane
-    if (plane_only(MODE) || nd.kind == KIND_PLANE_W) hit = isect_plane(nd.wp[0], CUDART_NAN, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, px, py, pz);
+    if (plane_only(MODE) && CAMERA_RAY) hit = isect_plane_u(nd.wp[0], r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.l2, h.dist);
+    else if (plane_only(MODE) || nd.kind == KIND_PLANE_W) hit = isect_plane(nd.wp[0], CUDART_NAN, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, px, py, pz);
     else if ((MODE & MODE_BOUNDED) && nd.kind == KIND_SPHERE_W) hit = isect_sphere(nd.wp, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, px, py, pz);
     else if ((MODE & MODE_BOUNDED) && nd.kind == KIND_CUBE_W) hit = isect_cube(nd.wp, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, px, py, pz, face);
     else if (MODE & MODE_GENERIC) return generic_intersect<MODE>(ni, r, h);
@@ -616,7 +669,7 @@ template <int MODE>
 __device__ __forceinline__ bool node_intersect(int ni, const Ray& r, HitRec& h, float tmaxf) {
     const DevNode& nd = c_scene.nodes[ni];
     if ((MODE & MODE_BOUNDED) && !(nd.flags & NODE_UNBOUNDED) && cull(nd, r, tmaxf)) return false;
-    return node_exact<MODE>(ni, nd, r, h);
+    return node_exact<MODE, true>(ni, nd, r, h);
 }
 
 // scene.d:62-78 testVisibility.  (fx,fy,fz) is the shadow-ray origin, D = to - from (unnormalised),
@@ -661,8 +714,35 @@ __device__ __forceinline__ bool occluded(double fx, double fy, double fz, double
                 h.dist = len2 * inv;
                 exact = true;
             }
-            if (node_exact<MODE>(i, nd, r, h)) return true;
+            if (node_exact<MODE, false>(i, nd, r, h)) return true;
         }
+    }
+    return false;
+}
+
+// testVisibility for the plane-only scene classes.  Dy = light.y - from.y in FP64 settles almost every plane by sign;
+// the full FP64 shadow ray (scene.d:66-71) is only built for a plane that lies between the two heights.
+template <int MODE>
+__device__ __forceinline__ bool occluded_planes(double fx, double fy, double fz, const DevLight& L, double Dy) {
+    bool exact = false;
+    Ray r;
+    HitRec h;
+    const int n = (MODE & MODE_SOLO) ? 1 : c_scene.n_nodes;
+#pragma unroll 1
+    for (int i = 0; i < n; i++) {
+        const DevNode& nd = c_scene.nodes[(MODE & MODE_SOLO) ? 0 : i];
+        const double y = nd.wp[0];
+        if ((fy > y && Dy >= 0) || (fy < y && Dy <= 0)) continue;   // implied by geometry.d:35-36
+        if (!exact) {
+            const double Dx = L.pos[0] - fx, Dz = L.pos[2] - fz;
+            const double len2 = dot3(Dx, Dy, Dz, Dx, Dy, Dz);
+            const double inv = rsqrt64(len2);
+            r.ox = fx; r.oy = fy; r.oz = fz;
+            r.dx = Dx * inv; r.dy = Dy * inv; r.dz = Dz * inv;
+            h.dist = len2 * inv;
+            exact = true;
+        }
+        if (node_exact<MODE, false>(i, nd, r, h)) return true;
     }
     return false;
 }
@@ -720,7 +800,7 @@ __device__ __forceinline__ Col sample_texture(int ti, double u, double v) {
     v = v - floor(v);
     float x = (float)u * (float)t.w;
     float y = (float)v * (float)t.h;
-    if (!(x >= 0.f) || !(y >= 0.f) || (unsigned)x >= (unsigned)t.w || (unsigned)y >= (unsigned)t.h)
+    if (!(x >= 0.f) || !(y >= 0.f) || !(x < (float)t.w) || !(y < (float)t.h))   // (t.w, t.h are integers: x < w <=> (size_t)x < w)
         return mkcol(1.f, 0.f, 0.f);  // NamedColors.red
     int tx = (int)x, ty = (int)y;
     int txn = tx + 1 == t.w ? 0 : tx + 1, tyn = ty + 1 == t.h ? 0 : ty + 1;
@@ -848,13 +928,24 @@ __device__ __forceinline__ Col shade(const FrameParams& fp, const Ray& ray, cons
         // one sample per PointLight (light.d:56-59): avg / numSamples is a division by 1.0f
         if (!L.lit) continue;
         n_shadow++;
-        const double Dx = L.pos[0] - fx, Dy = L.pos[1] - fy, Dz = L.pos[2] - fz;
-        const double len2 = dot3(Dx, Dy, Dz, Dx, Dy, Dz);
-        if (occluded<MODE>(fx, fy, fz, Dx, Dy, Dz, len2)) continue;
+        double Dx, Dy, Dz;
+        float fDx, fDy, fDz, d2;
+        if (plane_only(MODE)) {
+            // among planes only the sign of D.y decides visibility: D.y in FP64, the rest of the light vector in FP32
+            Dy = L.pos[1] - fy;
+            if (occluded_planes<MODE>(fx, fy, fz, L, Dy)) continue;
+            fDx = L.posf[0] - (float)fx; fDy = (float)Dy; fDz = L.posf[2] - (float)fz;
+            d2 = dot3f(fDx, fDy, fDz, fDx, fDy, fDz);
+        } else {
+            Dx = L.pos[0] - fx; Dy = L.pos[1] - fy; Dz = L.pos[2] - fz;
+            const double len2 = dot3(Dx, Dy, Dz, Dx, Dy, Dz);
+            if (occluded<MODE>(fx, fy, fz, Dx, Dy, Dz, len2)) continue;
+            fDx = (float)Dx; fDy = (float)Dy; fDz = (float)Dz;
+            d2 = (float)len2;
+        }
         // lighting in FP32 (the reference narrows every factor to float before it touches a Color: SURVEY.md App. C.1)
-        const float d2 = (float)len2;
         const float rs = rsqrtf(d2);
-        const float lx = (float)Dx * rs, ly = (float)Dy * rs, lz = (float)Dz * rs;
+        const float lx = fDx * rs, ly = fDy * rs, lz = fDz * rs;
         const float inv_d2 = rs * rs;
         const float cosTheta = plane_only(MODE) ? (facing ? ly : -ly) : dot3f(lx, ly, lz, Nx, Ny, Nz);
         const float br = L.color[0] * inv_d2, bg = L.color[1] * inv_d2, bb = L.color[2] * inv_d2;
@@ -869,10 +960,16 @@ __device__ __forceinline__ Col shade(const FrameParams& fp, const Ray& ray, cons
                 // reflect(-lightDir, N) . (-ray.dir)  (imported_types.d:62-67, shader.d:235-239)
                 const float k = 2.f * cosTheta;
                 const float rx = fmaf(k, Nx, -lx), ry = fmaf(k, Ny, -ly), rz = fmaf(k, Nz, -lz);
-                const float cosGamma = -dot3f(rx, ry, rz, (float)ray.dx, (float)ray.dy, (float)ray.dz);
+                float vx = (float)ray.dx, vy = (float)ray.dy, vz = (float)ray.dz;
+                if (plane_only(MODE)) {   // un-normalised camera ray (gen_ray)
+                    const float iv = rsqrtf((float)ray.l2);
+                    vx *= iv; vy *= iv; vz *= iv;
+                }
+                const float cosGamma = -dot3f(rx, ry, rz, vx, vy, vz);
                 pw = cosGamma > 0 ? powf(cosGamma, (float)sh.exponent) : 0.f;
             } else {
                 // very sharp lobes amplify FP32 rounding of cosGamma by `exponent`: keep FP64 here
+                if (plane_only(MODE)) { Dx = L.pos[0] - fx; Dz = L.pos[2] - fz; }
                 double ldx = Dx, ldy = Dy, ldz = Dz;
                 normalize3(ldx, ldy, ldz);
                 double nx = Nx, ny = Ny, nz = Nz;
@@ -881,6 +978,7 @@ __device__ __forceinline__ Col shade(const FrameParams& fp, const Ray& ray, cons
                 double rx = k * nx - ldx, ry = k * ny - ldy, rz = k * nz - ldz;
                 normalize3(rx, ry, rz);
                 double cg = -dot3(rx, ry, rz, ray.dx, ray.dy, ray.dz);
+                if (plane_only(MODE)) cg *= rsqrt64(ray.l2);   // un-normalised camera ray (gen_ray)
                 pw = cg > 0 ? (float)pow(cg, sh.exponent) : 0.f;
             }
             const float w = pw * sh.strength;
@@ -1010,7 +1108,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS) render_frame_kernel
 
     unsigned n_primary = 0, n_shadow = 0;
     Col c = mkcol(0.f, 0.f, 0.f);
-    if (active) {
+    if (fp.gi) c = mkcol(fp.gi_fill, fp.gi_fill, fp.gi_fill);   // renderSampleGI: provably black (c2rt_api.cu fill_params)
+    else if (active) {
         // renderer.d:223-251: tap 0 at the pixel corner, then +(.3,.3) (.6,0) (0,.6) (.6,.6); mean of 5 in FP32
         int taps = fp.aa ? 5 : 1;
         uint32_t sx = x, sy = y;

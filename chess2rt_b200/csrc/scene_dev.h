@@ -58,6 +58,8 @@ struct DevLight {
     double pos[3];
     float color[3];   // lightColor * lightPower, the FP32 product of light.d:11-14
     int lit;          // color.intensity() != 0 (shader.d:88,219)
+    float posf[3];    // FP32 copy of pos (plane-only scene classes take the horizontal light vector in FP32)
+    int pad;
 };
 
 // Two-level culling: contiguous runs of node indices (scene order is kept, so the reference's
@@ -95,6 +97,8 @@ struct FrameParams {
     float ambient[3];
     int count_rays;
     uint32_t prepass_bucket;          // > 0: prepassOnly frame (16x16-block preview inside buckets of this size)
+    int gi;                           // GI frame: every pixel is gi_fill (see c2rt_api.cu fill_params)
+    float gi_fill;
     // interleaved row bands
     uint32_t rank, n_ranks, tiles_per_band, compact;
     uint32_t tile_row0;               // first local tile row of this launch (frames are launched in chunks to overlap the D2H copy)

@@ -223,6 +223,7 @@ c2rt_settings flattenSettings(const GlobalSettings& s, uint64_t rngSeed, bool co
     o.rng_seed = rngSeed;
     o.count_rays = countRays;
     o.bucket_size = s.bucketSize;
+    o.paths_per_pixel = s.pathsPerPixel;
     return o;
 }
 

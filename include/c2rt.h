@@ -38,7 +38,7 @@ extern "C" {
 typedef enum c2rt_status {
     C2RT_OK = 0,
     C2RT_ERR_INVALID_ARG = -1,   /* null pointer, bad index, inconsistent sizes */
-    C2RT_ERR_UNSUPPORTED = -2,   /* feature outside the hot-path scope (GI, CSG nesting beyond the limit) */
+    C2RT_ERR_UNSUPPORTED = -2,   /* input the path cannot honour (GI on a Phong-shaded scene, CSG nesting beyond the limit) */
     C2RT_ERR_CUDA = -3,          /* CUDA runtime error or no usable device */
     C2RT_ERR_NOT_INITIALISED = -4,
     C2RT_ERR_LIMIT = -5          /* scene exceeds a compiled-in capacity (C2RT_MAX_*) */
@@ -132,7 +132,10 @@ typedef struct c2rt_camera {
 typedef struct c2rt_settings {
     uint32_t frame_width, frame_height;   /* output size */
     int32_t aa_enabled;                   /* AAEnabled: 5 samples per pixel for ALL pixels (renderer.d:183-186) */
-    int32_t gi_enabled;                   /* must be 0 */
+    int32_t gi_enabled;                   /* GIEnabled: path tracing when the camera has no DOF (renderer.d:256-263).  With the only light
+                                             type of the reference (PointLight, solidAngle 0: light.d:72-75) every path returns exactly
+                                             black, so the frame is black; a Phong-shaded node makes the reference halt (shader.d:252-262)
+                                             and is refused with C2RT_ERR_UNSUPPORTED */
     int32_t prepass_enabled;              /* accepted and ignored: the prepass is fully overwritten (renderer.d:110-142) */
     int32_t prepass_only;                 /* prepassOnly: with prepass_enabled, the frame is the 16x16-block preview of renderer.d:110-130
                                              (one sample per block, replicated); without it nothing is rendered, like the reference */
@@ -141,6 +144,8 @@ typedef struct c2rt_settings {
     uint64_t rng_seed;                    /* DOF only: seed of the pinned counter-based generator (c2rt_rng_u31) */
     int32_t count_rays;                   /* non-zero: fill c2rt_stats.primary_rays / shadow_rays (slightly slower) */
     uint32_t bucket_size;                 /* bucketSize (global_settings.d:16); only the prepass block grid depends on it; 0 = 48 */
+    uint32_t paths_per_pixel;             /* pathsPerPixel (renderer.d:293-300): GI frames only; 0 makes the mean 0/0 = NaN like the reference */
+    uint32_t reserved;
 } c2rt_settings;
 
 /* Interleaved row bands (multi-GPU): row y belongs to rank ((y / band_rows) % n_ranks).

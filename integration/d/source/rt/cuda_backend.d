@@ -42,6 +42,7 @@ struct c2rt_settings
     float[3] ambient_light;
     ulong rng_seed;
     int count_rays; uint bucket_size;
+    uint paths_per_pixel, reserved;
 }
 
 struct c2rt_stats { double kernel_ms, total_ms; ulong primary_rays, shadow_rays; uint n_gpus, launches; }

@@ -116,6 +116,6 @@ c2rt_settings flattenSettings(const GlobalSettings s, ulong seed = 0)
     o.frame_width = s.frameWidth; o.frame_height = s.frameHeight;
     o.aa_enabled = s.AAEnabled; o.gi_enabled = s.GIEnabled; o.prepass_enabled = s.prepassEnabled; o.prepass_only = s.prepassOnly;
     o.max_trace_depth = s.maxTraceDepth; o.ambient_light = s.ambientLightColor.components; o.rng_seed = seed;
-    o.bucket_size = s.bucketSize;
+    o.bucket_size = s.bucketSize; o.paths_per_pixel = s.pathsPerPixel;
     return o;
 }

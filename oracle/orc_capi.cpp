@@ -20,6 +20,7 @@ struct orc_scene {
 struct orc_stats {
     uint64_t primary_rays, shadow_rays, flops, prepass_rays, prepass_flops, csg_max_crossings;
     double seconds;
+    uint64_t gi_bounce_rays;   // GI: continuation rays (renderer.d:452-458)
 };
 
 static thread_local std::string g_err;
@@ -32,11 +33,6 @@ orc_scene* orc_scene_load(const char* path) {
     try {
         auto h = new orc_scene;
         h->scene = parseSceneFromFile(path);
-        if (h->scene->settings.GIEnabled) {
-            delete h;
-            g_err = "GIEnabled scenes are outside the hot-path scope";
-            return nullptr;
-        }
         return h;
     } catch (const std::exception& e) {
         g_err = e.what();
@@ -104,6 +100,7 @@ int orc_render(orc_scene* s, float* rgb, unsigned threads, int rng_mode, uint64_
             st->prepass_flops = pre.flops;
             st->csg_max_crossings = std::max(fin.csg_max_crossings, pre.csg_max_crossings);
             st->seconds = std::chrono::duration<double>(t1 - t0).count();
+            st->gi_bounce_rays = fin.bounce;
         }
         return 0;
     } catch (const std::exception& e) {

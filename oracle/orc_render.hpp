@@ -5,11 +5,12 @@
 //   getBucketsList :194-213, drawRect :215-220, renderPixelNoAA :223-228, renderPixelAA :233-251,
 //   renderSample :254-268, renderSampleDof :270-287, renderSampleDefault :303-313,
 //   trace :325-358, raytrace_impl :361-376; environment.d:7-10 (miss = black).
-// GI (renderSampleGI / pathtrace) and stereo are outside the hot-path scope
-// and rejected at load.  Worker scheduling mirrors std.parallelism's dynamic hand-out of
+//   renderSampleGI :289-301, pathtrace :320-323, pathtrace_impl :378-463 (GI branch).
+// Worker scheduling mirrors std.parallelism's dynamic hand-out of
 // buckets (renderer.d:133-136) with a shared atomic bucket counter.
 #pragma once
 #include <atomic>
+#include <exception>
 #include <mutex>
 #include <thread>
 
@@ -70,6 +71,51 @@ struct Renderer {
         return closestNode->shader->shade(ray, data);
     }
 
+    // renderer.d:320-358 with TraceType.Path.  `pathtrace` drops its pathMultiplier argument and `trace` restarts
+    // pathtrace_impl from Color(1, 1, 1) (:322, :356) — reproduced: the multiplier never accumulates.
+    Color pathtrace(const Ray& ray) const {
+        if ((uint32_t)ray.depth > scene.settings.maxTraceDepth) return Color::fromFloats(0, 0, 0);
+        IntersectionData data;
+        data.dist = mk_real(1e99);
+        const Node* closestNode = nullptr;
+        for (auto& node : scene.nodes)
+            if (node->intersect(ray, data)) closestNode = node.get();
+        // PointLight.intersect is false (light.d:67-70): hitLight never set, the :380-393 branch is dead
+        const Color pathMultiplier = Color::fromFloats(1, 1, 1);
+        if (!closestNode) return Color::fromFloats(0, 0, 0) * pathMultiplier;  // :396-397, environment.d:7-10
+        Color resultDirect = Color::fromFloats(0, 0, 0);
+        if (!scene.lights.empty()) {  // :404-445
+            const size_t lightIndex = uniformIndex(scene.lights.size());
+            const PointLight& light = *scene.lights[lightIndex];
+            const size_t lightSampleIdx = uniformIndex(light.getNumSamples());
+            Vec3 pointOnLight;
+            Color lightColor;
+            light.getNthSample(lightSampleIdx, data.p, pointOnLight, lightColor);
+            if (raw(lightColor.intensity()) > 0 && scene.testVisibility(data.p + data.normal * mk_real(1e-6), pointOnLight)) {
+                Ray w_out;
+                w_out.orig = data.p + data.normal * mk_real(1e-6);
+                w_out.dir = pointOnLight - w_out.orig;
+                normalize(w_out.dir);
+                const float solidAngle = light.solidAngle(w_out.orig);
+                Color brdfAtPoint = closestNode->shader->eval(data, ray, w_out);
+                lightColor = light.color() * mk_colf(solidAngle) / mk_colf((float)(2 * PI_L));
+                const float pdfChooseLight = 1.0f / (float)scene.lights.size();
+                const float pdfInLight = (float)(1 / (2 * PI_L));
+                const float pdf = pdfChooseLight * pdfInLight;
+                if (raw(brdfAtPoint.intensity()) > 0) resultDirect = lightColor * pathMultiplier * brdfAtPoint / mk_colf(pdf);
+            }
+        }
+        Ray w_out;
+        Color brdfEval;
+        float pdf;
+        closestNode->shader->spawnRay(data, ray, w_out, brdfEval, pdf);  // :452
+        if (pdf < 0) return Color::fromFloats(1, 0, 0);
+        if (pdf == 0) return Color::fromFloats(0, 0, 0);
+        tl_stats().bounce++;
+        Color resultGi = pathtrace(w_out);  // :458 (the multiplier argument is dropped by pathtrace)
+        return resultDirect + resultGi;
+    }
+
     Color renderSample(real x, real y, int dx, int dy, uint32_t tap) const {  // renderer.d:254-313
         RngState& rs = tl_rng();
         rs.tap = tap;
@@ -96,6 +142,18 @@ struct Renderer {
                 }
             }
             return average / mk_colf((float)scene.camera.numSamples);
+        }
+        if (scene.settings.GIEnabled) {  // renderer.d:260-263,289-301 (after the dof test: DOF wins)
+            Color average = Color::fromFloats(0, 0, 0);
+            for (uint32_t i = 0; i < scene.settings.pathsPerPixel; i++) {
+                rs.sample = i;
+                rs.draw = 0;
+                real jx = x + uniform01() * mk_real((double)dx);
+                real jy = y + uniform01() * mk_real((double)dy);
+                tl_stats().primary++;
+                average += pathtrace(scene.camera.getScreenRay(jx, jy));
+            }
+            return average / mk_colf((float)scene.settings.pathsPerPixel);
         }
         if (stereo) {  // renderer.d:307-312
             tl_stats().primary += 2;
@@ -129,21 +187,29 @@ struct Renderer {
     void parallelBuckets(const std::vector<Box2i>& buckets, unsigned nthreads, Stats& total, F&& body) {
         std::atomic<size_t> next{0};
         std::mutex m;
+        std::exception_ptr failure;
         auto worker = [&]() {
             tl_stats() = Stats();
 #ifdef ORC_COUNT_FLOPS
             FlopCounter::tl() = 0;
 #endif
-            for (;;) {
-                size_t i = next.fetch_add(1);
-                if (i >= buckets.size()) break;
-                const Box2i& b = buckets[i];
-                for (int y = b.y0; y < b.y1; y++)
-                    for (int x = b.x0; x < b.x1; x++) body(x, y);
+            try {
+                for (;;) {
+                    size_t i = next.fetch_add(1);
+                    if (i >= buckets.size()) break;
+                    const Box2i& b = buckets[i];
+                    for (int y = b.y0; y < b.y1; y++)
+                        for (int x = b.x0; x < b.x1; x++) body(x, y);
+                }
+            } catch (...) {   // ReferenceHalts (GI on a Phong surface): reported by the calling thread
+                std::lock_guard<std::mutex> g(m);
+                if (!failure) failure = std::current_exception();
+                next.store(buckets.size());
             }
             std::lock_guard<std::mutex> g(m);
             total.primary += tl_stats().primary;
             total.shadow += tl_stats().shadow;
+            total.bounce += tl_stats().bounce;
             total.csg_max_crossings = std::max(total.csg_max_crossings, tl_stats().csg_max_crossings);
 #ifdef ORC_COUNT_FLOPS
             total.flops += FlopCounter::tl();
@@ -151,11 +217,12 @@ struct Renderer {
         };
         if (nthreads <= 1) {
             worker();
-            return;
+        } else {
+            std::vector<std::thread> th;
+            for (unsigned t = 0; t < nthreads; t++) th.emplace_back(worker);
+            for (auto& t : th) t.join();
         }
-        std::vector<std::thread> th;
-        for (unsigned t = 0; t < nthreads; t++) th.emplace_back(worker);
-        for (auto& t : th) t.join();
+        if (failure) std::rethrow_exception(failure);
     }
 
     // Returns the ray/flop counts of the passes that reach the final image (pass 2 + pass 3);

@@ -10,6 +10,7 @@
 // Geometry in `real` (FP64), colour in `colf` (FP32); every double->float narrowing is where
 // the D code narrows.
 #pragma once
+#include <stdexcept>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -84,6 +85,7 @@ struct Geometry;
 struct Ray {
     Vec3 orig, dir;
     int depth = 0;
+    bool diffuse = false;   // RayFlags.Diffuse (ray.d:6-25), set by Lambert.spawnRay
 };
 
 struct IntersectionData {
@@ -123,6 +125,7 @@ inline Vec3 faceforward(const Vec3& ray, const Vec3& norm) { // imported_types.d
 // ------------------------------------------------------------------ geometry.d
 struct Stats {
     uint64_t primary = 0, shadow = 0, flops = 0, csg_max_crossings = 0;
+    uint64_t bounce = 0;   // GI: continuation rays spawned (renderer.d:452-458)
 };
 inline Stats& tl_stats() {
     static thread_local Stats s;
@@ -475,6 +478,7 @@ struct PointLight {
     colf lightPower = mk_colf(std::numeric_limits<float>::quiet_NaN());
     Color color() const { return lightColor * lightPower; }  // light.d:11-14
     size_t getNumSamples() const { return 1; }               // :56-59
+    float solidAngle(const Vec3&) const { return 0.f; }      // :72-75
     void getNthSample(size_t, const Vec3&, Vec3& samplePos, Color& c) const {  // :61-65
         samplePos = pos;
         c = color();
@@ -614,6 +618,13 @@ struct Shader {
     const Scene* scene = nullptr;
     virtual ~Shader() = default;
     virtual Color shade(const Ray& ray, const IntersectionData& data) const = 0;
+    // GI branch (shader.d:107-135 Lambert; :252-262 Phong = assert(0), which D keeps in release builds: the reference halts)
+    virtual Color eval(const IntersectionData& x, const Ray& w_in, const Ray& w_out) const = 0;
+    virtual void spawnRay(const IntersectionData& x, const Ray& w_in, Ray& w_out, Color& colorEval, float& pdf) const = 0;
+};
+
+struct ReferenceHalts : std::runtime_error {
+    using std::runtime_error::runtime_error;
 };
 
 struct Node {  // node.d:7-49
@@ -670,7 +681,25 @@ struct Scene {  // scene.d:38-78
     }
 };
 
-struct Lambert final : Shader {  // shader.d:54-105
+// util/random.d:12-28 for integer arguments: a + (r / RAND_MAX) * (b - a), truncated.  r == RAND_MAX yields b, one past
+// the range (an out-of-bounds index in the reference): clamped here.
+inline size_t uniformIndex(size_t n) {
+    double r = raw(uniform01());
+    size_t i = (size_t)(0 + r * (double)n);
+    return i < n ? i : n - 1;
+}
+
+inline Vec3 hemisphereSample(const Vec3& normal) {  // shader.d:156-174
+    real u = uniform01(), v = uniform01();
+    real theta = mk_real((double)(2 * PI_L * (long double)raw(u)));
+    real phi = mk_real((double)((long double)std::acos(2 * raw(v) - 1) - PI_L / 2));
+    orc_flops(5);
+    Vec3 res(r_cos(theta) * r_cos(phi), r_sin(phi), r_sin(theta) * r_cos(phi));
+    if (dot(res, normal) < 0) res = -res;
+    return res;
+}
+
+struct Lambert final : Shader {  // shader.d:54-135
     const Texture* texture = nullptr;
     Lambert() { color = Color::fromFloats(1, 1, 1); }
     Color shade(const Ray& ray, const IntersectionData& data) const override {
@@ -693,6 +722,24 @@ struct Lambert final : Shader {  // shader.d:54-105
             lightContrib += avgColor / mk_colf((float)light->getNumSamples());
         }
         return diffuseColor * lightContrib;
+    }
+    Color eval(const IntersectionData& x, const Ray& w_in, const Ray& w_out) const override {  // shader.d:107-116
+        Vec3 N = faceforward(w_in.dir, x.normal);
+        Color diffuseColor = texture ? texture->getTexColor(w_in, x.u, x.v, N) : color;
+        real c = dot(w_out.dir, N);
+        return diffuseColor * mk_colf((float)(1 / PI_L)) * narrow(c > 0 ? c : mk_real(0.0));
+    }
+    void spawnRay(const IntersectionData& x, const Ray& w_in, Ray& w_out, Color& colorEval, float& pdf) const override {  // :118-135
+        Vec3 N = faceforward(w_in.dir, x.normal);
+        Color diffuseColor = texture ? texture->getTexColor(w_in, x.u, x.v, N) : color;
+        w_out = w_in;
+        w_out.depth++;
+        w_out.orig = x.p + N * mk_real(1e-6);
+        w_out.dir = hemisphereSample(N);
+        w_out.diffuse = true;
+        real c = dot(w_out.dir, N);
+        colorEval = diffuseColor * mk_colf((float)(1 / PI_L)) * narrow(c > 0 ? c : mk_real(0.0));
+        pdf = (float)(1 / (2 * PI_L));
     }
 };
 
@@ -730,6 +777,12 @@ struct Phong final : Shader {  // shader.d:177-250
             specular += avgSpecular / mk_colf((float)numSamples);
         }
         return diffuseColor * lightContrib + specular;
+    }
+    Color eval(const IntersectionData&, const Ray&, const Ray&) const override {  // shader.d:258-262
+        throw ReferenceHalts("Phong.eval is assert(0) (shader.d:258-262): the reference halts when a GI path lights a Phong surface");
+    }
+    void spawnRay(const IntersectionData&, const Ray&, Ray&, Color&, float&) const override {  // shader.d:252-256
+        throw ReferenceHalts("Phong.spawnRay is assert(0) (shader.d:252-256): the reference halts when a GI path hits a Phong surface");
     }
 };
 

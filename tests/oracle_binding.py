@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 class OrcStats(C.Structure):
     _fields_ = [("primary_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("flops", C.c_uint64),
                 ("prepass_rays", C.c_uint64), ("prepass_flops", C.c_uint64), ("csg_max_crossings", C.c_uint64),
-                ("seconds", C.c_double)]
+                ("seconds", C.c_double), ("gi_bounce_rays", C.c_uint64)]
 
 
 def _bind(path):

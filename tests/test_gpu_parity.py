@@ -275,12 +275,37 @@ def test_ray_counters_device_path():
     assert c2.read_ray_counters(g.device_scene(), stream) == (0, 0)
 
 
+def test_gi_frames(tmp_path):
+    """GIEnabled (renderer.d:260-263,289-301): black like the literal oracle walk; Phong scenes are refused (the reference
+    halts in Phong.spawnRay); under DOF the GI flag is ignored."""
+    from test_oracle_kat import GI_SCENE
+    p = tmp_path / "gi.sdl"
+    p.write_text(GI_SCENE.format(paths=3, cam="", ball_shader="Lambert"))
+    g, o = both(str(p))
+    rgb, argb, _ = g.render(argb=True, seed=2)
+    ref, _ = o.render(seed=2)
+    np.testing.assert_array_equal(rgb, ref)
+    assert not rgb.any() and not argb.any()
+    p.write_text(GI_SCENE.format(paths=0, cam="", ball_shader="Lambert"))
+    assert np.all(np.isnan(c2.HostScene(str(p)).render()[0]))
+    p.write_text(GI_SCENE.format(paths=3, cam="", ball_shader="Phong"))
+    with pytest.raises(c2.C2rtError, match="Phong"):
+        c2.HostScene(str(p)).render()
+    p.write_text(GI_SCENE.format(paths=3, cam="; dof true; numSamples 2; focalPlaneDist 120; fNumber 8", ball_shader="Phong"))
+    g, o = both(str(p))
+    rgb, _, st = g.render(seed=3, count_rays=True)
+    ref, ost = o.render(seed=3)
+    assert_parity(rgb, ref, what="GI flag under DOF")
+    assert (st.primary_rays, st.shadow_rays) == (ost.primary_rays, ost.shadow_rays)
+
+
 def test_unsupported_features_are_errors_not_fallbacks():
-    g = c2.HostScene(os.path.join(SC, "lecture4.sdl"))
+    g = c2.HostScene(os.path.join(SC, "lecture5.sdl"))   # has Phong-shaded nodes
     cam, st = g.frame_blocks()
     rgb = np.zeros((480, 640, 3), np.float32)
     st.gi_enabled = 1
     assert api.lib.c2rt_render(g.device_scene(), C.byref(cam), C.byref(st), rgb.ctypes.data, None, None) == -2
+    assert api.lib.c2rt_render_pixel(g.device_scene(), C.byref(cam), C.byref(st), 3, 3, (C.c_float * 3)(), None) == -2
     st.gi_enabled = 0
     assert api.lib.c2rt_render(g.device_scene(), C.byref(cam), C.byref(st), None, None, None) == -1
     assert api.lib.c2rt_render(g.device_scene(), C.byref(cam), C.byref(st), rgb.ctypes.data, None, None) == 0

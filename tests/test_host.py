@@ -39,7 +39,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header_sizes():
     # sizes the C compiler gives the ABI structs (x86-64 SysV): guards the ctypes mirrors
     assert C.sizeof(api.Camera) == 7 * 24 + 4 * 4 + 3 * 8
-    assert C.sizeof(api.Settings) == 56
+    assert C.sizeof(api.Settings) == 64
     assert C.sizeof(api.Band) == 16
     assert C.sizeof(api.Stats) == 40
     assert C.sizeof(api.Hit) == 8 + 8 + 24 + 24 + 16

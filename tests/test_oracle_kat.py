@@ -247,6 +247,42 @@ def test_samples_at_pixel_corner():
     assert hit[0] == 0
 
 
+GI_SCENE = """Scene {{
+  GlobalSettings {{ frameWidth 96; frameHeight 64; GIEnabled true; pathsPerPixel {paths}; maxTraceDepth 3; ambientLightColor 0.2 0.2 0.2 }}
+  Camera {{ pos 0 60 -120; pitch -20; fov 70{cam} }}
+  Lights {{ PointLight "l" {{ pos -40 120 -60; color 1 1 1; power 40000 }} PointLight "m" {{ pos 60 90 -20; color 0.4 0.5 1; power 9000 }} }}
+  Geometries {{ Plane "floor" {{ y 0 }} Sphere "ball" {{ center 0 25 0; R 25 }} Cube "box" {{ center 50 15 10; side 30 }} }}
+  Textures {{ Checker "chk" {{ color1 0.1 0.1 0.1; color2 0.9 0.9 0.9; size 10 }} }}
+  Shaders {{ Lambert "f" {{ texture "chk" }} {ball_shader} "b" {{ color 0.9 0.2 0.2 }} }}
+  Nodes {{ Node "n1" {{ geometry "floor"; shader "f" }} Node "n2" {{ geometry "ball"; shader "b" }} Node "n3" {{ geometry "box"; shader "f"; scale 1 1.5 1 }} }}
+}}
+"""
+
+
+def test_gi_literal_walk_is_black_and_halts_on_phong(tmp_path):
+    """renderSampleGI / pathtrace_impl (renderer.d:289-301,378-463) restated literally: with PointLights (solidAngle 0,
+    light.d:72-75) every path sums to exactly black whatever the random walk; a Phong surface makes the reference halt."""
+    p = tmp_path / "gi.sdl"
+    p.write_text(GI_SCENE.format(paths=6, cam="", ball_shader="Lambert"))
+    o = OracleScene(str(p))
+    for seed, mode in ((0, 1), (7, 1), (0, 0)):   # pinned generator twice, libc rand once
+        rgb, st = o.render(seed=seed, rng_mode=mode)
+        assert np.all(rgb == 0.0)
+        assert st.primary_rays == 96 * 64 * 5 * 6
+        # every surface hit sends one shadow ray and spawns one continuation ray, up to maxTraceDepth
+        assert st.shadow_rays == st.gi_bounce_rays and 0 < st.gi_bounce_rays <= st.primary_rays * 4
+    p.write_text(GI_SCENE.format(paths=0, cam="", ball_shader="Lambert"))
+    rgb, _ = OracleScene(str(p)).render()
+    assert np.all(np.isnan(rgb))      # mean of zero paths: 0 / 0 (renderer.d:300)
+    p.write_text(GI_SCENE.format(paths=2, cam="", ball_shader="Phong"))
+    with pytest.raises(Exception, match="assert"):
+        OracleScene(str(p)).render()
+    # the DOF branch is tested first (renderer.d:256-259): GIEnabled is ignored under DOF
+    p.write_text(GI_SCENE.format(paths=2, cam="; dof true; numSamples 2; focalPlaneDist 120; fNumber 8", ball_shader="Phong"))
+    rgb, _ = OracleScene(str(p)).render()
+    assert rgb.max() > 0.1
+
+
 def test_golden_fixtures_reproduce():
     meta = json.load(open(os.path.join(GOLD, "golden.json")))
     for name, m in meta.items():
