@@ -487,8 +487,9 @@ __device__ __forceinline__ bool isect_csg(int gi, double ox, double oy, double o
     face = id >> 2;
     leaf = (id & 2) ? g.right : g.left;
     if (g.type == C2RT_GEOM_CSG_DIFF) {
-        bool a = geom_inside(g.right, px - dx * 1e-6, py - dy * 1e-6, pz - dz * 1e-6);
-        bool b = geom_inside(g.right, px + dx * 1e-6, py + dy * 1e-6, pz + dz * 1e-6);
+        const DevGeom& gr = c_scene.geoms[g.right];   // a primitive: this closed form is only used for CSGs of primitives
+        bool a = prim_inside(gr, px - dx * 1e-6, py - dy * 1e-6, pz - dz * 1e-6);
+        bool b = prim_inside(gr, px + dx * 1e-6, py + dy * 1e-6, pz + dz * 1e-6);
         if (a != b) face |= FACE_FLIP;
     }
     return true;
