@@ -553,6 +553,8 @@ void fill_params(FrameParams& fp, const c2rt_camera* cam, const c2rt_settings* s
         fp.front_dir[k] = cam->front_dir[k];
         fp.ambient[k] = set->ambient_light[k];
     }
+    for (int k = 0; k < 3; k++) fp.posf[k] = (float)cam->pos[k];
+    fp.posf_len = sqrtf(fp.posf[0] * fp.posf[0] + fp.posf[1] * fp.posf[1] + fp.posf[2] * fp.posf[2]);
     fp.inv_w = 1.0 / (double)cam->frame_width;
     fp.inv_h = 1.0 / (double)cam->frame_height;
     static const double kx[5] = {0.0, 0.3, 0.6, 0.0, 0.6}, ky[5] = {0.0, 0.3, 0.0, 0.6, 0.6};

@@ -109,10 +109,21 @@ __device__ __forceinline__ float cvt_keep(double x) {
     return f;
 #endif
 }
-__device__ __forceinline__ void set_shadow(Ray& r) {
-    r.fox = cvt_keep(r.ox); r.foy = cvt_keep(r.oy); r.foz = cvt_keep(r.oz);
-    r.fdx = cvt_keep(r.dx); r.fdy = cvt_keep(r.dy); r.fdz = cvt_keep(r.dz);
-    r.olen = sqrtf(dot3f(r.fox, r.foy, r.foz, r.fox, r.foy, r.foz));
+// FP32 shadow of a camera ray for the conservative cull.  `r.d` is still UN-normalised here: the FP32 direction is
+// normalised in FP32 from it (error ~3 ulp, inside the cull's margins) instead of being a conversion of the FP64 unit
+// vector — ptxas rematerialises such a conversion (F2F, quarter-rate XU pipe) in every iteration of the node loops.
+template <int MODE>
+__device__ __forceinline__ void set_shadow(const FrameParams& fp, Ray& r) {
+    if (MODE & MODE_SAMPLING) {   // DOF / stereo move the origin per ray
+        r.fox = cvt_keep(r.ox); r.foy = cvt_keep(r.oy); r.foz = cvt_keep(r.oz);
+        r.olen = sqrtf(dot3f(r.fox, r.foy, r.foz, r.fox, r.foy, r.foz));
+    } else {                      // the camera position: converted once per frame on the host
+        r.fox = fp.posf[0]; r.foy = fp.posf[1]; r.foz = fp.posf[2];
+        r.olen = fp.posf_len;
+    }
+    const float vx = (float)r.dx, vy = (float)r.dy, vz = (float)r.dz;
+    const float inv = rsqrtf(dot3f(vx, vy, vz, vx, vy, vz));
+    r.fdx = vx * inv; r.fdy = vy * inv; r.fdz = vz * inv;
 }
 
 // ---------------------------------------------------------------- pinned RNG (c2rt.h c2rt_rng_u31)
@@ -190,9 +201,10 @@ __device__ __forceinline__ void gen_ray(const FrameParams& fp, double vx, double
     constexpr bool UNNORM = plane_only(MODE);
     r.dx = vx; r.dy = vy; r.dz = vz;
     r.ox = fp.pos[0]; r.oy = fp.pos[1]; r.oz = fp.pos[2];
-    if (!UNNORM) normalize3(r.dx, r.dy, r.dz);
     const double sep = eye > 0 ? fp.stereo_sep : -fp.stereo_sep;
     if ((MODE & MODE_SAMPLING) && eye != 0) { r.ox += fp.right_dir[0] * sep; r.oy += fp.right_dir[1] * sep; r.oz += fp.right_dir[2] * sep; }
+    if ((MODE & MODE_BOUNDED) && !((MODE & MODE_SAMPLING) && fp.dof)) set_shadow<MODE>(fp, r);   // (a DOF ray gets its final origin and direction below)
+    if (!UNNORM) normalize3(r.dx, r.dy, r.dz);
     if ((MODE & MODE_SAMPLING) && fp.dof) {
         double cosTheta = dot3(r.dx, r.dy, r.dz, fp.front_dir[0], fp.front_dir[1], fp.front_dir[2]);
         double M = fp.focal_plane_dist * rcp64(cosTheta);
@@ -209,10 +221,10 @@ __device__ __forceinline__ void gen_ray(const FrameParams& fp, double vx, double
         r.oz = fp.pos[2] + ddx * fp.right_dir[2] + ddy * fp.up_dir[2];
         if (eye != 0) { r.ox += fp.right_dir[0] * sep; r.oy += fp.right_dir[1] * sep; r.oz += fp.right_dir[2] * sep; }
         r.dx = Tx - r.ox; r.dy = Ty - r.oy; r.dz = Tz - r.oz;
+        if (MODE & MODE_BOUNDED) set_shadow<MODE>(fp, r);
         if (!UNNORM) normalize3(r.dx, r.dy, r.dz);
     }
     if (UNNORM) r.l2 = dot3(r.dx, r.dy, r.dz, r.dx, r.dy, r.dz);
-    if (MODE & MODE_BOUNDED) set_shadow(r);
 }
 
 // ---------------------------------------------------------------- primitives
@@ -997,7 +1009,7 @@ __device__ __forceinline__ Col trace(const FrameParams& fp, const Ray& ray, unsi
     HitRec h;
     h.dist = 1e99;
     h.node = -1;
-    float tmaxf = CUDART_INF_F;
+    float tmaxf = 3.0e38f;   // (not +inf = (float)1e99: ptxas would prove tmaxf == (float)h.dist * k and re-convert it in every iteration)
     const int ncl = (MODE & MODE_CLUSTERS) ? c_scene.n_clusters : 1;
     if (MODE & MODE_SOLO) node_intersect<MODE>(0, ray, h, tmaxf);
     else for (int ci = 0; ci < ncl; ci++) {

@@ -85,6 +85,7 @@ struct FrameParams {
     // camera.d:123-147 with the frame invariants hoisted: ul_rel = upLeft - pos, du = upRight - upLeft,
     // dv = downLeft - upLeft, inv_w / inv_h = 1 / camera.frameWidth, 1 / camera.frameHeight
     double pos[3], ul_rel[3], du[3], dv[3];
+    float posf[3], posf_len;          // FP32 copy of pos and its length (the cull's ray shadow, render_kernel.cu set_shadow)
     double right_dir[3], up_dir[3], front_dir[3];
     double inv_w, inv_h;
     double tap_d[5][3];               // ray-direction offset of AA tap k: du * kx/W + dv * ky/H (renderer.d:235-247)
