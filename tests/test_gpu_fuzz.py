@@ -8,7 +8,7 @@ import pytest
 
 import chess2rt_b200 as c2
 from oracle_binding import OracleScene, pack_rgb32, parity_report
-from scene_fuzz import generate
+from scene_fuzz import generate, generate_planes
 
 pytestmark = pytest.mark.gpu
 
@@ -37,3 +37,18 @@ def test_random_scene_matches_oracle(seed, tmp_path):
     assert st.primary_rays == ost.primary_rays
     assert abs(int(st.shadow_rays) - int(ost.shadow_rays)) <= max(2, int(1e-3 * ost.shadow_rays)), (st.shadow_rays, ost.shadow_rays)
     assert ost.csg_max_crossings <= 8
+
+
+@pytest.mark.parametrize("seed", list(range(32)))
+def test_random_plane_scene_matches_oracle(seed, tmp_path):
+    """The MODE_SOLO and plane-only kernel classes (un-normalised camera rays, sign-test shadowing among planes)."""
+    path = tmp_path / f"planes{seed}.sdl"
+    path.write_text(generate_planes(seed))
+    g, o = c2.HostScene(path), OracleScene(path)
+    rgb, argb, st = g.render(argb=True, seed=seed, count_rays=True)
+    ref, ost = o.render(threads=0, seed=seed)
+    rep = parity_report(rgb, ref, argb)
+    assert rep["frac_over_1e-3"] <= 1e-3, (seed, rep)
+    assert rep["frac_over_1lsb"] <= 1e-3, (seed, rep)
+    np.testing.assert_array_equal(argb, pack_rgb32(rgb))
+    assert (st.primary_rays, st.shadow_rays) == (ost.primary_rays, ost.shadow_rays)
