@@ -151,26 +151,33 @@ __device__ __forceinline__ double uniform01(const FrameParams& fp, uint32_t px, 
 // sin(2 pi u), cos(2 pi u) for u in [0, 1] in FP64 (|err| < 3e-16): quadrant by the 2^52 rounding trick, then the
 // classic degree-13 / degree-14 minimax kernels on |t| <= pi/4.  Replaces sincos(u * 2 pi) of camera.d:260-263, whose
 // library form spends most of its ~75 instructions on argument ranges a unit-interval input cannot reach.
+// (coefficients in constant memory: a DFMA takes them as c[bank][imm] operands; FP64 literals would each cost two UMOVs)
+__constant__ double c_sincos[14] = {
+    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06, -1.98412698298579493134e-04,
+    8.33333333332248946124e-03, -1.66666666666666324348e-01,
+    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07, 2.48015872894767294178e-05,
+    -1.38888888888741095749e-03, 4.16666666666666019037e-02,
+    6.283185307179586476925, 6755399441055744.0};
 __device__ __forceinline__ void sincos_rev(double u, double& s, double& c) {
-    const double MAGIC = 6755399441055744.0;            // 1.5 * 2^52
+    const double MAGIC = c_sincos[13];                  // 1.5 * 2^52
     const double qm = fma(u, 4.0, MAGIC);               // nearest integer to 4u in the low mantissa bits
     const int q = __double2loint(qm);
     const double r = fma(qm - MAGIC, -0.25, u);         // exact: u - q/4 in [-1/8, 1/8]
-    const double t = r * 6.283185307179586476925;
+    const double t = r * c_sincos[12];
     const double z = t * t;
-    double ps = 1.58969099521155010221e-10;
-    ps = fma(ps, z, -2.50507602534068634195e-08);
-    ps = fma(ps, z, 2.75573137070700676789e-06);
-    ps = fma(ps, z, -1.98412698298579493134e-04);
-    ps = fma(ps, z, 8.33333333332248946124e-03);
-    ps = fma(ps, z, -1.66666666666666324348e-01);
+    double ps = c_sincos[0];
+    ps = fma(ps, z, c_sincos[1]);
+    ps = fma(ps, z, c_sincos[2]);
+    ps = fma(ps, z, c_sincos[3]);
+    ps = fma(ps, z, c_sincos[4]);
+    ps = fma(ps, z, c_sincos[5]);
     const double st = fma(t * z, ps, t);
-    double pc = -1.13596475577881948265e-11;
-    pc = fma(pc, z, 2.08757232129817482790e-09);
-    pc = fma(pc, z, -2.75573143513906633035e-07);
-    pc = fma(pc, z, 2.48015872894767294178e-05);
-    pc = fma(pc, z, -1.38888888888741095749e-03);
-    pc = fma(pc, z, 4.16666666666666019037e-02);
+    double pc = c_sincos[6];
+    pc = fma(pc, z, c_sincos[7]);
+    pc = fma(pc, z, c_sincos[8]);
+    pc = fma(pc, z, c_sincos[9]);
+    pc = fma(pc, z, c_sincos[10]);
+    pc = fma(pc, z, c_sincos[11]);
     const double ct = fma(z * z, pc, fma(z, -0.5, 1.0));
     // quadrant q mod 4: (s, c), (c, -s), (-s, -c), (-c, s)
     const double a = (q & 1) ? ct : st, b = (q & 1) ? st : ct;
@@ -202,7 +209,8 @@ __device__ __forceinline__ void gen_ray(const FrameParams& fp, double vx, double
     r.dx = vx; r.dy = vy; r.dz = vz;
     r.ox = fp.pos[0]; r.oy = fp.pos[1]; r.oz = fp.pos[2];
     const double sep = eye > 0 ? fp.stereo_sep : -fp.stereo_sep;
-    if ((MODE & MODE_SAMPLING) && eye != 0) { r.ox += fp.right_dir[0] * sep; r.oy += fp.right_dir[1] * sep; r.oz += fp.right_dir[2] * sep; }
+    const bool stereo = (MODE & MODE_SAMPLING) && fp.stereo_sep != 0 && eye != 0;   // (warp-uniform first term: a branch, not predication)
+    if (stereo) { r.ox += fp.right_dir[0] * sep; r.oy += fp.right_dir[1] * sep; r.oz += fp.right_dir[2] * sep; }
     if ((MODE & MODE_BOUNDED) && !((MODE & MODE_SAMPLING) && fp.dof)) set_shadow<MODE>(fp, r);   // (a DOF ray gets its final origin and direction below)
     if (!UNNORM) normalize3(r.dx, r.dy, r.dz);
     if ((MODE & MODE_SAMPLING) && fp.dof) {
@@ -219,7 +227,7 @@ __device__ __forceinline__ void gen_ray(const FrameParams& fp, double vx, double
         r.ox = fp.pos[0] + ddx * fp.right_dir[0] + ddy * fp.up_dir[0];
         r.oy = fp.pos[1] + ddx * fp.right_dir[1] + ddy * fp.up_dir[1];
         r.oz = fp.pos[2] + ddx * fp.right_dir[2] + ddy * fp.up_dir[2];
-        if (eye != 0) { r.ox += fp.right_dir[0] * sep; r.oy += fp.right_dir[1] * sep; r.oz += fp.right_dir[2] * sep; }
+        if (stereo) { r.ox += fp.right_dir[0] * sep; r.oy += fp.right_dir[1] * sep; r.oz += fp.right_dir[2] * sep; }
         r.dx = Tx - r.ox; r.dy = Ty - r.oy; r.dz = Tz - r.oz;
         if (MODE & MODE_BOUNDED) set_shadow<MODE>(fp, r);
         if (!UNNORM) normalize3(r.dx, r.dy, r.dz);
