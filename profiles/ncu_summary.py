@@ -41,5 +41,26 @@ def main():
             print(f"| {k} | {d[k][0]} | {d[k][1]} |")
 
 
+def opcode_mix(rep, top=16):
+    """Appendix: executed warp instructions and predicated-on thread instructions per SASS opcode (source page)."""
+    raw = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr = rows[1]
+    ia, ie, it = hdr.index('Source'), hdr.index('Instructions Executed'), hdr.index('Predicated-On Thread Instructions Executed')
+    warp, thread = {}, {}
+    for r in rows[2:]:
+        t = r[ia].split()
+        if not t:
+            continue
+        op = (t[1] if t[0].startswith('@') else t[0]).split('.')[0]
+        warp[op] = warp.get(op, 0) + int(r[ie])
+        thread[op] = thread.get(op, 0) + int(r[it])
+    tot = sum(warp.values())
+    print(f"\n## SASS opcode mix (source page; {tot} warp instructions)\n\n| opcode | warp instructions | share | predicated-on thread instructions |\n|---|---|---|---|")
+    for op, n in sorted(warp.items(), key=lambda kv: -kv[1])[:top]:
+        print(f"| {op} | {n} | {100.0 * n / tot:.1f} % | {thread[op]} |")
+
+
 if __name__ == '__main__':
     main()
+    opcode_mix(sys.argv[1])
