@@ -10,7 +10,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -84,6 +88,83 @@ struct Context {
 Context g_ctx;
 std::mutex g_mu;
 
+// One host thread per extra device (c2rt_init(N > 1)): c2rt_render hands every device's launch / copy sequence to its
+// own thread, so the ~10 driver calls per device are issued in parallel instead of one after the other (at 1080p the
+// serial submission of 8 devices cost more than rendering and copying the frame).  Workers spin for a short while after
+// a frame — an interactive loop or a benchmark asks for the next one immediately — and then sleep on a condition variable.
+class DevicePool {
+public:
+    void start(int n_workers) {
+        stop();
+        stop_ = false;
+        const uint64_t g0 = gen_.load(std::memory_order_acquire);
+        for (int w = 0; w < n_workers; w++) th_.emplace_back([this, w, g0] { loop(w, g0); });
+    }
+    void stop() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+            gen_.fetch_add(1, std::memory_order_release);
+        }
+        cv_work_.notify_all();
+        for (auto& t : th_) t.join();
+        th_.clear();
+    }
+    int size() const { return (int)th_.size(); }
+    // runs fn(w) on every worker w = 0..size()-1; returns immediately, wait() joins the round
+    void run(std::function<void(int)> fn) {
+        fn_ = std::move(fn);
+        pending_.store((int)th_.size(), std::memory_order_relaxed);
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            gen_.fetch_add(1, std::memory_order_release);
+        }
+        cv_work_.notify_all();
+    }
+    void wait() {
+        for (int k = 0; k < 200000 && pending_.load(std::memory_order_acquire) != 0; k++) relax();
+        if (pending_.load(std::memory_order_acquire) == 0) return;
+        std::unique_lock<std::mutex> lk(m_);
+        cv_done_.wait(lk, [this] { return pending_.load(std::memory_order_acquire) == 0; });
+    }
+    ~DevicePool() { stop(); }
+
+private:
+    static void relax() {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+    }
+    void loop(int w, uint64_t seen) {
+        for (;;) {
+            bool got = false;
+            for (int k = 0; k < 100000; k++) {
+                if (gen_.load(std::memory_order_acquire) != seen) { got = true; break; }
+                relax();
+            }
+            if (!got) {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_work_.wait(lk, [&] { return gen_.load(std::memory_order_acquire) != seen; });
+            }
+            seen = gen_.load(std::memory_order_acquire);
+            if (stop_) return;
+            fn_(w);
+            if (pending_.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+                std::lock_guard<std::mutex> lk(m_);
+                cv_done_.notify_one();
+            }
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_work_, cv_done_;
+    std::function<void(int)> fn_;
+    std::atomic<uint64_t> gen_{0};
+    std::atomic<int> pending_{0};
+    bool stop_ = false;
+};
+DevicePool g_pool;
+
 // color.d:194-207 convertTo8bit_sRGB, quirks kept: 12.02 linear slope, floor instead of round
 uint8_t srgb8(float x) {
     if (x <= 0) return 0;
@@ -116,6 +197,7 @@ int init_locked(int n_gpus, const int* ids) {
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0)
         return fail(C2RT_ERR_CUDA, "no CUDA device available (%s); libc2rt has no CPU fallback", cudaGetErrorString(e));
+    g_pool.stop();
     for (int i = 0; i < g_ctx.n; i++) destroy_device(g_ctx.d[i]);
     g_ctx.n = 0;
     g_ctx.inited = false;
@@ -151,6 +233,7 @@ int init_locked(int n_gpus, const int* ids) {
     }
     cudaSetDevice(g_ctx.d[0].dev);
     g_ctx.inited = true;
+    if (n_gpus > 1) g_pool.start(n_gpus - 1);   // worker w drives device w + 1; the caller's thread drives device 0
     return C2RT_OK;
 }
 
@@ -585,6 +668,74 @@ uint32_t local_tile_rows(uint32_t H, uint32_t rank, uint32_t n, uint32_t band_ro
     return (rows + TILE_H - 1) / TILE_H;
 }
 
+int render_direct_device(int i, int n, c2rt_scene* s, const c2rt_camera* cam, const c2rt_settings* set, float* rgb, uint32_t* argb,
+                         uint32_t* launches_out, float* kernel_ms_out) {
+    const uint32_t W = set->frame_width, H = set->frame_height;
+    const size_t npx = (size_t)W * H;
+    uint32_t launches = 0;
+    {
+        DeviceCtx& c = g_ctx.d[i];
+        CU(cudaSetDevice(c.dev));
+        FrameParams fp;
+        fill_params(fp, cam, set);
+        fp.rank = (uint32_t)i;
+        fp.n_ranks = (uint32_t)n;
+        fp.tiles_per_band = 1;
+        fp.compact = 1;
+        fp.counters = c.d_counters;
+        fp.lut = c.d_lut;
+        // 2..16 interleaved bands per device (one band per ~256k pixels): each band is one launch + one contiguous
+        // D2H copy, so small frames must not be cut into many bands (every launch / copy costs a few host microseconds)
+        uint32_t per_dev = (uint32_t)std::min<size_t>(16, std::max<size_t>(2, npx / (size_t)n / 262144));
+        uint32_t brows = (H / ((uint32_t)n * per_dev) + TILE_H - 1) / TILE_H * TILE_H;
+        if (brows < TILE_H) brows = TILE_H;
+        fp.tiles_per_band = brows / TILE_H;
+        const uint32_t rows_owned = c2rt_band_rows_owned(H, fp.rank, fp.n_ranks, brows);
+        const size_t need = (size_t)rows_owned * W;
+        if (c.rgb_cap < need * 3) {
+            cudaFree(c.d_rgb);
+            c.d_rgb = nullptr; c.rgb_cap = 0;
+            CU(cudaMalloc(&c.d_rgb, std::max<size_t>(need, 1) * 3 * sizeof(float)));
+            c.rgb_cap = need * 3;
+        }
+        if (argb && c.argb_cap < need) {
+            cudaFree(c.d_argb);
+            c.d_argb = nullptr; c.argb_cap = 0;
+            CU(cudaMalloc(&c.d_argb, std::max<size_t>(need, 1) * sizeof(uint32_t)));
+            c.argb_cap = need;
+        }
+        fp.rgb = c.d_rgb;
+        fp.argb = argb ? c.d_argb : nullptr;
+        CU(cudaEventRecord(c.e0, c.stream));
+        uint32_t local_row = 0, b = 0;
+        for (uint32_t y0 = (uint32_t)i * brows; y0 < H; y0 += (uint32_t)n * brows, b++) {
+            const uint32_t rows = std::min<uint32_t>(brows, H - y0);
+            if (b >= c.band_done.size()) {
+                cudaEvent_t e;
+                CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                c.band_done.push_back(e);
+            }
+            fp.tile_row0 = b * fp.tiles_per_band;
+            CU(launch_frame(fp, s->mode, (rows + TILE_H - 1) / TILE_H, c.stream));
+            launches++;
+            CU(cudaEventRecord(c.band_done[b], c.stream));
+            CU(cudaStreamWaitEvent(c.copy_stream, c.band_done[b], 0));
+            CU(cudaMemcpyAsync(rgb + (size_t)y0 * W * 3, c.d_rgb + (size_t)local_row * W * 3, (size_t)rows * W * 3 * sizeof(float),
+                               cudaMemcpyDeviceToHost, c.copy_stream));
+            if (argb)
+                CU(cudaMemcpyAsync(argb + (size_t)y0 * W, c.d_argb + (size_t)local_row * W, (size_t)rows * W * sizeof(uint32_t),
+                                   cudaMemcpyDeviceToHost, c.copy_stream));
+            local_row += rows;
+        }
+        CU(cudaEventRecord(c.e1, c.stream));
+        CU(cudaStreamSynchronize(c.copy_stream));
+        CU(cudaEventSynchronize(c.e1));
+        CU(cudaEventElapsedTime(kernel_ms_out, c.e0, c.e1));
+    }
+    *launches_out = launches;
+    return C2RT_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -609,6 +760,7 @@ int c2rt_init(int n_gpus, const int* device_ids) {
 
 void c2rt_shutdown(void) {
     std::lock_guard<std::mutex> g(g_mu);
+    g_pool.stop();
     for (int i = 0; i < g_ctx.n; i++) destroy_device(g_ctx.d[i]);
     g_ctx.n = 0;
     g_ctx.inited = false;
@@ -766,6 +918,7 @@ int c2rt_render(c2rt_scene* s, const c2rt_camera* cam, const c2rt_settings* set,
     }
     uint32_t launches = 0;
     bool copied = false;
+    double direct_kernel_ms = 0;
     if (n == 1) {
         // One device: launch the frame in up to 4 chunks of tile rows and copy each chunk back on a second
         // stream while the next one renders (the D2H copy of a float frame costs more than rendering it).
@@ -805,68 +958,37 @@ int c2rt_render(c2rt_scene* s, const c2rt_camera* cam, const c2rt_settings* set,
     // peers store their bands straight into it through peer-mapped pointers (NVLink), device 0 copies it back.
     const char* gather_env = getenv("C2RT_GATHER");
     const bool direct = n > 1 && !(gather_env && strcmp(gather_env, "root") == 0);
-    for (int i = 0; i < n && direct; i++) {
-        DeviceCtx& c = g_ctx.d[i];
-        CU(cudaSetDevice(c.dev));
-        rc = make_resident(s, i, c.stream);
-        if (rc) return rc;
-        FrameParams fp;
-        fill_params(fp, cam, set);
-        fp.rank = (uint32_t)i;
-        fp.n_ranks = (uint32_t)n;
-        fp.tiles_per_band = 1;
-        fp.compact = 1;
-        fp.counters = c.d_counters;
-        fp.lut = c.d_lut;
-        // 2..16 interleaved bands per device (one band per ~256k pixels): each band is one launch + one contiguous
-        // D2H copy, so small frames must not be cut into many bands (every launch / copy costs a few host microseconds)
-        uint32_t per_dev = (uint32_t)std::min<size_t>(16, std::max<size_t>(2, npx / (size_t)n / 262144));
-        uint32_t brows = (H / ((uint32_t)n * per_dev) + TILE_H - 1) / TILE_H * TILE_H;
-        if (brows < TILE_H) brows = TILE_H;
-        fp.tiles_per_band = brows / TILE_H;
-        const uint32_t rows_owned = c2rt_band_rows_owned(H, fp.rank, fp.n_ranks, brows);
-        const size_t need = (size_t)rows_owned * W;
-        if (c.rgb_cap < need * 3) {
-            cudaFree(c.d_rgb);
-            c.d_rgb = nullptr; c.rgb_cap = 0;
-            CU(cudaMalloc(&c.d_rgb, std::max<size_t>(need, 1) * 3 * sizeof(float)));
-            c.rgb_cap = need * 3;
-        }
-        if (argb && c.argb_cap < need) {
-            cudaFree(c.d_argb);
-            c.d_argb = nullptr; c.argb_cap = 0;
-            CU(cudaMalloc(&c.d_argb, std::max<size_t>(need, 1) * sizeof(uint32_t)));
-            c.argb_cap = need;
-        }
-        fp.rgb = c.d_rgb;
-        fp.argb = argb ? c.d_argb : nullptr;
-        CU(cudaEventRecord(c.e0, c.stream));
-        uint32_t local_row = 0, b = 0;
-        for (uint32_t y0 = (uint32_t)i * brows; y0 < H; y0 += (uint32_t)n * brows, b++) {
-            const uint32_t rows = std::min<uint32_t>(brows, H - y0);
-            if (b >= c.band_done.size()) {
-                cudaEvent_t e;
-                CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-                c.band_done.push_back(e);
-            }
-            fp.tile_row0 = b * fp.tiles_per_band;
-            CU(launch_frame(fp, s->mode, (rows + TILE_H - 1) / TILE_H, c.stream));
-            launches++;
-            CU(cudaEventRecord(c.band_done[b], c.stream));
-            CU(cudaStreamWaitEvent(c.copy_stream, c.band_done[b], 0));
-            CU(cudaMemcpyAsync(rgb + (size_t)y0 * W * 3, c.d_rgb + (size_t)local_row * W * 3, (size_t)rows * W * 3 * sizeof(float),
-                               cudaMemcpyDeviceToHost, c.copy_stream));
-            if (argb)
-                CU(cudaMemcpyAsync(argb + (size_t)y0 * W, c.d_argb + (size_t)local_row * W, (size_t)rows * W * sizeof(uint32_t),
-                                   cudaMemcpyDeviceToHost, c.copy_stream));
-            local_row += rows;
-        }
-        CU(cudaEventRecord(c.e1, c.stream));
-    }
     if (direct) {
+        // scene residency first, on this thread: make_resident patches the shared host copy of the scene block per device
         for (int i = 0; i < n; i++) {
+            if (g_ctx.d[i].uploaded_scene == s->id) continue;
             CU(cudaSetDevice(g_ctx.d[i].dev));
-            CU(cudaStreamSynchronize(g_ctx.d[i].copy_stream));
+            rc = make_resident(s, i, g_ctx.d[i].stream);
+            if (rc) return rc;
+        }
+        // one host thread per device (DevicePool): worker w drives device w + 1, this thread drives device 0
+        int rcs[C2RT_MAX_GPUS] = {};
+        uint32_t ls[C2RT_MAX_GPUS] = {};
+        float kms[C2RT_MAX_GPUS] = {};
+        std::string errs[C2RT_MAX_GPUS];
+        const bool pooled = g_pool.size() == n - 1;
+        if (pooled)
+            g_pool.run([&](int w) {
+                rcs[w + 1] = render_direct_device(w + 1, n, s, cam, set, rgb, argb, &ls[w + 1], &kms[w + 1]);
+                if (rcs[w + 1]) errs[w + 1] = g_err;
+            });
+        else
+            for (int i = 1; i < n; i++) {
+                rcs[i] = render_direct_device(i, n, s, cam, set, rgb, argb, &ls[i], &kms[i]);
+                if (rcs[i]) errs[i] = g_err;
+            }
+        rcs[0] = render_direct_device(0, n, s, cam, set, rgb, argb, &ls[0], &kms[0]);
+        if (rcs[0]) errs[0] = g_err;
+        if (pooled) g_pool.wait();
+        for (int i = 0; i < n; i++) {
+            if (rcs[i]) { g_err = errs[i]; return rcs[i]; }
+            launches += ls[i];
+            if (kms[i] > direct_kernel_ms) direct_kernel_ms = kms[i];
         }
         copied = true;
     }
@@ -923,8 +1045,8 @@ int c2rt_render(c2rt_scene* s, const c2rt_camera* cam, const c2rt_settings* set,
             }
         }
     }
-    double kernel_ms = 0;
-    for (int i = 0; i < n; i++) {
+    double kernel_ms = direct_kernel_ms;
+    for (int i = 0; i < n && !direct; i++) {
         DeviceCtx& c = g_ctx.d[i];
         CU(cudaSetDevice(c.dev));
         CU(cudaStreamSynchronize(c.stream));
