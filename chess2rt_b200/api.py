@@ -81,10 +81,12 @@ C_ABI_SYMBOLS = [
     "c2rt_scene_create", "c2rt_scene_destroy", "c2rt_render", "c2rt_render_device", "c2rt_read_ray_counters",
     "c2rt_deinterleave", "c2rt_render_pixel", "c2rt_band_rows_owned", "c2rt_rng_u31", "c2rt_srgb_table",
     "c2rt_frame_alloc", "c2rt_frame_free", "c2rt_frame_export", "c2rt_frame_import", "c2rt_frame_unimport", "c2rt_frame_download", "c2rt_pin_host_buffer", "c2rt_unpin_host_buffer", "c2rt_signal", "c2rt_wait_signals",
-    "c2rt_measure_fma_peak",
+    "c2rt_measure_fma_peak", "c2rt_selftest_device_pool",
 ]
 
 lib.c2rt_last_error.restype = C.c_char_p
+lib.c2rt_selftest_device_pool.argtypes = [C.c_int, C.c_int]
+lib.c2rt_selftest_device_pool.restype = C.c_longlong
 lib.c2rt_init.argtypes = [C.c_int, C.POINTER(C.c_int)]
 lib.c2rt_scene_create.argtypes = [C.POINTER(SceneDesc), C.POINTER(C.c_void_p)]
 lib.c2rt_scene_destroy.argtypes = [C.c_void_p]

@@ -1191,6 +1191,29 @@ int c2rt_unpin_host_buffer(void* ptr) {
     return C2RT_OK;
 }
 
+long long c2rt_selftest_device_pool(int workers, int rounds) {
+    if (workers < 1 || workers > 64 || rounds < 1) return -1;
+    DevicePool pool;   // a private pool: the library's own one is left alone
+    std::vector<std::atomic<long long>> hits(workers);
+    for (auto& h : hits) h.store(0);
+    long long total = 0;
+    for (int phase = 0; phase < 2; phase++) {   // phase 1 runs on a restarted pool
+        pool.start(workers);
+        for (int r = 0; r < rounds; r++) {
+            pool.run([&](int w) { hits[w].fetch_add(1, std::memory_order_relaxed); });
+            pool.wait();
+            // every so often let the workers fall asleep, so the condition-variable hand-off is taken too
+            if (r % 97 == 96) std::this_thread::sleep_for(std::chrono::milliseconds(3));
+        }
+        pool.stop();
+    }
+    for (auto& h : hits) {
+        if (h.load() != 2LL * rounds) return -2;   // a lost or duplicated round on some worker
+        total += h.load();
+    }
+    return total / 2;
+}
+
 int c2rt_measure_fma_peak(int fp64, double* tflops, double* sm_clock_mhz_est) {
     if (!tflops) return fail(C2RT_ERR_INVALID_ARG, "tflops is null");
     int dev = 0;

@@ -261,6 +261,12 @@ int c2rt_unpin_host_buffer(void* ptr);
  * dependent-free FFMA / DFMA throughput in TFLOP/s on the current device. */
 int c2rt_measure_fma_peak(int fp64, double* tflops, double* sm_clock_mhz_est);
 
+/* Test hook (no GPU needed): drives the helper-thread pool c2rt_render uses after c2rt_init(N > 1) through
+ * `rounds` frames of dummy work on `workers` threads, with the spin and the sleep hand-off paths both
+ * exercised, restarting the pool in between.  Returns the number of work items executed
+ * (== workers * rounds when nothing was lost or duplicated), negative on bad arguments. */
+long long c2rt_selftest_device_pool(int workers, int rounds);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,6 +36,14 @@ def test_library_exports_every_declared_symbol():
     assert declared <= exported
 
 
+@pytest.mark.parametrize("workers,rounds", [(1, 3000), (7, 3000), (15, 1000)])
+def test_device_pool_hands_every_frame_to_every_worker(workers, rounds):
+    """The helper threads of the multi-device c2rt_render (one per extra device): no frame lost or run twice,
+    across the spinning and the sleeping hand-off and a pool restart (no GPU involved)."""
+    assert api.lib.c2rt_selftest_device_pool(workers, rounds) == workers * rounds
+    assert api.lib.c2rt_selftest_device_pool(0, 1) < 0
+
+
 def test_struct_layouts_match_header_sizes():
     # sizes the C compiler gives the ABI structs (x86-64 SysV): guards the ctypes mirrors
     assert C.sizeof(api.Camera) == 7 * 24 + 4 * 4 + 3 * 8
