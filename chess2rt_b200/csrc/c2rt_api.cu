@@ -1,5 +1,6 @@
-// C ABI of libc2rt.so (include/c2rt.h): scene validation + upload, frame launches on 1..8 devices,
-// P2P band stores into device 0's frame, host copies, error reporting.  No CPU fallback anywhere:
+// C ABI of libc2rt.so (include/c2rt.h): scene validation + upload (scene class, bounding spheres, node runs), frame
+// launches on 1..8 devices (one helper thread per extra device: DevicePool), band copies to the host frame or P2P band
+// stores into device 0's frame, error reporting.  No CPU fallback anywhere:
 // every rendering entry point fails with C2RT_ERR_CUDA if the CUDA runtime cannot run the kernel.
 #include <cuda_runtime.h>
 
@@ -9,13 +10,13 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
-#include <cstring>
 #include <atomic>
 #include <condition_variable>
+#include <cstring>
 #include <functional>
 #include <mutex>
-#include <thread>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "scene_dev.h"

@@ -3,8 +3,8 @@
 // framebuffer stores staged through shared memory.
 //
 // What each device function replaces in the reference (paths relative to /root/reference/source):
-//   gen_ray            rt/camera.d:123-174 getScreenRay (+ :258-269 unitDiscSample, util/random.d:19-28)
-//   isect_plane        rt/geometry.d:30-59
+//   gen_ray            rt/camera.d:123-174 getScreenRay (+ :258-269 unitDiscSample via sincos_rev, util/random.d:19-28)
+//   isect_plane        rt/geometry.d:30-59 (isect_plane_u: the same test for the un-normalised camera rays of plane-only scenes)
 //   isect_sphere       rt/geometry.d:92-125
 //   isect_cube         rt/geometry.d:172-235
 //   isect_csg          rt/geometry.d:271-332, :382-397; util/array.d:95-111 (shell sort) — closed form, primitive children
@@ -12,15 +12,18 @@
 //   geom_inside        rt/geometry.d:25-28,127-130,165-170,334-337
 //   node_intersect / generic_intersect   rt/node.d:23-49 + rt/transform.d:57-86
 //   cull_sphere        (no counterpart: conservative FP32 bounding-sphere rejection, one and two level)
-//   occluded           rt/scene.d:62-78 testVisibility
-//   sample_texture     rt/texture.d:36-54,77-86,116-126 + rt/bitmap.d:48-63
+//   occluded           rt/scene.d:62-78 testVisibility (occluded_planes: plane-only scenes, settled by the sign of D.y)
+//   sample_texture     rt/texture.d:36-54,77-86 (Procedure2's sines through sin_rev),116-126 + rt/bitmap.d:48-63
 //   shade              rt/shader.d:67-105 (Lambert), :197-250 (Phong)
 //   trace              rt/renderer.d:325-376 (+ rt/environment.d:7-10)
 //   render_sample      rt/renderer.d:254-313 (renderSampleDefault / renderSampleDof, stereo via color.d:10-15)
-//   render_frame_kernel rt/renderer.d:83-251 (renderRT: 1-spp + AA passes fused per pixel; prepassOnly preview)
+//   render_frame_kernel rt/renderer.d:83-251 (renderRT: 1-spp + AA passes fused per pixel; prepassOnly preview;
+//                      GI frames, renderer.d:289-301,378-463, are black by construction: fp.gi, see c2rt_api.cu fill_params)
 //   render_pixel_kernel rt/renderer.d:46-57 (renderPixel)
 //   pack_rgb32         rt/color.d:154-162,209-214
 // Decisions and coordinates run in FP64, colours in FP32 (precision plan below).
+// The kernel is instantiated per scene class (MODE_* in scene_dev.h): one plane + one light scenes (MODE_SOLO) address
+// every scene constant statically and compile the texture / shader kind in; launch_frame at the end of the file dispatches.
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
