@@ -81,6 +81,18 @@ def test_loader_and_flattener_lecture5():
     np.testing.assert_array_equal(got, tex0)
 
 
+def test_settings_block_carries_the_gi_fields(tmp_path):
+    """GlobalSettings -> c2rt_settings (flatten.cpp flattenSettings): GIEnabled / pathsPerPixel / bucketSize reach the ABI."""
+    from test_oracle_kat import GI_SCENE
+    p = tmp_path / "gi.sdl"
+    p.write_text(GI_SCENE.format(paths=6, cam="", ball_shader="Lambert"))
+    _, st = c2.HostScene(str(p)).frame_blocks(seed=9)
+    assert (st.gi_enabled, st.paths_per_pixel, st.max_trace_depth, st.bucket_size, st.rng_seed) == (1, 6, 3, 48, 9)
+    assert (st.frame_width, st.frame_height, st.aa_enabled) == (96, 64, 1)
+    _, st = c2.HostScene(os.path.join(SC, "lecture4.sdl")).frame_blocks()
+    assert (st.gi_enabled, st.paths_per_pixel) == (0, 40)   # global_settings.d:8-35 defaults
+
+
 def test_loader_json_equals_sdl_and_quirks():
     a = c2.HostScene(os.path.join(SC, "lecture4.sdl"))
     b = c2.HostScene(os.path.join(SC, "lecture4.json"))
