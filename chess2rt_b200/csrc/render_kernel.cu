@@ -1016,14 +1016,20 @@ __device__ __forceinline__ Col shade(const FrameParams& fp, const Ray& ray, cons
 }
 
 template <int MODE>
-__device__ __forceinline__ Col trace(const FrameParams& fp, const Ray& ray, unsigned& n_shadow, HitRec* out_hit) {
+__device__ __forceinline__ Col trace(const FrameParams& fp, const Ray& ray, unsigned& n_shadow, HitRec* out_hit, unsigned long long tile_nodes) {
     HitRec h;
     h.dist = 1e99;
     h.node = -1;
     float tmaxf = 3.0e38f;   // (not +inf = (float)1e99: ptxas would prove tmaxf == (float)h.dist * k and re-convert it in every iteration)
     const int ncl = (MODE & MODE_CLUSTERS) ? c_scene.n_clusters : 1;
     if (MODE & MODE_SOLO) node_intersect<MODE>(0, ray, h, tmaxf);
-    else for (int ci = 0; ci < ncl; ci++) {
+    else if (tile_culled(MODE)) {
+        // camera rays of this CTA only visit the nodes its tile cone can reach (tile_node_mask), in scene order
+        for (unsigned long long m = tile_nodes; m; m &= m - 1) {
+            const int i = __ffsll((long long)m) - 1;
+            if (node_intersect<MODE>(i, ray, h, tmaxf)) tmaxf = (float)h.dist * 1.000001f;
+        }
+    } else for (int ci = 0; ci < ncl; ci++) {
         int begin = 0, end = c_scene.n_nodes;
         if (MODE & MODE_CLUSTERS) {
             const DevCluster& cl = c_scene.clusters[ci];
@@ -1061,13 +1067,14 @@ __device__ __forceinline__ Col combine_stereo(Col left, Col right) {
 
 template <int MODE>
 __device__ __forceinline__ Col render_sample(const FrameParams& fp, double bx, double by, double bz, double x, double y, uint32_t px,
-                                             uint32_t py, uint32_t tap, double jw, double jh, unsigned& n_primary, unsigned& n_shadow, HitRec* out_hit) {
+                                             uint32_t py, uint32_t tap, double jw, double jh, unsigned& n_primary, unsigned& n_shadow, HitRec* out_hit,
+                                             unsigned long long tile_nodes) {
     Ray r;
     if (!(MODE & MODE_SAMPLING)) {               // renderSampleDefault without stereo (renderer.d:303-306): one ray
         uint32_t draw = 0;
         n_primary++;
         gen_ray<MODE>(fp, bx + fp.tap_d[tap][0], by + fp.tap_d[tap][1], bz + fp.tap_d[tap][2], px, py, tap, 0, draw, 0, r);
-        return trace<MODE>(fp, r, n_shadow, out_hit);
+        return trace<MODE>(fp, r, n_shadow, out_hit, tile_nodes);
     }
     const bool stereo = fp.stereo_sep != 0;      // renderer.d:276-284,305-312: one ray per eye, then combineStereo
     const int n_eyes = stereo ? 2 : 1;
@@ -1090,7 +1097,7 @@ __device__ __forceinline__ Col render_sample(const FrameParams& fp, double bx, d
             }
             n_primary++;
             gen_ray<MODE>(fp, vx, vy, vz, px, py, tap, i, draw, stereo ? (e ? +1 : -1) : 0, r);
-            c = trace<MODE>(fp, r, n_shadow, (out_hit && i == 0 && e == 0) ? out_hit : nullptr);
+            c = trace<MODE>(fp, r, n_shadow, (out_hit && i == 0 && e == 0) ? out_hit : nullptr, tile_nodes);
             if (e == 0) left = c;
         }
         if (stereo) c = combine_stereo(left, c);
@@ -1108,6 +1115,43 @@ __device__ __forceinline__ uint32_t lut8(const uint8_t* lut, float x) {  // colo
 }
 __device__ __forceinline__ uint32_t pack_rgb32(const uint8_t* lut, Col c) {  // color.d:154-162
     return lut8(lut, c.b) | (lut8(lut, c.g) << 8) | (lut8(lut, c.r) << 16);
+}
+
+// ---------------------------------------------------------------- per-tile node mask
+// Which nodes can a camera ray of this CTA's 16x8 pixel tile reach?  All those rays start at the camera position and pass
+// through the screen rectangle [x0, x0+16] x [y0, y0+8] (pixel corners plus the AA tap offsets <= 0.6), so they lie in the
+// circular cone around the normalised sum of the four corner directions whose half-angle reaches the farthest corner (a circular
+// cone of less than 90 degrees is convex and contains the convex cone the corners span).  A node whose bounding sphere does not
+// touch that cone cannot be hit by any of them; the others are visited in scene order, so the reference's closest-hit and
+// tie rules (geometry.d:43,111,214) are untouched.  FP64 throughout (one thread per node, once per CTA), radius padded by
+// 1e-6 (r + distance): the sphere is already a conservative bound, this test only has to never drop a reachable node.
+__device__ __forceinline__ bool tile_reaches_node(const FrameParams& fp, uint32_t x0, uint32_t y0, int ni) {
+    const DevNode& nd = c_scene.nodes[ni];
+    if (nd.flags & NODE_UNBOUNDED) return true;
+    double u[4][3];
+    double ax = 0, ay = 0, az = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const double sx = (double)x0 + ((k & 1) ? (double)TILE_W : -0.01), sy = (double)y0 + ((k & 2) ? (double)TILE_H : -0.01);
+        screen_dir(fp, sx, sy, u[k][0], u[k][1], u[k][2]);
+        normalize3(u[k][0], u[k][1], u[k][2]);
+        ax += u[k][0]; ay += u[k][1]; az += u[k][2];
+    }
+    normalize3(ax, ay, az);
+    double cosphi = 1.0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) cosphi = fmin(cosphi, dot3(ax, ay, az, u[k][0], u[k][1], u[k][2]));
+    if (!(cosphi > 0.5)) return true;   // a tile wider than 60 degrees (tiny frames): no culling
+    const double sinphi = sqrt(fmax(0.0, 1.0 - cosphi * cosphi));
+    const double vx = (double)nd.bcf[0] - fp.pos[0], vy = (double)nd.bcf[1] - fp.pos[1], vz = (double)nd.bcf[2] - fp.pos[2];
+    const double d2 = dot3(vx, vy, vz, vx, vy, vz);
+    const double d = sqrt(d2);
+    const double r = (double)nd.brf * (1.0 + 1e-6) + 1e-6 * d;
+    if (!(d > r)) return true;                       // the camera is inside the sphere (or a NaN bound): keep
+    const double xa = dot3(vx, vy, vz, ax, ay, az);  // along the axis
+    const double ya = sqrt(fmax(0.0, d2 - xa * xa)); // away from it
+    if (xa * cosphi + ya * sinphi >= 0) return !(ya * cosphi - xa * sinphi > r);   // nearest cone point on the lateral surface
+    return false;                                    // nearest cone point is the apex, and d > r
 }
 
 // ---------------------------------------------------------------- frame kernel
@@ -1129,6 +1173,18 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS) render_frame_kernel
     const uint32_t ly = (warp >> 1) * 4 + (lane >> 3);
     const uint32_t x = x0 + lx, y = y0 + ly;
     const bool active = x < fp.W && y < fp.H;
+
+    // nodes this tile's camera rays can reach (one thread per node; C2RT_MAX_NODES <= 64 <= BLOCK_THREADS)
+    static_assert(C2RT_MAX_NODES <= 64 && C2RT_MAX_NODES <= BLOCK_THREADS, "the tile node mask is one 64-bit word filled by one thread per node");
+    __shared__ unsigned long long s_tile_nodes;
+    unsigned long long tile_nodes = 0;
+    if (tile_culled(MODE)) {
+        if (threadIdx.x == 0) s_tile_nodes = 0;
+        __syncthreads();
+        if ((int)threadIdx.x < c_scene.n_nodes && tile_reaches_node(fp, x0, y0, (int)threadIdx.x)) atomicOr(&s_tile_nodes, 1ull << threadIdx.x);
+        __syncthreads();
+        tile_nodes = s_tile_nodes;
+    }
 
     unsigned n_primary = 0, n_shadow = 0;
     Col c = mkcol(0.f, 0.f, 0.f);
@@ -1155,7 +1211,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS) render_frame_kernel
         screen_dir(fp, xd, yd, bx, by, bz);
 #pragma unroll 1
         for (int s = 0; s < taps; s++) {
-            Col t = render_sample<MODE>(fp, bx, by, bz, xd, yd, sx, sy, s, jw, jh, n_primary, n_shadow, nullptr);
+            Col t = render_sample<MODE>(fp, bx, by, bz, xd, yd, sx, sy, s, jw, jh, n_primary, n_shadow, nullptr, tile_nodes);
             c.r += t.r; c.g += t.g; c.b += t.b;
         }
         if (taps == 5) { c.r = c.r / 5.f; c.g = c.g / 5.f; c.b = c.b / 5.f; }  // accum / 5 (renderer.d:249)
@@ -1212,7 +1268,7 @@ __global__ void render_pixel_kernel(const FrameParams fp, int x, int y, PixelOut
     h.dist = 1e99;
     double bx, by, bz;
     screen_dir(fp, (double)x, (double)y, bx, by, bz);
-    Col c = render_sample<MODE_BOUNDED | MODE_GENERIC | MODE_NESTED | MODE_CLUSTERS | MODE_SAMPLING>(fp, bx, by, bz, (double)x, (double)y, (uint32_t)x, (uint32_t)y, 0, 1.0, 1.0, a, b, &h);
+    Col c = render_sample<MODE_BOUNDED | MODE_GENERIC | MODE_NESTED | MODE_CLUSTERS | MODE_SAMPLING>(fp, bx, by, bz, (double)x, (double)y, (uint32_t)x, (uint32_t)y, 0, 1.0, 1.0, a, b, &h, 0ull);
     out->rgb[0] = c.r; out->rgb[1] = c.g; out->rgb[2] = c.b;
     out->node = h.node;
     out->dist = h.dist;

@@ -128,6 +128,19 @@ __host__ __device__
 #endif
 constexpr bool plane_only(int mode) { return (mode & (MODE_BOUNDED | MODE_GENERIC | MODE_NESTED | MODE_CLUSTERS)) == 0; }
 
+// scene classes whose camera rays go through the per-tile node mask (render_kernel.cu tile_node_mask): bounded nodes exist and
+// every camera ray starts at the camera position (no DOF / stereo sampling loop)
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+constexpr bool tile_culled(int mode) {
+#ifdef C2RT_NO_TILE_CULL
+    return false && mode;
+#else
+    return (mode & MODE_BOUNDED) && !(mode & MODE_SAMPLING);
+#endif
+}
+
 constexpr int TILE_W = 16;
 constexpr int TILE_H = 8;
 constexpr int BLOCK_THREADS = TILE_W * TILE_H;
