@@ -283,6 +283,58 @@ def test_gi_literal_walk_is_black_and_halts_on_phong(tmp_path):
     assert rgb.max() > 0.1
 
 
+def test_tile_cone_keeps_every_node_a_camera_ray_hits():
+    """The geometry behind the kernel's per-tile node mask (render_kernel.cu tile_reaches_node), replayed in numpy with the same
+    formulae: every camera ray of a 16x8 pixel tile lies in the circular cone around the normalised sum of the tile's corner
+    directions, so a node whose bounding sphere misses that cone cannot be the oracle's hit for any pixel of the tile."""
+    import random
+    W, H = 960, 540
+    o = OracleScene(os.path.join(ROOT, "scenes", "chessboard.sdl"))
+    o.set_frame_size(W, H)
+    cv = o.camera_vectors()
+    pos, ul, ur, dl = cv[0], cv[1], cv[2], cv[3]
+    du, dv, ulrel = ur - ul, dl - ul, ul - pos
+    centres = [None] + [np.array([(f - 3.5) * 20.0, 12.0, (rank - 4.5) * 20.0]) for rank in (1, 2, 7, 8) for f in range(8)]
+    R = 24.0   # every piece of chess2rt_b200/chessboard.py fits in this sphere around (x, 12, z)
+
+    def reaches(x0, y0, c, r):
+        u = []
+        for k in range(4):
+            d = ulrel + du * ((x0 + (16 if k & 1 else -0.01)) / W) + dv * ((y0 + (8 if k & 2 else -0.01)) / H)
+            u.append(d / np.linalg.norm(d))
+        a = sum(u)
+        a /= np.linalg.norm(a)
+        cosphi = min(float(a @ uk) for uk in u)
+        if not cosphi > 0.5:
+            return True
+        sinphi = np.sqrt(max(0.0, 1 - cosphi * cosphi))
+        v = c - pos
+        d2 = float(v @ v)
+        d = np.sqrt(d2)
+        rr = r * (1 + 1e-6) + 1e-6 * d
+        if not d > rr:
+            return True
+        xa = float(v @ a)
+        ya = np.sqrt(max(0.0, d2 - xa * xa))
+        if xa * cosphi + ya * sinphi >= 0:
+            return not (ya * cosphi - xa * sinphi > rr)
+        return False
+
+    rnd = random.Random(1)
+    piece_hits, kept = 0, []
+    for _ in range(1500):
+        x, y = rnd.randrange(W), rnd.randrange(H)
+        _, hit = o.render_pixel(x, y)
+        node = int(hit[0])
+        mask = [i for i in range(1, 33) if reaches(x // 16 * 16, y // 8 * 8, centres[i], R)]
+        kept.append(len(mask))
+        if node >= 1:
+            piece_hits += 1
+            assert node in mask, (x, y, node, mask)
+    assert piece_hits > 200            # the sample does look at the pieces
+    assert np.mean(kept) < 4           # and the cone does cull: 32 pieces, a handful per tile
+
+
 def test_golden_fixtures_reproduce():
     meta = json.load(open(os.path.join(GOLD, "golden.json")))
     for name, m in meta.items():
