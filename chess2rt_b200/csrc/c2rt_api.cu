@@ -322,73 +322,6 @@ Bound bound_of(const c2rt_scene_desc* d, int gi) {
     return b;
 }
 
-// Partition of the node list into contiguous runs sharing a bounding sphere (DevCluster).  Cost model: a run
-// of k > 1 nodes costs one sphere test plus k node tests with probability (r_run / r_all)^2 (the chance that
-// a ray through the scene's bound also passes through the run's bound); a run of one node costs its own test.
-// Unbounded nodes (planes) are always runs of one.  O(n^2) dynamic programme, n <= 64.
-void build_clusters(DevScene& h) {
-    const int n = h.n_nodes;
-    h.n_clusters = 0;
-    if (n == 0) return;
-    auto sphere_of = [&](int i) {
-        Bound b{};
-        b.finite = !(h.nodes[i].flags & NODE_UNBOUNDED);
-        b.c[0] = h.nodes[i].bcf[0]; b.c[1] = h.nodes[i].bcf[1]; b.c[2] = h.nodes[i].bcf[2];
-        b.r = h.nodes[i].brf;
-        return b;
-    };
-    Bound all{};
-    bool any = false;
-    for (int i = 0; i < n; i++) {
-        Bound b = sphere_of(i);
-        if (!b.finite) continue;
-        all = any ? union_bound(all, b) : b;
-        any = true;
-    }
-    const double rall = any && all.r > 0 ? all.r : 1.0;
-    std::vector<double> best(n + 1, 0.0);
-    std::vector<int> from(n + 1, 0);
-    for (int i = 1; i <= n; i++) {
-        best[i] = best[i - 1] + 1.0;  // run of one
-        from[i] = i - 1;
-        Bound run = sphere_of(i - 1);
-        if (!run.finite) continue;
-        for (int j = i - 2; j >= 0; j--) {
-            Bound b = sphere_of(j);
-            if (!b.finite) break;  // runs never span an unbounded node
-            run = union_bound(b, run);
-            double p = (run.r / rall) * (run.r / rall);
-            if (p > 1) p = 1;
-            double cost = best[j] + 1.0 + p * (i - j);
-            if (cost < best[i]) { best[i] = cost; from[i] = j; }
-        }
-    }
-    // the two-level loop has its own overhead: keep the flat node loop unless the model predicts a clear win
-    if (best[n] > 0.6 * n)
-        for (int i = 1; i <= n; i++) from[i] = i - 1;
-    std::vector<std::pair<int, int>> runs;
-    for (int i = n; i > 0; i = from[i]) runs.push_back({from[i], i});
-    for (auto it = runs.rbegin(); it != runs.rend(); ++it) {
-        DevCluster& cl = h.clusters[h.n_clusters++];
-        memset(&cl, 0, sizeof cl);
-        cl.begin = it->first;
-        cl.end = it->second;
-        if (cl.end - cl.begin > 1) {
-            Bound run = sphere_of(cl.begin);
-            for (int k = cl.begin + 1; k < cl.end; k++) run = union_bound(run, sphere_of(k));
-            float fx = (float)run.c[0], fy = (float)run.c[1], fz = (float)run.c[2];
-            double shift = sqrt((run.c[0] - fx) * (run.c[0] - fx) + (run.c[1] - fy) * (run.c[1] - fy) + (run.c[2] - fz) * (run.c[2] - fz));
-            double r = (run.r + shift) * (1.0 + 1e-6);
-            float rf = (float)r;
-            if ((double)rf < r) rf = nextafterf(rf, INFINITY);
-            cl.c[0] = fx; cl.c[1] = fy; cl.c[2] = fz;
-            cl.r = rf;
-            cl.r2 = nextafterf(rf * rf, INFINITY);
-            cl.clen = nextafterf(sqrtf(fx * fx + fy * fy + fz * fz), INFINITY);
-        }
-    }
-}
-
 bool is_identity(const double* m) {
     for (int i = 0; i < 9; i++)
         if (m[i] != ((i % 4 == 0) ? 1.0 : 0.0)) return false;
@@ -548,16 +481,15 @@ int validate_and_build(const c2rt_scene_desc* d, c2rt_scene* s) {
                 nd.wp[1] = nd.Minv[0];
                 nd.wp[2] = nd.Minv[8];
             }
-        } else if ((nd.flags & NODE_IDENTITY) && (g.type == C2RT_GEOM_SPHERE || g.type == C2RT_GEOM_CUBE)) {
+        } else if ((nd.flags & NODE_IDENTITY) && !(nd.flags & NODE_UNBOUNDED) && (g.type == C2RT_GEOM_SPHERE || g.type == C2RT_GEOM_CUBE)) {
+            // (a sphere / cube whose bound was rejected — non-finite or overflowing radius — stays KIND_GENERIC: the
+            // plane-only and bounded kernel classes assume every KIND_*_W sphere / cube carries a finite bound)
             nd.kind = g.type == C2RT_GEOM_SPHERE ? KIND_SPHERE_W : KIND_CUBE_W;
             nd.wp[0] = g.p[0] + nd.off[0]; nd.wp[1] = g.p[1] + nd.off[1]; nd.wp[2] = g.p[2] + nd.off[2];
             nd.wp[3] = g.p[3];
         }
     }
-    build_clusters(h);
     s->mode = 0;
-    for (int c = 0; c < h.n_clusters; c++)
-        if (h.clusters[c].end - h.clusters[c].begin > 1) s->mode |= 8 | 1;  // MODE_CLUSTERS
     for (uint32_t i = 0; i < d->n_nodes; i++) {
         if (!(h.nodes[i].flags & NODE_UNBOUNDED)) s->mode |= 1;   // MODE_BOUNDED
         if (h.nodes[i].kind == KIND_GENERIC) s->mode |= 2;        // MODE_GENERIC

@@ -11,10 +11,12 @@
 //   isect_geom_lit     the same walk replayed literally for CSG nested inside CSG
 //   geom_inside        rt/geometry.d:25-28,127-130,165-170,334-337
 //   node_intersect / generic_intersect   rt/node.d:23-49 + rt/transform.d:57-86
-//   cull_sphere        (no counterpart: conservative FP32 bounding-sphere rejection, one and two level)
-//   occluded           rt/scene.d:62-78 testVisibility (occluded_planes: plane-only scenes, settled by the sign of D.y)
+//   cull_sphere        (no counterpart: conservative FP32 bounding-sphere rejection per ray)
+//   camera_mask / shadow_mask  (no counterpart: per-warp node masks by warp ballot — which nodes can ANY ray of the warp reach)
+//   occluded_warp      rt/scene.d:62-78 testVisibility, walked warp-uniformly over the shadow mask, left through __all_sync
+//                      (occluded_planes: plane-only scenes, settled by the sign of D.y)
 //   sample_texture     rt/texture.d:36-54,77-86 (Procedure2's sines through sin_rev),116-126 + rt/bitmap.d:48-63
-//   shade              rt/shader.d:67-105 (Lambert), :197-250 (Phong)
+//   shade / shade_warp rt/shader.d:67-105 (Lambert), :197-250 (Phong)
 //   trace              rt/renderer.d:325-376 (+ rt/environment.d:7-10)
 //   render_sample      rt/renderer.d:254-313 (renderSampleDefault / renderSampleDof, stereo via color.d:10-15)
 //   render_frame_kernel rt/renderer.d:83-251 (renderRT: 1-spp + AA passes fused per pixel; prepassOnly preview;
@@ -696,11 +698,97 @@ __device__ __forceinline__ bool node_intersect(int ni, const Ray& r, HitRec& h, 
     return node_exact<MODE, true>(ni, nd, r, h);
 }
 
-// scene.d:62-78 testVisibility.  (fx,fy,fz) is the shadow-ray origin, D = to - from (unnormalised),
-// len2 = |D|^2.  The FP64 normalisation (scene.d:66-71) is done lazily: most nodes are rejected by a
-// sign test (planes) or the FP32 cull, which only need FP32 directions.
+// ---------------------------------------------------------------- per-warp node masks (warp ballot / vote)
+// The reference tests every ray against every node (renderer.d:336-338, scene.d:73-75).  Here the 32 lanes of a warp
+// (an 8x4 pixel patch) first decide TOGETHER which nodes any of their rays can reach: lane l tests the bounding spheres of
+// nodes l, l + 32, ... against a volume that contains all 32 rays, and one __ballot_sync per 32 nodes turns the answers
+// into a bit mask that every lane then walks in scene order (so the reference's closest-hit and tie rules,
+// geometry.d:43,111,214, are untouched).  The walk is warp-uniform — same node for all lanes, per-lane work predicated —
+// and a shadow walk is left through __all_sync as soon as every lane that needs an answer has found an occluder
+// (the reference's early return at the first occluder, scene.d:73-75, taken by the whole warp at once).
+constexpr int MASK_WORDS = (C2RT_MAX_NODES + 31) / 32;
+constexpr unsigned FULL_WARP = 0xffffffffu;
+struct NodeMask {
+    uint32_t w[MASK_WORDS];
+};
+__device__ __forceinline__ NodeMask all_nodes_mask() {
+    NodeMask m;
+#pragma unroll
+    for (int k = 0; k < MASK_WORDS; k++) {
+        const int left = c_scene.n_nodes - 32 * k;
+        m.w[k] = left >= 32 ? 0xffffffffu : left > 0 ? (1u << left) - 1u : 0u;
+    }
+    return m;
+}
+// warp-wide FP32 min / max in one instruction each (CREDUX, sm_100a), result in a uniform register
+__device__ __forceinline__ float warp_min(float v) {
+    float r;
+    asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float warp_max(float v) {
+    float r;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
+
+// Which nodes can a shadow ray of this warp reach?  Every shadow segment runs from a lane's origin to the light, so all of
+// them lie in the convex hull of {light} and the lanes' origins, which lies in the capsule around the segment
+// (centre of the origins' bounding box -> light) with the box's half-diagonal as radius.  A node whose bounding sphere
+// stays clear of that capsule cannot occlude any lane.  FP32 with an explicit rounding margin (8e-6 of the magnitudes
+// involved: the arithmetic below loses < 1e-6 of them); the node spheres are already inflated (c2rt_api.cu).
 template <int MODE>
-__device__ __forceinline__ bool occluded(double fx, double fy, double fz, double Dx, double Dy, double Dz, double len2) {
+__device__ __forceinline__ NodeMask shadow_mask(bool need, const Ray& r, const DevLight& L, bool& any) {
+    NodeMask m = all_nodes_mask();
+    any = true;
+    if (!(MODE & MODE_BOUNDED)) { any = __any_sync(FULL_WARP, need); return m; }
+#ifdef C2RT_NO_WARP_MASK
+    any = __any_sync(FULL_WARP, need);
+    return m;
+#else
+    const float INF = __int_as_float(0x7f800000);
+    const float mnx = warp_min(need ? r.fox : INF), mxx = warp_max(need ? r.fox : -INF);
+    const float mny = warp_min(need ? r.foy : INF), mxy = warp_max(need ? r.foy : -INF);
+    const float mnz = warp_min(need ? r.foz : INF), mxz = warp_max(need ? r.foz : -INF);
+    any = mnx <= mxx;
+    if (!any) return m;   // no lane of this warp needs a shadow ray (warp-uniform)
+    const float cx = 0.5f * (mnx + mxx), cy = 0.5f * (mny + mxy), cz = 0.5f * (mnz + mxz);
+    const float hx = mxx - cx, hy = mxy - cy, hz = mxz - cz;
+    const float rho = sqrtf(dot3f(hx, hy, hz, hx, hy, hz));
+    const float dx = L.posf[0] - cx, dy = L.posf[1] - cy, dz = L.posf[2] - cz;   // capsule axis: box centre -> light
+    const float dd = dot3f(dx, dy, dz, dx, dy, dz);
+    const float inv_dd = dd > 0.f ? 1.0f / dd : 0.f;
+    const float mag = sqrtf(dot3f(cx, cy, cz, cx, cy, cz)) + sqrtf(dd);
+    const unsigned lane = threadIdx.x & 31u;
+#pragma unroll
+    for (int k = 0; k < MASK_WORDS; k++) {
+        if (32 * k >= c_scene.n_nodes) { m.w[k] = 0; continue; }
+        const int i = 32 * k + (int)lane;
+        bool reach = false;
+        if (i < c_scene.n_nodes) {
+            const DevNode& nd = c_scene.nodes[i];
+            if (nd.flags & NODE_UNBOUNDED) reach = true;
+            else {
+                const float ax = nd.bcf[0] - cx, ay = nd.bcf[1] - cy, az = nd.bcf[2] - cz;
+                const float t = fminf(fmaxf(dot3f(ax, ay, az, dx, dy, dz) * inv_dd, 0.f), 1.f);
+                const float qx = fmaf(-t, dx, ax), qy = fmaf(-t, dy, ay), qz = fmaf(-t, dz, az);
+                const float reachr = nd.brf + rho + 8e-6f * (mag + nd.bclen + rho);
+                reach = !(dot3f(qx, qy, qz, qx, qy, qz) > reachr * reachr);   // (a NaN bound keeps the node)
+            }
+        }
+        m.w[k] = __ballot_sync(FULL_WARP, reach);
+    }
+    return m;
+#endif
+}
+
+// scene.d:62-78 testVisibility for the warp: lane-wise `need` says whether this lane has a shadow ray at all (it hit
+// something and the light is lit); (fx,fy,fz) is its origin, D = to - from (unnormalised), len2 = |D|^2.  All 32 lanes
+// call this together.  The FP64 normalisation (scene.d:66-71) is done lazily per lane: most nodes are rejected by a sign
+// test (planes) or the FP32 cull, which only need FP32 directions.
+template <int MODE>
+__device__ __forceinline__ bool occluded_warp(bool need, double fx, double fy, double fz, double Dx, double Dy, double Dz, double len2,
+                                              const DevLight& L) {
     Ray r;
     r.ox = fx; r.oy = fy; r.oz = fz;
     float tmaxf = 0.f;
@@ -712,36 +800,39 @@ __device__ __forceinline__ bool occluded(double fx, double fy, double fz, double
         r.olen = sqrtf(dot3f(r.fox, r.foy, r.foz, r.fox, r.foy, r.foz));
         tmaxf = l2f * rsf * 1.000001f;
     }
-    bool exact = false;
+    bool any;
+    const NodeMask m = shadow_mask<MODE>(need, r, L, any);
+    if (!any) return false;
+    bool occl = false, exact = false;
     HitRec h;
-    const int ncl = (MODE & MODE_CLUSTERS) ? c_scene.n_clusters : 1;
-    for (int ci = 0; ci < ncl; ci++) {
-        int begin = 0, end = (MODE & MODE_SOLO) ? 1 : c_scene.n_nodes;
-        if (MODE & MODE_CLUSTERS) {
-            const DevCluster& cl = c_scene.clusters[ci];
-            if (cl.end - cl.begin > 1 && cull_sphere(cl.c[0], cl.c[1], cl.c[2], cl.r, cl.r2, cl.clen, r, tmaxf)) continue;
-            begin = cl.begin; end = cl.end;
-        }
-#pragma unroll 1
-        for (int i = begin; i < end; i++) {
-            const DevNode& nd = c_scene.nodes[(MODE & MODE_SOLO) ? 0 : i];
-            if (plane_only(MODE) || nd.kind == KIND_PLANE_W) {
-                // implied by geometry.d:35-36 (dir.y has the sign of D.y): the common "light above the floor" case
-                const double y = nd.wp[0];
-                if ((fy > y && Dy >= 0) || (fy < y && Dy <= 0)) continue;
-            } else if ((MODE & MODE_BOUNDED) && !(nd.flags & NODE_UNBOUNDED)) {
-                if (cull(nd, r, tmaxf)) continue;
+#pragma unroll
+    for (int k = 0; k < MASK_WORDS; k++) {
+        for (uint32_t bits = m.w[k]; bits; bits &= bits - 1) {
+            const int i = 32 * k + __ffs((int)bits) - 1;   // warp-uniform
+            const DevNode& nd = c_scene.nodes[i];
+            if (need && !occl) {
+                bool skip = false;
+                if (nd.kind == KIND_PLANE_W) {
+                    // implied by geometry.d:35-36 (dir.y has the sign of D.y): the common "light above the floor" case
+                    const double y = nd.wp[0];
+                    skip = (fy > y && Dy >= 0) || (fy < y && Dy <= 0);
+                } else if ((MODE & MODE_BOUNDED) && !(nd.flags & NODE_UNBOUNDED)) {
+                    skip = cull(nd, r, tmaxf);
+                }
+                if (!skip) {
+                    if (!exact) {
+                        const double inv = rsqrt64(len2);
+                        r.dx = Dx * inv; r.dy = Dy * inv; r.dz = Dz * inv;
+                        h.dist = len2 * inv;
+                        exact = true;
+                    }
+                    if (node_exact<MODE, false>(i, nd, r, h)) occl = true;
+                }
             }
-            if (!exact) {
-                const double inv = rsqrt64(len2);
-                r.dx = Dx * inv; r.dy = Dy * inv; r.dz = Dz * inv;
-                h.dist = len2 * inv;
-                exact = true;
-            }
-            if (node_exact<MODE, false>(i, nd, r, h)) return true;
+            if (__all_sync(FULL_WARP, !need || occl)) return occl;   // every lane that asked has its occluder
         }
     }
-    return false;
+    return occl;
 }
 
 // testVisibility for the plane-only scene classes.  Dy = light.y - from.y in FP64 settles almost every plane by sign;
@@ -925,8 +1016,10 @@ __device__ __forceinline__ void surface_of(const HitRec& hin, const Ray* ray, bo
     s.nx = fx * inv; s.ny = fy * inv; s.nz = fz * inv;
 }
 
+// Per-lane form: the plane-only scene classes (shadow rays among planes are settled by signs, occluded_planes)
 template <int MODE>
 __device__ __forceinline__ Col shade(const FrameParams& fp, const Ray& ray, const HitRec& h, unsigned& n_shadow) {
+    static_assert(plane_only(MODE), "scene classes with bounded / generic nodes shade through shade_warp");
     constexpr bool SOLO = (MODE & MODE_SOLO) != 0;
     const DevShader& sh = c_scene.shaders[SOLO ? 0 : c_scene.nodes[h.node].shader];
     const bool has_tex = SOLO ? (MODE & MODE_TEX_MASK) != 0 : sh.tex >= 0;
@@ -961,11 +1054,7 @@ __device__ __forceinline__ Col shade(const FrameParams& fp, const Ray& ray, cons
             fDx = L.posf[0] - (float)fx; fDy = (float)Dy; fDz = L.posf[2] - (float)fz;
             d2 = dot3f(fDx, fDy, fDz, fDx, fDy, fDz);
         } else {
-            Dx = L.pos[0] - fx; Dy = L.pos[1] - fy; Dz = L.pos[2] - fz;
-            const double len2 = dot3(Dx, Dy, Dz, Dx, Dy, Dz);
-            if (occluded<MODE>(fx, fy, fz, Dx, Dy, Dz, len2)) continue;
-            fDx = (float)Dx; fDy = (float)Dy; fDz = (float)Dz;
-            d2 = (float)len2;
+            Dx = Dy = Dz = 0; fDx = fDy = fDz = 0.f; d2 = 1.f;   // (not instantiated: see the static_assert)
         }
         // lighting in FP32 (the reference narrows every factor to float before it touches a Color: SURVEY.md App. C.1)
         const float rs = rsqrtf(d2);
@@ -1015,31 +1104,107 @@ __device__ __forceinline__ Col shade(const FrameParams& fp, const Ray& ray, cons
                  fmaf(diffuse.b, lightContrib.b, specular.b));
 }
 
+// Lambert / Phong for the scene classes with bounded or generic nodes, called by all 32 lanes together (`hit` says whether
+// this lane has a surface to shade): the surface and the texture lookup are per lane, the light loop is warp-uniform and
+// each light's shadow rays go through occluded_warp.
 template <int MODE>
-__device__ __forceinline__ Col trace(const FrameParams& fp, const Ray& ray, unsigned& n_shadow, HitRec* out_hit, unsigned long long tile_nodes) {
+__device__ __forceinline__ Col shade_warp(const FrameParams& fp, const Ray& ray, const HitRec& h, bool hit, unsigned& n_shadow) {
+    Surface s;
+    float Nx = 0.f, Ny = 0.f, Nz = 0.f;
+    Col diffuse = mkcol(0.f, 0.f, 0.f);
+    double fx = 0, fy = 0, fz = 0;
+    bool phong = false;
+    float strength = 0.f;
+    double exponent = 1.0;
+    if (hit) {
+        const DevShader& sh = c_scene.shaders[c_scene.nodes[h.node].shader];
+        const bool has_tex = sh.tex >= 0;
+        surface_of<MODE>(h, &ray, has_tex, s);
+        // faceforward (imported_types.d:69-73): the sign decision in FP64, the vector itself in FP32
+        Nx = s.nx; Ny = s.ny; Nz = s.nz;
+        if (!(dot3(ray.dx, ray.dy, ray.dz, s.gx, s.gy, s.gz) < 0)) { Nx = -Nx; Ny = -Ny; Nz = -Nz; }
+        diffuse = has_tex ? sample_texture<MODE>(sh.tex, s.u, s.v) : mkcol(sh.color[0], sh.color[1], sh.color[2]);
+        phong = sh.type == C2RT_SHADER_PHONG;
+        strength = sh.strength;
+        exponent = sh.exponent;
+        // shadow-ray origin p + N * 1e-6 (shader.d:88,219)
+        fx = s.px + (double)Nx * 1e-6; fy = s.py + (double)Ny * 1e-6; fz = s.pz + (double)Nz * 1e-6;
+    }
+    Col lightContrib = mkcol(fp.ambient[0], fp.ambient[1], fp.ambient[2]);
+    Col specular = mkcol(0.f, 0.f, 0.f);
+    const int nl = c_scene.n_lights;
+    for (int li = 0; li < nl; li++) {
+        const DevLight& L = c_scene.lights[li];
+        // one sample per PointLight (light.d:56-59): avg / numSamples is a division by 1.0f
+        if (!L.lit) continue;
+        if (hit) n_shadow++;
+        const double Dx = L.pos[0] - fx, Dy = L.pos[1] - fy, Dz = L.pos[2] - fz;
+        const double len2 = dot3(Dx, Dy, Dz, Dx, Dy, Dz);
+        const bool occl = occluded_warp<MODE>(hit, fx, fy, fz, Dx, Dy, Dz, len2, L);
+        if (!hit || occl) continue;
+        // lighting in FP32 (the reference narrows every factor to float before it touches a Color: SURVEY.md App. C.1)
+        const float fDx = (float)Dx, fDy = (float)Dy, fDz = (float)Dz, d2 = (float)len2;
+        const float rs = rsqrtf(d2);
+        const float lx = fDx * rs, ly = fDy * rs, lz = fDz * rs;
+        const float inv_d2 = rs * rs;
+        const float cosTheta = dot3f(lx, ly, lz, Nx, Ny, Nz);
+        const float br = L.color[0] * inv_d2, bg = L.color[1] * inv_d2, bb = L.color[2] * inv_d2;
+        if (cosTheta > 0) {
+            lightContrib.r = fmaf(br, cosTheta, lightContrib.r);
+            lightContrib.g = fmaf(bg, cosTheta, lightContrib.g);
+            lightContrib.b = fmaf(bb, cosTheta, lightContrib.b);
+        }
+        if (phong) {
+            float pw;
+            if (exponent <= 2048.0) {
+                // reflect(-lightDir, N) . (-ray.dir)  (imported_types.d:62-67, shader.d:235-239)
+                const float k = 2.f * cosTheta;
+                const float rx = fmaf(k, Nx, -lx), ry = fmaf(k, Ny, -ly), rz = fmaf(k, Nz, -lz);
+                const float cosGamma = -dot3f(rx, ry, rz, (float)ray.dx, (float)ray.dy, (float)ray.dz);
+                pw = cosGamma > 0 ? powf(cosGamma, (float)exponent) : 0.f;
+            } else {
+                // very sharp lobes amplify FP32 rounding of cosGamma by `exponent`: keep FP64 here
+                double ldx = Dx, ldy = Dy, ldz = Dz;
+                normalize3(ldx, ldy, ldz);
+                double nx = Nx, ny = Ny, nz = Nz;
+                normalize3(nx, ny, nz);
+                double k = 2 * dot3(ldx, ldy, ldz, nx, ny, nz);
+                double rx = k * nx - ldx, ry = k * ny - ldy, rz = k * nz - ldz;
+                normalize3(rx, ry, rz);
+                double cg = -dot3(rx, ry, rz, ray.dx, ray.dy, ray.dz);
+                pw = cg > 0 ? (float)pow(cg, exponent) : 0.f;
+            }
+            const float w = pw * strength;
+            specular.r = fmaf(br, w, specular.r);
+            specular.g = fmaf(bg, w, specular.g);
+            specular.b = fmaf(bb, w, specular.b);
+        }
+    }
+    return mkcol(fmaf(diffuse.r, lightContrib.r, specular.r), fmaf(diffuse.g, lightContrib.g, specular.g),
+                 fmaf(diffuse.b, lightContrib.b, specular.b));
+}
+
+// renderer.d:325-376.  Plane-only scene classes: per lane (`live` lanes only call it).  The other classes: all 32 lanes of
+// the warp call it together, `live` says whether this lane has a ray at all, `cam` is the warp's node mask for camera rays.
+template <int MODE>
+__device__ __forceinline__ Col trace(const FrameParams& fp, const Ray& ray, bool live, unsigned& n_shadow, HitRec* out_hit, const NodeMask& cam) {
     HitRec h;
     h.dist = 1e99;
     h.node = -1;
     float tmaxf = 3.0e38f;   // (not +inf = (float)1e99: ptxas would prove tmaxf == (float)h.dist * k and re-convert it in every iteration)
-    const int ncl = (MODE & MODE_CLUSTERS) ? c_scene.n_clusters : 1;
     if (MODE & MODE_SOLO) node_intersect<MODE>(0, ray, h, tmaxf);
-    else if (tile_culled(MODE)) {
-        // camera rays of this CTA only visit the nodes its tile cone can reach (tile_node_mask), in scene order
-        for (unsigned long long m = tile_nodes; m; m &= m - 1) {
-            const int i = __ffsll((long long)m) - 1;
-            if (node_intersect<MODE>(i, ray, h, tmaxf)) tmaxf = (float)h.dist * 1.000001f;
-        }
-    } else for (int ci = 0; ci < ncl; ci++) {
-        int begin = 0, end = c_scene.n_nodes;
-        if (MODE & MODE_CLUSTERS) {
-            const DevCluster& cl = c_scene.clusters[ci];
-            if (cl.end - cl.begin > 1 && cull_sphere(cl.c[0], cl.c[1], cl.c[2], cl.r, cl.r2, cl.clen, ray, tmaxf)) continue;
-            begin = cl.begin; end = cl.end;
-        }
+    else if (plane_only(MODE)) {
 #pragma unroll 1
-        for (int i = begin; i < end; i++)
-            if (node_intersect<MODE>(i, ray, h, tmaxf)) {
-                if (MODE & MODE_BOUNDED) tmaxf = (float)h.dist * 1.000001f;
+        for (int i = 0; i < c_scene.n_nodes; i++) node_intersect<MODE>(i, ray, h, tmaxf);
+    } else {
+        // the nodes this warp's camera rays can reach, in scene order; the walk is warp-uniform
+#pragma unroll
+        for (int k = 0; k < MASK_WORDS; k++)
+            for (uint32_t bits = cam.w[k]; bits; bits &= bits - 1) {
+                const int i = 32 * k + __ffs((int)bits) - 1;
+                if (live && node_intersect<MODE>(i, ray, h, tmaxf)) {
+                    if (MODE & MODE_BOUNDED) tmaxf = (float)h.dist * 1.000001f;
+                }
             }
     }
     if (out_hit) {
@@ -1048,8 +1213,14 @@ __device__ __forceinline__ Col trace(const FrameParams& fp, const Ray& ray, unsi
             out_hit->px = fma(ray.dx, h.dist, ray.ox); out_hit->py = fma(ray.dy, h.dist, ray.oy); out_hit->pz = fma(ray.dz, h.dist, ray.oz);
         }
     }
-    if (h.node < 0) return mkcol(0.f, 0.f, 0.f);  // environment.d:7-10
-    return shade<MODE>(fp, ray, h, n_shadow);
+    if constexpr (plane_only(MODE)) {
+        if (h.node < 0) return mkcol(0.f, 0.f, 0.f);  // environment.d:7-10
+        return shade<MODE>(fp, ray, h, n_shadow);
+    } else {
+        const bool hit = live && h.node >= 0;
+        const Col c = shade_warp<MODE>(fp, ray, h, hit, n_shadow);
+        return hit ? c : mkcol(0.f, 0.f, 0.f);        // miss: environment.d:7-10
+    }
 }
 
 // renderer.d:254-313 renderSample (default and DOF branches).  (bx, by, bz) is the un-normalised
@@ -1067,14 +1238,14 @@ __device__ __forceinline__ Col combine_stereo(Col left, Col right) {
 
 template <int MODE>
 __device__ __forceinline__ Col render_sample(const FrameParams& fp, double bx, double by, double bz, double x, double y, uint32_t px,
-                                             uint32_t py, uint32_t tap, double jw, double jh, unsigned& n_primary, unsigned& n_shadow, HitRec* out_hit,
-                                             unsigned long long tile_nodes) {
+                                             uint32_t py, uint32_t tap, double jw, double jh, bool live, unsigned& n_primary, unsigned& n_shadow,
+                                             HitRec* out_hit, const NodeMask& cam) {
     Ray r;
     if (!(MODE & MODE_SAMPLING)) {               // renderSampleDefault without stereo (renderer.d:303-306): one ray
         uint32_t draw = 0;
-        n_primary++;
+        n_primary += live;
         gen_ray<MODE>(fp, bx + fp.tap_d[tap][0], by + fp.tap_d[tap][1], bz + fp.tap_d[tap][2], px, py, tap, 0, draw, 0, r);
-        return trace<MODE>(fp, r, n_shadow, out_hit, tile_nodes);
+        return trace<MODE>(fp, r, live, n_shadow, out_hit, cam);
     }
     const bool stereo = fp.stereo_sep != 0;      // renderer.d:276-284,305-312: one ray per eye, then combineStereo
     const int n_eyes = stereo ? 2 : 1;
@@ -1095,9 +1266,9 @@ __device__ __forceinline__ Col render_sample(const FrameParams& fp, double bx, d
             } else {
                 vx = bx + fp.tap_d[tap][0]; vy = by + fp.tap_d[tap][1]; vz = bz + fp.tap_d[tap][2];
             }
-            n_primary++;
+            n_primary += live;
             gen_ray<MODE>(fp, vx, vy, vz, px, py, tap, i, draw, stereo ? (e ? +1 : -1) : 0, r);
-            c = trace<MODE>(fp, r, n_shadow, (out_hit && i == 0 && e == 0) ? out_hit : nullptr, tile_nodes);
+            c = trace<MODE>(fp, r, live, n_shadow, (out_hit && i == 0 && e == 0) ? out_hit : nullptr, cam);
             if (e == 0) left = c;
         }
         if (stereo) c = combine_stereo(left, c);
@@ -1117,41 +1288,64 @@ __device__ __forceinline__ uint32_t pack_rgb32(const uint8_t* lut, Col c) {  // 
     return lut8(lut, c.b) | (lut8(lut, c.g) << 8) | (lut8(lut, c.r) << 16);
 }
 
-// ---------------------------------------------------------------- per-tile node mask
-// Which nodes can a camera ray of this CTA's 16x8 pixel tile reach?  All those rays start at the camera position and pass
-// through the screen rectangle [x0, x0+16] x [y0, y0+8] (pixel corners plus the AA tap offsets <= 0.6), so they lie in the
+// ---------------------------------------------------------------- per-warp camera-ray node mask
+// Which nodes can a camera ray of this warp's 8x4 pixel patch reach?  All those rays start at the camera position and pass
+// through the screen rectangle [x0, x0+8] x [y0, y0+4] (pixel corners plus the AA tap offsets <= 0.6), so they lie in the
 // circular cone around the normalised sum of the four corner directions whose half-angle reaches the farthest corner (a circular
 // cone of less than 90 degrees is convex and contains the convex cone the corners span).  A node whose bounding sphere does not
-// touch that cone cannot be hit by any of them; the others are visited in scene order, so the reference's closest-hit and
-// tie rules (geometry.d:43,111,214) are untouched.  FP64 throughout (one thread per node, once per CTA), radius padded by
-// 1e-6 (r + distance): the sphere is already a conservative bound, this test only has to never drop a reachable node.
-__device__ __forceinline__ bool tile_reaches_node(const FrameParams& fp, uint32_t x0, uint32_t y0, int ni) {
-    const DevNode& nd = c_scene.nodes[ni];
-    if (nd.flags & NODE_UNBOUNDED) return true;
+// touch that cone cannot be hit by any of them.  Lane l tests nodes l, l + 32, ...; one ballot per 32 nodes gives the mask.
+// FP64 throughout (once per pixel, amortised over the AA taps), radius padded by 1e-6 (r + distance): the sphere is already
+// a conservative bound, this test only has to never drop a reachable node.
+constexpr int PATCH_W = 8, PATCH_H = 4;   // pixels of one warp
+struct PatchCone {
+    double ax, ay, az, cosphi, sinphi;
+    bool wide;   // wider than 60 degrees (tiny frames): no culling
+};
+__device__ __forceinline__ PatchCone patch_cone(const FrameParams& fp, uint32_t x0, uint32_t y0) {
+    PatchCone c;
     double u[4][3];
-    double ax = 0, ay = 0, az = 0;
+    c.ax = 0; c.ay = 0; c.az = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const double sx = (double)x0 + ((k & 1) ? (double)TILE_W : -0.01), sy = (double)y0 + ((k & 2) ? (double)TILE_H : -0.01);
+        const double sx = (double)x0 + ((k & 1) ? (double)PATCH_W : -0.01), sy = (double)y0 + ((k & 2) ? (double)PATCH_H : -0.01);
         screen_dir(fp, sx, sy, u[k][0], u[k][1], u[k][2]);
         normalize3(u[k][0], u[k][1], u[k][2]);
-        ax += u[k][0]; ay += u[k][1]; az += u[k][2];
+        c.ax += u[k][0]; c.ay += u[k][1]; c.az += u[k][2];
     }
-    normalize3(ax, ay, az);
-    double cosphi = 1.0;
+    normalize3(c.ax, c.ay, c.az);
+    c.cosphi = 1.0;
 #pragma unroll
-    for (int k = 0; k < 4; k++) cosphi = fmin(cosphi, dot3(ax, ay, az, u[k][0], u[k][1], u[k][2]));
-    if (!(cosphi > 0.5)) return true;   // a tile wider than 60 degrees (tiny frames): no culling
-    const double sinphi = sqrt(fmax(0.0, 1.0 - cosphi * cosphi));
+    for (int k = 0; k < 4; k++) c.cosphi = fmin(c.cosphi, dot3(c.ax, c.ay, c.az, u[k][0], u[k][1], u[k][2]));
+    c.wide = !(c.cosphi > 0.5);
+    c.sinphi = sqrt(fmax(0.0, 1.0 - c.cosphi * c.cosphi));
+    return c;
+}
+__device__ __forceinline__ bool cone_reaches_node(const FrameParams& fp, const PatchCone& c, const DevNode& nd) {
+    if ((nd.flags & NODE_UNBOUNDED) || c.wide) return true;
     const double vx = (double)nd.bcf[0] - fp.pos[0], vy = (double)nd.bcf[1] - fp.pos[1], vz = (double)nd.bcf[2] - fp.pos[2];
     const double d2 = dot3(vx, vy, vz, vx, vy, vz);
     const double d = sqrt(d2);
     const double r = (double)nd.brf * (1.0 + 1e-6) + 1e-6 * d;
     if (!(d > r)) return true;                       // the camera is inside the sphere (or a NaN bound): keep
-    const double xa = dot3(vx, vy, vz, ax, ay, az);  // along the axis
-    const double ya = sqrt(fmax(0.0, d2 - xa * xa)); // away from it
-    if (xa * cosphi + ya * sinphi >= 0) return !(ya * cosphi - xa * sinphi > r);   // nearest cone point on the lateral surface
+    const double xa = dot3(vx, vy, vz, c.ax, c.ay, c.az);  // along the axis
+    const double ya = sqrt(fmax(0.0, d2 - xa * xa));       // away from it
+    if (xa * c.cosphi + ya * c.sinphi >= 0) return !(ya * c.cosphi - xa * c.sinphi > r);   // nearest cone point on the lateral surface
     return false;                                    // nearest cone point is the apex, and d > r
+}
+template <int MODE>
+__device__ __forceinline__ NodeMask camera_mask(const FrameParams& fp, uint32_t x0, uint32_t y0) {
+    NodeMask m = all_nodes_mask();
+    if (!camera_masked(MODE)) return m;
+    const PatchCone c = patch_cone(fp, x0, y0);
+    const unsigned lane = threadIdx.x & 31u;
+#pragma unroll
+    for (int k = 0; k < MASK_WORDS; k++) {
+        if (32 * k >= c_scene.n_nodes) { m.w[k] = 0; continue; }
+        const int i = 32 * k + (int)lane;
+        const bool reach = i < c_scene.n_nodes && cone_reaches_node(fp, c, c_scene.nodes[i]);
+        m.w[k] = __ballot_sync(FULL_WARP, reach);
+    }
+    return m;
 }
 
 // ---------------------------------------------------------------- frame kernel
@@ -1174,22 +1368,14 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS) render_frame_kernel
     const uint32_t x = x0 + lx, y = y0 + ly;
     const bool active = x < fp.W && y < fp.H;
 
-    // nodes this tile's camera rays can reach (one thread per node; C2RT_MAX_NODES <= 64 <= BLOCK_THREADS)
-    static_assert(C2RT_MAX_NODES <= 64 && C2RT_MAX_NODES <= BLOCK_THREADS, "the tile node mask is one 64-bit word filled by one thread per node");
-    __shared__ unsigned long long s_tile_nodes;
-    unsigned long long tile_nodes = 0;
-    if (tile_culled(MODE)) {
-        if (threadIdx.x == 0) s_tile_nodes = 0;
-        __syncthreads();
-        if ((int)threadIdx.x < c_scene.n_nodes && tile_reaches_node(fp, x0, y0, (int)threadIdx.x)) atomicOr(&s_tile_nodes, 1ull << threadIdx.x);
-        __syncthreads();
-        tile_nodes = s_tile_nodes;
-    }
+    // nodes this warp's camera rays can reach (lane l tests nodes l, l + 32; warp ballot)
+    NodeMask cam = {};
+    if constexpr (!plane_only(MODE)) cam = camera_mask<MODE>(fp, x0 + (warp & 1) * PATCH_W, y0 + (warp >> 1) * PATCH_H);
 
     unsigned n_primary = 0, n_shadow = 0;
     Col c = mkcol(0.f, 0.f, 0.f);
     if (fp.gi) c = mkcol(fp.gi_fill, fp.gi_fill, fp.gi_fill);   // renderSampleGI: provably black (c2rt_api.cu fill_params)
-    else if (active) {
+    else if (active || !plane_only(MODE)) {   // (scene classes with warp masks: every lane runs, lanes off the frame carry no ray)
         // renderer.d:223-251: tap 0 at the pixel corner, then +(.3,.3) (.6,0) (0,.6) (.6,.6); mean of 5 in FP32
         int taps = fp.aa ? 5 : 1;
         uint32_t sx = x, sy = y;
@@ -1199,7 +1385,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS) render_frame_kernel
             // inside each bucket, clipped to it), jitter extent = block size, the colour replicated over the block
             const uint32_t B = fp.prepass_bucket;
             const uint32_t bx0 = x / B * B, by0 = y / B * B;
-            const uint32_t rw = min(B, fp.W - bx0), rh = min(B, fp.H - by0);
+            const uint32_t rw = min(B, fp.W - min(bx0, fp.W)), rh = min(B, fp.H - min(by0, fp.H));
             const uint32_t dxl = (x - bx0) / 16 * 16, dyl = (y - by0) / 16 * 16;
             sx = bx0 + dxl; sy = by0 + dyl;
             jw = (double)(min(rw, dxl + 16) - dxl);
@@ -1211,7 +1397,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS) render_frame_kernel
         screen_dir(fp, xd, yd, bx, by, bz);
 #pragma unroll 1
         for (int s = 0; s < taps; s++) {
-            Col t = render_sample<MODE>(fp, bx, by, bz, xd, yd, sx, sy, s, jw, jh, n_primary, n_shadow, nullptr, tile_nodes);
+            Col t = render_sample<MODE>(fp, bx, by, bz, xd, yd, sx, sy, s, jw, jh, active, n_primary, n_shadow, nullptr, cam);
             c.r += t.r; c.g += t.g; c.b += t.b;
         }
         if (taps == 5) { c.r = c.r / 5.f; c.g = c.g / 5.f; c.b = c.b / 5.f; }  // accum / 5 (renderer.d:249)
@@ -1261,14 +1447,18 @@ struct PixelOut {
 };
 
 __global__ void render_pixel_kernel(const FrameParams fp, int x, int y, PixelOut* out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    // one warp; lane 0 carries the ray, the other lanes only take part in the warp-wide votes of trace / occluded_warp
+    const bool live = threadIdx.x == 0;
     unsigned a = 0, b = 0;
     HitRec h;
     h.node = -1;
     h.dist = 1e99;
     double bx, by, bz;
     screen_dir(fp, (double)x, (double)y, bx, by, bz);
-    Col c = render_sample<MODE_BOUNDED | MODE_GENERIC | MODE_NESTED | MODE_CLUSTERS | MODE_SAMPLING>(fp, bx, by, bz, (double)x, (double)y, (uint32_t)x, (uint32_t)y, 0, 1.0, 1.0, a, b, &h, 0ull);
+    constexpr int M = MODE_BOUNDED | MODE_GENERIC | MODE_NESTED | MODE_SAMPLING;
+    const NodeMask cam = all_nodes_mask();
+    Col c = render_sample<M>(fp, bx, by, bz, (double)x, (double)y, (uint32_t)x, (uint32_t)y, 0, 1.0, 1.0, live, a, b, &h, cam);
+    if (!live) return;
     out->rgb[0] = c.r; out->rgb[1] = c.g; out->rgb[2] = c.b;
     out->node = h.node;
     out->dist = h.dist;
@@ -1371,7 +1561,7 @@ static void launch_solo(const FrameParams& fp, bool sampling, dim3 grid, cudaStr
 cudaError_t launch_frame(const FrameParams& fp, int mode, uint32_t local_tile_rows, cudaStream_t st) {
     if (local_tile_rows == 0) return cudaSuccess;
     dim3 grid((fp.W + TILE_W - 1) / TILE_W, local_tile_rows);
-    constexpr int FULL = MODE_BOUNDED | MODE_GENERIC, ALL = FULL | MODE_NESTED | MODE_CLUSTERS;
+    constexpr int FULL = MODE_BOUNDED | MODE_GENERIC, ALL = FULL | MODE_NESTED;
     const bool sampling = fp.dof || fp.stereo_sep != 0 || fp.prepass_bucket;
     if (mode & MODE_SOLO) {
         switch (((mode & MODE_TEX_MASK) >> MODE_TEX_SHIFT) | ((mode & MODE_PHONG) ? 4 : 0)) {
@@ -1386,11 +1576,9 @@ cudaError_t launch_frame(const FrameParams& fp, int mode, uint32_t local_tile_ro
         }
     } else if (sampling) {
         // DOF / stereo / prepass-only frames: two general kernels only (the per-sample loop dominates, the scene class matters less)
-        if (mode & (MODE_NESTED | MODE_CLUSTERS)) render_frame_kernel<ALL | MODE_SAMPLING, 2><<<grid, BLOCK_THREADS, 0, st>>>(fp);
+        if (mode & MODE_NESTED) render_frame_kernel<ALL | MODE_SAMPLING, 2><<<grid, BLOCK_THREADS, 0, st>>>(fp);
         else render_frame_kernel<FULL | MODE_SAMPLING, C2RT_MINBLOCKS_SAMPLING><<<grid, BLOCK_THREADS, 0, st>>>(fp);
     } else if (mode & MODE_NESTED) render_frame_kernel<ALL, 2><<<grid, BLOCK_THREADS, 0, st>>>(fp);
-    else if ((mode & MODE_CLUSTERS) && (mode & MODE_GENERIC)) render_frame_kernel<FULL | MODE_CLUSTERS, C2RT_MINBLOCKS_FULL><<<grid, BLOCK_THREADS, 0, st>>>(fp);
-    else if (mode & MODE_CLUSTERS) render_frame_kernel<MODE_BOUNDED | MODE_CLUSTERS, C2RT_MINBLOCKS_BOUNDED><<<grid, BLOCK_THREADS, 0, st>>>(fp);
     else if (mode & MODE_GENERIC) render_frame_kernel<FULL, C2RT_MINBLOCKS_FULL><<<grid, BLOCK_THREADS, 0, st>>>(fp);
     else if (mode & MODE_BOUNDED) render_frame_kernel<MODE_BOUNDED, C2RT_MINBLOCKS_BOUNDED><<<grid, BLOCK_THREADS, 0, st>>>(fp);
     else render_frame_kernel<0, C2RT_MINBLOCKS_SIMPLE><<<grid, BLOCK_THREADS, 0, st>>>(fp);

@@ -62,18 +62,8 @@ struct DevLight {
     int pad;
 };
 
-// Two-level culling: contiguous runs of node indices (scene order is kept, so the reference's
-// "later node wins an exact tie" rule, geometry.d:43,111,214, is untouched) with a common bounding
-// sphere.  Runs are chosen at scene-create time by a small dynamic programme (c2rt_api.cu).
-struct DevCluster {
-    float c[3];       // bounding sphere of the run's node spheres
-    float r, r2, clen;
-    int begin, end;   // node index range [begin, end); runs of one node carry no sphere of their own
-};
-
 struct DevScene {
-    int n_nodes, n_geoms, n_shaders, n_textures, n_lights, n_clusters, pad1, pad2;
-    DevCluster clusters[C2RT_MAX_NODES];
+    int n_nodes, n_geoms, n_shaders, n_textures, n_lights, pad0, pad1, pad2;
     DevNode nodes[C2RT_MAX_NODES];
     DevGeom geoms[C2RT_MAX_GEOMS];
     DevShader shaders[C2RT_MAX_SHADERS];
@@ -114,30 +104,31 @@ struct FrameParams {
 //   MODE_BOUNDED  some node has a finite bounding sphere -> FP32 ray shadow + conservative cull
 //   MODE_GENERIC  some node needs the object-space path (non-identity transform, CSG, bounded plane)
 //   MODE_NESTED   some CSG has a CSG child -> literal emulation of the reference's recursive walk
-//   MODE_CLUSTERS the scene-create partition found runs of nodes worth a common bounding sphere (two-level cull)
+//                 (bit 8 was MODE_CLUSTERS, the two-level cull of round 1: replaced by the per-warp node masks, render_kernel.cu)
 //   MODE_SAMPLING the CAMERA asks for depth of field and/or stereo: several rays per sample (chosen per frame)
 //   MODE_SOLO     one world-space plane node and one light (lecture4*, zaphod): node / shader / texture / light records
 //                 sit at index 0 (c2rt_api.cu moves them there), so every scene constant is read through a static
 //                 c[3][imm] operand instead of an indexed LDC, no loop survives, and the texture kind
 //                 (MODE_TEX_SHIFT: 0 none, 1 + C2RT_TEX_*) and shader kind (MODE_PHONG) are compile-time
-constexpr int MODE_BOUNDED = 1, MODE_GENERIC = 2, MODE_NESTED = 4, MODE_CLUSTERS = 8, MODE_SAMPLING = 16;
+constexpr int MODE_BOUNDED = 1, MODE_GENERIC = 2, MODE_NESTED = 4, MODE_SAMPLING = 16;
 constexpr int MODE_SOLO = 32, MODE_TEX_SHIFT = 6, MODE_TEX_MASK = 3 << MODE_TEX_SHIFT, MODE_PHONG = 256;
 // every node is a world-space plane (KIND_PLANE_W): no bounded and no generic node exists
 #ifdef __CUDACC__
 __host__ __device__
 #endif
-constexpr bool plane_only(int mode) { return (mode & (MODE_BOUNDED | MODE_GENERIC | MODE_NESTED | MODE_CLUSTERS)) == 0; }
+constexpr bool plane_only(int mode) { return (mode & (MODE_BOUNDED | MODE_GENERIC | MODE_NESTED)) == 0; }
 
-// scene classes whose camera rays go through the per-tile node mask (render_kernel.cu tile_node_mask): bounded nodes exist and
-// every camera ray starts at the camera position (no DOF / stereo sampling loop)
+// Scene classes whose rays go through per-warp node masks (render_kernel.cu camera_mask / shadow_mask): every scene class
+// but the plane-only ones.  Camera rays get a mask only when they all start at the camera position (no DOF / stereo
+// sampling loop); shadow rays always do.  -DC2RT_NO_WARP_MASK builds the kernels with all-node masks (A/B tuning aid).
 #ifdef __CUDACC__
 __host__ __device__
 #endif
-constexpr bool tile_culled(int mode) {
-#ifdef C2RT_NO_TILE_CULL
+constexpr bool camera_masked(int mode) {
+#ifdef C2RT_NO_WARP_MASK
     return false && mode;
 #else
-    return (mode & MODE_BOUNDED) && !(mode & MODE_SAMPLING);
+    return !plane_only(mode) && !(mode & MODE_SAMPLING);
 #endif
 }
 

@@ -192,6 +192,41 @@ int orc_render_pixel(orc_scene* s, int x, int y, int rng_mode, uint64_t seed, fl
     }
 }
 
+// Conditioning probe of one pixel for the parity tests: out[0] = farthest camera-ray hit of the pixel, out[1] = smallest
+// relative gap to a tie met while rendering it (orc_scene.hpp Diag), out[2] = largest colour change of the ORACLE's own
+// pixel when every sample position is shifted by (+-eps, +-eps) pixels, out[3..5] = the unshifted colour.
+int orc_pixel_diag(orc_scene* s, int x, int y, int rng_mode, uint64_t seed, double eps, double out[6]) {
+    try {
+        Scene& sc = *s->scene;
+        sc.beginFrame();
+        float dummy[3];
+        Renderer r(sc, dummy);
+        r.rngMode = rng_mode;
+        r.seed = seed;
+        Diag& dg = tl_diag();
+        dg = Diag();
+        dg.on = true;
+        Color base = r.renderPixelShifted(x, y, 0.0, 0.0);
+        dg.on = false;
+        out[0] = dg.max_dist;
+        out[1] = dg.min_gap;
+        double worst = 0;
+        for (int k = 0; k < 4; k++) {
+            Color c = r.renderPixelShifted(x, y, (k & 1) ? eps : -eps, (k & 2) ? eps : -eps);
+            worst = std::max(worst, (double)std::fabs(raw(c.r) - raw(base.r)));
+            worst = std::max(worst, (double)std::fabs(raw(c.g) - raw(base.g)));
+            worst = std::max(worst, (double)std::fabs(raw(c.b) - raw(base.b)));
+        }
+        out[2] = worst;
+        out[3] = raw(base.r); out[4] = raw(base.g); out[5] = raw(base.b);
+        return 0;
+    } catch (const std::exception& e) {
+        tl_diag().on = false;
+        g_err = e.what();
+        return -1;
+    }
+}
+
 // 8-bit packing of a float frame through the reference LUT (color.d:154-162,194-229).
 void orc_pack_rgb32(const float* rgb, size_t npx, uint32_t* out) {
     static const SrgbLut lut;

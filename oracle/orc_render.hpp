@@ -65,6 +65,17 @@ struct Renderer {
         const Node* closestNode = nullptr;
         for (auto& node : scene.nodes)
             if (node->intersect(ray, data)) closestNode = node.get();
+        if (tl_diag().on && closestNode) {   // conditioning probe (orc_pixel_diag): hit distance, nearest competing node
+            Diag& dg = tl_diag();
+            const double d1 = raw(data.dist);
+            if (d1 > dg.max_dist) dg.max_dist = d1;
+            for (auto& node : scene.nodes) {
+                if (node.get() == closestNode) continue;
+                IntersectionData probe;
+                probe.dist = mk_real(1e99);
+                if (node->intersect(ray, probe)) dg.gap(std::fabs(raw(probe.dist) - d1) / std::max(1.0, std::fabs(d1)));
+            }
+        }
         // lights are never intersectable (light.d:67-70) -> hitLight stays false
         if (!closestNode) return Color::fromFloats(0, 0, 0);  // environment.d:7-10
         // bumpmap.modifyNormal is a no-op (texture.d:10-12)
@@ -181,6 +192,23 @@ struct Renderer {
                                   (uint32_t)sample);
         setPx(x, y, accum / mk_colf(5.f));
         return getPx(x, y);
+    }
+
+    // One whole pixel (corner sample + the AA taps) with every sample position shifted by (ox, oy) pixels; writes nothing.
+    // Used by the conditioning probe: a pixel whose colour moves under a 1e-7 pixel shift sits on a discontinuity of the
+    // reference's own image.
+    Color renderPixelShifted(int x, int y, double ox, double oy) const {
+        static const double kernel[5][2] = {{0.0, 0.0}, {0.3, 0.3}, {0.6, 0.0}, {0.0, 0.6}, {0.6, 0.6}};
+        RngState& rs = tl_rng();
+        rs.mode = rngMode; rs.seed = seed; rs.px = (uint32_t)x; rs.py = (uint32_t)y;
+        const int taps = scene.settings.AAEnabled ? 5 : 1;
+        Color accum = Color::fromFloats(0, 0, 0);
+        for (int t = 0; t < taps; t++) {
+            Color c = renderSample(mk_real((double)x + ox) + mk_real(kernel[t][0]), mk_real((double)y + oy) + mk_real(kernel[t][1]), 1, 1, (uint32_t)t);
+            if (t == 0) accum = c;
+            else accum += c;
+        }
+        return taps == 5 ? accum / mk_colf(5.f) : accum;
     }
 
     template <class F>

@@ -131,6 +131,18 @@ inline Stats& tl_stats() {
     static thread_local Stats s;
     return s;
 }
+// Conditioning probe for the parity tests (orc_capi.cpp orc_pixel_diag): while `on`, the walk records how far the
+// farthest camera-ray hit of a pixel lies and how close the pixel's decisions came to a tie — two node candidates, two
+// CSG crossings, an occluder against the light's distance, a checker cell edge (relative gaps).  Off in every timed path.
+struct Diag {
+    bool on = false;
+    double max_dist = 0, min_gap = 1e300;
+    void gap(double g) { if (g < min_gap) min_gap = g; }
+};
+inline Diag& tl_diag() {
+    static thread_local Diag d;
+    return d;
+}
 
 struct Geometry {
     virtual ~Geometry() = default;
@@ -312,10 +324,19 @@ struct CsgOp : Geometry {  // geometry.d:250-337
         shell_sort(allData);
         bool inL = leftData.size() % 2 == 1;
         bool inR = rightData.size() % 2 == 1;
+        size_t walked = 0;
         for (auto& current : allData) {
+            if (tl_diag().on) {   // gap to the next crossing of the sorted list (a tie would swap the walk order)
+                if (walked + 1 < allData.size()) {
+                    const double a = raw(current.dist), b = raw(allData[walked + 1].dist);
+                    tl_diag().gap(std::fabs(b - a) / std::max(1.0, std::fabs(a)));
+                }
+                walked++;
+            }
             if (current.g == left) inL = !inL;
             else inR = !inR;
             if (boolOp(inL, inR)) {
+                if (tl_diag().on) tl_diag().gap(std::fabs(raw(current.dist) - raw(data.dist)) / std::max(1.0, std::fabs(raw(current.dist))));
                 if (current.dist > data.dist) return false;
                 data = current;
                 return true;
@@ -396,6 +417,11 @@ struct Checker final : Texture {  // texture.d:20-54
     real size;
     Checker() : color1(Color::fromFloats(0, 0, 0)), color2(Color::fromFloats(1, 1, 1)), size(mk_real(1.0)) {}
     Color getTexColor(const Ray&, real u, real v, Vec3&) const override {
+        if (tl_diag().on) {   // distance to the nearest cell edge, in cells
+            const double a = raw(u / size), b = raw(v / size);
+            tl_diag().gap(std::fabs(a - std::nearbyint(a)));
+            tl_diag().gap(std::fabs(b - std::nearbyint(b)));
+        }
         int32_t x = d_cast_int(raw(r_floor(u / size)));
         int32_t y = d_cast_int(raw(r_floor(v / size)));
         int32_t white = (int32_t)((uint32_t)x + (uint32_t)y) % 2;
@@ -675,6 +701,14 @@ struct Scene {  // scene.d:38-78
         normalize(ray.dir);
         IntersectionData temp;
         temp.dist = length(to - from);
+        if (tl_diag().on) {   // an occluder candidate right at the light's distance
+            const double maxd = raw(temp.dist);
+            for (auto& node : nodes) {
+                IntersectionData probe;
+                probe.dist = mk_real(1e99);
+                if (node->intersect(ray, probe)) tl_diag().gap(std::fabs(raw(probe.dist) - maxd) / std::max(1.0, maxd));
+            }
+        }
         for (auto& node : nodes)
             if (node->intersect(ray, temp)) return false;
         return true;

@@ -20,6 +20,36 @@ def _ctx():
     c2.shutdown()
 
 
+FAR_HIT = 1e5      # a camera-ray hit farther than this: the reference's own formulation (upLeft holds the camera position,
+                   # which is subtracted again) is ill-conditioned to ~1e-9 relative there
+TIE_GAP = 1e-9     # two candidates / crossings / an occluder and the light / a checker edge closer than this (relative)
+SHIFT_EPS = 1e-7   # a pixel whose ORACLE colour moves by > 1e-3 when its samples shift by 1e-7 pixel sits on a
+                   # discontinuity of the reference image (silhouette, grazing hit, coincident surfaces)
+
+
+def assert_every_outlier_is_classified(o, rgb, ref, seed, what):
+    """BASELINE.json's float bar is per pixel (1e-3 absolute).  Every pixel over it must be an ill-conditioned sample of the
+    REFERENCE's own image, shown by the oracle's conditioning probe (oracle/orc_capi.cpp orc_pixel_diag), and there may be
+    at most 0.1 % of them; anything else fails."""
+    per_px = np.abs(rgb.astype(np.float64) - ref.astype(np.float64)).max(axis=-1)
+    ys, xs = np.nonzero(per_px > 1e-3)
+    assert len(ys) <= 1e-3 * per_px.size, (what, seed, len(ys))
+    classes = {}
+    for y, x in zip(ys.tolist(), xs.tolist()):
+        d = o.pixel_diag(x, y, seed=seed, eps=SHIFT_EPS)
+        if d["max_dist"] > FAR_HIT:
+            cls = "far_hit"
+        elif d["min_gap"] < TIE_GAP:
+            cls = "tie"
+        elif d["shift_delta"] > 1e-3:
+            cls = "discontinuity"
+        else:
+            raise AssertionError(f"{what} seed {seed}: pixel ({x},{y}) differs by {per_px[y, x]:.3g} and is well conditioned: {d}, "
+                                 f"gpu {rgb[y, x]}, oracle {ref[y, x]}")
+        classes[cls] = classes.get(cls, 0) + 1
+    return classes
+
+
 @pytest.mark.parametrize("seed", list(range(48)))
 def test_random_scene_matches_oracle(seed, tmp_path):
     path = tmp_path / f"fuzz{seed}.sdl"
@@ -28,14 +58,16 @@ def test_random_scene_matches_oracle(seed, tmp_path):
     rgb, argb, st = g.render(argb=True, seed=seed, count_rays=True)
     ref, ost = o.render(threads=0, seed=seed)
     rep = parity_report(rgb, ref, argb)
-    # The bar of BASELINE.json: float RGB within 1e-3; <= 0.1 % of 8-bit pixels off by more than 1 LSB.  Random scenes
-    # contain exactly coincident surfaces (a CSG child flush with its sibling, pieces cut by the floor plane), where a
-    # 1-ulp difference legitimately flips a hit: allow the 0.1 % there, but never a systematic difference.
-    assert rep["frac_over_1e-3"] <= 1e-3, (seed, rep)
+    # The bar of BASELINE.json: float RGB within 1e-3 per pixel; <= 0.1 % of 8-bit pixels off by more than 1 LSB.  Random
+    # scenes contain exactly coincident surfaces (a CSG child flush with its sibling, pieces cut by the floor plane) and
+    # horizon pixels, where a 1-ulp difference legitimately flips a hit: each such pixel must be shown to be one.
+    classes = assert_every_outlier_is_classified(o, rgb, ref, seed, "fuzz")
     assert rep["frac_over_1lsb"] <= 1e-3, (seed, rep)
     np.testing.assert_array_equal(argb, pack_rgb32(rgb))
     assert st.primary_rays == ost.primary_rays
-    assert abs(int(st.shadow_rays) - int(ost.shadow_rays)) <= max(2, int(1e-3 * ost.shadow_rays)), (st.shadow_rays, ost.shadow_rays)
+    # a flipped hit changes whether a shadow ray is shot: the counts may differ by the classified outliers' rays only
+    n_out = sum(classes.values())
+    assert abs(int(st.shadow_rays) - int(ost.shadow_rays)) <= n_out * 5 * 4 * 3, (st.shadow_rays, ost.shadow_rays, classes)
     assert ost.csg_max_crossings <= 8
 
 
@@ -48,7 +80,7 @@ def test_random_plane_scene_matches_oracle(seed, tmp_path):
     rgb, argb, st = g.render(argb=True, seed=seed, count_rays=True)
     ref, ost = o.render(threads=0, seed=seed)
     rep = parity_report(rgb, ref, argb)
-    assert rep["frac_over_1e-3"] <= 1e-3, (seed, rep)
+    assert_every_outlier_is_classified(o, rgb, ref, seed, "planes")
     assert rep["frac_over_1lsb"] <= 1e-3, (seed, rep)
     np.testing.assert_array_equal(argb, pack_rgb32(rgb))
     assert (st.primary_rays, st.shadow_rays) == (ost.primary_rays, ost.shadow_rays)
