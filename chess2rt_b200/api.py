@@ -43,7 +43,8 @@ class Settings(C.Structure):
 
 
 class Band(C.Structure):
-    _fields_ = [("rank", C.c_uint32), ("n_ranks", C.c_uint32), ("band_rows", C.c_uint32), ("compact", C.c_uint32)]
+    _fields_ = [("rank", C.c_uint32), ("n_ranks", C.c_uint32), ("band_rows", C.c_uint32), ("compact", C.c_uint32),
+                ("done_flags", C.c_void_p), ("frame_no", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class Stats(C.Structure):
@@ -80,7 +81,7 @@ C_ABI_SYMBOLS = [
     "c2rt_init", "c2rt_shutdown", "c2rt_abi_version", "c2rt_device_count", "c2rt_last_error",
     "c2rt_scene_create", "c2rt_scene_destroy", "c2rt_render", "c2rt_render_device", "c2rt_read_ray_counters",
     "c2rt_deinterleave", "c2rt_render_pixel", "c2rt_band_rows_owned", "c2rt_rng_u31", "c2rt_srgb_table",
-    "c2rt_frame_alloc", "c2rt_frame_free", "c2rt_frame_export", "c2rt_frame_import", "c2rt_frame_unimport", "c2rt_frame_download", "c2rt_pin_host_buffer", "c2rt_unpin_host_buffer", "c2rt_signal", "c2rt_wait_signals",
+    "c2rt_frame_alloc", "c2rt_frame_free", "c2rt_frame_export", "c2rt_frame_import", "c2rt_frame_unimport", "c2rt_frame_download", "c2rt_pin_host_buffer", "c2rt_unpin_host_buffer", "c2rt_gate",
     "c2rt_measure_fma_peak", "c2rt_selftest_device_pool",
 ]
 
@@ -113,8 +114,7 @@ lib.c2rt_frame_unimport.argtypes = [C.c_void_p]
 lib.c2rt_frame_download.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
 lib.c2rt_pin_host_buffer.argtypes = [C.c_void_p, C.c_size_t]
 lib.c2rt_unpin_host_buffer.argtypes = [C.c_void_p]
-lib.c2rt_signal.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
-lib.c2rt_wait_signals.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+lib.c2rt_gate.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
 lib.c2rt_measure_fma_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
 
 host_lib.c2rt_host_last_error.restype = C.c_char_p

@@ -28,8 +28,7 @@ cudaError_t launch_pixel(const FrameParams& fp, int x, int y, void* d_out, cudaS
 cudaError_t launch_deinterleave(const void* src, void* dst, uint32_t row_words, uint32_t height, uint32_t n_ranks,
                                 uint32_t band_rows, uint32_t rows_pad, cudaStream_t st);
 cudaError_t launch_fma_peak(bool fp64, int blocks, int threads, int iters, void* d_out, cudaStream_t st);
-cudaError_t launch_signal(void* flag, uint32_t value, cudaStream_t st);
-cudaError_t launch_wait_signals(void* flags, uint32_t n_ranks, uint32_t value, cudaStream_t st);
+cudaError_t launch_gate(void* gate, void* local_round, uint32_t n_ranks, void* err, cudaStream_t st);
 size_t pixel_out_size();
 }  // namespace c2rt
 
@@ -70,6 +69,7 @@ struct DeviceCtx {
     std::vector<cudaEvent_t> band_done;
     uint64_t uploaded_scene = 0;   // id of the scene currently in this device's constant memory
     unsigned long long* d_counters = nullptr;
+    uint32_t* d_sync = nullptr;    // [0] CTAs of the current launch that finished (in-kernel completion), [1] gate round
     uint8_t* d_lut = nullptr;
     void* d_pixel = nullptr;
     float* d_rgb = nullptr;
@@ -185,6 +185,7 @@ void destroy_device(DeviceCtx& c) {
     if (c.e0) cudaEventDestroy(c.e0);
     if (c.e1) cudaEventDestroy(c.e1);
     cudaFree(c.d_counters);
+    cudaFree(c.d_sync);
     cudaFree(c.d_lut);
     cudaFree(c.d_pixel);
     cudaFree(c.d_rgb);
@@ -216,6 +217,8 @@ int init_locked(int n_gpus, const int* ids) {
         CU(cudaEventCreate(&c.e1));
         CU(cudaMalloc(&c.d_counters, 2 * sizeof(unsigned long long)));
         CU(cudaMemset(c.d_counters, 0, 2 * sizeof(unsigned long long)));
+        CU(cudaMalloc(&c.d_sync, 2 * sizeof(uint32_t)));
+        CU(cudaMemset(c.d_sync, 0, 2 * sizeof(uint32_t)));
         CU(cudaMalloc(&c.d_lut, 4097));
         CU(cudaMemcpy(c.d_lut, g_ctx.lut, 4097, cudaMemcpyHostToDevice));
         CU(cudaMalloc(&c.d_pixel, pixel_out_size()));
@@ -262,6 +265,7 @@ struct c2rt_scene {
     std::vector<float4> texels;          // all bitmaps, float4 per texel
     std::vector<size_t> tex_offset;      // per texture, in texels (bitmaps only)
     float4* d_texels[C2RT_MAX_GPUS];     // per context device
+    float4* d_bounds[C2RT_MAX_GPUS];     // per context device: node bounding spheres for the per-warp masks (FrameParams.bounds)
     int n_dev;
     int mode;                            // kernel specialisation (render_kernel.cu MODE_*)
 };
@@ -520,7 +524,17 @@ int validate_and_build(const c2rt_scene_desc* d, c2rt_scene* s) {
 
 int upload_to_devices(c2rt_scene* s) {
     s->n_dev = g_ctx.n;
-    for (int i = 0; i < C2RT_MAX_GPUS; i++) s->d_texels[i] = nullptr;
+    for (int i = 0; i < C2RT_MAX_GPUS; i++) { s->d_texels[i] = nullptr; s->d_bounds[i] = nullptr; }
+    std::vector<float4> bounds((size_t)std::max(1, s->host.n_nodes));
+    for (int k = 0; k < s->host.n_nodes; k++) {
+        const DevNode& nd = s->host.nodes[k];
+        bounds[k] = (nd.flags & NODE_UNBOUNDED) ? make_float4(0.f, 0.f, 0.f, -1.f) : make_float4(nd.bcf[0], nd.bcf[1], nd.bcf[2], nd.brf);
+    }
+    for (int i = 0; i < g_ctx.n; i++) {
+        CU(cudaSetDevice(g_ctx.d[i].dev));
+        CU(cudaMalloc(&s->d_bounds[i], bounds.size() * sizeof(float4)));
+        CU(cudaMemcpy(s->d_bounds[i], bounds.data(), bounds.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    }
     if (s->texels.empty()) return C2RT_OK;
     for (int i = 0; i < g_ctx.n; i++) {
         CU(cudaSetDevice(g_ctx.d[i].dev));
@@ -534,6 +548,14 @@ int upload_to_devices(c2rt_scene* s) {
 int make_resident(c2rt_scene* s, int di, cudaStream_t st) {
     DeviceCtx& c = g_ctx.d[di];
     if (c.uploaded_scene == s->id) return C2RT_OK;
+    // A device holds ONE scene block (constant memory).  Frames of the scene it replaces may still be running on other
+    // streams of this device and read that block: wait for them before overwriting it.  (A scene switch therefore cannot
+    // happen inside a stream capture; first use of a scene on a device must come before the capture: c2rt.h.)
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    CU(cudaStreamIsCapturing(st, &cap));
+    if (cap != cudaStreamCaptureStatusNone)
+        return fail(C2RT_ERR_INVALID_ARG, "the scene is not resident on this device yet: render it once outside the stream capture first");
+    CU(cudaDeviceSynchronize());
     for (int t = 0; t < s->host.n_textures; t++)
         s->host.textures[t].texels = (s->host.textures[t].type == C2RT_TEX_BITMAP) ? s->d_texels[di] + s->tex_offset[t] : nullptr;
     CU(upload_scene(s->host, st));
@@ -557,8 +579,9 @@ int check_frame_args(const c2rt_scene* s, const c2rt_camera* cam, const c2rt_set
     return C2RT_OK;
 }
 
-void fill_params(FrameParams& fp, const c2rt_camera* cam, const c2rt_settings* set) {
+void fill_params(FrameParams& fp, const c2rt_camera* cam, const c2rt_settings* set, const c2rt_scene* s, int di) {
     memset(&fp, 0, sizeof fp);
+    fp.bounds = s->d_bounds[di];
     for (int k = 0; k < 3; k++) {
         fp.pos[k] = cam->pos[k];
         fp.ul_rel[k] = cam->up_left[k] - cam->pos[k];
@@ -610,7 +633,7 @@ int render_direct_device(int i, int n, c2rt_scene* s, const c2rt_camera* cam, co
         DeviceCtx& c = g_ctx.d[i];
         CU(cudaSetDevice(c.dev));
         FrameParams fp;
-        fill_params(fp, cam, set);
+        fill_params(fp, cam, set, s, i);
         fp.rank = (uint32_t)i;
         fp.n_ranks = (uint32_t)n;
         fp.tiles_per_band = 1;
@@ -747,9 +770,10 @@ void c2rt_scene_destroy(c2rt_scene* s) {
     if (!s) return;
     std::lock_guard<std::mutex> g(g_mu);
     for (int i = 0; i < s->n_dev && i < g_ctx.n; i++) {
-        if (s->d_texels[i]) {
+        if (s->d_texels[i] || s->d_bounds[i]) {
             cudaSetDevice(g_ctx.d[i].dev);
             cudaFree(s->d_texels[i]);
+            cudaFree(s->d_bounds[i]);
         }
         if (g_ctx.d[i].uploaded_scene == s->id) g_ctx.d[i].uploaded_scene = 0;
     }
@@ -774,7 +798,7 @@ int c2rt_render_device(c2rt_scene* s, const c2rt_camera* cam, const c2rt_setting
     rc = make_resident(s, di, st);
     if (rc) return rc;
     FrameParams fp;
-    fill_params(fp, cam, set);
+    fill_params(fp, cam, set, s, di);
     uint32_t band_rows = TILE_H;
     if (band) {
         if (band->n_ranks == 0 || band->rank >= band->n_ranks || band->band_rows == 0 || band->band_rows % TILE_H != 0)
@@ -784,7 +808,15 @@ int c2rt_render_device(c2rt_scene* s, const c2rt_camera* cam, const c2rt_setting
         fp.n_ranks = band->n_ranks;
         fp.compact = band->compact != 0;
         band_rows = band->band_rows;
+        if (band->done_flags) {
+            if (band->n_ranks > 32) return fail(C2RT_ERR_INVALID_ARG, "done_flags: at most 32 ranks");
+            fp.done_flags = (uint32_t*)band->done_flags;
+            fp.done_counter = c->d_sync;
+            fp.frame_no = band->frame_no;
+        }
     }
+    if (((uintptr_t)d_rgb & 15u) && (fp.W & 3u) == 0)
+        return fail(C2RT_ERR_INVALID_ARG, "d_rgb must be 16-byte aligned when the frame width is a multiple of 4 (float4 band stores)");
     fp.tiles_per_band = band_rows / TILE_H;
     fp.rgb = d_rgb;
     fp.argb = d_argb;
@@ -859,7 +891,7 @@ int c2rt_render(c2rt_scene* s, const c2rt_camera* cam, const c2rt_settings* set,
         rc = make_resident(s, 0, c.stream);
         if (rc) return rc;
         FrameParams fp;
-        fill_params(fp, cam, set);
+        fill_params(fp, cam, set, s, 0);
         fp.counters = c.d_counters;
         fp.lut = c.d_lut;
         fp.rgb = root.d_rgb;
@@ -931,7 +963,7 @@ int c2rt_render(c2rt_scene* s, const c2rt_camera* cam, const c2rt_settings* set,
         rc = make_resident(s, i, c.stream);
         if (rc) return rc;
         FrameParams fp;
-        fill_params(fp, cam, set);
+        fill_params(fp, cam, set, s, i);
         fp.rank = (uint32_t)i;
         fp.n_ranks = (uint32_t)n;
         fp.tiles_per_band = band_rows / TILE_H;
@@ -1031,7 +1063,7 @@ int c2rt_render_pixel(c2rt_scene* s, const c2rt_camera* cam, const c2rt_settings
     rc = make_resident(s, 0, c.stream);
     if (rc) return rc;
     FrameParams fp;
-    fill_params(fp, cam, set);
+    fill_params(fp, cam, set, s, 0);
     fp.counters = c.d_counters;
     fp.lut = c.d_lut;
     fp.count_rays = 0;
@@ -1093,14 +1125,16 @@ int c2rt_frame_download(void* host_dst, const void* d_src, size_t bytes, void* s
     return C2RT_OK;
 }
 
-int c2rt_signal(void* d_flag, uint32_t value, void* stream) {
-    if (!d_flag) return fail(C2RT_ERR_INVALID_ARG, "bad signal arguments");
-    CU(launch_signal(d_flag, value, (cudaStream_t)stream));
-    return C2RT_OK;
-}
-int c2rt_wait_signals(void* d_flags, uint32_t n_ranks, uint32_t value, void* stream) {
-    if (!d_flags || n_ranks < 1 || n_ranks > 32) return fail(C2RT_ERR_INVALID_ARG, "bad wait_signals arguments");
-    CU(launch_wait_signals(d_flags, n_ranks, value, (cudaStream_t)stream));
+int c2rt_gate(void* d_flags, uint32_t n_ranks, void* stream) {
+    if (!d_flags || n_ranks < 1 || n_ranks > 32) return fail(C2RT_ERR_INVALID_ARG, "bad gate arguments");
+    std::lock_guard<std::mutex> g(g_mu);
+    if (!g_ctx.inited) return fail(C2RT_ERR_NOT_INITIALISED, "c2rt_init has not been called");
+    int dev = -1;
+    CU(cudaGetDevice(&dev));
+    DeviceCtx* c = find_device(dev);
+    if (!c) return fail(C2RT_ERR_INVALID_ARG, "current device %d is not part of the c2rt context", dev);
+    uint32_t* flags = (uint32_t*)d_flags;
+    CU(launch_gate(flags, c->d_sync + 1, n_ranks, flags + n_ranks, (cudaStream_t)stream));
     return C2RT_OK;
 }
 

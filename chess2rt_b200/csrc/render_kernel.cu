@@ -93,6 +93,14 @@ __device__ __forceinline__ double rsqrt64(double a) {
     y = fma(h, e, y);
     return y;
 }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void normalize3(double& x, double& y, double& z) {
     double inv = rsqrt64(dot3(x, y, z, x, y, z));
     x *= inv; y *= inv; z *= inv;
@@ -738,7 +746,7 @@ __device__ __forceinline__ float warp_max(float v) {
 // stays clear of that capsule cannot occlude any lane.  FP32 with an explicit rounding margin (8e-6 of the magnitudes
 // involved: the arithmetic below loses < 1e-6 of them); the node spheres are already inflated (c2rt_api.cu).
 template <int MODE>
-__device__ __forceinline__ NodeMask shadow_mask(bool need, const Ray& r, const DevLight& L, bool& any) {
+__device__ __forceinline__ NodeMask shadow_mask(const float4* __restrict__ bounds, bool need, const Ray& r, const DevLight& L, bool& any) {
     NodeMask m = all_nodes_mask();
     any = true;
     if (!(MODE & MODE_BOUNDED)) { any = __any_sync(FULL_WARP, need); return m; }
@@ -766,13 +774,15 @@ __device__ __forceinline__ NodeMask shadow_mask(bool need, const Ray& r, const D
         const int i = 32 * k + (int)lane;
         bool reach = false;
         if (i < c_scene.n_nodes) {
-            const DevNode& nd = c_scene.nodes[i];
-            if (nd.flags & NODE_UNBOUNDED) reach = true;
+            // per-lane index: the bound comes from GLOBAL memory (one coalesced 16-byte load per lane) — a constant-bank read
+            // with 32 different addresses would be replayed 32 times
+            const float4 b = __ldg(&bounds[i]);
+            if (b.w < 0.f) reach = true;   // unbounded (planes)
             else {
-                const float ax = nd.bcf[0] - cx, ay = nd.bcf[1] - cy, az = nd.bcf[2] - cz;
+                const float ax = b.x - cx, ay = b.y - cy, az = b.z - cz;
                 const float t = fminf(fmaxf(dot3f(ax, ay, az, dx, dy, dz) * inv_dd, 0.f), 1.f);
                 const float qx = fmaf(-t, dx, ax), qy = fmaf(-t, dy, ay), qz = fmaf(-t, dz, az);
-                const float reachr = nd.brf + rho + 8e-6f * (mag + nd.bclen + rho);
+                const float reachr = b.w + rho + 8e-6f * (mag + sqrtf(dot3f(b.x, b.y, b.z, b.x, b.y, b.z)) + rho);
                 reach = !(dot3f(qx, qy, qz, qx, qy, qz) > reachr * reachr);   // (a NaN bound keeps the node)
             }
         }
@@ -787,8 +797,8 @@ __device__ __forceinline__ NodeMask shadow_mask(bool need, const Ray& r, const D
 // call this together.  The FP64 normalisation (scene.d:66-71) is done lazily per lane: most nodes are rejected by a sign
 // test (planes) or the FP32 cull, which only need FP32 directions.
 template <int MODE>
-__device__ __forceinline__ bool occluded_warp(bool need, double fx, double fy, double fz, double Dx, double Dy, double Dz, double len2,
-                                              const DevLight& L) {
+__device__ __forceinline__ bool occluded_warp(const FrameParams& fp, bool need, double fx, double fy, double fz, double Dx, double Dy, double Dz,
+                                              double len2, const DevLight& L) {
     Ray r;
     r.ox = fx; r.oy = fy; r.oz = fz;
     float tmaxf = 0.f;
@@ -801,7 +811,7 @@ __device__ __forceinline__ bool occluded_warp(bool need, double fx, double fy, d
         tmaxf = l2f * rsf * 1.000001f;
     }
     bool any;
-    const NodeMask m = shadow_mask<MODE>(need, r, L, any);
+    const NodeMask m = shadow_mask<MODE>(fp.bounds, need, r, L, any);
     if (!any) return false;
     bool occl = false, exact = false;
     HitRec h;
@@ -1140,7 +1150,7 @@ __device__ __forceinline__ Col shade_warp(const FrameParams& fp, const Ray& ray,
         if (hit) n_shadow++;
         const double Dx = L.pos[0] - fx, Dy = L.pos[1] - fy, Dz = L.pos[2] - fz;
         const double len2 = dot3(Dx, Dy, Dz, Dx, Dy, Dz);
-        const bool occl = occluded_warp<MODE>(hit, fx, fy, fz, Dx, Dy, Dz, len2, L);
+        const bool occl = occluded_warp<MODE>(fp, hit, fx, fy, fz, Dx, Dy, Dz, len2, L);
         if (!hit || occl) continue;
         // lighting in FP32 (the reference narrows every factor to float before it touches a Color: SURVEY.md App. C.1)
         const float fDx = (float)Dx, fDy = (float)Dy, fDz = (float)Dz, d2 = (float)len2;
@@ -1320,12 +1330,12 @@ __device__ __forceinline__ PatchCone patch_cone(const FrameParams& fp, uint32_t 
     c.sinphi = sqrt(fmax(0.0, 1.0 - c.cosphi * c.cosphi));
     return c;
 }
-__device__ __forceinline__ bool cone_reaches_node(const FrameParams& fp, const PatchCone& c, const DevNode& nd) {
-    if ((nd.flags & NODE_UNBOUNDED) || c.wide) return true;
-    const double vx = (double)nd.bcf[0] - fp.pos[0], vy = (double)nd.bcf[1] - fp.pos[1], vz = (double)nd.bcf[2] - fp.pos[2];
+__device__ __forceinline__ bool cone_reaches_node(const FrameParams& fp, const PatchCone& c, const float4 b) {
+    if (b.w < 0.f || c.wide) return true;   // unbounded node (planes) / a patch too wide to cull
+    const double vx = (double)b.x - fp.pos[0], vy = (double)b.y - fp.pos[1], vz = (double)b.z - fp.pos[2];
     const double d2 = dot3(vx, vy, vz, vx, vy, vz);
     const double d = sqrt(d2);
-    const double r = (double)nd.brf * (1.0 + 1e-6) + 1e-6 * d;
+    const double r = (double)b.w * (1.0 + 1e-6) + 1e-6 * d;
     if (!(d > r)) return true;                       // the camera is inside the sphere (or a NaN bound): keep
     const double xa = dot3(vx, vy, vz, c.ax, c.ay, c.az);  // along the axis
     const double ya = sqrt(fmax(0.0, d2 - xa * xa));       // away from it
@@ -1342,7 +1352,7 @@ __device__ __forceinline__ NodeMask camera_mask(const FrameParams& fp, uint32_t 
     for (int k = 0; k < MASK_WORDS; k++) {
         if (32 * k >= c_scene.n_nodes) { m.w[k] = 0; continue; }
         const int i = 32 * k + (int)lane;
-        const bool reach = i < c_scene.n_nodes && cone_reaches_node(fp, c, c_scene.nodes[i]);
+        const bool reach = i < c_scene.n_nodes && cone_reaches_node(fp, c, __ldg(&fp.bounds[i]));   // (global, not constant: per-lane index)
         m.w[k] = __ballot_sync(FULL_WARP, reach);
     }
     return m;
@@ -1426,6 +1436,32 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS) render_frame_kernel
     }
     if (fp.argb && active) fp.argb[(size_t)(out_y0 + ly) * fp.W + x] = pack_rgb32(fp.lut, c);
 
+    // Frame-complete signalling folded into the kernel (c2rt.h c2rt_band.done_flags; one process per GPU, bands stored into
+    // rank 0's frame over NVLink).  Every CTA: barrier, then thread 0 fences at system scope — cumulative over the CTA's band
+    // stores — and counts the CTA in.  The last CTA of the launch: a peer rank releases its flag in rank 0's memory, rank 0
+    // waits there for all peers' flags, so the end of rank 0's kernel IS the complete frame (no signal / wait launches).
+    if (fp.done_flags) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            if (atomicAdd(fp.done_counter, 1u) == gridDim.x * gridDim.y - 1u) {
+                *fp.done_counter = 0u;   // ready for the next launch on this device (stream order)
+                __threadfence_system();
+                if (fp.rank != 0) st_release_sys(fp.done_flags + fp.rank, fp.frame_no);
+                else {
+                    const long long t0 = clock64();
+                    for (uint32_t r = 1; r < fp.n_ranks; r++)
+                        // frame numbers only grow; the signed difference tolerates wrap-around
+                        while ((int)(ld_acquire_sys(fp.done_flags + r) - fp.frame_no) < 0)
+                            if (clock64() - t0 > 4000000000ll) {   // ~2 s: a peer died; do not hang the device, report it
+                                atomicAdd(fp.done_flags + fp.n_ranks, 1u);
+                                break;
+                            }
+                }
+            }
+        }
+    }
+
     if (fp.count_rays) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -1485,30 +1521,19 @@ __global__ void deinterleave_kernel(const uint32_t* __restrict__ src, uint32_t* 
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < row_words; i += gridDim.x * blockDim.x) d[i] = s[i];
 }
 
-// frame-complete signalling between ranks (c2rt.h c2rt_signal / c2rt_wait_signals)
-__global__ void signal_kernel(volatile uint32_t* flag, uint32_t value) {
-    __threadfence_system();   // this rank's band stores (previous kernel on the stream) are ordered before the flag
-    if (value) *flag = value;
-    else atomicAdd_system((uint32_t*)flag, 1u);   // counting mode: replayable from a CUDA graph
+// Device-side start gate between ranks (c2rt.h c2rt_gate): every rank adds 1 to a counter in rank 0's memory and waits until
+// all n_ranks of this round have arrived.  Enqueued in front of a frame it (i) starts the ranks' kernels together without a host
+// round trip and (ii) keeps a fast peer from storing bands of frame k + 1 while rank 0's stream still works on frame k.
+__global__ void gate_kernel(uint32_t* gate, uint32_t* local_round, uint32_t n_ranks, uint32_t* err) {
+    const uint32_t target = ++*local_round * n_ranks;
     __threadfence_system();
-}
-__global__ void wait_signals_kernel(volatile uint32_t* flags, uint32_t n_ranks, uint32_t value) {
-    __shared__ uint32_t s_expected;
-    if (threadIdx.x == 0) s_expected = value ? value : ++*(uint32_t*)&flags[n_ranks + 1];   // counting mode: own frame counter
-    __syncthreads();
-    const uint32_t expected = s_expected;
-    const uint32_t r = threadIdx.x + 1;
-    if (r < n_ranks) {
-        const long long t0 = clock64();
-        // frame numbers only grow; the signed difference tolerates wrap-around
-        while ((int)(flags[r] - expected) < 0) {
-            if (clock64() - t0 > 4000000000ll) {   // ~2 s at 2 GHz: a peer died; do not hang the device
-                atomicAdd((uint32_t*)&flags[n_ranks], 1u);
-                break;
-            }
+    atomicAdd_system(gate, 1u);
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(gate) - target) < 0)
+        if (clock64() - t0 > 4000000000ll) {   // ~2 s: a rank never arrived
+            atomicAdd_system(err, 1u);
+            break;
         }
-    }
-    __threadfence_system();
 }
 
 // dependent-free FMA streams for the roofline denominators (c2rt.h c2rt_measure_fma_peak)
@@ -1597,12 +1622,8 @@ cudaError_t launch_deinterleave(const void* src, void* dst, uint32_t row_words, 
     return cudaGetLastError();
 }
 
-cudaError_t launch_signal(void* flag, uint32_t value, cudaStream_t st) {
-    signal_kernel<<<1, 1, 0, st>>>((volatile uint32_t*)flag, value);
-    return cudaGetLastError();
-}
-cudaError_t launch_wait_signals(void* flags, uint32_t n_ranks, uint32_t value, cudaStream_t st) {
-    wait_signals_kernel<<<1, 32, 0, st>>>((volatile uint32_t*)flags, n_ranks, value);
+cudaError_t launch_gate(void* gate, void* local_round, uint32_t n_ranks, void* err, cudaStream_t st) {
+    gate_kernel<<<1, 1, 0, st>>>((uint32_t*)gate, (uint32_t*)local_round, n_ranks, (uint32_t*)err);
     return cudaGetLastError();
 }
 

@@ -93,6 +93,13 @@ struct FrameParams {
     // interleaved row bands
     uint32_t rank, n_ranks, tiles_per_band, compact;
     uint32_t tile_row0;               // first local tile row of this launch (frames are launched in chunks to overlap the D2H copy)
+    // per-node bounding spheres (x, y, z, radius; radius < 0: unbounded) in GLOBAL memory for the per-warp node masks, whose
+    // lanes each test a different node (render_kernel.cu camera_mask / shadow_mask)
+    const float4* bounds;
+    // frame-complete signalling folded into the kernel (render_frame_kernel epilogue); done_flags == nullptr: off
+    uint32_t* done_flags;             // in rank 0's memory: [r] = last frame number rank r completed, [n_ranks] = wait time-outs
+    uint32_t* done_counter;           // this device: CTAs of the current launch that have finished
+    uint32_t frame_no, pad_frame;
     // outputs
     float* rgb;
     uint32_t* argb;

@@ -125,7 +125,8 @@ typedef struct c2rt_camera {
     uint32_t num_samples;                           /* camera.d:44 */
     double focal_plane_dist;                        /* camera.d:40 */
     double disc_multiplier;                         /* camera.d:42,252 = 10 / fNumber */
-    double stereo_separation;                       /* camera.d:45; must be 0 (stereo is out of scope) */
+    double stereo_separation;                       /* camera.d:45; 0 = off, otherwise every sample traces a left and a right
+                                                       eye ray and combines them (combineStereo, color.d:10-15) */
 } c2rt_camera;
 
 /* GlobalSettings fields the render path reads (global_settings.d:8-35) + the pinned-RNG seed. */
@@ -153,6 +154,17 @@ typedef struct c2rt_settings {
 typedef struct c2rt_band {
     uint32_t rank, n_ranks, band_rows;
     uint32_t compact;   /* 0: outputs are full frames (row y at y*W); 1: outputs hold only this rank's rows, in order */
+    /* Frame-complete signalling inside the render kernel (one process per GPU, bands stored into rank 0's frame through a
+     * c2rt_frame_import mapping).  NULL: off.  Otherwise uint32 flags[n_ranks + 1] in RANK 0's frame allocation, zero at
+     * start: [0] is the start gate's counter (c2rt_gate), [r] the last frame_no rank r > 0 completed, [n_ranks] counts
+     * time-outs.  The last CTA of a peer's kernel stores frame_no into flags[rank] (st.release.sys, after every CTA's band
+     * stores were fenced at system scope); the last CTA of rank 0's kernel waits for flags[1..n_ranks-1] >= frame_no, so
+     * rank 0's kernel ends when the whole frame is in its memory.  It gives up after ~2 s and bumps flags[n_ranks] instead
+     * of hanging the device: read that word back before trusting a frame.  frame_no must grow by one per frame (1, 2, ...);
+     * one such launch in flight per device. */
+    void* done_flags;
+    uint32_t frame_no;
+    uint32_t reserved;
 } c2rt_band;
 
 typedef struct c2rt_stats {
@@ -202,7 +214,11 @@ int c2rt_render(c2rt_scene* scene, const c2rt_camera* camera, const c2rt_setting
 /* Same frame, outputs in DEVICE memory of the CURRENT device, launched on `stream`
  * (a cudaStream_t, NULL = default stream) and NOT synchronised.  One process per GPU uses this
  * with its own band; a single-GPU caller passes band == NULL.  d_argb may be NULL.
- * stats (nullable) gets launches only; timing belongs to the caller's events. */
+ * stats (nullable) gets launches only; timing belongs to the caller's events.
+ * d_rgb must be 16-byte aligned when frame_width is a multiple of 4 (bands are written with float4 stores).
+ * A device holds ONE scene block at a time: rendering a different scene than the previous call on this device first waits
+ * for all work on the device and re-uploads the block, so (i) frames of two scenes never overlap on one device and
+ * (ii) the first frame of a scene on a device must be issued outside any CUDA stream capture (later ones may be captured). */
 int c2rt_render_device(c2rt_scene* scene, const c2rt_camera* camera, const c2rt_settings* settings,
                        const c2rt_band* band, float* d_rgb, uint32_t* d_argb, void* stream, c2rt_stats* stats);
 
@@ -241,15 +257,12 @@ int c2rt_frame_unimport(void* d_ptr);
 /* asynchronous device->host copy of (part of) such a frame on `stream` (host memory should be pinned) */
 int c2rt_frame_download(void* host_dst, const void* d_src, size_t bytes, void* stream);
 
-/* Frame-complete signalling for the one-process-per-GPU path, without a collective: rank r > 0 enqueues
- * c2rt_signal(&flags[r], frame_no) after its render kernel (flags live in rank 0's exported allocation, so the store
- * crosses NVLink after the band stores it follows); rank 0 enqueues c2rt_wait_signals(flags, n_ranks, frame_no) after
- * its own kernel: a one-warp kernel that polls flags[1..n_ranks-1] until all reached frame_no (it gives up after
- * ~2 s and bumps flags[n_ranks], which the caller can read back, instead of hanging the device).
- * value == 0 selects the counting mode, which can be captured once into a CUDA graph and replayed: c2rt_signal
- * increments its flag, c2rt_wait_signals waits for its own call count (kept in flags[n_ranks + 1]). */
-int c2rt_signal(void* d_flag, uint32_t value, void* stream);
-int c2rt_wait_signals(void* d_flags, uint32_t n_ranks, uint32_t value, void* stream);
+/* Device-side start gate for the one-process-per-GPU path: every rank enqueues c2rt_gate(flags, n_ranks, stream) in front
+ * of a frame; the one-thread kernel adds 1 to flags[0] (rank 0's memory, over NVLink for the peers) and waits until all n_ranks
+ * arrived for this round.  The ranks' render kernels then start together without a host round trip, and no peer can store
+ * bands of frame k + 1 while rank 0's stream still works on (renders, copies out, clears) frame k.  Same ~2 s time-out rule and
+ * error word (flags[n_ranks]) as c2rt_band.done_flags.  Every rank must call it the same number of times. */
+int c2rt_gate(void* d_flags, uint32_t n_ranks, void* stream);
 
 /* Page-locks a caller-owned host buffer (e.g. the D host's Image!Color.pixels, which is ordinary GC memory) so
  * that c2rt_render's device->host copies run asynchronously at full PCIe rate and overlap with rendering.
