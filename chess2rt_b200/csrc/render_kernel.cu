@@ -10,14 +10,13 @@
 //   isect_csg          rt/geometry.d:271-332, :382-397; util/array.d:95-111 (shell sort) — closed form, primitive children
 //   isect_geom_lit     the same walk replayed literally for CSG nested inside CSG
 //   geom_inside        rt/geometry.d:25-28,127-130,165-170,334-337
-//   node_intersect / generic_intersect   rt/node.d:23-49 + rt/transform.d:57-86
+//   node_hit           rt/node.d:23-49 + rt/transform.d:57-86 around the primitive / CSG test (node_exact: plane-only scene classes)
 //   cull_sphere        (no counterpart: conservative FP32 bounding-sphere rejection per ray)
 //   camera_mask / shadow_mask  (no counterpart: per-warp node masks by warp ballot — which nodes can ANY ray of the warp reach)
-//   occluded_warp      rt/scene.d:62-78 testVisibility, walked warp-uniformly over the shadow mask, left through __all_sync
-//                      (occluded_planes: plane-only scenes, settled by the sign of D.y)
+//   trace_warp         rt/renderer.d:325-376 trace + rt/shader.d:67-105,197-250 Lambert / Phong + rt/scene.d:62-78 testVisibility:
+//                      camera ray and shadow rays share ONE warp-uniform node walk over the masks; shadow walks are left
+//                      through __all_sync (trace / shade / occluded_planes: plane-only scenes, shadows settled by the sign of D.y)
 //   sample_texture     rt/texture.d:36-54,77-86 (Procedure2's sines through sin_rev),116-126 + rt/bitmap.d:48-63
-//   shade / shade_warp rt/shader.d:67-105 (Lambert), :197-250 (Phong)
-//   trace              rt/renderer.d:325-376 (+ rt/environment.d:7-10)
 //   render_sample      rt/renderer.d:254-313 (renderSampleDefault / renderSampleDof, stereo via color.d:10-15)
 //   render_frame_kernel rt/renderer.d:83-251 (renderRT: 1-spp + AA passes fused per pixel; prepassOnly preview;
 //                      GI frames, renderer.d:289-301,378-463, are black by construction: fp.gi, see c2rt_api.cu fill_params)
@@ -645,65 +644,59 @@ __device__ __forceinline__ bool cull(const DevNode& nd, const Ray& r, float tmax
     return cull_sphere(nd.bcf[0], nd.bcf[1], nd.bcf[2], nd.brf, nd.br2f, nd.bclen, r, tmaxf);
 }
 
-// node.d:23-49 for a transformed node: world ray -> object space, exact FP64 geometry test
+// Exact FP64 test of node `ni` for the scene classes with bounded / generic nodes: node.d:23-49 + transform.d:57-86 around the
+// primitive / CSG test.  ONE copy serves camera and shadow rays (trace_warp), and one copy of each primitive test serves the
+// world-space fast-path kinds (identity-transform primitives and diagonally scaled unbounded planes, tested against their
+// pre-offset parameters nd.wp with the world ray) and the object-space path: the kernel's instruction footprint is what
+// its issue rate hangs on.  Every branch on nd / g fields is warp-uniform (the node index is).
+// Returns true and updates `h` iff the node yields a hit with dist <= h.dist; h.p is in the node's local frame.
 template <int MODE>
-__device__ __forceinline__ bool generic_intersect(int ni, const Ray& r, HitRec& h) {
-    const DevNode& nd = c_scene.nodes[ni];
-    double ox, oy, oz, dx, dy, dz, len;
-    double tx = r.ox - nd.off[0], ty = r.oy - nd.off[1], tz = r.oz - nd.off[2];
-    if (nd.flags & NODE_IDENTITY) {
-        ox = tx; oy = ty; oz = tz;
-        dx = r.dx; dy = r.dy; dz = r.dz;
-        len = 1.0;
-    } else {
+__device__ __forceinline__ bool node_hit(int ni, const DevNode& nd, const Ray& r, HitRec& h) {
+    const DevGeom& g = c_scene.geoms[nd.geom];
+    // (a scene class without MODE_GENERIC holds world-space fast-path nodes only: the object-space code compiles away)
+    const bool world = !(MODE & MODE_GENERIC) || nd.kind != KIND_GENERIC;
+    const bool plain = world || (nd.flags & NODE_IDENTITY);   // no matrix: at most an offset
+    double ox = r.ox, oy = r.oy, oz = r.oz, dx = r.dx, dy = r.dy, dz = r.dz, len = 1.0;
+    if (!world) { ox -= nd.off[0]; oy -= nd.off[1]; oz -= nd.off[2]; }
+    if (!plain) {
+        const double tx = ox, ty = oy, tz = oz;
         mulvm(nd.Minv, tx, ty, tz, ox, oy, oz);
         mulvm(nd.Minv, r.dx, r.dy, r.dz, dx, dy, dz);
-        double l2 = dot3(dx, dy, dz, dx, dy, dz);
-        double inv = rsqrt64(l2);
+        const double l2 = dot3(dx, dy, dz, dx, dy, dz);
+        const double inv = rsqrt64(l2);
         len = l2 * inv;
         dx *= inv; dy *= inv; dz *= inv;
     }
-    double dist = h.dist * len;
+    double dist = plain ? h.dist : h.dist * len;
     double px, py, pz;
     int face = 0, leaf = nd.geom;
-    const DevGeom& g = c_scene.geoms[nd.geom];
+    const double* prm = world ? nd.wp : g.p;
     bool hit;
-    if (g.type <= C2RT_GEOM_CUBE) hit = isect_prim(g, ox, oy, oz, dx, dy, dz, dist, px, py, pz, face);
+    if (g.type == C2RT_GEOM_PLANE) hit = isect_plane(prm[0], world ? CUDART_NAN : prm[1], ox, oy, oz, dx, dy, dz, dist, px, py, pz);
+    else if (g.type == C2RT_GEOM_SPHERE) hit = isect_sphere(prm, ox, oy, oz, dx, dy, dz, dist, px, py, pz);
+    else if (g.type == C2RT_GEOM_CUBE) hit = isect_cube(prm, ox, oy, oz, dx, dy, dz, dist, px, py, pz, face);
+    else if (!(MODE & MODE_GENERIC)) hit = false;   // (CSG nodes are KIND_GENERIC)
     else if ((MODE & MODE_NESTED) && g.pad != 1) hit = isect_geom_lit<NESTED_MAX_DEPTH>(nd.geom, ox, oy, oz, dx, dy, dz, dist, px, py, pz, face, leaf);
     else hit = isect_csg(nd.geom, ox, oy, oz, dx, dy, dz, dist, px, py, pz, face, leaf);
     if (!hit) return false;
-    h.dist = (nd.flags & NODE_IDENTITY) ? dist : dist * rcp64(len);
+    h.dist = plain ? dist : dist * rcp64(len);
     h.px = px; h.py = py; h.pz = pz;
     h.node = ni; h.leaf = leaf; h.face = face;
     return true;
 }
 
-// Returns true and updates `h` iff node `ni` yields a hit with dist <= h.dist.
-// Exact FP64 test of node `ni` (after the cull).  Returns true and updates `h` iff the node yields a hit
-// with dist <= h.dist.  Spheres and cubes always have a finite bound, so a scene class without
-// MODE_BOUNDED cannot contain KIND_SPHERE_W / KIND_CUBE_W nodes and those branches compile away.
-// CAMERA_RAY: `r` comes from gen_ray (un-normalised in the plane-only scene classes); shadow rays are always unit
+// Plane-only scene classes: no bounded and no generic node exists, i.e. every node is a world-space plane.
+// CAMERA_RAY: `r` comes from gen_ray (un-normalised there); shadow rays are always unit.  The hit point is o + d * dist,
+// computed for the winning hit only (surface_of).
 template <int MODE, bool CAMERA_RAY>
 __device__ __forceinline__ bool node_exact(int ni, const DevNode& nd, const Ray& r, HitRec& h) {
-    int face = 0;
+    static_assert(plane_only(MODE), "scene classes with bounded / generic nodes go through node_hit");
     bool hit;
-    double px, py, pz;   // world-space kinds: the hit point is o + d * dist, recomputed for the winning hit only (surface_of)
-    // plane-only scene classes: no bounded and no generic node exists, i.e. every node is a world-space plane
-    if (plane_only(MODE) && CAMERA_RAY) hit = isect_plane_u(nd.wp[0], r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.l2, h.dist);
-    else if (plane_only(MODE) || nd.kind == KIND_PLANE_W) hit = isect_plane(nd.wp[0], CUDART_NAN, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, px, py, pz);
-    else if ((MODE & MODE_BOUNDED) && nd.kind == KIND_SPHERE_W) hit = isect_sphere(nd.wp, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, px, py, pz);
-    else if ((MODE & MODE_BOUNDED) && nd.kind == KIND_CUBE_W) hit = isect_cube(nd.wp, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, px, py, pz, face);
-    else if (MODE & MODE_GENERIC) return generic_intersect<MODE>(ni, r, h);
-    else return false;
-    if (hit) { h.node = ni; h.leaf = nd.geom; h.face = face; }
+    double px, py, pz;
+    if (CAMERA_RAY) hit = isect_plane_u(nd.wp[0], r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.l2, h.dist);
+    else hit = isect_plane(nd.wp[0], CUDART_NAN, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, h.dist, px, py, pz);
+    if (hit) { h.node = ni; h.leaf = nd.geom; h.face = 0; }
     return hit;
-}
-
-template <int MODE>
-__device__ __forceinline__ bool node_intersect(int ni, const Ray& r, HitRec& h, float tmaxf) {
-    const DevNode& nd = c_scene.nodes[ni];
-    if ((MODE & MODE_BOUNDED) && !(nd.flags & NODE_UNBOUNDED) && cull(nd, r, tmaxf)) return false;
-    return node_exact<MODE, true>(ni, nd, r, h);
 }
 
 // ---------------------------------------------------------------- per-warp node masks (warp ballot / vote)
@@ -714,18 +707,19 @@ __device__ __forceinline__ bool node_intersect(int ni, const Ray& r, HitRec& h, 
 // geometry.d:43,111,214, are untouched).  The walk is warp-uniform — same node for all lanes, per-lane work predicated —
 // and a shadow walk is left through __all_sync as soon as every lane that needs an answer has found an occluder
 // (the reference's early return at the first occluder, scene.d:73-75, taken by the whole warp at once).
-constexpr int MASK_WORDS = (C2RT_MAX_NODES + 31) / 32;
+static_assert(C2RT_MAX_NODES <= 64, "a node mask of the constant-memory scene block is one 64-bit word");
 constexpr unsigned FULL_WARP = 0xffffffffu;
-struct NodeMask {
-    uint32_t w[MASK_WORDS];
-};
+typedef unsigned long long NodeMask;
 __device__ __forceinline__ NodeMask all_nodes_mask() {
-    NodeMask m;
-#pragma unroll
-    for (int k = 0; k < MASK_WORDS; k++) {
-        const int left = c_scene.n_nodes - 32 * k;
-        m.w[k] = left >= 32 ? 0xffffffffu : left > 0 ? (1u << left) - 1u : 0u;
-    }
+    const int n = c_scene.n_nodes;
+    return n >= 64 ? ~0ull : (1ull << n) - 1ull;
+}
+// lane l answers for nodes l and l + 32; two ballots make the 64-bit mask (the second only when the scene has > 32 nodes)
+template <class F>
+__device__ __forceinline__ NodeMask ballot_nodes(F&& reaches) {
+    const int lane = (int)(threadIdx.x & 31u), n = c_scene.n_nodes;
+    NodeMask m = __ballot_sync(FULL_WARP, lane < n && reaches(lane));
+    if (n > 32) m |= (NodeMask)__ballot_sync(FULL_WARP, lane + 32 < n && reaches(lane + 32)) << 32;
     return m;
 }
 // warp-wide FP32 min / max in one instruction each (CREDUX, sm_100a), result in a uniform register
@@ -767,82 +761,18 @@ __device__ __forceinline__ NodeMask shadow_mask(const float4* __restrict__ bound
     const float dd = dot3f(dx, dy, dz, dx, dy, dz);
     const float inv_dd = dd > 0.f ? 1.0f / dd : 0.f;
     const float mag = sqrtf(dot3f(cx, cy, cz, cx, cy, cz)) + sqrtf(dd);
-    const unsigned lane = threadIdx.x & 31u;
-#pragma unroll
-    for (int k = 0; k < MASK_WORDS; k++) {
-        if (32 * k >= c_scene.n_nodes) { m.w[k] = 0; continue; }
-        const int i = 32 * k + (int)lane;
-        bool reach = false;
-        if (i < c_scene.n_nodes) {
-            // per-lane index: the bound comes from GLOBAL memory (one coalesced 16-byte load per lane) — a constant-bank read
-            // with 32 different addresses would be replayed 32 times
-            const float4 b = __ldg(&bounds[i]);
-            if (b.w < 0.f) reach = true;   // unbounded (planes)
-            else {
-                const float ax = b.x - cx, ay = b.y - cy, az = b.z - cz;
-                const float t = fminf(fmaxf(dot3f(ax, ay, az, dx, dy, dz) * inv_dd, 0.f), 1.f);
-                const float qx = fmaf(-t, dx, ax), qy = fmaf(-t, dy, ay), qz = fmaf(-t, dz, az);
-                const float reachr = b.w + rho + 8e-6f * (mag + sqrtf(dot3f(b.x, b.y, b.z, b.x, b.y, b.z)) + rho);
-                reach = !(dot3f(qx, qy, qz, qx, qy, qz) > reachr * reachr);   // (a NaN bound keeps the node)
-            }
-        }
-        m.w[k] = __ballot_sync(FULL_WARP, reach);
-    }
-    return m;
+    return ballot_nodes([&](int i) {
+        // per-lane index: the bound comes from GLOBAL memory (one coalesced 16-byte load per lane) — a constant-bank read
+        // with 32 different addresses would be replayed 32 times
+        const float4 b = __ldg(&bounds[i]);
+        if (b.w < 0.f) return true;   // unbounded (planes)
+        const float ax = b.x - cx, ay = b.y - cy, az = b.z - cz;
+        const float t = fminf(fmaxf(dot3f(ax, ay, az, dx, dy, dz) * inv_dd, 0.f), 1.f);
+        const float qx = fmaf(-t, dx, ax), qy = fmaf(-t, dy, ay), qz = fmaf(-t, dz, az);
+        const float reachr = b.w + rho + 8e-6f * (mag + sqrtf(dot3f(b.x, b.y, b.z, b.x, b.y, b.z)) + rho);
+        return !(dot3f(qx, qy, qz, qx, qy, qz) > reachr * reachr);   // (a NaN bound keeps the node)
+    });
 #endif
-}
-
-// scene.d:62-78 testVisibility for the warp: lane-wise `need` says whether this lane has a shadow ray at all (it hit
-// something and the light is lit); (fx,fy,fz) is its origin, D = to - from (unnormalised), len2 = |D|^2.  All 32 lanes
-// call this together.  The FP64 normalisation (scene.d:66-71) is done lazily per lane: most nodes are rejected by a sign
-// test (planes) or the FP32 cull, which only need FP32 directions.
-template <int MODE>
-__device__ __forceinline__ bool occluded_warp(const FrameParams& fp, bool need, double fx, double fy, double fz, double Dx, double Dy, double Dz,
-                                              double len2, const DevLight& L) {
-    Ray r;
-    r.ox = fx; r.oy = fy; r.oz = fz;
-    float tmaxf = 0.f;
-    if (MODE & MODE_BOUNDED) {
-        const float l2f = (float)len2;
-        const float rsf = rsqrtf(l2f);
-        r.fox = cvt_keep(fx); r.foy = cvt_keep(fy); r.foz = cvt_keep(fz);
-        r.fdx = cvt_keep(Dx) * rsf; r.fdy = cvt_keep(Dy) * rsf; r.fdz = cvt_keep(Dz) * rsf;
-        r.olen = sqrtf(dot3f(r.fox, r.foy, r.foz, r.fox, r.foy, r.foz));
-        tmaxf = l2f * rsf * 1.000001f;
-    }
-    bool any;
-    const NodeMask m = shadow_mask<MODE>(fp.bounds, need, r, L, any);
-    if (!any) return false;
-    bool occl = false, exact = false;
-    HitRec h;
-#pragma unroll
-    for (int k = 0; k < MASK_WORDS; k++) {
-        for (uint32_t bits = m.w[k]; bits; bits &= bits - 1) {
-            const int i = 32 * k + __ffs((int)bits) - 1;   // warp-uniform
-            const DevNode& nd = c_scene.nodes[i];
-            if (need && !occl) {
-                bool skip = false;
-                if (nd.kind == KIND_PLANE_W) {
-                    // implied by geometry.d:35-36 (dir.y has the sign of D.y): the common "light above the floor" case
-                    const double y = nd.wp[0];
-                    skip = (fy > y && Dy >= 0) || (fy < y && Dy <= 0);
-                } else if ((MODE & MODE_BOUNDED) && !(nd.flags & NODE_UNBOUNDED)) {
-                    skip = cull(nd, r, tmaxf);
-                }
-                if (!skip) {
-                    if (!exact) {
-                        const double inv = rsqrt64(len2);
-                        r.dx = Dx * inv; r.dy = Dy * inv; r.dz = Dz * inv;
-                        h.dist = len2 * inv;
-                        exact = true;
-                    }
-                    if (node_exact<MODE, false>(i, nd, r, h)) occl = true;
-                }
-            }
-            if (__all_sync(FULL_WARP, !need || occl)) return occl;   // every lane that asked has its occluder
-        }
-    }
-    return occl;
 }
 
 // testVisibility for the plane-only scene classes.  Dy = light.y - from.y in FP64 settles almost every plane by sign;
@@ -1029,7 +959,7 @@ __device__ __forceinline__ void surface_of(const HitRec& hin, const Ray* ray, bo
 // Per-lane form: the plane-only scene classes (shadow rays among planes are settled by signs, occluded_planes)
 template <int MODE>
 __device__ __forceinline__ Col shade(const FrameParams& fp, const Ray& ray, const HitRec& h, unsigned& n_shadow) {
-    static_assert(plane_only(MODE), "scene classes with bounded / generic nodes shade through shade_warp");
+    static_assert(plane_only(MODE), "scene classes with bounded / generic nodes shade inside trace_warp");
     constexpr bool SOLO = (MODE & MODE_SOLO) != 0;
     const DevShader& sh = c_scene.shaders[SOLO ? 0 : c_scene.nodes[h.node].shader];
     const bool has_tex = SOLO ? (MODE & MODE_TEX_MASK) != 0 : sh.tex >= 0;
@@ -1114,123 +1044,174 @@ __device__ __forceinline__ Col shade(const FrameParams& fp, const Ray& ray, cons
                  fmaf(diffuse.b, lightContrib.b, specular.b));
 }
 
-// Lambert / Phong for the scene classes with bounded or generic nodes, called by all 32 lanes together (`hit` says whether
-// this lane has a surface to shade): the surface and the texture lookup are per lane, the light loop is warp-uniform and
-// each light's shadow rays go through occluded_warp.
+// renderer.d:325-376 (trace) + shader.d:67-105,197-250 (Lambert / Phong with their shadow rays, scene.d:62-78) for the scene
+// classes with bounded or generic nodes.  All 32 lanes of the warp call it together; `live` says whether this lane has a ray at
+// all, `cam_mask` is the warp's node mask for camera rays.  The camera ray and then one shadow ray per lit light go through the
+// SAME node walk (one copy of the cull and of the exact tests in the kernel): phase -1 is the camera ray (closest hit, every
+// node of the mask), phase li >= 0 the shadow ray towards light li (any hit; left through __all_sync once every lane that
+// needs an answer has its occluder: the reference's early return, scene.d:73-75, taken by the whole warp).
 template <int MODE>
-__device__ __forceinline__ Col shade_warp(const FrameParams& fp, const Ray& ray, const HitRec& h, bool hit, unsigned& n_shadow) {
-    Surface s;
-    float Nx = 0.f, Ny = 0.f, Nz = 0.f;
-    Col diffuse = mkcol(0.f, 0.f, 0.f);
-    double fx = 0, fy = 0, fz = 0;
-    bool phong = false;
-    float strength = 0.f;
-    double exponent = 1.0;
-    if (hit) {
-        const DevShader& sh = c_scene.shaders[c_scene.nodes[h.node].shader];
-        const bool has_tex = sh.tex >= 0;
-        surface_of<MODE>(h, &ray, has_tex, s);
-        // faceforward (imported_types.d:69-73): the sign decision in FP64, the vector itself in FP32
-        Nx = s.nx; Ny = s.ny; Nz = s.nz;
-        if (!(dot3(ray.dx, ray.dy, ray.dz, s.gx, s.gy, s.gz) < 0)) { Nx = -Nx; Ny = -Ny; Nz = -Nz; }
-        diffuse = has_tex ? sample_texture<MODE>(sh.tex, s.u, s.v) : mkcol(sh.color[0], sh.color[1], sh.color[2]);
-        phong = sh.type == C2RT_SHADER_PHONG;
-        strength = sh.strength;
-        exponent = sh.exponent;
-        // shadow-ray origin p + N * 1e-6 (shader.d:88,219)
-        fx = s.px + (double)Nx * 1e-6; fy = s.py + (double)Ny * 1e-6; fz = s.pz + (double)Nz * 1e-6;
-    }
-    Col lightContrib = mkcol(fp.ambient[0], fp.ambient[1], fp.ambient[2]);
-    Col specular = mkcol(0.f, 0.f, 0.f);
-    const int nl = c_scene.n_lights;
-    for (int li = 0; li < nl; li++) {
-        const DevLight& L = c_scene.lights[li];
-        // one sample per PointLight (light.d:56-59): avg / numSamples is a division by 1.0f
-        if (!L.lit) continue;
-        if (hit) n_shadow++;
-        const double Dx = L.pos[0] - fx, Dy = L.pos[1] - fy, Dz = L.pos[2] - fz;
-        const double len2 = dot3(Dx, Dy, Dz, Dx, Dy, Dz);
-        const bool occl = occluded_warp<MODE>(fp, hit, fx, fy, fz, Dx, Dy, Dz, len2, L);
-        if (!hit || occl) continue;
-        // lighting in FP32 (the reference narrows every factor to float before it touches a Color: SURVEY.md App. C.1)
-        const float fDx = (float)Dx, fDy = (float)Dy, fDz = (float)Dz, d2 = (float)len2;
-        const float rs = rsqrtf(d2);
-        const float lx = fDx * rs, ly = fDy * rs, lz = fDz * rs;
-        const float inv_d2 = rs * rs;
-        const float cosTheta = dot3f(lx, ly, lz, Nx, Ny, Nz);
-        const float br = L.color[0] * inv_d2, bg = L.color[1] * inv_d2, bb = L.color[2] * inv_d2;
-        if (cosTheta > 0) {
-            lightContrib.r = fmaf(br, cosTheta, lightContrib.r);
-            lightContrib.g = fmaf(bg, cosTheta, lightContrib.g);
-            lightContrib.b = fmaf(bb, cosTheta, lightContrib.b);
-        }
-        if (phong) {
-            float pw;
-            if (exponent <= 2048.0) {
-                // reflect(-lightDir, N) . (-ray.dir)  (imported_types.d:62-67, shader.d:235-239)
-                const float k = 2.f * cosTheta;
-                const float rx = fmaf(k, Nx, -lx), ry = fmaf(k, Ny, -ly), rz = fmaf(k, Nz, -lz);
-                const float cosGamma = -dot3f(rx, ry, rz, (float)ray.dx, (float)ray.dy, (float)ray.dz);
-                pw = cosGamma > 0 ? powf(cosGamma, (float)exponent) : 0.f;
-            } else {
-                // very sharp lobes amplify FP32 rounding of cosGamma by `exponent`: keep FP64 here
-                double ldx = Dx, ldy = Dy, ldz = Dz;
-                normalize3(ldx, ldy, ldz);
-                double nx = Nx, ny = Ny, nz = Nz;
-                normalize3(nx, ny, nz);
-                double k = 2 * dot3(ldx, ldy, ldz, nx, ny, nz);
-                double rx = k * nx - ldx, ry = k * ny - ldy, rz = k * nz - ldz;
-                normalize3(rx, ry, rz);
-                double cg = -dot3(rx, ry, rz, ray.dx, ray.dy, ray.dz);
-                pw = cg > 0 ? (float)pow(cg, exponent) : 0.f;
-            }
-            const float w = pw * strength;
-            specular.r = fmaf(br, w, specular.r);
-            specular.g = fmaf(bg, w, specular.g);
-            specular.b = fmaf(bb, w, specular.b);
-        }
-    }
-    return mkcol(fmaf(diffuse.r, lightContrib.r, specular.r), fmaf(diffuse.g, lightContrib.g, specular.g),
-                 fmaf(diffuse.b, lightContrib.b, specular.b));
-}
-
-// renderer.d:325-376.  Plane-only scene classes: per lane (`live` lanes only call it).  The other classes: all 32 lanes of
-// the warp call it together, `live` says whether this lane has a ray at all, `cam` is the warp's node mask for camera rays.
-template <int MODE>
-__device__ __forceinline__ Col trace(const FrameParams& fp, const Ray& ray, bool live, unsigned& n_shadow, HitRec* out_hit, const NodeMask& cam) {
+__device__ __forceinline__ Col trace_warp(const FrameParams& fp, const Ray& cam_ray, bool live, unsigned& n_shadow, HitRec* out_hit,
+                                          NodeMask cam_mask) {
+    __shared__ double s_view[3][BLOCK_THREADS];   // FP64 camera-ray direction, parked for Phong lobes sharper than 2048
+    Ray r = cam_ray;
     HitRec h;
     h.dist = 1e99;
     h.node = -1;
     float tmaxf = 3.0e38f;   // (not +inf = (float)1e99: ptxas would prove tmaxf == (float)h.dist * k and re-convert it in every iteration)
-    if (MODE & MODE_SOLO) node_intersect<MODE>(0, ray, h, tmaxf);
-    else if (plane_only(MODE)) {
+    NodeMask mask = cam_mask;
+    bool want = live, found = false, ray_ready = true;
+    double Dx = r.dx, Dy = r.dy, Dz = r.dz, len2 = 1.0;   // shadow phases: light - origin (un-normalised), |D|^2
+    // shading state of this lane's hit
+    bool hit = false, phong = false;
+    float Nx = 0.f, Ny = 0.f, Nz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f, strength = 0.f;
+    double exponent = 1.0;
+    Col diffuse = mkcol(0.f, 0.f, 0.f), specular = mkcol(0.f, 0.f, 0.f);
+    Col lightContrib = mkcol(fp.ambient[0], fp.ambient[1], fp.ambient[2]);
+    const int nl = c_scene.n_lights;
+    int li = -1;
+    for (;;) {
+        const bool anyhit = li >= 0;
+        // ---- the node walk: warp-uniform over the mask, in scene order; per-lane work predicated
 #pragma unroll 1
-        for (int i = 0; i < c_scene.n_nodes; i++) node_intersect<MODE>(i, ray, h, tmaxf);
-    } else {
-        // the nodes this warp's camera rays can reach, in scene order; the walk is warp-uniform
-#pragma unroll
-        for (int k = 0; k < MASK_WORDS; k++)
-            for (uint32_t bits = cam.w[k]; bits; bits &= bits - 1) {
-                const int i = 32 * k + __ffs((int)bits) - 1;
-                if (live && node_intersect<MODE>(i, ray, h, tmaxf)) {
-                    if (MODE & MODE_BOUNDED) tmaxf = (float)h.dist * 1.000001f;
+        for (NodeMask bits = mask; bits; bits &= bits - 1) {
+            const int i = __ffsll((long long)bits) - 1;
+            const DevNode& nd = c_scene.nodes[i];
+            if (want && !found) {
+                bool skip = false;
+                if (nd.kind == KIND_PLANE_W) {
+                    // implied by geometry.d:35-36 (dir.y has the sign of D.y): the common "above the floor, looking / lit from above" case
+                    const double y = nd.wp[0];
+                    skip = (r.oy > y && Dy >= 0) || (r.oy < y && Dy <= 0);
+                } else if ((MODE & MODE_BOUNDED) && !(nd.flags & NODE_UNBOUNDED)) {
+                    skip = cull(nd, r, tmaxf);
+                }
+                if (!skip) {
+                    if (!ray_ready) {   // the FP64 normalisation of a shadow ray (scene.d:66-71), only once a node survives
+                        const double inv = rsqrt64(len2);
+                        r.dx = Dx * inv; r.dy = Dy * inv; r.dz = Dz * inv;
+                        h.dist = len2 * inv;
+                        ray_ready = true;
+                    }
+                    if (node_hit<MODE>(i, nd, r, h)) {
+                        if (anyhit) found = true;
+                        else if (MODE & MODE_BOUNDED) tmaxf = (float)h.dist * 1.000001f;
+                    }
                 }
             }
+            if (anyhit && __all_sync(FULL_WARP, !want || found)) break;   // every lane that asked has its occluder
+        }
+        if (!anyhit) {
+            // ---- the camera ray is traced: complete the hit (per lane)
+            if (out_hit) *out_hit = h;
+            hit = live && h.node >= 0;
+            vx = (float)r.dx; vy = (float)r.dy; vz = (float)r.dz;
+            s_view[0][threadIdx.x] = r.dx; s_view[1][threadIdx.x] = r.dy; s_view[2][threadIdx.x] = r.dz;
+            if (hit) {
+                const DevShader& sh = c_scene.shaders[c_scene.nodes[h.node].shader];
+                const bool has_tex = sh.tex >= 0;
+                Surface s;
+                surface_of<MODE>(h, nullptr, has_tex, s);
+                // faceforward (imported_types.d:69-73): the sign decision in FP64, the vector itself in FP32
+                Nx = s.nx; Ny = s.ny; Nz = s.nz;
+                if (!(dot3(r.dx, r.dy, r.dz, s.gx, s.gy, s.gz) < 0)) { Nx = -Nx; Ny = -Ny; Nz = -Nz; }
+                diffuse = has_tex ? sample_texture<MODE>(sh.tex, s.u, s.v) : mkcol(sh.color[0], sh.color[1], sh.color[2]);
+                phong = sh.type == C2RT_SHADER_PHONG;
+                strength = sh.strength;
+                exponent = sh.exponent;
+                // shadow-ray origin p + N * 1e-6 (shader.d:88,219)
+                r.ox = s.px + (double)Nx * 1e-6; r.oy = s.py + (double)Ny * 1e-6; r.oz = s.pz + (double)Nz * 1e-6;
+            }
+        } else if (want && !found) {
+            // ---- light li is visible from this lane's hit: lighting in FP32 (the reference narrows every factor to float
+            // before it touches a Color: SURVEY.md App. C.1)
+            const DevLight& L = c_scene.lights[li];
+            const float fDx = (float)Dx, fDy = (float)Dy, fDz = (float)Dz, d2 = (float)len2;
+            const float rs = rsqrtf(d2);
+            const float lx = fDx * rs, ly = fDy * rs, lz = fDz * rs;
+            const float inv_d2 = rs * rs;
+            const float cosTheta = dot3f(lx, ly, lz, Nx, Ny, Nz);
+            const float br = L.color[0] * inv_d2, bg = L.color[1] * inv_d2, bb = L.color[2] * inv_d2;
+            if (cosTheta > 0) {
+                lightContrib.r = fmaf(br, cosTheta, lightContrib.r);
+                lightContrib.g = fmaf(bg, cosTheta, lightContrib.g);
+                lightContrib.b = fmaf(bb, cosTheta, lightContrib.b);
+            }
+            if (phong) {
+                float pw;
+                if (exponent <= 2048.0) {
+                    // reflect(-lightDir, N) . (-ray.dir)  (imported_types.d:62-67, shader.d:235-239)
+                    const float k = 2.f * cosTheta;
+                    const float rx = fmaf(k, Nx, -lx), ry = fmaf(k, Ny, -ly), rz = fmaf(k, Nz, -lz);
+                    const float cosGamma = -dot3f(rx, ry, rz, vx, vy, vz);
+                    pw = cosGamma > 0 ? powf(cosGamma, (float)exponent) : 0.f;
+                } else {
+                    // very sharp lobes amplify FP32 rounding of cosGamma by `exponent`: keep FP64 here
+                    double ldx = Dx, ldy = Dy, ldz = Dz;
+                    normalize3(ldx, ldy, ldz);
+                    double nx = Nx, ny = Ny, nz = Nz;
+                    normalize3(nx, ny, nz);
+                    double k = 2 * dot3(ldx, ldy, ldz, nx, ny, nz);
+                    double rx = k * nx - ldx, ry = k * ny - ldy, rz = k * nz - ldz;
+                    normalize3(rx, ry, rz);
+                    double cg = -dot3(rx, ry, rz, s_view[0][threadIdx.x], s_view[1][threadIdx.x], s_view[2][threadIdx.x]);
+                    pw = cg > 0 ? (float)pow(cg, exponent) : 0.f;
+                }
+                const float w = pw * strength;
+                specular.r = fmaf(br, w, specular.r);
+                specular.g = fmaf(bg, w, specular.g);
+                specular.b = fmaf(bb, w, specular.b);
+            }
+        }
+        // ---- next lit light (one sample per PointLight, light.d:56-59: avg / numSamples is a division by 1.0f)
+        do li++; while (li < nl && !c_scene.lights[li].lit);
+        if (li >= nl) break;
+        const DevLight& L = c_scene.lights[li];
+        want = hit;
+        found = false;
+        ray_ready = false;
+        n_shadow += hit;
+        Dx = L.pos[0] - r.ox; Dy = L.pos[1] - r.oy; Dz = L.pos[2] - r.oz;
+        len2 = dot3(Dx, Dy, Dz, Dx, Dy, Dz);
+        if (MODE & MODE_BOUNDED) {   // FP32 shadow of the ray for the conservative cull
+            const float l2f = (float)len2;
+            const float rsf = rsqrtf(l2f);
+            r.fox = cvt_keep(r.ox); r.foy = cvt_keep(r.oy); r.foz = cvt_keep(r.oz);
+            r.fdx = cvt_keep(Dx) * rsf; r.fdy = cvt_keep(Dy) * rsf; r.fdz = cvt_keep(Dz) * rsf;
+            r.olen = sqrtf(dot3f(r.fox, r.foy, r.foz, r.fox, r.foy, r.foz));
+            tmaxf = l2f * rsf * 1.000001f;
+        }
+        bool any;
+        mask = shadow_mask<MODE>(fp.bounds, want, r, L, any);
+        if (!any) mask = 0;   // no lane of this warp has a shadow ray for this light (warp-uniform)
+    }
+    if (!hit) return mkcol(0.f, 0.f, 0.f);   // miss: environment.d:7-10
+    return mkcol(fmaf(diffuse.r, lightContrib.r, specular.r), fmaf(diffuse.g, lightContrib.g, specular.g),
+                 fmaf(diffuse.b, lightContrib.b, specular.b));
+}
+
+// renderer.d:325-376 for the plane-only scene classes (per lane; only lanes with a ray call it)
+template <int MODE>
+__device__ __forceinline__ Col trace(const FrameParams& fp, const Ray& ray, unsigned& n_shadow, HitRec* out_hit) {
+    HitRec h;
+    h.dist = 1e99;
+    h.node = -1;
+    if (MODE & MODE_SOLO) node_exact<MODE, true>(0, c_scene.nodes[0], ray, h);
+    else {
+#pragma unroll 1
+        for (int i = 0; i < c_scene.n_nodes; i++) node_exact<MODE, true>(i, c_scene.nodes[i], ray, h);
     }
     if (out_hit) {
         *out_hit = h;
-        if (h.node >= 0 && c_scene.nodes[h.node].kind != KIND_GENERIC) {
-            out_hit->px = fma(ray.dx, h.dist, ray.ox); out_hit->py = fma(ray.dy, h.dist, ray.oy); out_hit->pz = fma(ray.dz, h.dist, ray.oz);
-        }
+        if (h.node >= 0) { out_hit->px = fma(ray.dx, h.dist, ray.ox); out_hit->py = fma(ray.dy, h.dist, ray.oy); out_hit->pz = fma(ray.dz, h.dist, ray.oz); }
     }
-    if constexpr (plane_only(MODE)) {
-        if (h.node < 0) return mkcol(0.f, 0.f, 0.f);  // environment.d:7-10
-        return shade<MODE>(fp, ray, h, n_shadow);
-    } else {
-        const bool hit = live && h.node >= 0;
-        const Col c = shade_warp<MODE>(fp, ray, h, hit, n_shadow);
-        return hit ? c : mkcol(0.f, 0.f, 0.f);        // miss: environment.d:7-10
-    }
+    if (h.node < 0) return mkcol(0.f, 0.f, 0.f);  // environment.d:7-10
+    return shade<MODE>(fp, ray, h, n_shadow);
+}
+template <int MODE>
+__device__ __forceinline__ Col trace_any(const FrameParams& fp, const Ray& ray, bool live, unsigned& n_shadow, HitRec* out_hit, NodeMask cam) {
+    if constexpr (plane_only(MODE)) return trace<MODE>(fp, ray, n_shadow, out_hit);
+    else return trace_warp<MODE>(fp, ray, live, n_shadow, out_hit, cam);
 }
 
 // renderer.d:254-313 renderSample (default and DOF branches).  (bx, by, bz) is the un-normalised
@@ -1249,13 +1230,13 @@ __device__ __forceinline__ Col combine_stereo(Col left, Col right) {
 template <int MODE>
 __device__ __forceinline__ Col render_sample(const FrameParams& fp, double bx, double by, double bz, double x, double y, uint32_t px,
                                              uint32_t py, uint32_t tap, double jw, double jh, bool live, unsigned& n_primary, unsigned& n_shadow,
-                                             HitRec* out_hit, const NodeMask& cam) {
+                                             HitRec* out_hit, NodeMask cam) {
     Ray r;
     if (!(MODE & MODE_SAMPLING)) {               // renderSampleDefault without stereo (renderer.d:303-306): one ray
         uint32_t draw = 0;
         n_primary += live;
         gen_ray<MODE>(fp, bx + fp.tap_d[tap][0], by + fp.tap_d[tap][1], bz + fp.tap_d[tap][2], px, py, tap, 0, draw, 0, r);
-        return trace<MODE>(fp, r, live, n_shadow, out_hit, cam);
+        return trace_any<MODE>(fp, r, live, n_shadow, out_hit, cam);
     }
     const bool stereo = fp.stereo_sep != 0;      // renderer.d:276-284,305-312: one ray per eye, then combineStereo
     const int n_eyes = stereo ? 2 : 1;
@@ -1278,7 +1259,7 @@ __device__ __forceinline__ Col render_sample(const FrameParams& fp, double bx, d
             }
             n_primary += live;
             gen_ray<MODE>(fp, vx, vy, vz, px, py, tap, i, draw, stereo ? (e ? +1 : -1) : 0, r);
-            c = trace<MODE>(fp, r, live, n_shadow, (out_hit && i == 0 && e == 0) ? out_hit : nullptr, cam);
+            c = trace_any<MODE>(fp, r, live, n_shadow, (out_hit && i == 0 && e == 0) ? out_hit : nullptr, cam);
             if (e == 0) left = c;
         }
         if (stereo) c = combine_stereo(left, c);
@@ -1344,18 +1325,9 @@ __device__ __forceinline__ bool cone_reaches_node(const FrameParams& fp, const P
 }
 template <int MODE>
 __device__ __forceinline__ NodeMask camera_mask(const FrameParams& fp, uint32_t x0, uint32_t y0) {
-    NodeMask m = all_nodes_mask();
-    if (!camera_masked(MODE)) return m;
+    if (!camera_masked(MODE)) return all_nodes_mask();
     const PatchCone c = patch_cone(fp, x0, y0);
-    const unsigned lane = threadIdx.x & 31u;
-#pragma unroll
-    for (int k = 0; k < MASK_WORDS; k++) {
-        if (32 * k >= c_scene.n_nodes) { m.w[k] = 0; continue; }
-        const int i = 32 * k + (int)lane;
-        const bool reach = i < c_scene.n_nodes && cone_reaches_node(fp, c, __ldg(&fp.bounds[i]));   // (global, not constant: per-lane index)
-        m.w[k] = __ballot_sync(FULL_WARP, reach);
-    }
-    return m;
+    return ballot_nodes([&](int i) { return cone_reaches_node(fp, c, __ldg(&fp.bounds[i])); });   // (global, not constant: per-lane index)
 }
 
 // ---------------------------------------------------------------- frame kernel
@@ -1379,7 +1351,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS) render_frame_kernel
     const bool active = x < fp.W && y < fp.H;
 
     // nodes this warp's camera rays can reach (lane l tests nodes l, l + 32; warp ballot)
-    NodeMask cam = {};
+    NodeMask cam = 0;
     if constexpr (!plane_only(MODE)) cam = camera_mask<MODE>(fp, x0 + (warp & 1) * PATCH_W, y0 + (warp >> 1) * PATCH_H);
 
     unsigned n_primary = 0, n_shadow = 0;
@@ -1483,7 +1455,7 @@ struct PixelOut {
 };
 
 __global__ void render_pixel_kernel(const FrameParams fp, int x, int y, PixelOut* out) {
-    // one warp; lane 0 carries the ray, the other lanes only take part in the warp-wide votes of trace / occluded_warp
+    // one warp; lane 0 carries the ray, the other lanes only take part in the warp-wide votes of trace_warp
     const bool live = threadIdx.x == 0;
     unsigned a = 0, b = 0;
     HitRec h;
@@ -1566,7 +1538,7 @@ cudaError_t upload_scene(const DevScene& s, cudaStream_t st) {
 #define C2RT_MINBLOCKS_SAMPLING 4
 #endif
 #ifndef C2RT_MINBLOCKS_FULL
-#define C2RT_MINBLOCKS_FULL 5
+#define C2RT_MINBLOCKS_FULL 4   // 128 registers: the shared node walk of trace_warp spills at 96 (profiles/r2_variant_sweeps.log)
 #endif
 #ifndef C2RT_MINBLOCKS_SOLO
 #define C2RT_MINBLOCKS_SOLO 7
