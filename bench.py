@@ -5,8 +5,10 @@ A "step" is ONE FRAME of the workload rendered by the hot path.  At N=1 the work
 BASELINE.json configs[1]: data/lecture4-proc-texture.sdl at 1920x1080 (procedural texture + Lambert +
 shadow rays, 5 samples per pixel).  With N>1 ranks (one process per GPU, torchrun) the same frame is
 split into interleaved 8-row bands, each rank renders its bands, and the bands are gathered to rank 0
-(NCCL gather + the library's scatter kernel, or — `--gather p2p` — stores straight into rank 0's
-frame through a CUDA-IPC mapping over NVLink); total work is fixed, so scaling is "strong".
+(`--gather p2p`, the default: kernels store straight into rank 0's frame through a CUDA-IPC mapping over
+NVLink, completion is signalled inside the render kernel and the ranks start each frame through a
+device-side gate; `--gather nccl`: NCCL gather + the library's scatter kernel); total work is fixed, so
+scaling is "strong".
 
   value      device-resident throughput: inputs (scene, camera) already on the GPU, output left in HBM
   e2e        the same metric through the public host API (c2rt_render via the host mirror) with HOST
@@ -17,6 +19,8 @@ frame through a CUDA-IPC mapping over NVLink); total work is fixed, so scaling i
              chess2rt_b200/workloads.json) / mean kernel time (CUDA events)
   cpu_baseline  the CPU oracle (C++ restatement of the reference: the D reference cannot be built in
              this image) timed on the box's host cores on the same frame
+  scaling_targets  BASELINE.json configs[2..4] (lecture5 4K, zaphod 4K DOF, chessboard 8K) measured in the same run
+             at the same N: ms per frame, efficiency against rank 0 rendering the frame alone, frame check
 `--impl reference` times that CPU implementation alone with the same metric/config.
 `--workload` picks another configuration (c0..c4, chess1080, chess4k); the default is the headline one.
 """
@@ -44,6 +48,13 @@ WORKLOADS = {
     "lecture5_1080": ("scenes/lecture5.sdl", 1920, 1080, {}),
 }
 DEFAULT_WORKLOAD = "c1"
+SCALING_TARGETS = ["c2", "c3", "c4"]   # BASELINE.json configs[2], [3], [4]
+
+
+def workload_label(name):
+    """config.workload: the same string in both arms (ours and --impl reference)."""
+    path, w, h, _ = WORKLOADS[name]
+    return "%s: %s at %dx%d" % (name, path, w, h)
 BAND_ROWS = 8
 RNG_SEED = 0xC2E55
 L2_FLUSH_BYTES = 256 << 20  # > 126 MB L2
@@ -188,7 +199,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "Mrays/s at %dx%d" % (w, h), "value": val, "unit": "Mrays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "frames_per_s": 1e3 / ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64 geometry / f32 colour", "data": "synthetic (bundled scene file, no external data)",
-        "config": {"workload": "%s: %s at %dx%d" % (args.workload, path, w, h), "rays_per_frame": rays},
+        "config": {"workload": workload_label(args.workload), "rays_per_frame": rays},
         "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -297,137 +308,153 @@ def main():
                         raise SystemExit("--gather p2p: CUDA IPC mapping of rank 0's frame failed")
                     self.mode = "nccl"   # auto: fall back to the NCCL gather
             if self.mode == "p2p":
-                self.band = api.Band(rank, world, BAND_ROWS, 0)
+                # uint32 flags[world + 1] behind the frame, in rank 0's memory: [0] start-gate counter, [r] last frame rank r
+                # completed, [world] time-outs (c2rt.h c2rt_band.done_flags, c2rt_gate)
+                self.flags_ptr = self.peer_frame_ptr + H * W * 12
+                self.band = api.Band(rank, world, BAND_ROWS, 0, self.flags_ptr, 0, 0)
                 self.out_ptr = self.peer_frame_ptr
-                self.flags_ptr = self.peer_frame_ptr + H * W * 12   # uint32 flags[world + 1] behind the frame, in rank 0's memory
                 self.frame_no = 0
                 dist.barrier()   # c2rt_frame_alloc zero-fills: the flags start at 0 before any rank signals
             else:
-                self.band = api.Band(rank, world, BAND_ROWS, 1)
+                self.band = api.Band(rank, world, BAND_ROWS, 1, None, 0, 0)
                 self.mine = torch.empty((self.pad, W, 3), dtype=torch.float32, device="cuda")
                 self.gathered = torch.empty((world, self.pad, W, 3), dtype=torch.float32, device="cuda") if rank == 0 else None
                 self.frame = torch.empty((H, W, 3), dtype=torch.float32, device="cuda") if rank == 0 else None
                 self.out_ptr = self.mine.data_ptr()
 
-        def render(self, cam=None, st=None):
-            c2.render_device(self.handle, cam or self.cam, st or self.st, self.out_ptr, None, self.band,
-                             torch.cuda.current_stream().cuda_stream)
+        def step(self, cam=None, st=None):
+            """One frame on this rank's stream: [start gate] render [gather].  With p2p the gather IS the render kernel: peers
+            store their bands into rank 0's frame, the last CTA of each peer kernel releases that rank's flag, the last CTA of
+            rank 0's kernel waits for all flags — one kernel launch per rank and frame (+ the one-thread gate)."""
+            cur = torch.cuda.current_stream().cuda_stream
+            if self.mode == "p2p":
+                api._check(api.lib.c2rt_gate(self.flags_ptr, world, cur))
+                self.frame_no += 1
+                self.band.frame_no = self.frame_no
+                self.launches += 1
+            c2.render_device(self.handle, cam or self.cam, st or self.st, self.out_ptr, None, self.band, cur)
             self.launches += 1
-
-        def gather(self):
             if self.mode == "nccl":
                 dist.gather(self.mine, list(self.gathered.unbind(0)) if rank == 0 else None, dst=0)
                 if rank == 0:
-                    c2.deinterleave(self.gathered.data_ptr(), self.frame.data_ptr(), self.W, self.H, 3, world, BAND_ROWS, self.pad,
-                                    torch.cuda.current_stream().cuda_stream)
+                    c2.deinterleave(self.gathered.data_ptr(), self.frame.data_ptr(), self.W, self.H, 3, world, BAND_ROWS, self.pad, cur)
                     self.launches += 1
-            elif self.mode == "p2p":
-                # completion without a collective: peers raise a flag in rank 0's memory after their band stores,
-                # rank 0 waits for all flags on its stream (c2rt_signal / c2rt_wait_signals)
-                # (counting mode, value 0: the same two launches can be replayed from a CUDA graph)
-                cur = torch.cuda.current_stream().cuda_stream
-                if rank == 0:
-                    api._check(api.lib.c2rt_wait_signals(self.flags_ptr, world, 0, cur))
-                else:
-                    api._check(api.lib.c2rt_signal(self.flags_ptr + 4 * rank, 0, cur))
+
+        def timeouts(self):
+            """flags[world]: gate / completion waits that gave up (a rank died or never arrived).  Must be 0."""
+            if self.mode != "p2p":
+                return 0
+            import ctypes as C
+            t = torch.zeros(1, dtype=torch.int32, device="cuda")
+            if rank == 0:
+                got = torch.zeros(1, dtype=torch.int32).pin_memory()
+                api._check(api.lib.c2rt_frame_download(got.data_ptr(), C.c_void_p(self.flags_ptr + 4 * world), 4, torch.cuda.current_stream().cuda_stream))
+                torch.cuda.synchronize()
+                t[0] = int(got[0])
+            dist.broadcast(t, src=0)
+            return int(t[0])
 
         def count_rays(self):
             cam_c, st_c = self.scene.frame_blocks(seed=RNG_SEED, count_rays=True)
-            self.render(cam_c, st_c)
+            self.step(cam_c, st_c)
             prim, shad = c2.read_ray_counters(self.handle, stream)
             counts = torch.tensor([prim, shad], dtype=torch.int64, device="cuda")
             if world > 1:
                 dist.all_reduce(counts)
             return int(counts[0]), int(counts[1])
 
-        def capture(self):
-            """One frame (render + completion signal) as a CUDA graph: a single launch per step instead of several
-            calls through ctypes.  Not used with the NCCL gather."""
-            if self.mode == "nccl":
-                return None
-            g = torch.cuda.CUDAGraph()
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                self.render()          # scene block resident, kernels loaded: nothing but launches is left to capture
-                self.gather()
-            torch.cuda.current_stream().wait_stream(side)
-            barrier()
-            n0 = self.launches
-            with torch.cuda.graph(g, stream=side):
-                self.render()
-                self.gather()
-            self.launches_per_step = self.launches - n0
-            return g
-
-        def time_steps(self, steps, warmup, sampler=None, use_graph=True):
+        def time_steps(self, steps, warmup):
             """EXACTLY `steps` timed frames; L2 flushed between them (untimed); per-step CUDA events; max over ranks.
-            Returns (ms per step, ms per render kernel, launches).  The step is replayed from a CUDA graph when
-            possible; the kernel-only time comes from a second pass with an event right after the render kernel."""
+            Each step is enqueued behind its (untimed) L2-flush kernel, so the host's launch latency is hidden and the
+            events bracket device work only; with N > 1 the device-side gate lines the ranks up right before e0.
+            Returns (ms per step, launches in the timed region)."""
             for _ in range(warmup):
                 flush_buf.fill_(1)
-                self.render()
-                self.gather()
+                self.step()
             barrier()
-            graph = self.capture() if (use_graph and world > 1) else None   # one GPU: a single kernel launch, nothing to batch
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            self.launches = 0
             barrier()
-            if sampler is not None:
-                sampler.start()
-
-            def run(use):
-                ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-                      for _ in range(steps)]
-                self.launches = 0
-                barrier()
-                for e0, ek, e1 in ev:
-                    flush_buf.fill_(1)
-                    if world > 1:
-                        dist.barrier()  # ranks start each frame together, as one frame request would
+            cur = torch.cuda.current_stream().cuda_stream
+            for e0, e1 in ev:
+                flush_buf.fill_(1)
+                if self.mode == "p2p":
+                    # gate in front of e0: waiting for the slowest rank's flush is not frame time
+                    api._check(api.lib.c2rt_gate(self.flags_ptr, world, cur))
+                    self.frame_no += 1
+                    self.band.frame_no = self.frame_no
                     e0.record()
-                    if use is not None:
-                        use.replay()
-                        ek.record()
-                    else:
-                        self.render()
-                        ek.record()
-                        self.gather()
-                    e1.record()
-                barrier()
-                t = torch.tensor([sum(e0.elapsed_time(e1) for e0, ek, e1 in ev), sum(e0.elapsed_time(ek) for e0, ek, e1 in ev)],
-                                 dtype=torch.float64, device="cuda")
-                if world > 1:
-                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                return float(t[0]) / steps, float(t[1]) / steps
+                    c2.render_device(self.handle, self.cam, self.st, self.out_ptr, None, self.band, cur)
+                    self.launches += 1
+                elif self.mode == "nccl":
+                    dist.barrier()
+                    e0.record()
+                    self.step()
+                else:
+                    e0.record()
+                    self.step()
+                e1.record()
+            barrier()
+            t = torch.tensor([sum(e0.elapsed_time(e1) for e0, e1 in ev)], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            n_to = self.timeouts() if world > 1 else 0
+            if n_to:
+                raise SystemExit(f"{self.name}: {n_to} gate / frame-complete wait(s) timed out: the timed frames are not complete frames")
+            return float(t[0]) / steps, self.launches
 
-            ms_plain, kernel_ms = run(None)
-            n_launches = self.launches
-            if graph is None:
-                return ms_plain, kernel_ms, n_launches, "direct launches"
-            ms_graph, _ = run(graph)
-            return ms_graph, kernel_ms, steps * self.launches_per_step, "CUDA graph replay (1 graph launch per step)"
+        def time_alone(self, steps, warmup=2):
+            """(N > 1) rank 0 renders the whole frame alone, the other ranks idle: the T(1) of the efficiency figure, same run."""
+            ms = 0.0
+            if rank == 0:
+                alone = torch.empty((self.H, self.W, 3), dtype=torch.float32, device="cuda")
+                ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+                cur = torch.cuda.current_stream().cuda_stream
+                for _ in range(warmup):
+                    c2.render_device(self.handle, self.cam, self.st, alone.data_ptr(), None, None, cur)
+                for e0, e1 in ev:
+                    flush_buf.fill_(1)
+                    e0.record()
+                    c2.render_device(self.handle, self.cam, self.st, alone.data_ptr(), None, None, cur)
+                    e1.record()
+                torch.cuda.synchronize()
+                ms = sum(e0.elapsed_time(e1) for e0, e1 in ev) / steps
+                del alone
+            if world > 1:
+                dist.barrier(group=cpu_group)   # (not an NCCL barrier: its kernel would spin on the idle GPUs' SMs)
+            return ms
 
         def verify(self):
             """(untimed) rank 0: the frame assembled from all ranks' bands equals, bit for bit, the same frame rendered by
-            rank 0 alone."""
+            rank 0 alone.  The shared frame is filled with NaNs first, so a band that did not arrive cannot pass for the one a
+            previous frame left there."""
             if world == 1:
                 return None
-            self.render()
-            self.gather()
+            import ctypes as C
+            cur = torch.cuda.current_stream().cuda_stream
+            if self.mode == "p2p" and rank == 0:
+                api._check(api.lib.c2rt_frame_memset(C.c_void_p(self.peer_frame_ptr), 0xFF, self.H * self.W * 12, cur))
+            elif self.mode == "nccl" and rank == 0:
+                self.frame.fill_(float("nan"))
+            self.step()   # (p2p: the gate inside keeps the peers' stores behind rank 0's memset)
             barrier()
+            n_to = self.timeouts()
             if rank != 0:
                 return None
             W, H = self.W, self.H
             alone = torch.empty((H, W, 3), dtype=torch.float32, device="cuda")
-            c2.render_device(self.handle, self.cam, self.st, alone.data_ptr(), None, None, torch.cuda.current_stream().cuda_stream)
+            c2.render_device(self.handle, self.cam, self.st, alone.data_ptr(), None, None, cur)
             if self.mode == "p2p":
                 got = torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True)
-                api._check(api.lib.c2rt_frame_download(got.data_ptr(), self.peer_frame_ptr, H * W * 12, torch.cuda.current_stream().cuda_stream))
+                api._check(api.lib.c2rt_frame_download(got.data_ptr(), self.peer_frame_ptr, H * W * 12, cur))
                 torch.cuda.synchronize()
                 same = bool(torch.equal(got, alone.cpu()))
             else:
                 torch.cuda.synchronize()
                 same = bool(torch.equal(self.frame, alone))
-            return "bit-identical to the frame rendered by rank 0 alone" if same else "MISMATCH"
+            if n_to:
+                return "MISMATCH (%d wait time-outs)" % n_to
+            return "bit-identical to the frame rendered by rank 0 alone (shared frame NaN-filled first)" if same else "MISMATCH"
 
         def close(self):
             import ctypes as C
@@ -450,32 +477,48 @@ def main():
     rays_per_frame = prim + shad
     flops_per_frame = cal["flops"] if cal else None
 
+    # ---- roofline denominators: measured on this device before anything is timed -------------------
+    peak_tf, peak_mhz = c2.measure_fma_peak(False)
+    peak64_tf, _ = c2.measure_fma_peak(True)
+    sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    peaks = {"fp32_tflops": peak_tf, "fp64_tflops": peak64_tf, "sm_mhz_effective": peak_mhz, "sms": sms}
+
     # ---- timed region ------------------------------------------------------------------------------
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler is not None:
         sampler.start()   # sampled from before the warm-up to the end of the e2e leg (a 1080p frame takes 0.16 ms:
                           # the timed loops alone are shorter than one nvidia-smi period)
-    ms_per_step, kernel_ms, n_launches, launch_how = run.time_steps(args.steps, args.warmup, None)
+    ms_per_step, n_launches = run.time_steps(args.steps, args.warmup)
+    kernel_ms = ms_per_step   # one render kernel per rank and step is the whole step (N > 1: it also carries the band gather)
 
     frame_check = run.verify()
     if world > 1:
         dist.barrier()
-    if frame_check == "MISMATCH":
-        raise SystemExit("multi-GPU frame differs from the single-GPU frame")
+    if frame_check and frame_check.startswith("MISMATCH"):
+        raise SystemExit("multi-GPU frame differs from the single-GPU frame: " + frame_check)
 
-    # ---- the scaling target of BASELINE.json (8K chessboard), measured beside the headline workload ----
-    scaling_target = None
+    # ---- BASELINE.json configs[2..4] beside the headline workload: lecture5 4K, zaphod 4K DOF, chessboard 8K at this N ----
+    scaling_targets = []
     if args.workload == DEFAULT_WORKLOAD and not args.no_scaling_target:
-        run4 = DeviceRun("c4", args.gather)
-        p4, s4 = run4.count_rays()
-        ms4, k4, _, _ = run4.time_steps(max(3, args.steps // 4), 3)
-        cal4 = load_calibration().get("c4") or {}
-        scaling_target = {"workload": "c4: scenes/chessboard.sdl at 7680x4320 (32 CSG pieces, Phong, AA)", "n_gpus": world,
-                          "ms_per_step": ms4, "kernel_ms": k4, "value": (p4 + s4) / (ms4 * 1e-3) / 1e6, "unit": "Mrays/s",
-                          "frames_per_s": 1e3 / ms4, "steps": max(3, args.steps // 4), "gather": run4.mode,
-                          "algorithmic_flops_per_frame": cal4.get("flops"),
-                          "achieved_tflops_per_gpu": (cal4["flops"] / world / (k4 * 1e-3) / 1e12) if cal4.get("flops") else None}
-        run4.close()
+        for name in SCALING_TARGETS:
+            rn = DeviceRun(name, args.gather)
+            pn, sn = rn.count_rays()
+            k = max(3, args.steps // 4)
+            ms_n, _ = rn.time_steps(k, 3)
+            check_n = rn.verify()
+            if check_n and check_n.startswith("MISMATCH"):
+                raise SystemExit(f"{name}: multi-GPU frame differs from the single-GPU frame: {check_n}")
+            ms_1 = rn.time_alone(k) if world > 1 else ms_n
+            cal_n = load_calibration().get(name) or {}
+            ex_n = executed_fractions(name, ms_1, peaks) if rank == 0 else None
+            scaling_targets.append({
+                "workload": workload_label(name), "n_gpus": world, "ms_per_step": ms_n, "ms_per_step_1gpu_same_run": ms_1,
+                "efficiency": ms_1 / (world * ms_n), "value": (pn + sn) / (ms_n * 1e-3) / 1e6, "unit": "Mrays/s",
+                "frames_per_s": 1e3 / ms_n, "steps": k, "gather": rn.mode, "frame_check": check_n,
+                "algorithmic_flops_per_frame": cal_n.get("flops"),
+                "achieved_tflops_per_gpu": (cal_n["flops"] / world / (ms_n * 1e-3) / 1e12) if cal_n.get("flops") else None,
+                "executed_1gpu": ex_n})
+            rn.close()
 
     # ---- e2e: public host API, HOST buffers, copies inside the timed region ------------------------
     pinned = torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True) if rank == 0 else None
@@ -517,13 +560,8 @@ def main():
 
     if rank == 0:
         value = rays_per_frame / (ms_per_step * 1e-3) / 1e6
-        if world > 1:
-            c2.init(1, [local_rank])
-        peak_tf, peak_mhz = c2.measure_fma_peak(False)
-        peak64_tf, _ = c2.measure_fma_peak(True)
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
         mp = json.load(open(peaks_file)) if os.path.exists(peaks_file) else {}
-        sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
         nominal_tf = 2 * 128 * sms * mp.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -537,21 +575,28 @@ def main():
                 "traffic": traffic, "peak_source": "FFMA micro-benchmark measured in this run (c2rt_measure_fma_peak)",
                 "peak_nominal": nominal_tf, "frac_nominal": achieved / nominal_tf, "fp64_peak_measured": peak64_tf,
                 "algorithmic_flops_per_frame": flops_per_frame, "kernel_ms": kernel_ms,
-                "note": "achieved = algorithmic FLOPs of the reference's arithmetic (oracle counting scalar) / kernel time; "
-                        "culled and simplified work still counts, so frac can exceed 1 on many-node scenes",
+                "note": "achieved = ALGORITHMIC FLOPs of the reference's arithmetic (oracle counting scalar) / kernel time; culled and "
+                        "simplified work still counts, so frac can exceed 1 on many-node scenes.  What the hardware executed is in `executed`",
+                "executed": executed_fractions(args.workload, kernel_ms, peaks) if world == 1 else None,
                 "hbm": {"achieved": W * H * 12 / world / (kernel_ms * 1e-3) / 1e9, "peak": mp.get("hbm_gbs"), "unit": "GB/s",
                         "note": "framebuffer bytes written per kernel; far below the HBM roof, the kernel is FMA-bound"},
             }
+        ingest = None
+        if world > 1:
+            nb = (world - 1) * W * H * 12 // world
+            ingest = {"nvlink_ingest_bytes_per_frame": nb, "floor_ms_at_900GBs": nb / 900e9 * 1e3,
+                      "note": "bytes the peers store into rank 0's frame per frame; rank 0's NVLink ingest bounds the gathered frame"}
         line = {
             "metric": "Mrays/s at %dx%d" % (W, H), "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "frames_per_s": 1e3 / ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64 geometry / f32 colour (as the reference)",
             "data": "synthetic (bundled scene file rendered from a fixed camera; no external data)",
-            "config": {"workload": "%s: %s at %dx%d, AA 5 samples/px, 1 light" % (args.workload, path, W, H),
+            "config": {"workload": workload_label(args.workload), "samples_per_px": prim // (W * H),
                        "rays_per_frame": rays_per_frame, "primary_rays": prim, "shadow_rays": shad,
                        "l2": "flushed between timed steps (256 MiB fill, untimed); per-step CUDA events summed",
                        "parallelism": "row bands of %d rows, interleaved over %d GPU(s), gather=%s" % (BAND_ROWS, world, gather_mode),
-                       "launch": launch_how},
+                       "launch": "one render kernel per rank and step" + (" (+ a one-thread start gate); completion signalled inside the kernel" if gather_mode == "p2p" else ""),
+                       "timing": "each step enqueued behind its untimed L2-flush kernel; CUDA events around the step; max over ranks"},
             "roofline": roofline,
             "e2e": {"value": rays_per_frame / (e2e_ms_mean * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms_mean,
                     "frames_per_s": 1e3 / e2e_ms_mean, "h2d_bytes_per_step": C_sizeof_frame_blocks(api) * world, "d2h_bytes_per_step": W * H * 12,
@@ -560,8 +605,9 @@ def main():
                             "one process driving %d devices (c2rt_init(%d)), each device copies its own bands to the host" % (world, world))},
             "gpu_launches": n_launches,
             "clocks": clocks,
-            "scaling_target": scaling_target,
+            "scaling_targets": scaling_targets,
             "multi_gpu_frame_check": frame_check,
+            "nvlink": ingest,
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
@@ -573,8 +619,13 @@ def main():
                 s_, rays_, done = cpu_rows_seconds(path, W, H, over, threads, rows=128)
                 sec, rays = s_ * H / done, rays_ * H / done
                 sample = "128 rows (16 windows of 8 rows spread over the frame), scaled to the frame"
+            # one thread beside it (comparable with the reference's published single-thread numbers, perf-results.md:21):
+            # 96 rows spread over the frame, scaled
+            s1, r1, done1 = cpu_rows_seconds(path, W, H, over, 1, rows=96)
             line["cpu_baseline"] = {"value": rays / sec / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
                                     "sample": sample, "frames_per_s": 1.0 / sec,
+                                    "single_thread": {"value": r1 / s1 / 1e6, "unit": "Mrays/s", "cores": 1, "frames_per_s": done1 / (s1 * H),
+                                                      "sample": "%d rows (windows of 8 rows spread over the frame), scaled to the frame" % done1},
                                     "note": "C++ restatement of the reference (oracle/), g++ -O2; the D reference cannot be built here"}
         print(json.dumps(line), flush=True)
 
@@ -582,6 +633,23 @@ def main():
         dist.barrier(group=cpu_group)
         dist.destroy_process_group()
     c2.shutdown()
+
+
+def executed_fractions(workload, kernel_ms, peaks):
+    """What the hardware executed for one frame of `workload` (profiles/executed.json: thread-level FP32 / FP64 FLOPs and
+    warp instructions of the render kernel, extracted from a committed ncu report by profiles/ncu_executed.py) against the
+    time measured in THIS run: fractions of the measured FP32 / FP64 FMA peaks and of the issue slots."""
+    p = os.path.join(ROOT, "profiles", "executed.json")
+    ex = (json.load(open(p)) if os.path.exists(p) else {}).get(workload)
+    if not ex or not kernel_ms:
+        return None
+    t = kernel_ms * 1e-3
+    slots = peaks["sms"] * 4 * peaks["sm_mhz_effective"] * 1e6 * t   # 4 SMSPs per SM, one warp instruction per clock each
+    return {"fp32_flop": ex["fp32_flop"], "fp64_flop": ex["fp64_flop"], "warp_inst": ex["warp_inst"],
+            "fp32_frac": ex["fp32_flop"] / t / 1e12 / peaks["fp32_tflops"], "fp64_frac": ex["fp64_flop"] / t / 1e12 / peaks["fp64_tflops"],
+            "issue_frac": ex["warp_inst"] / slots, "kernel": ex.get("kernel"), "source": ex.get("source"),
+            "note": "counts from the ncu report named in `source` (same kernel build); time and peaks from this run; "
+                    "sm clock = the FFMA micro-benchmark's effective clock"}
 
 
 def C_sizeof_frame_blocks(api):

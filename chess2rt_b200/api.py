@@ -81,7 +81,7 @@ C_ABI_SYMBOLS = [
     "c2rt_init", "c2rt_shutdown", "c2rt_abi_version", "c2rt_device_count", "c2rt_last_error",
     "c2rt_scene_create", "c2rt_scene_destroy", "c2rt_render", "c2rt_render_device", "c2rt_read_ray_counters",
     "c2rt_deinterleave", "c2rt_render_pixel", "c2rt_band_rows_owned", "c2rt_rng_u31", "c2rt_srgb_table",
-    "c2rt_frame_alloc", "c2rt_frame_free", "c2rt_frame_export", "c2rt_frame_import", "c2rt_frame_unimport", "c2rt_frame_download", "c2rt_pin_host_buffer", "c2rt_unpin_host_buffer", "c2rt_gate",
+    "c2rt_frame_alloc", "c2rt_frame_free", "c2rt_frame_export", "c2rt_frame_import", "c2rt_frame_unimport", "c2rt_frame_memset", "c2rt_frame_download", "c2rt_pin_host_buffer", "c2rt_unpin_host_buffer", "c2rt_gate",
     "c2rt_measure_fma_peak", "c2rt_selftest_device_pool",
 ]
 
@@ -111,6 +111,7 @@ lib.c2rt_frame_free.argtypes = [C.c_void_p]
 lib.c2rt_frame_export.argtypes = [C.c_void_p, C.c_void_p]
 lib.c2rt_frame_import.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
 lib.c2rt_frame_unimport.argtypes = [C.c_void_p]
+lib.c2rt_frame_memset.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p]
 lib.c2rt_frame_download.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
 lib.c2rt_pin_host_buffer.argtypes = [C.c_void_p, C.c_size_t]
 lib.c2rt_unpin_host_buffer.argtypes = [C.c_void_p]

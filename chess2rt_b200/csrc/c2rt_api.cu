@@ -1119,6 +1119,12 @@ int c2rt_frame_unimport(void* d_ptr) {
     return C2RT_OK;
 }
 
+int c2rt_frame_memset(void* d_ptr, int byte_value, size_t bytes, void* stream) {
+    if (!d_ptr) return fail(C2RT_ERR_INVALID_ARG, "bad frame_memset arguments");
+    CU(cudaMemsetAsync(d_ptr, byte_value, bytes, (cudaStream_t)stream));
+    return C2RT_OK;
+}
+
 int c2rt_frame_download(void* host_dst, const void* d_src, size_t bytes, void* stream) {
     if (!host_dst || !d_src) return fail(C2RT_ERR_INVALID_ARG, "bad frame_download arguments");
     CU(cudaMemcpyAsync(host_dst, d_src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));

@@ -254,6 +254,9 @@ int c2rt_frame_free(void* d_ptr);
 int c2rt_frame_export(void* d_ptr, uint8_t handle[64]);
 int c2rt_frame_import(const uint8_t handle[64], void** d_ptr);
 int c2rt_frame_unimport(void* d_ptr);
+/* asynchronous byte fill of (part of) such a frame on `stream` (e.g. 0xFF = NaN pixels before a checked frame, so that a band
+ * that never arrived cannot pass for one left over from the previous frame) */
+int c2rt_frame_memset(void* d_ptr, int byte_value, size_t bytes, void* stream);
 /* asynchronous device->host copy of (part of) such a frame on `stream` (host memory should be pinned) */
 int c2rt_frame_download(void* host_dst, const void* d_src, size_t bytes, void* stream);
 

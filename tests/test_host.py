@@ -48,7 +48,7 @@ def test_struct_layouts_match_header_sizes():
     # sizes the C compiler gives the ABI structs (x86-64 SysV): guards the ctypes mirrors
     assert C.sizeof(api.Camera) == 7 * 24 + 4 * 4 + 3 * 8
     assert C.sizeof(api.Settings) == 64
-    assert C.sizeof(api.Band) == 16
+    assert C.sizeof(api.Band) == 16 + 8 + 4 + 4   # + done_flags pointer, frame_no, reserved
     assert C.sizeof(api.Stats) == 40
     assert C.sizeof(api.Hit) == 8 + 8 + 24 + 24 + 16
     s = c2.HostScene(os.path.join(SC, "lecture4.sdl"))
