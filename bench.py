@@ -324,16 +324,16 @@ def main():
 
         def step(self, cam=None, st=None):
             """One frame on this rank's stream: [start gate] render [gather].  With p2p the gather IS the render kernel: peers
-            store their bands into rank 0's frame, the last CTA of each peer kernel releases that rank's flag, the last CTA of
-            rank 0's kernel waits for all flags — one kernel launch per rank and frame (+ the one-thread gate)."""
+            store their bands into rank 0's frame and raise their flag from a one-thread kernel behind it, the last CTA of
+            rank 0's kernel waits for all flags (c2rt.h c2rt_band.done_flags)."""
             cur = torch.cuda.current_stream().cuda_stream
             if self.mode == "p2p":
-                api._check(api.lib.c2rt_gate(self.flags_ptr, world, cur))
                 self.frame_no += 1
+                api._check(api.lib.c2rt_gate(self.flags_ptr, world, self.frame_no, cur))   # (one gate per frame: round == frame number)
                 self.band.frame_no = self.frame_no
                 self.launches += 1
             c2.render_device(self.handle, cam or self.cam, st or self.st, self.out_ptr, None, self.band, cur)
-            self.launches += 1
+            self.launches += 2 if (self.mode == "p2p" and rank != 0) else 1   # peers: render kernel + the one-thread flag kernel
             if self.mode == "nccl":
                 dist.gather(self.mine, list(self.gathered.unbind(0)) if rank == 0 else None, dst=0)
                 if rank == 0:
@@ -380,12 +380,12 @@ def main():
                 flush_buf.fill_(1)
                 if self.mode == "p2p":
                     # gate in front of e0: waiting for the slowest rank's flush is not frame time
-                    api._check(api.lib.c2rt_gate(self.flags_ptr, world, cur))
                     self.frame_no += 1
+                    api._check(api.lib.c2rt_gate(self.flags_ptr, world, self.frame_no, cur))
                     self.band.frame_no = self.frame_no
                     e0.record()
                     c2.render_device(self.handle, self.cam, self.st, self.out_ptr, None, self.band, cur)
-                    self.launches += 1
+                    self.launches += 2 if rank != 0 else 1   # peers: render kernel + the one-thread flag kernel
                 elif self.mode == "nccl":
                     dist.barrier()
                     e0.record()
@@ -595,7 +595,7 @@ def main():
                        "rays_per_frame": rays_per_frame, "primary_rays": prim, "shadow_rays": shad,
                        "l2": "flushed between timed steps (256 MiB fill, untimed); per-step CUDA events summed",
                        "parallelism": "row bands of %d rows, interleaved over %d GPU(s), gather=%s" % (BAND_ROWS, world, gather_mode),
-                       "launch": "one render kernel per rank and step" + (" (+ a one-thread start gate); completion signalled inside the kernel" if gather_mode == "p2p" else ""),
+                       "launch": "one render kernel per rank and step" + (" (+ a one-thread start gate in front of the timed region; peers raise a flag from a one-thread kernel, rank 0 waits for the flags inside its render kernel)" if gather_mode == "p2p" else ""),
                        "timing": "each step enqueued behind its untimed L2-flush kernel; CUDA events around the step; max over ranks"},
             "roofline": roofline,
             "e2e": {"value": rays_per_frame / (e2e_ms_mean * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms_mean,

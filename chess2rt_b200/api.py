@@ -115,7 +115,7 @@ lib.c2rt_frame_memset.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p]
 lib.c2rt_frame_download.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
 lib.c2rt_pin_host_buffer.argtypes = [C.c_void_p, C.c_size_t]
 lib.c2rt_unpin_host_buffer.argtypes = [C.c_void_p]
-lib.c2rt_gate.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+lib.c2rt_gate.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
 lib.c2rt_measure_fma_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
 
 host_lib.c2rt_host_last_error.restype = C.c_char_p

@@ -28,7 +28,8 @@ cudaError_t launch_pixel(const FrameParams& fp, int x, int y, void* d_out, cudaS
 cudaError_t launch_deinterleave(const void* src, void* dst, uint32_t row_words, uint32_t height, uint32_t n_ranks,
                                 uint32_t band_rows, uint32_t rows_pad, cudaStream_t st);
 cudaError_t launch_fma_peak(bool fp64, int blocks, int threads, int iters, void* d_out, cudaStream_t st);
-cudaError_t launch_gate(void* gate, void* local_round, uint32_t n_ranks, void* err, cudaStream_t st);
+cudaError_t launch_gate(void* gate, uint32_t round, uint32_t n_ranks, void* err, cudaStream_t st);
+cudaError_t launch_signal(void* flag, uint32_t frame_no, cudaStream_t st);
 size_t pixel_out_size();
 }  // namespace c2rt
 
@@ -69,7 +70,7 @@ struct DeviceCtx {
     std::vector<cudaEvent_t> band_done;
     uint64_t uploaded_scene = 0;   // id of the scene currently in this device's constant memory
     unsigned long long* d_counters = nullptr;
-    uint32_t* d_sync = nullptr;    // [0] CTAs of the current launch that finished (in-kernel completion), [1] gate round
+    uint32_t* d_sync = nullptr;    // [0] CTAs of the current launch that finished (in-kernel completion)
     uint8_t* d_lut = nullptr;
     void* d_pixel = nullptr;
     float* d_rgb = nullptr;
@@ -810,9 +811,11 @@ int c2rt_render_device(c2rt_scene* s, const c2rt_camera* cam, const c2rt_setting
         band_rows = band->band_rows;
         if (band->done_flags) {
             if (band->n_ranks > 32) return fail(C2RT_ERR_INVALID_ARG, "done_flags: at most 32 ranks");
-            fp.done_flags = (uint32_t*)band->done_flags;
-            fp.done_counter = c->d_sync;
             fp.frame_no = band->frame_no;
+            if (band->rank == 0) {   // rank 0 waits inside its kernel; peers signal behind theirs (below)
+                fp.done_flags = (uint32_t*)band->done_flags;
+                fp.done_counter = c->d_sync;
+            }
         }
     }
     if (((uintptr_t)d_rgb & 15u) && (fp.W & 3u) == 0)
@@ -823,10 +826,12 @@ int c2rt_render_device(c2rt_scene* s, const c2rt_camera* cam, const c2rt_setting
     fp.counters = c->d_counters;
     fp.lut = c->d_lut;
     CU(launch_frame(fp, s->mode, local_tile_rows(fp.H, fp.rank, fp.n_ranks, band_rows), st));
+    const bool signals = band && band->done_flags && band->rank != 0;
+    if (signals) CU(launch_signal((uint32_t*)band->done_flags + band->rank, band->frame_no, st));
     if (stats) {
         memset(stats, 0, sizeof *stats);
         stats->n_gpus = 1;
-        stats->launches = 1;
+        stats->launches = signals ? 2 : 1;
     }
     return C2RT_OK;
 }
@@ -1131,16 +1136,10 @@ int c2rt_frame_download(void* host_dst, const void* d_src, size_t bytes, void* s
     return C2RT_OK;
 }
 
-int c2rt_gate(void* d_flags, uint32_t n_ranks, void* stream) {
-    if (!d_flags || n_ranks < 1 || n_ranks > 32) return fail(C2RT_ERR_INVALID_ARG, "bad gate arguments");
-    std::lock_guard<std::mutex> g(g_mu);
-    if (!g_ctx.inited) return fail(C2RT_ERR_NOT_INITIALISED, "c2rt_init has not been called");
-    int dev = -1;
-    CU(cudaGetDevice(&dev));
-    DeviceCtx* c = find_device(dev);
-    if (!c) return fail(C2RT_ERR_INVALID_ARG, "current device %d is not part of the c2rt context", dev);
+int c2rt_gate(void* d_flags, uint32_t n_ranks, uint32_t round, void* stream) {
+    if (!d_flags || n_ranks < 1 || n_ranks > 32 || round == 0) return fail(C2RT_ERR_INVALID_ARG, "bad gate arguments");
     uint32_t* flags = (uint32_t*)d_flags;
-    CU(launch_gate(flags, c->d_sync + 1, n_ranks, flags + n_ranks, (cudaStream_t)stream));
+    CU(launch_gate(flags, round, n_ranks, flags + n_ranks, (cudaStream_t)stream));
     return C2RT_OK;
 }
 

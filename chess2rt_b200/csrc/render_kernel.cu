@@ -1408,29 +1408,23 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS) render_frame_kernel
     }
     if (fp.argb && active) fp.argb[(size_t)(out_y0 + ly) * fp.W + x] = pack_rgb32(fp.lut, c);
 
-    // Frame-complete signalling folded into the kernel (c2rt.h c2rt_band.done_flags; one process per GPU, bands stored into
-    // rank 0's frame over NVLink).  Every CTA: barrier, then thread 0 fences at system scope — cumulative over the CTA's band
-    // stores — and counts the CTA in.  The last CTA of the launch: a peer rank releases its flag in rank 0's memory, rank 0
-    // waits there for all peers' flags, so the end of rank 0's kernel IS the complete frame (no signal / wait launches).
-    if (fp.done_flags) {
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence_system();
-            if (atomicAdd(fp.done_counter, 1u) == gridDim.x * gridDim.y - 1u) {
-                *fp.done_counter = 0u;   // ready for the next launch on this device (stream order)
-                __threadfence_system();
-                if (fp.rank != 0) st_release_sys(fp.done_flags + fp.rank, fp.frame_no);
-                else {
-                    const long long t0 = clock64();
-                    for (uint32_t r = 1; r < fp.n_ranks; r++)
-                        // frame numbers only grow; the signed difference tolerates wrap-around
-                        while ((int)(ld_acquire_sys(fp.done_flags + r) - fp.frame_no) < 0)
-                            if (clock64() - t0 > 4000000000ll) {   // ~2 s: a peer died; do not hang the device, report it
-                                atomicAdd(fp.done_flags + fp.n_ranks, 1u);
-                                break;
-                            }
-                }
-            }
+    // Frame-complete wait folded into RANK 0's kernel (c2rt.h c2rt_band.done_flags; one process per GPU, peers store their bands
+    // into rank 0's frame over NVLink and raise flags[rank] from a one-thread kernel behind their render kernel — a kernel
+    // boundary, so every band store is performed at system scope before the flag).  The last CTA of rank 0's launch to finish
+    // waits for all peers' flags: the end of rank 0's kernel IS the complete frame, with no extra launch on its critical path.
+    // (A per-CTA __threadfence_system() + flag store inside the PEERS' kernels was measured too: the fence waits for the
+    // CTA's remote stores and held every CTA ~4 us — 21 % on the 8K chessboard; profiles/r2_inkernel_fence.log.)
+    if (fp.done_flags && threadIdx.x == 0) {
+        if (atomicAdd(fp.done_counter, 1u) == gridDim.x * gridDim.y - 1u) {
+            *fp.done_counter = 0u;   // ready for the next launch on this device (stream order)
+            const long long t0 = clock64();
+            for (uint32_t r = 1; r < fp.n_ranks; r++)
+                // frame numbers only grow; the signed difference tolerates wrap-around
+                while ((int)(ld_acquire_sys(fp.done_flags + r) - fp.frame_no) < 0)
+                    if (clock64() - t0 > 4000000000ll) {   // ~2 s: a peer died; do not hang the device, report it
+                        atomicAdd(fp.done_flags + fp.n_ranks, 1u);
+                        break;
+                    }
         }
     }
 
@@ -1496,8 +1490,14 @@ __global__ void deinterleave_kernel(const uint32_t* __restrict__ src, uint32_t* 
 // Device-side start gate between ranks (c2rt.h c2rt_gate): every rank adds 1 to a counter in rank 0's memory and waits until
 // all n_ranks of this round have arrived.  Enqueued in front of a frame it (i) starts the ranks' kernels together without a host
 // round trip and (ii) keeps a fast peer from storing bands of frame k + 1 while rank 0's stream still works on frame k.
-__global__ void gate_kernel(uint32_t* gate, uint32_t* local_round, uint32_t n_ranks, uint32_t* err) {
-    const uint32_t target = ++*local_round * n_ranks;
+// peer ranks: raise flags[rank] = frame_no behind the render kernel (stream order: the kernel boundary has performed its band
+// stores at system scope; the release store orders the flag after them for rank 0's acquire loads)
+__global__ void signal_kernel(uint32_t* flag, uint32_t frame_no) {
+    __threadfence_system();
+    st_release_sys(flag, frame_no);
+}
+__global__ void gate_kernel(uint32_t* gate, uint32_t round, uint32_t n_ranks, uint32_t* err) {
+    const uint32_t target = round * n_ranks;
     __threadfence_system();
     atomicAdd_system(gate, 1u);
     const long long t0 = clock64();
@@ -1594,8 +1594,12 @@ cudaError_t launch_deinterleave(const void* src, void* dst, uint32_t row_words, 
     return cudaGetLastError();
 }
 
-cudaError_t launch_gate(void* gate, void* local_round, uint32_t n_ranks, void* err, cudaStream_t st) {
-    gate_kernel<<<1, 1, 0, st>>>((uint32_t*)gate, (uint32_t*)local_round, n_ranks, (uint32_t*)err);
+cudaError_t launch_signal(void* flag, uint32_t frame_no, cudaStream_t st) {
+    signal_kernel<<<1, 1, 0, st>>>((uint32_t*)flag, frame_no);
+    return cudaGetLastError();
+}
+cudaError_t launch_gate(void* gate, uint32_t round, uint32_t n_ranks, void* err, cudaStream_t st) {
+    gate_kernel<<<1, 1, 0, st>>>((uint32_t*)gate, round, n_ranks, (uint32_t*)err);
     return cudaGetLastError();
 }
 

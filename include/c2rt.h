@@ -154,14 +154,15 @@ typedef struct c2rt_settings {
 typedef struct c2rt_band {
     uint32_t rank, n_ranks, band_rows;
     uint32_t compact;   /* 0: outputs are full frames (row y at y*W); 1: outputs hold only this rank's rows, in order */
-    /* Frame-complete signalling inside the render kernel (one process per GPU, bands stored into rank 0's frame through a
-     * c2rt_frame_import mapping).  NULL: off.  Otherwise uint32 flags[n_ranks + 1] in RANK 0's frame allocation, zero at
-     * start: [0] is the start gate's counter (c2rt_gate), [r] the last frame_no rank r > 0 completed, [n_ranks] counts
-     * time-outs.  The last CTA of a peer's kernel stores frame_no into flags[rank] (st.release.sys, after every CTA's band
-     * stores were fenced at system scope); the last CTA of rank 0's kernel waits for flags[1..n_ranks-1] >= frame_no, so
-     * rank 0's kernel ends when the whole frame is in its memory.  It gives up after ~2 s and bumps flags[n_ranks] instead
-     * of hanging the device: read that word back before trusting a frame.  frame_no must grow by one per frame (1, 2, ...);
-     * one such launch in flight per device. */
+    /* Frame-complete signalling for one process per GPU (bands stored into rank 0's frame through a c2rt_frame_import
+     * mapping).  NULL: off.  Otherwise uint32 flags[n_ranks + 1] in RANK 0's frame allocation, zero at start: [0] is the
+     * start gate's counter (c2rt_gate), [r] the last frame_no rank r > 0 completed, [n_ranks] counts time-outs.  A peer's
+     * c2rt_render_device enqueues a one-thread kernel behind its render kernel that stores frame_no into flags[rank]
+     * (st.release.sys; the kernel boundary has performed the band stores at system scope).  The last CTA of RANK 0's render
+     * kernel waits for flags[1..n_ranks-1] >= frame_no, so rank 0's kernel ends when the whole frame is in its memory — no
+     * wait launch on its critical path.  The wait gives up after ~2 s and bumps flags[n_ranks] instead of hanging the device:
+     * read that word back before trusting a frame.  frame_no must grow by one per frame (1, 2, ...); one such launch in
+     * flight per device. */
     void* done_flags;
     uint32_t frame_no;
     uint32_t reserved;
@@ -260,12 +261,13 @@ int c2rt_frame_memset(void* d_ptr, int byte_value, size_t bytes, void* stream);
 /* asynchronous device->host copy of (part of) such a frame on `stream` (host memory should be pinned) */
 int c2rt_frame_download(void* host_dst, const void* d_src, size_t bytes, void* stream);
 
-/* Device-side start gate for the one-process-per-GPU path: every rank enqueues c2rt_gate(flags, n_ranks, stream) in front
- * of a frame; the one-thread kernel adds 1 to flags[0] (rank 0's memory, over NVLink for the peers) and waits until all n_ranks
- * arrived for this round.  The ranks' render kernels then start together without a host round trip, and no peer can store
- * bands of frame k + 1 while rank 0's stream still works on (renders, copies out, clears) frame k.  Same ~2 s time-out rule and
- * error word (flags[n_ranks]) as c2rt_band.done_flags.  Every rank must call it the same number of times. */
-int c2rt_gate(void* d_flags, uint32_t n_ranks, void* stream);
+/* Device-side start gate for the one-process-per-GPU path: every rank enqueues c2rt_gate(flags, n_ranks, round, stream) in
+ * front of a frame, with round = 1, 2, 3, ... counted per flags allocation; the one-thread kernel adds 1 to flags[0] (rank 0's
+ * memory, over NVLink for the peers) and waits until it reaches round * n_ranks, i.e. until every rank arrived.  The ranks'
+ * render kernels then start together without a host round trip, and no peer can store bands of frame k + 1 while rank 0's
+ * stream still works on (renders, copies out, clears) frame k.  Same ~2 s time-out rule and error word (flags[n_ranks]) as
+ * c2rt_band.done_flags. */
+int c2rt_gate(void* d_flags, uint32_t n_ranks, uint32_t round, void* stream);
 
 /* Page-locks a caller-owned host buffer (e.g. the D host's Image!Color.pixels, which is ordinary GC memory) so
  * that c2rt_render's device->host copies run asynchronously at full PCIe rate and overlap with rendering.
