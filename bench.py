@@ -41,7 +41,8 @@ WORKLOADS = {
     "c0": ("scenes/lecture4.sdl", 640, 480, {}),
     "c1": ("scenes/lecture4-proc-texture.sdl", 1920, 1080, {}),
     "c2": ("scenes/lecture5.sdl", 3840, 2160, {}),
-    "c3": ("scenes/zaphod.sdl", 3840, 2160, {}),
+    "c3": ("scenes/zaphod-sky.sdl", 3840, 2160, {}),      # configs[3]: zaphod.sdl + the cubemap-environment extension
+    "c3_nosky": ("scenes/zaphod.sdl", 3840, 2160, {}),   # the scene file as the reference ships it (same frame: no ray of it misses)
     "c4": ("scenes/chessboard.sdl", 7680, 4320, {}),
     "chess1080": ("scenes/chessboard.sdl", 1920, 1080, {}),
     "chess4k": ("scenes/chessboard.sdl", 3840, 2160, {}),

@@ -73,6 +73,8 @@ class SceneDesc(C.Structure):
         ("tex_texel_offset", C.POINTER(C.c_uint64)), ("texels", C.POINTER(C.c_float)), ("n_texels", C.c_uint64),
         ("n_lights", C.c_uint32), ("light_pos", C.POINTER(C.c_double)), ("light_color", C.POINTER(C.c_float)),
         ("light_power", C.POINTER(C.c_float)),
+        ("env_type", C.c_int32), ("env_reserved", C.c_int32), ("env_face_width", C.c_int32 * 6), ("env_face_height", C.c_int32 * 6),
+        ("env_face_texel_offset", C.c_uint64 * 6),
     ]
 
 

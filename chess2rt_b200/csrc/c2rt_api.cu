@@ -17,6 +17,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "scene_dev.h"
@@ -263,9 +264,15 @@ DeviceCtx* find_device(int dev) {
 struct c2rt_scene {
     uint64_t id;
     DevScene host;                       // texel pointers patched per device at upload
-    std::vector<float4> texels;          // all bitmaps, float4 per texel
-    std::vector<size_t> tex_offset;      // per texture, in texels (bitmaps only)
+    std::vector<float4> texels;          // bitmaps in the general form, float4 per texel
+    std::vector<size_t> tex_offset;      // per texture, in texels (general-form bitmaps only)
     float4* d_texels[C2RT_MAX_GPUS];     // per context device
+    // bitmaps with <= 256 distinct colours (scene_dev.h DevTex::quads): index quads + 256-entry palettes
+    std::vector<uint32_t> quads;
+    std::vector<float4> palettes;
+    std::vector<long long> quad_offset, pal_offset;   // per texture; -1 = general form
+    uint32_t* d_quads[C2RT_MAX_GPUS];
+    float4* d_palettes[C2RT_MAX_GPUS];
     float4* d_bounds[C2RT_MAX_GPUS];     // per context device: node bounding spheres for the per-warp masks (FrameParams.bounds)
     int n_dev;
     int mode;                            // kernel specialisation (render_kernel.cu MODE_*)
@@ -333,6 +340,55 @@ bool is_identity(const double* m) {
     return true;
 }
 
+// Device form of one bitmap (a texture or an environment face): palette-index quads when it has <= 256 distinct texel
+// colours (scene_dev.h DevTex::quads), float4 texels otherwise.  `slot` indexes the scene's offset tables.
+void build_bitmap(c2rt_scene* s, const DevTex& t, const float* src, int slot) {
+    const uint64_t n = (uint64_t)t.w * t.h;
+    const int i = slot;
+    // <= 256 distinct texel colours -> palette form (C2RT_NO_PALETTE=1: test hook, keep the general form)
+    const char* no_pal = getenv("C2RT_NO_PALETTE");
+    std::vector<uint8_t> idx;
+    std::vector<float4> pal;
+    if (!(no_pal && no_pal[0] == '1')) {
+        struct Key { uint32_t r, g, b; bool operator==(const Key& o) const { return r == o.r && g == o.g && b == o.b; } };
+        struct KeyHash { size_t operator()(const Key& k) const { return (size_t)k.r * 0x9E3779B1u ^ (size_t)k.g * 0x85EBCA77u ^ (size_t)k.b * 0xC2B2AE3Du; } };
+        std::unordered_map<Key, int, KeyHash> seen;
+        idx.resize(n);
+        for (uint64_t k = 0; k < n; k++) {
+            Key key;
+            memcpy(&key, src + 3 * k, 12);   // bit patterns: -0 / NaN payloads stay distinct, the palette returns the same bits
+            auto it = seen.find(key);
+            if (it == seen.end()) {
+                if (seen.size() == 256) { idx.clear(); break; }
+                it = seen.emplace(key, (int)seen.size()).first;
+                pal.push_back(make_float4(src[3 * k], src[3 * k + 1], src[3 * k + 2], 0.f));
+            }
+            idx[k] = (uint8_t)it->second;
+        }
+    }
+    if (!idx.empty()) {
+        s->quad_offset[i] = (long long)s->quads.size();
+        s->pal_offset[i] = (long long)s->palettes.size();
+        pal.resize(256, make_float4(0.f, 0.f, 0.f, 0.f));
+        s->palettes.insert(s->palettes.end(), pal.begin(), pal.end());
+        s->quads.resize(s->quads.size() + n);
+        uint32_t* q = s->quads.data() + s->quad_offset[i];
+        for (int y = 0; y < t.h; y++) {
+            const int yn = y + 1 == t.h ? 0 : y + 1;
+            for (int x = 0; x < t.w; x++) {
+                const int xn = x + 1 == t.w ? 0 : x + 1;
+                q[(size_t)y * t.w + x] = (uint32_t)idx[(size_t)y * t.w + x] | ((uint32_t)idx[(size_t)y * t.w + xn] << 8) |
+                                         ((uint32_t)idx[(size_t)yn * t.w + x] << 16) | ((uint32_t)idx[(size_t)yn * t.w + xn] << 24);
+            }
+        }
+    } else {
+        s->tex_offset[i] = s->texels.size();
+        s->texels.resize(s->texels.size() + n);
+        float4* dst = s->texels.data() + s->tex_offset[i];
+        for (uint64_t k = 0; k < n; k++) dst[k] = make_float4(src[3 * k], src[3 * k + 1], src[3 * k + 2], 0.f);
+    }
+}
+
 int validate_and_build(const c2rt_scene_desc* d, c2rt_scene* s) {
     if (!d) return fail(C2RT_ERR_INVALID_ARG, "scene description is null");
     if (d->struct_size != sizeof(c2rt_scene_desc) || d->abi_version != C2RT_ABI_VERSION)
@@ -377,7 +433,9 @@ int validate_and_build(const c2rt_scene_desc* d, c2rt_scene* s) {
             if (lit && lit[0] == '1' && g.pad == 1) g.pad = -1;
         }
     }
-    s->tex_offset.assign(d->n_textures, 0);
+    s->tex_offset.assign(d->n_textures + 6, 0);     // + 6: the environment faces
+    s->quad_offset.assign(d->n_textures + 6, -1);
+    s->pal_offset.assign(d->n_textures + 6, -1);
     for (uint32_t i = 0; i < d->n_textures; i++) {
         DevTex& t = h.textures[i];
         t.type = d->tex_type[i];
@@ -392,13 +450,22 @@ int validate_and_build(const c2rt_scene_desc* d, c2rt_scene* s) {
             if (t.w <= 0 || t.h <= 0) return fail(C2RT_ERR_INVALID_ARG, "texture %u: empty bitmap", i);
             uint64_t off = d->tex_texel_offset[i], n = (uint64_t)t.w * t.h;
             if (!d->texels || off + n > d->n_texels) return fail(C2RT_ERR_INVALID_ARG, "texture %u: texel range outside `texels`", i);
-            s->tex_offset[i] = s->texels.size();
-            s->texels.resize(s->texels.size() + n);
-            float4* dst = s->texels.data() + s->tex_offset[i];
-            const float* src = d->texels + 3 * off;
-            for (uint64_t k = 0; k < n; k++) dst[k] = make_float4(src[3 * k], src[3 * k + 1], src[3 * k + 2], 0.f);
+            build_bitmap(s, t, d->texels + 3 * off, (int)i);
         }
     }
+    // environment (c2rt.h C2RT_ENV_CUBEMAP): six more bitmap records, slots n_textures .. n_textures + 5 of the offset tables
+    h.env_type = d->env_type;
+    if (d->env_type != C2RT_ENV_BLACK && d->env_type != C2RT_ENV_CUBEMAP) return fail(C2RT_ERR_INVALID_ARG, "unknown environment type %d", d->env_type);
+    if (d->env_type == C2RT_ENV_CUBEMAP)
+        for (int f = 0; f < 6; f++) {
+            DevTex& t = h.env_faces[f];
+            t.type = C2RT_TEX_BITMAP;
+            t.w = d->env_face_width[f]; t.h = d->env_face_height[f];
+            if (t.w <= 0 || t.h <= 0) return fail(C2RT_ERR_INVALID_ARG, "environment face %d: empty bitmap", f);
+            uint64_t off = d->env_face_texel_offset[f], n = (uint64_t)t.w * t.h;
+            if (!d->texels || off + n > d->n_texels) return fail(C2RT_ERR_INVALID_ARG, "environment face %d: texel range outside `texels`", f);
+            build_bitmap(s, t, d->texels + 3 * off, (int)d->n_textures + f);
+        }
     for (uint32_t i = 0; i < d->n_shaders; i++) {
         DevShader& sh = h.shaders[i];
         sh.type = d->shader_type[i];
@@ -512,6 +579,8 @@ int validate_and_build(const c2rt_scene_desc* d, c2rt_scene* s) {
         if (ti >= 0) {
             std::swap(h.textures[0], h.textures[ti]);
             std::swap(s->tex_offset[0], s->tex_offset[ti]);
+            std::swap(s->quad_offset[0], s->quad_offset[ti]);
+            std::swap(s->pal_offset[0], s->pal_offset[ti]);
             for (int k = 0; k < h.n_shaders; k++) {
                 if (h.shaders[k].tex == 0) h.shaders[k].tex = ti;
                 else if (h.shaders[k].tex == ti) h.shaders[k].tex = 0;
@@ -525,7 +594,7 @@ int validate_and_build(const c2rt_scene_desc* d, c2rt_scene* s) {
 
 int upload_to_devices(c2rt_scene* s) {
     s->n_dev = g_ctx.n;
-    for (int i = 0; i < C2RT_MAX_GPUS; i++) { s->d_texels[i] = nullptr; s->d_bounds[i] = nullptr; }
+    for (int i = 0; i < C2RT_MAX_GPUS; i++) { s->d_texels[i] = nullptr; s->d_bounds[i] = nullptr; s->d_quads[i] = nullptr; s->d_palettes[i] = nullptr; }
     std::vector<float4> bounds((size_t)std::max(1, s->host.n_nodes));
     for (int k = 0; k < s->host.n_nodes; k++) {
         const DevNode& nd = s->host.nodes[k];
@@ -536,11 +605,18 @@ int upload_to_devices(c2rt_scene* s) {
         CU(cudaMalloc(&s->d_bounds[i], bounds.size() * sizeof(float4)));
         CU(cudaMemcpy(s->d_bounds[i], bounds.data(), bounds.size() * sizeof(float4), cudaMemcpyHostToDevice));
     }
-    if (s->texels.empty()) return C2RT_OK;
     for (int i = 0; i < g_ctx.n; i++) {
         CU(cudaSetDevice(g_ctx.d[i].dev));
-        CU(cudaMalloc(&s->d_texels[i], s->texels.size() * sizeof(float4)));
-        CU(cudaMemcpy(s->d_texels[i], s->texels.data(), s->texels.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        if (!s->texels.empty()) {
+            CU(cudaMalloc(&s->d_texels[i], s->texels.size() * sizeof(float4)));
+            CU(cudaMemcpy(s->d_texels[i], s->texels.data(), s->texels.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        }
+        if (!s->quads.empty()) {
+            CU(cudaMalloc(&s->d_quads[i], s->quads.size() * sizeof(uint32_t)));
+            CU(cudaMemcpy(s->d_quads[i], s->quads.data(), s->quads.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            CU(cudaMalloc(&s->d_palettes[i], s->palettes.size() * sizeof(float4)));
+            CU(cudaMemcpy(s->d_palettes[i], s->palettes.data(), s->palettes.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        }
     }
     return C2RT_OK;
 }
@@ -557,8 +633,14 @@ int make_resident(c2rt_scene* s, int di, cudaStream_t st) {
     if (cap != cudaStreamCaptureStatusNone)
         return fail(C2RT_ERR_INVALID_ARG, "the scene is not resident on this device yet: render it once outside the stream capture first");
     CU(cudaDeviceSynchronize());
-    for (int t = 0; t < s->host.n_textures; t++)
-        s->host.textures[t].texels = (s->host.textures[t].type == C2RT_TEX_BITMAP) ? s->d_texels[di] + s->tex_offset[t] : nullptr;
+    const int n_bmp_slots = s->host.n_textures + (s->host.env_type == C2RT_ENV_CUBEMAP ? 6 : 0);
+    for (int t = 0; t < n_bmp_slots; t++) {
+        DevTex& tx = t < s->host.n_textures ? s->host.textures[t] : s->host.env_faces[t - s->host.n_textures];
+        const bool bmp = tx.type == C2RT_TEX_BITMAP, pal = bmp && s->quad_offset[t] >= 0;
+        tx.texels = (bmp && !pal) ? s->d_texels[di] + s->tex_offset[t] : nullptr;
+        tx.quads = pal ? s->d_quads[di] + s->quad_offset[t] : nullptr;
+        tx.palette = pal ? s->d_palettes[di] + s->pal_offset[t] : nullptr;
+    }
     CU(upload_scene(s->host, st));
     CU(cudaStreamSynchronize(st));  // the source is pageable host memory that the next device patches
     c.uploaded_scene = s->id;
@@ -575,6 +657,9 @@ int check_frame_args(const c2rt_scene* s, const c2rt_camera* cam, const c2rt_set
             if (s->host.shaders[s->host.nodes[i].shader].type == C2RT_SHADER_PHONG)
                 return fail(C2RT_ERR_UNSUPPORTED, "GIEnabled with a Phong-shaded node: Phong.spawnRay / eval are assert(0) in the reference "
                                                   "(shader.d:252-262), it halts as soon as a path reaches that node");
+    if (set->gi_enabled && !cam->dof && s->host.env_type != C2RT_ENV_BLACK)
+        return fail(C2RT_ERR_UNSUPPORTED, "GIEnabled with a cubemap environment: GI frames are only built for the reference's black environment "
+                                          "(every path is provably black there: DESIGN.md section 0, row f-4)");
     if (!std::isfinite(cam->stereo_separation)) return fail(C2RT_ERR_INVALID_ARG, "stereoSeparation is not finite");
     if (cam->dof && cam->num_samples == 0) return fail(C2RT_ERR_INVALID_ARG, "DOF camera with numSamples == 0");
     return C2RT_OK;
@@ -771,10 +856,12 @@ void c2rt_scene_destroy(c2rt_scene* s) {
     if (!s) return;
     std::lock_guard<std::mutex> g(g_mu);
     for (int i = 0; i < s->n_dev && i < g_ctx.n; i++) {
-        if (s->d_texels[i] || s->d_bounds[i]) {
+        if (s->d_texels[i] || s->d_bounds[i] || s->d_quads[i]) {
             cudaSetDevice(g_ctx.d[i].dev);
             cudaFree(s->d_texels[i]);
             cudaFree(s->d_bounds[i]);
+            cudaFree(s->d_quads[i]);
+            cudaFree(s->d_palettes[i]);
         }
         if (g_ctx.d[i].uploaded_scene == s->id) g_ctx.d[i].uploaded_scene = 0;
     }

@@ -16,7 +16,8 @@
 //   trace_warp         rt/renderer.d:325-376 trace + rt/shader.d:67-105,197-250 Lambert / Phong + rt/scene.d:62-78 testVisibility:
 //                      camera ray and shadow rays share ONE warp-uniform node walk over the masks; shadow walks are left
 //                      through __all_sync (trace / shade / occluded_planes: plane-only scenes, shadows settled by the sign of D.y)
-//   sample_texture     rt/texture.d:36-54,77-86 (Procedure2's sines through sin_rev),116-126 + rt/bitmap.d:48-63
+//   sample_texture     rt/texture.d:36-54,77-86 (Procedure2's sines through sin_rev),116-126; bitmap_fetch rt/bitmap.d:48-63
+//   env_lookup         rt/environment.d:7-10 (black) + the cubemap EXTENSION (no counterpart in the reference)
 //   render_sample      rt/renderer.d:254-313 (renderSampleDefault / renderSampleDof, stereo via color.d:10-15)
 //   render_frame_kernel rt/renderer.d:83-251 (renderRT: 1-spp + AA passes fused per pixel; prepassOnly preview;
 //                      GI frames, renderer.d:289-301,378-463, are black by construction: fp.gi, see c2rt_api.cu fill_params)
@@ -823,6 +824,32 @@ __device__ __forceinline__ float sin_rev(double u, double f) {
     return __sinf(x * 6.2831853f);
 }
 
+// Bitmap.getFilteredPixel (bitmap.d:48-63): bilinear fetch at float texel coordinates (x, y), wrapping at the edges;
+// out-of-range coordinates (incl. NaN) give NamedColors.red
+__device__ __forceinline__ Col bitmap_fetch(const DevTex& t, float x, float y) {
+    if (!(x >= 0.f) || !(y >= 0.f) || !(x < (float)t.w) || !(y < (float)t.h))   // (t.w, t.h are integers: x < w <=> (size_t)x < w)
+        return mkcol(1.f, 0.f, 0.f);
+    int tx = (int)x, ty = (int)y;
+    int txn = tx + 1 == t.w ? 0 : tx + 1, tyn = ty + 1 == t.h ? 0 : ty + 1;
+    float p = x - (float)tx, q = y - (float)ty;
+    float4 a, b, c, d;
+    if (t.quads) {   // palette form (scene_dev.h DevTex): one 4-byte load, then the 4 KB palette (L1-resident)
+        const uint32_t k = __ldg(&t.quads[(size_t)ty * t.w + tx]);
+        a = __ldg(&t.palette[k & 255u]);
+        b = __ldg(&t.palette[(k >> 8) & 255u]);
+        c = __ldg(&t.palette[(k >> 16) & 255u]);
+        d = __ldg(&t.palette[k >> 24]);
+    } else {
+        a = __ldg(&t.texels[(size_t)ty * t.w + tx]);
+        b = __ldg(&t.texels[(size_t)ty * t.w + txn]);
+        c = __ldg(&t.texels[(size_t)tyn * t.w + tx]);
+        d = __ldg(&t.texels[(size_t)tyn * t.w + txn]);
+    }
+    float wa = (1.0f - p) * (1.0f - q), wb = p * (1.0f - q), wc = (1.0f - p) * q, wd = p * q;
+    return mkcol(a.x * wa + b.x * wb + c.x * wc + d.x * wd, a.y * wa + b.y * wb + c.y * wc + d.y * wd,
+                 a.z * wa + b.z * wb + c.z * wc + d.z * wd);
+}
+
 // Texture lookup at (u, v): texture.d:36-54 (Checker), :77-86 (Procedure2), :116-126 + bitmap.d:48-63 (bitmap, bilinear)
 // MODE_SOLO: the texture is record 0 and its kind is a template constant
 template <int MODE>
@@ -853,20 +880,33 @@ __device__ __forceinline__ Col sample_texture(int ti, double u, double v) {
     v *= t.d[0];
     u = u - floor(u);
     v = v - floor(v);
-    float x = (float)u * (float)t.w;
-    float y = (float)v * (float)t.h;
-    if (!(x >= 0.f) || !(y >= 0.f) || !(x < (float)t.w) || !(y < (float)t.h))   // (t.w, t.h are integers: x < w <=> (size_t)x < w)
-        return mkcol(1.f, 0.f, 0.f);  // NamedColors.red
-    int tx = (int)x, ty = (int)y;
-    int txn = tx + 1 == t.w ? 0 : tx + 1, tyn = ty + 1 == t.h ? 0 : ty + 1;
-    float p = x - (float)tx, q = y - (float)ty;
-    float4 a = __ldg(&t.texels[(size_t)ty * t.w + tx]);
-    float4 b = __ldg(&t.texels[(size_t)ty * t.w + txn]);
-    float4 c = __ldg(&t.texels[(size_t)tyn * t.w + tx]);
-    float4 d = __ldg(&t.texels[(size_t)tyn * t.w + txn]);
-    float wa = (1.0f - p) * (1.0f - q), wb = p * (1.0f - q), wc = (1.0f - p) * q, wd = p * q;
-    return mkcol(a.x * wa + b.x * wb + c.x * wc + d.x * wd, a.y * wa + b.y * wb + c.y * wc + d.y * wd,
-                 a.z * wa + b.z * wb + c.z * wc + d.z * wd);
+    return bitmap_fetch(t, (float)u * (float)t.w, (float)v * (float)t.h);
+}
+
+// environment.d:7-10 for a miss (renderer.d:366-368): black, or — EXTENSION, no counterpart in the reference (c2rt.h
+// C2RT_ENV_CUBEMAP, oracle/orc_scene.hpp Environment) — the bilinear sample of the cube face the direction's largest component
+// points at.  (dx, dy, dz) need not be unit: only ratios of its components are used.
+__device__ __forceinline__ Col env_lookup(double dx, double dy, double dz) {
+    if (c_scene.env_type != C2RT_ENV_CUBEMAP) return mkcol(0.f, 0.f, 0.f);
+    const double ax = fabs(dx), ay = fabs(dy), az = fabs(dz);
+    int face;
+    double sx, sy;   // face coordinates in [-1, 1]
+    if (ax >= ay && ax >= az) {
+        if (!(ax > 0)) return mkcol(0.f, 0.f, 0.f);
+        const double inv = rcp64(ax), vy = dy * inv, vz = dz * inv;
+        face = dx < 0 ? 1 : 0;
+        sx = dx < 0 ? vz : -vz; sy = -vy;
+    } else if (ay >= az) {
+        const double inv = rcp64(ay), vx = dx * inv, vz = dz * inv;
+        face = dy < 0 ? 3 : 2;
+        sx = vx; sy = dy < 0 ? -vz : vz;
+    } else {
+        const double inv = rcp64(az), vx = dx * inv, vy = dy * inv;
+        face = dz < 0 ? 5 : 4;
+        sx = dz < 0 ? -vx : vx; sy = -vy;
+    }
+    const DevTex& t = c_scene.env_faces[face];
+    return bitmap_fetch(t, (float)((sx + 1.0) * 0.5 * (double)(t.w - 1)), (float)((sy + 1.0) * 0.5 * (double)(t.h - 1)));
 }
 
 // ---------------------------------------------------------------- hit completion + shading
@@ -1121,6 +1161,8 @@ __device__ __forceinline__ Col trace_warp(const FrameParams& fp, const Ray& cam_
                 exponent = sh.exponent;
                 // shadow-ray origin p + N * 1e-6 (shader.d:88,219)
                 r.ox = s.px + (double)Nx * 1e-6; r.oy = s.py + (double)Ny * 1e-6; r.oz = s.pz + (double)Nz * 1e-6;
+            } else if (live) {
+                diffuse = env_lookup(r.dx, r.dy, r.dz);   // a miss: renderer.d:366-368 (black unless the cubemap extension is on)
             }
         } else if (want && !found) {
             // ---- light li is visible from this lane's hit: lighting in FP32 (the reference narrows every factor to float
@@ -1185,7 +1227,7 @@ __device__ __forceinline__ Col trace_warp(const FrameParams& fp, const Ray& cam_
         mask = shadow_mask<MODE>(fp.bounds, want, r, L, any);
         if (!any) mask = 0;   // no lane of this warp has a shadow ray for this light (warp-uniform)
     }
-    if (!hit) return mkcol(0.f, 0.f, 0.f);   // miss: environment.d:7-10
+    if (!hit) return diffuse;   // miss: the environment's colour (environment.d:7-10: black), computed in the camera phase
     return mkcol(fmaf(diffuse.r, lightContrib.r, specular.r), fmaf(diffuse.g, lightContrib.g, specular.g),
                  fmaf(diffuse.b, lightContrib.b, specular.b));
 }
@@ -1205,7 +1247,7 @@ __device__ __forceinline__ Col trace(const FrameParams& fp, const Ray& ray, unsi
         *out_hit = h;
         if (h.node >= 0) { out_hit->px = fma(ray.dx, h.dist, ray.ox); out_hit->py = fma(ray.dy, h.dist, ray.oy); out_hit->pz = fma(ray.dz, h.dist, ray.oz); }
     }
-    if (h.node < 0) return mkcol(0.f, 0.f, 0.f);  // environment.d:7-10
+    if (h.node < 0) return env_lookup(ray.dx, ray.dy, ray.dz);  // renderer.d:366-368
     return shade<MODE>(fp, ray, h, n_shadow);
 }
 template <int MODE>

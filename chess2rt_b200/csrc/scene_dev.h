@@ -51,7 +51,13 @@ struct DevTex {
     double d[6];      // checker: size, 1/size | procedure2: freqU[3] / 2pi, freqV[3] / 2pi | bitmap: scaling
     float c[18];      // checker: color1, color2 | procedure2: colorU[3][3], colorV[3][3]
     int type, w, h, pad;
-    const float4* texels;  // bitmap only
+    const float4* texels;    // bitmap, general form: one float4 per texel (post-gamma values, exactly the host's Image!Color)
+    // bitmap with <= 256 distinct texel colours (every 8-bit-palette BMP; the load-time gamma maps equal inputs to equal
+    // outputs): `quads` holds, per texel, the palette indices of the four texels a bilinear lookup at that texel reads —
+    // (x, y), (x+1, y), (x, y+1), (x+1, y+1) with the wrap of bitmap.d:55-56, one byte each, low byte first — so a lookup is ONE
+    // 4-byte load plus four reads of the 4 KB palette instead of four 16-byte gathers.  Bit-identical to the general form.
+    const uint32_t* quads;
+    const float4* palette;
 };
 
 struct DevLight {
@@ -63,7 +69,8 @@ struct DevLight {
 };
 
 struct DevScene {
-    int n_nodes, n_geoms, n_shaders, n_textures, n_lights, pad0, pad1, pad2;
+    int n_nodes, n_geoms, n_shaders, n_textures, n_lights, env_type, pad1, pad2;
+    DevTex env_faces[6];   // C2RT_ENV_CUBEMAP: +x, -x, +y, -y, +z, -z as bitmap records (render_kernel.cu env_lookup)
     DevNode nodes[C2RT_MAX_NODES];
     DevGeom geoms[C2RT_MAX_GEOMS];
     DevShader shaders[C2RT_MAX_SHADERS];

@@ -131,6 +131,22 @@ FlatScene flatten(const Scene& scene) {
         f.light_power.push_back(pl->lightPower);
     }
 
+    // environment (cubemap extension: rt.hpp Environment): the six faces follow the bitmap textures' texels
+    if (scene.environment.cubemap) {
+        f.env_type = C2RT_ENV_CUBEMAP;
+        for (int k = 0; k < 6; k++) {
+            const Bitmap& b = scene.environment.faces[k];
+            f.env_face_width[k] = (int32_t)b.width();
+            f.env_face_height[k] = (int32_t)b.height();
+            f.env_face_texel_offset[k] = f.texels.size() / 3;
+            for (const Color& c : b.data.pixels) {
+                f.texels.push_back(c.r);
+                f.texels.push_back(c.g);
+                f.texels.push_back(c.b);
+            }
+        }
+    }
+
     // nodes
     for (auto& n : scene.nodes) {
         int g = indexOf(scene.geometries, n->geom), s = indexOf(scene.shaders, n->shader);
@@ -183,6 +199,12 @@ c2rt_scene_desc FlatScene::desc() const {
     d.light_pos = light_pos.data();
     d.light_color = light_color.data();
     d.light_power = light_power.data();
+    d.env_type = env_type;
+    for (int k = 0; k < 6; k++) {
+        d.env_face_width[k] = env_face_width[k];
+        d.env_face_height[k] = env_face_height[k];
+        d.env_face_texel_offset[k] = env_face_texel_offset[k];
+    }
     return d;
 }
 

@@ -28,6 +28,9 @@ struct FlatScene {
     std::vector<float> texels;
     std::vector<double> light_pos;
     std::vector<float> light_color, light_power;
+    int32_t env_type = C2RT_ENV_BLACK;
+    int32_t env_face_width[6] = {0}, env_face_height[6] = {0};
+    uint64_t env_face_texel_offset[6] = {0};
 
     c2rt_scene_desc desc() const;  // borrows the vectors above
 };

@@ -146,7 +146,6 @@ private:
     Vector upLeft_, upRight_, downLeft_, frontDir_, rightDir_, upDir_;
 };
 
-struct Environment {};  // rt/environment.d:5-15: stub, always black
 
 // ------------------------------------------------------------------ geometry
 struct Geometry {
@@ -194,6 +193,15 @@ struct Bitmap {  // rt/bitmap.d:11-136 (load + gamma only; filtering runs on the
 struct BitmapTexture : Texture {
     Bitmap bmp;
     float scaling = 1;
+    float assumedGamma = 2.2f;
+};
+
+// rt/environment.d:5-15 is a stub that always returns black and reads no keys.  EXTENSION (no counterpart in the reference,
+// DESIGN.md "Cubemap environment"): an optional `folder` key names a directory holding posx/negx/posy/negy/posz/negz .bmp;
+// `assumedGamma` is applied at load time exactly like BitmapTexture's (texture.d:137-141).  The lookup runs on the GPU.
+struct Environment {
+    Bitmap faces[6];   // +x, -x, +y, -y, +z, -z
+    bool cubemap = false;
     float assumedGamma = 2.2f;
 };
 

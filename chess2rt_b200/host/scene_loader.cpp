@@ -273,7 +273,24 @@ std::unique_ptr<Scene> parseSceneFromFile(const std::string& filename) {
         ctx.set(scene->name, *root, "Name");
         if (root->isSpecified("GlobalSettings")) deserialize(scene->settings, *root->getChild("GlobalSettings"), ctx);
         if (root->isSpecified("Camera")) deserialize(scene->camera, *root->getChild("Camera"), ctx);
-        // Environment has no keys (environment.d:12-14)
+        // environment.d:12-14 reads no keys; the cubemap extension reads `folder` / `assumedGamma` (rt.hpp Environment)
+        if (root->isSpecified("Environment")) {
+            const auto enp = root->getChild("Environment");   // (keep the node alive: getChild returns it by value)
+            const DscNode& en = *enp;
+            std::string folder;
+            ctx.set(folder, en, "folder");
+            if (!folder.empty()) {
+                static const char* names[6] = {"posx", "negx", "posy", "negy", "posz", "negz"};
+                Environment& e = scene->environment;
+                ctx.set(e.assumedGamma, en, "assumedGamma");
+                for (int f = 0; f < 6; f++) {
+                    e.faces[f].loadImage(ctx.resolveRelativePath(folder + "/" + names[f] + ".bmp"));
+                    if (e.assumedGamma == 2.2f) e.faces[f].decompressGamma_sRGB();
+                    else if (e.assumedGamma != 1 && e.assumedGamma > 0 && e.assumedGamma < 10) e.faces[f].decompressGamma(e.assumedGamma);
+                }
+                e.cubemap = true;
+            }
+        }
         loadArray(*root, "Lights", scene->lights, scene->namedEntities.lights, ctx, makeLight);
         loadArray(*root, "Geometries", scene->geometries, scene->namedEntities.geometries, ctx, makeGeometry);
         loadArray(*root, "Textures", scene->textures, scene->namedEntities.textures, ctx, makeTexture);

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define C2RT_ABI_VERSION 1
+#define C2RT_ABI_VERSION 2
 
 typedef enum c2rt_status {
     C2RT_OK = 0,
@@ -58,6 +58,9 @@ enum { C2RT_GEOM_PLANE = 0, C2RT_GEOM_SPHERE = 1, C2RT_GEOM_CUBE = 2, C2RT_GEOM_
 enum { C2RT_SHADER_LAMBERT = 0, C2RT_SHADER_PHONG = 1 };
 /* Texture kinds — texture.d:20 Checker, :70 Procedure2, :103 BitmapTexture */
 enum { C2RT_TEX_CHECKER = 0, C2RT_TEX_PROCEDURE2 = 1, C2RT_TEX_BITMAP = 2 };
+/* Environment kinds — environment.d:5-15: the reference has the black stub only.  CUBEMAP is an EXTENSION (no counterpart in the
+ * reference, parity unpinned; DESIGN.md "Cubemap environment"): six bitmap faces, looked up by the ray direction of a miss. */
+enum { C2RT_ENV_BLACK = 0, C2RT_ENV_CUBEMAP = 1 };
 
 /* Flattened scene: structure of arrays, indices instead of object references.
  * One D object -> one index; objects shared by several nodes keep one entry (lecture5.sdl's
@@ -113,6 +116,13 @@ typedef struct c2rt_scene_desc {
     const double* light_pos;       /* [n_lights*3] */
     const float* light_color;      /* [n_lights*3] lightColor (NOT premultiplied) */
     const float* light_power;      /* [n_lights]   lightPower */
+
+    /* environment — environment.d:5-15 (what `scene.environment.getEnvironment(ray.dir)` returns for a miss, renderer.d:366-368) */
+    int32_t env_type;              /* C2RT_ENV_* */
+    int32_t env_reserved;
+    int32_t env_face_width[6];     /* CUBEMAP: faces in the order +x, -x, +y, -y, +z, -z */
+    int32_t env_face_height[6];
+    uint64_t env_face_texel_offset[6]; /* offset, in texels, of each face inside `texels` (post-gamma values like the bitmaps) */
 } c2rt_scene_desc;
 
 /* Camera state AFTER Camera.beginFrame (camera.d:77-117) and setFrameSize (camera.d:231-236). */

@@ -192,6 +192,16 @@ int orc_render_pixel(orc_scene* s, int x, int y, int rng_mode, uint64_t seed, fl
     }
 }
 
+// Environment.getEnvironment(dir) (environment.d:7-10 black stub; cubemap EXTENSION in orc_scene.hpp) -> rgb; returns 1 when the
+// scene's environment is a cubemap, 0 when it is the reference's black one.
+int orc_environment(orc_scene* s, const double dir[3], float rgb[3]) {
+    Vec3 d;
+    d.x = mk_real(dir[0]); d.y = mk_real(dir[1]); d.z = mk_real(dir[2]);
+    Color c = s->scene->environment.getEnvironment(d);
+    rgb[0] = raw(c.r); rgb[1] = raw(c.g); rgb[2] = raw(c.b);
+    return s->scene->environment.cubemap ? 1 : 0;
+}
+
 // Conditioning probe of one pixel for the parity tests: out[0] = farthest camera-ray hit of the pixel, out[1] = smallest
 // relative gap to a tie met while rendering it (orc_scene.hpp Diag), out[2] = largest colour change of the ORACLE's own
 // pixel when every sample position is shifted by (+-eps, +-eps) pixels, out[3..5] = the unshifted colour.

@@ -361,6 +361,23 @@ struct Loader {
             scene->textures.push_back(std::move(t));
         }
     }
+    // environment.d:12-14 reads no keys.  EXTENSION (orc_scene.hpp Environment): `folder` names a directory with the six face
+    // BMPs, `assumedGamma` is applied at load time exactly like BitmapTexture's (texture.d:137-141).
+    void loadEnvironment(const DscNode& root) {
+        if (!root.isSpecified("Environment")) return;
+        auto n = root.getChild("Environment");
+        std::string folder;
+        set(folder, *n, "folder");
+        if (folder.empty()) return;
+        Environment& e = scene->environment;
+        set(e.assumedGamma, *n, "assumedGamma");
+        for (int f = 0; f < 6; f++) {
+            load_bitmap(resolveRelativePath(folder + "/" + Environment::faceName(f) + ".bmp"), e.faces[f]);
+            if (e.assumedGamma == 2.2f) e.faces[f].decompressGamma_sRGB();
+            else if (e.assumedGamma != 1 && e.assumedGamma > 0 && e.assumedGamma < 10) e.faces[f].decompressGamma(e.assumedGamma);
+        }
+        e.cubemap = true;
+    }
     const Texture* optionalTexture(const DscNode& n) {
         std::string t;
         set(t, n, "texture");
@@ -431,7 +448,7 @@ inline std::unique_ptr<Scene> parseSceneFromFile(const std::string& filename) { 
     if (root->isSpecified("Name")) scene->name = root->getChild("Name")->getString();
     L.loadSettings(*root);
     L.loadCamera(*root);
-    // Environment: no keys (environment.d:12-14)
+    L.loadEnvironment(*root);
     L.loadLights(*root);
     L.loadGeometries(*root);
     L.loadTextures(*root);

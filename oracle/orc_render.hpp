@@ -77,7 +77,7 @@ struct Renderer {
             }
         }
         // lights are never intersectable (light.d:67-70) -> hitLight stays false
-        if (!closestNode) return Color::fromFloats(0, 0, 0);  // environment.d:7-10
+        if (!closestNode) return scene.environment.getEnvironment(ray.dir);  // renderer.d:366-368; environment.d:7-10 (black) or the cubemap extension
         // bumpmap.modifyNormal is a no-op (texture.d:10-12)
         return closestNode->shader->shade(ray, data);
     }
@@ -93,7 +93,7 @@ struct Renderer {
             if (node->intersect(ray, data)) closestNode = node.get();
         // PointLight.intersect is false (light.d:67-70): hitLight never set, the :380-393 branch is dead
         const Color pathMultiplier = Color::fromFloats(1, 1, 1);
-        if (!closestNode) return Color::fromFloats(0, 0, 0) * pathMultiplier;  // :396-397, environment.d:7-10
+        if (!closestNode) return scene.environment.getEnvironment(ray.dir) * pathMultiplier;  // :396-397, environment.d:7-10
         Color resultDirect = Color::fromFloats(0, 0, 0);
         if (!scene.lights.empty()) {  // :404-445
             const size_t lightIndex = uniformIndex(scene.lights.size());

@@ -497,6 +497,44 @@ struct BitmapTexture final : Texture {  // texture.d:103-161
     }
 };
 
+// ------------------------------------------------------------------ environment.d
+// environment.d:5-15: the reference's Environment is a stub that returns black, and no cubemap class, loader key or asset
+// exists in it.  EXTENSION, PARITY UNPINNED: the same class with an optional `folder` key holds six BMP faces
+// (posx, negx, posy, negy, posz, negz .bmp; load-time gamma like BitmapTexture, texture.d:137-141) and getEnvironment(dir)
+// returns the bilinear sample of the face the direction's largest component points at — the face / uv convention of the
+// ancestor project the README credits (README.md:67).  Oracle and kernel define this together; nothing in the reference pins it.
+struct Environment {
+    enum Face { PosX, NegX, PosY, NegY, PosZ, NegZ };
+    Bitmap faces[6];
+    bool cubemap = false;
+    float assumedGamma = 2.2f;
+    static const char* faceName(int f) {
+        static const char* n[6] = {"posx", "negx", "posy", "negy", "posz", "negz"};
+        return n[f];
+    }
+    Color getSide(const Bitmap& bmp, real x, real y) const {   // (x, y) in [-1, 1] -> texel coordinates in [0, size - 1]
+        colf tx = narrow((x + mk_real(1.0)) * mk_real(0.5) * mk_real((double)(bmp.width - 1)));
+        colf ty = narrow((y + mk_real(1.0)) * mk_real(0.5) * mk_real((double)(bmp.height - 1)));
+        return bmp.getFilteredPixel(tx, ty);
+    }
+    Color getEnvironment(const Vec3& dir) const {
+        if (!cubemap) return Color::fromFloats(0, 0, 0);   // environment.d:7-10
+        const real ax = r_fabs(dir.x), ay = r_fabs(dir.y), az = r_fabs(dir.z);
+        // the face of the largest component (x wins ties over y over z), the other two divided by it
+        if (ax >= ay && ax >= az) {
+            if (!(raw(ax) > 0)) return Color::fromFloats(0, 0, 0);   // zero / NaN direction
+            const real vy = dir.y / ax, vz = dir.z / ax;
+            return raw(dir.x) < 0 ? getSide(faces[NegX], vz, -vy) : getSide(faces[PosX], -vz, -vy);
+        }
+        if (ay >= az) {
+            const real vx = dir.x / ay, vz = dir.z / ay;
+            return raw(dir.y) < 0 ? getSide(faces[NegY], vx, -vz) : getSide(faces[PosY], vx, vz);
+        }
+        const real vx = dir.x / az, vy = dir.y / az;
+        return raw(dir.z) < 0 ? getSide(faces[NegZ], -vx, -vy) : getSide(faces[PosZ], vx, -vy);
+    }
+};
+
 // ------------------------------------------------------------------ light.d
 struct PointLight {
     Vec3 pos;
@@ -685,6 +723,7 @@ struct Scene {  // scene.d:38-78
     std::string name;
     GlobalSettings settings;
     Camera camera;
+    Environment environment;
     std::vector<std::unique_ptr<PointLight>> lights;
     std::vector<std::unique_ptr<Geometry>> geometries;
     std::vector<std::unique_ptr<Texture>> textures;

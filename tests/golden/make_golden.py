@@ -29,6 +29,8 @@ CASES = [  # name, scene path, (w, h), overrides, seed
     ("nested", "tests/scenes/nested.sdl", (160, 100), {}, 0),
     ("stereo", "tests/scenes/stereo.sdl", (128, 96), {}, 0),
     ("stereo_dof", "tests/scenes/stereo_dof.sdl", (129, 86), {}, 77),
+    ("sky", "tests/scenes/sky.sdl", (160, 100), {}, 0),              # cubemap-environment EXTENSION (no reference counterpart)
+    ("sky_plane", "tests/scenes/sky_plane.sdl", (161, 101), {}, 0),
 ]
 
 

@@ -38,6 +38,7 @@ def _bind(path):
                                     C.POINTER(OrcStats)]
     lib.orc_render_pixel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_float),
                                      C.POINTER(C.c_double)]
+    lib.orc_environment.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     lib.orc_pixel_diag.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_double, C.POINTER(C.c_double)]
     lib.orc_pack_rgb32.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
     lib.orc_pack_rgb32.restype = None
@@ -137,6 +138,13 @@ class OracleScene:
         if self.lib.orc_render_pixel(self._h, x, y, rng_mode, seed, rgb, hit) != 0:
             raise RuntimeError(self.lib.orc_last_error().decode())
         return np.array(list(rgb), np.float32), np.array(list(hit))
+
+    def environment(self, direction):
+        """Environment.getEnvironment(dir) -> (is_cubemap, rgb)."""
+        d = (C.c_double * 3)(*direction)
+        rgb = (C.c_float * 3)()
+        kind = self.lib.orc_environment(self._h, d, rgb)
+        return bool(kind), np.array(list(rgb), np.float32)
 
     def pixel_diag(self, x, y, rng_mode=1, seed=0, eps=1e-7):
         """Conditioning of one pixel of the oracle's own image -> dict(max_dist, min_gap, shift_delta, rgb)."""

@@ -56,6 +56,10 @@ CASES = [
     ("../tests/scenes/nested.sdl", None, {}),   # CSG inside CSG: literal emulation path
     ("../tests/scenes/stereo.sdl", None, {}),       # anaglyph stereo: two eyes per sample, combineStereo
     ("../tests/scenes/stereo_dof.sdl", None, {}),   # stereo + DOF: each eye draws its own jitter and lens sample
+    ("../tests/scenes/sky.sdl", None, {}),          # cubemap-environment EXTENSION: misses sample the sky faces (warp-mask kernels)
+    ("../tests/scenes/sky_plane.sdl", None, {}),    # the same on the one-plane scene class (MODE_SOLO kernels), assumedGamma 1.8
+    ("../tests/scenes/sky.sdl", (97, 61), {"aa": 0}),
+    ("zaphod-sky.sdl", (215, 143), {"num_samples": 4}),   # configs[3] "with cubemap skybox": DOF over the page, sky behind the camera
 ]
 
 
@@ -145,6 +149,43 @@ def test_solo_scene_class_kernels(shader, tex, variant, tmp_path, monkeypatch):
     assert np.abs(rgb - rgb2).max() < 1e-5
 
 
+@pytest.mark.parametrize("name,size,over", [("zaphod.sdl", (322, 214), {"num_samples": 3}), ("lecture5.sdl", (330, 203), {}),
+                                            ("zaphod.sdl", (160, 90), {"dof": 0})])
+def test_palette_quad_bitmaps_equal_float4_texels(name, size, over, monkeypatch):
+    """Bitmaps with <= 256 distinct colours are stored as palette-index quads (one 4-byte load per bilinear lookup,
+    scene_dev.h DevTex::quads): the frame must be BIT-identical to the float4-texel form (C2RT_NO_PALETTE=1)."""
+    g = c2.HostScene(os.path.join(SC, name))
+    g.set_frame_size(*size)
+    g.override(**over)
+    pal, pal_a, _ = g.render(argb=True, seed=7)
+    monkeypatch.setenv("C2RT_NO_PALETTE", "1")   # read at scene-create time
+    h = c2.HostScene(os.path.join(SC, name))
+    h.set_frame_size(*size)
+    h.override(**over)
+    flt, flt_a, _ = h.render(argb=True, seed=7)
+    np.testing.assert_array_equal(pal, flt)
+    np.testing.assert_array_equal(pal_a, flt_a)
+    assert pal.max() > 0.05
+
+
+def test_cubemap_extension_is_inert_where_no_ray_misses_and_refuses_gi(tmp_path):
+    """zaphod-sky.sdl = zaphod.sdl + the cubemap environment: its camera looks down at the page, no ray misses, so the frame is
+    bit-identical to zaphod.sdl's.  GI frames are only built for the reference's black environment: refused with a cubemap."""
+    a = c2.HostScene(os.path.join(SC, "zaphod.sdl"))
+    b = c2.HostScene(os.path.join(SC, "zaphod-sky.sdl"))
+    for s in (a, b):
+        s.set_frame_size(200, 133)
+        s.override(num_samples=3)
+    np.testing.assert_array_equal(a.render(seed=4)[0], b.render(seed=4)[0])
+    txt = open(os.path.join(ROOT, "tests", "scenes", "sky.sdl")).read()
+    txt = txt.replace('"../../scenes/skybox"', '"%s/skybox"' % SC).replace("AAEnabled true", "AAEnabled true\n    GIEnabled true")
+    txt = txt.replace('Phong "shiny" { color 0.8 0.3 0.2; exponent 40; strength 0.7 }', 'Lambert "shiny" { color 0.8 0.3 0.2 }')
+    p = tmp_path / "gi_sky.sdl"
+    p.write_text(txt)
+    with pytest.raises(c2.C2rtError, match="cubemap"):
+        c2.HostScene(str(p)).render()
+
+
 def test_golden_fixtures():
     meta = json.load(open(os.path.join(GOLD, "golden.json")))
     for name, m in meta.items():
@@ -175,8 +216,9 @@ def test_config_c2_4k_row_windows():
 
 
 def test_config_c3_zaphod_4k_dof_windows():
-    # configs[3]: zaphod.sdl at 3840x2160 with DOF (25 samples x 5 taps), pinned RNG; no cubemap exists
-    g, o = both(os.path.join(SC, "zaphod.sdl"), (3840, 2160))
+    # configs[3]: zaphod.sdl at 3840x2160 with DOF (25 samples x 5 taps), pinned RNG, "with cubemap skybox": the reference has no
+    # cubemap; zaphod-sky.sdl adds the extension's environment block
+    g, o = both(os.path.join(SC, "zaphod-sky.sdl"), (3840, 2160))
     rgb, _, _ = g.render(seed=99)
     for y0 in (8, 1080, 2150):
         ref, _ = o.render_rows(y0, y0 + 4, seed=99)

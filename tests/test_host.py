@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(api.C_ABI_SYMBOLS), declared ^ set(api.C_ABI_SYMBOLS)
     for name in declared:
         assert hasattr(api.lib, name), name
-    assert api.lib.c2rt_abi_version() == 1
+    assert api.lib.c2rt_abi_version() == 2
     # no torch / C++ types at the boundary: the exported names are unmangled C
     out = subprocess.run(["nm", "-D", "--defined-only", os.path.join(ROOT, "chess2rt_b200", "libc2rt.so")],
                          capture_output=True, text=True).stdout
@@ -79,6 +79,27 @@ def test_loader_and_flattener_lecture5():
     tex0 = o.texture_texels(0)
     got = np.ctypeslib.as_array(d.texels, shape=(d.n_texels * 3,))[: 256 * 256 * 3].reshape(256, 256, 3)
     np.testing.assert_array_equal(got, tex0)
+
+
+def test_cubemap_environment_extension_is_loaded_and_flattened(tmp_path):
+    """Environment { folder ... } (EXTENSION; the reference's Environment reads no keys, environment.d:12-14): six faces loaded
+    with the BitmapTexture gamma rule and appended to the flat texel array; scenes without it keep C2RT_ENV_BLACK."""
+    d = c2.HostScene(os.path.join(SC, "lecture5.sdl")).desc().contents
+    assert d.env_type == 0 and d.n_texels == 256 * 256 + 800 * 400
+    s = c2.HostScene(os.path.join(ROOT, "tests", "scenes", "sky.sdl"))
+    d = s.desc().contents
+    assert d.env_type == 1 and d.n_textures == 1 and d.n_texels == 6 * 128 * 128
+    assert list(d.env_face_width) == [128] * 6 and list(d.env_face_height) == [128] * 6
+    assert list(d.env_face_texel_offset) == [k * 128 * 128 for k in range(6)]
+    # the texels handed over equal the oracle's post-gamma faces (posy, top-left texel, through its lookup at the face corner)
+    o = OracleScene(os.path.join(ROOT, "tests", "scenes", "sky.sdl"))
+    got = np.ctypeslib.as_array(d.texels, shape=(d.n_texels * 3,)).reshape(6, 128, 128, 3)
+    np.testing.assert_array_equal(got[2, 0, 0], o.environment((-1, 1, -1))[1])      # posy: (sx, sy) = (vx, vz) = (-1, -1)
+    np.testing.assert_array_equal(got[5, 127, 127], o.environment((-1, -1, -1))[1])  # negz: (-vx, -vy) = (1, 1) -> last texel
+    p = tmp_path / "nofaces.sdl"
+    p.write_text('Scene { Environment { folder "nowhere" } }')
+    with pytest.raises(c2.C2rtError):
+        c2.HostScene(p)
 
 
 def test_settings_block_carries_the_gi_fields(tmp_path):

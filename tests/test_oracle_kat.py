@@ -283,10 +283,10 @@ def test_gi_literal_walk_is_black_and_halts_on_phong(tmp_path):
     assert rgb.max() > 0.1
 
 
-def test_tile_cone_keeps_every_node_a_camera_ray_hits():
-    """The geometry behind the kernel's per-tile node mask (render_kernel.cu tile_reaches_node), replayed in numpy with the same
-    formulae: every camera ray of a 16x8 pixel tile lies in the circular cone around the normalised sum of the tile's corner
-    directions, so a node whose bounding sphere misses that cone cannot be the oracle's hit for any pixel of the tile."""
+def test_patch_cone_keeps_every_node_a_camera_ray_hits():
+    """The geometry behind the kernel's per-warp camera-ray node mask (render_kernel.cu patch_cone / cone_reaches_node), replayed in
+    numpy with the same formulae: every camera ray of a warp's 8x4 pixel patch lies in the circular cone around the normalised sum of
+    the patch's corner directions, so a node whose bounding sphere misses that cone cannot be the oracle's hit for any pixel of it."""
     import random
     W, H = 960, 540
     o = OracleScene(os.path.join(ROOT, "scenes", "chessboard.sdl"))
@@ -300,7 +300,7 @@ def test_tile_cone_keeps_every_node_a_camera_ray_hits():
     def reaches(x0, y0, c, r):
         u = []
         for k in range(4):
-            d = ulrel + du * ((x0 + (16 if k & 1 else -0.01)) / W) + dv * ((y0 + (8 if k & 2 else -0.01)) / H)
+            d = ulrel + du * ((x0 + (8 if k & 1 else -0.01)) / W) + dv * ((y0 + (4 if k & 2 else -0.01)) / H)
             u.append(d / np.linalg.norm(d))
         a = sum(u)
         a /= np.linalg.norm(a)
@@ -326,13 +326,107 @@ def test_tile_cone_keeps_every_node_a_camera_ray_hits():
         x, y = rnd.randrange(W), rnd.randrange(H)
         _, hit = o.render_pixel(x, y)
         node = int(hit[0])
-        mask = [i for i in range(1, 33) if reaches(x // 16 * 16, y // 8 * 8, centres[i], R)]
+        mask = [i for i in range(1, 33) if reaches(x // 8 * 8, y // 4 * 4, centres[i], R)]
         kept.append(len(mask))
         if node >= 1:
             piece_hits += 1
             assert node in mask, (x, y, node, mask)
     assert piece_hits > 200            # the sample does look at the pieces
-    assert np.mean(kept) < 4           # and the cone does cull: 32 pieces, a handful per tile
+    assert np.mean(kept) < 4           # and the cone does cull: 32 pieces, a handful per patch
+
+
+def test_shadow_capsule_keeps_every_node_a_shadow_ray_can_touch():
+    """The geometry behind the per-warp shadow-ray node mask (render_kernel.cu shadow_mask), replayed in float32 numpy with the
+    same formulae: 32 shadow origins, their bounding box, the capsule (box centre -> light, radius = half diagonal) against node
+    spheres.  Whenever ANY of the 32 exact FP64 segments origin -> light comes within a sphere's radius, the capsule test must
+    keep that sphere (it may keep more); and it must cull most far-away spheres."""
+    rnd = np.random.default_rng(5)
+    f32 = np.float32
+    kept_n, total_n, must = 0, 0, 0
+    for trial in range(400):
+        light = rnd.uniform([-300, 100, -300], [300, 400, 300])
+        base = rnd.uniform([-150, 0, -150], [150, 40, 150])
+        spread = 10 ** rnd.uniform(-2, 1.3)
+        origins = base + rnd.uniform(-spread, spread, size=(32, 3))
+        centres = rnd.uniform([-200, 0, -200], [200, 60, 200], size=(40, 3))
+        radii = rnd.uniform(2, 30, size=40)
+        # kernel side, FP32
+        o32 = origins.astype(f32)
+        mn, mx = o32.min(axis=0), o32.max(axis=0)
+        c = f32(0.5) * (mn + mx)
+        hdiag = mx - c
+        rho = np.sqrt(np.dot(hdiag, hdiag), dtype=f32)
+        d = light.astype(f32) - c
+        dd = np.dot(d, d)
+        inv_dd = f32(1.0) / dd if dd > 0 else f32(0)
+        mag = np.sqrt(np.dot(c, c), dtype=f32) + np.sqrt(dd, dtype=f32)
+        for k in range(40):
+            b = centres[k].astype(f32)
+            r = f32(radii[k])
+            a = b - c
+            t = np.clip(np.dot(a, d) * inv_dd, f32(0), f32(1))
+            q = a - t * d
+            reachr = r + rho + f32(8e-6) * (mag + np.sqrt(np.dot(b, b), dtype=f32) + rho)
+            keep = not (np.dot(q, q) > reachr * reachr)
+            # exact side, FP64: does any segment come within the sphere?
+            touches = False
+            for o in origins:
+                seg = light - o
+                tt = np.clip(np.dot(centres[k] - o, seg) / np.dot(seg, seg), 0.0, 1.0)
+                if np.linalg.norm(centres[k] - (o + tt * seg)) <= radii[k]:
+                    touches = True
+                    break
+            if touches:
+                must += 1
+                assert keep, (trial, k)
+            kept_n += keep
+            total_n += 1
+    assert must > 100                   # the sample does contain occluders
+    assert kept_n < 0.5 * total_n       # and the capsule does cull
+
+
+def test_cubemap_environment_extension_face_and_uv_convention():
+    """The cubemap environment is an EXTENSION (the reference's Environment is a black stub: environment.d:5-15).
+    This pins what the oracle defines: face = largest |component| (x wins ties over y over z), the other two components divided
+    by it give face coordinates in [-1, 1] -> texel coordinates in [0, size - 1] -> the ordinary bilinear fetch (bitmap.d:48-63),
+    after the same load-time sRGB decode as BitmapTexture (texture.d:137-141)."""
+    from PIL import Image
+    o = OracleScene(os.path.join(ROOT, "tests", "scenes", "sky.sdl"))
+    assert not OracleScene(os.path.join(SC, "lecture4.sdl")).environment((0, 1, 0))[0]       # the reference's black environment
+    np.testing.assert_array_equal(OracleScene(os.path.join(SC, "lecture4.sdl")).environment((0.3, 0.5, 1))[1], 0)
+
+    def srgb_decode(v8):   # bitmap.d:116-126 on x = v / 255 (color.d:60-66)
+        x = np.float32(v8) / np.float32(255.0)
+        if x == 0 or x == 1:
+            return np.float32(x)
+        if x <= np.float32(0.04045):
+            return np.float32(x / np.float32(12.92))
+        return np.float32(((np.float64(x) + np.float64(np.float32(0.055))) / np.float64(np.float32(1.055))) ** np.float64(np.float32(2.4)))
+
+    faces = {n: np.asarray(Image.open(os.path.join(SC, "skybox", n + ".bmp")).convert("RGB")) for n in ("posx", "negx", "posy", "negy", "posz", "negz")}
+
+    def expect(face, sx, sy):
+        img = faces[face]
+        h, w = img.shape[:2]
+        x, y = np.float32((sx + 1) * 0.5 * (w - 1)), np.float32((sy + 1) * 0.5 * (h - 1))
+        tx, ty = int(x), int(y)
+        p, q = np.float32(x - np.float32(tx)), np.float32(y - np.float32(ty))
+        out = np.zeros(3, np.float64)
+        for (xx, yy, wgt) in ((tx, ty, (1 - p) * (1 - q)), ((tx + 1) % w, ty, p * (1 - q)), (tx, (ty + 1) % h, (1 - p) * q), ((tx + 1) % w, (ty + 1) % h, p * q)):
+            out += np.array([srgb_decode(v) for v in img[yy, xx]], np.float64) * np.float64(wgt)
+        return out
+
+    cases = [((2, 0.5, -1), "posx", 0.5, -0.25), ((-4, 1, 2), "negx", 0.5, -0.25), ((0.3, 5, -1), "posy", 0.06, -0.2),
+             ((0.3, -5, -1), "negy", 0.06, 0.2), ((1, -0.5, 4), "posz", 0.25, 0.125), ((1, -0.5, -4), "negz", -0.25, 0.125),
+             ((1, 1, 0.2), "posx", -0.2, -1.0),      # tie |x| == |y|: x wins
+             ((0.1, -3, 3), "negy", 0.1 / 3, -1.0)]  # tie |y| == |z|: y wins
+    for d, face, sx, sy in cases:
+        is_cube, rgb = o.environment(d)
+        assert is_cube
+        np.testing.assert_allclose(rgb, expect(face, sx, sy), rtol=2e-6, atol=2e-7, err_msg=str((d, face)))
+    # scale invariance: only the direction matters
+    np.testing.assert_array_equal(o.environment((0.2, 0.4, 1.0))[1], o.environment((0.4, 0.8, 2.0))[1])
+    assert not o.environment((0, 0, 0))[1].any()
 
 
 def test_golden_fixtures_reproduce():
