@@ -25,7 +25,7 @@
 namespace c2rt {
 cudaError_t upload_scene(const DevScene& s, cudaStream_t st);
 cudaError_t launch_frame(const FrameParams& fp, int mode, uint32_t local_tile_rows, cudaStream_t st);
-cudaError_t launch_pixel(const FrameParams& fp, int x, int y, void* d_out, cudaStream_t st);
+cudaError_t launch_pixel(const FrameParams& fp, int mode, int x, int y, void* d_out, cudaStream_t st);
 cudaError_t launch_deinterleave(const void* src, void* dst, uint32_t row_words, uint32_t height, uint32_t n_ranks,
                                 uint32_t band_rows, uint32_t rows_pad, cudaStream_t st);
 cudaError_t launch_fma_peak(bool fp64, int blocks, int threads, int iters, void* d_out, cudaStream_t st);
@@ -263,7 +263,13 @@ DeviceCtx* find_device(int dev) {
 
 struct c2rt_scene {
     uint64_t id;
-    DevScene host;                       // texel pointers patched per device at upload
+    DevScene host;                       // constant block; record arrays copied in from the vectors below when they fit
+    std::vector<DevNode> nodes;          // the scene's records (texel pointers patched per device at upload)
+    std::vector<DevGeom> geoms;
+    std::vector<DevShader> shaders;
+    std::vector<DevTex> textures;
+    bool big = false;                    // beyond the constant block: the records go to global memory (MODE_BIG)
+    void* d_records[C2RT_MAX_GPUS][4];   // big scenes, per context device: nodes, geoms, shaders, textures
     std::vector<float4> texels;          // bitmaps in the general form, float4 per texel
     std::vector<size_t> tex_offset;      // per texture, in texels (general-form bitmaps only)
     float4* d_texels[C2RT_MAX_GPUS];     // per context device
@@ -394,11 +400,15 @@ int validate_and_build(const c2rt_scene_desc* d, c2rt_scene* s) {
     if (d->struct_size != sizeof(c2rt_scene_desc) || d->abi_version != C2RT_ABI_VERSION)
         return fail(C2RT_ERR_INVALID_ARG, "scene description ABI mismatch (size %u/%zu, version %u/%d)", d->struct_size,
                     sizeof(c2rt_scene_desc), d->abi_version, C2RT_ABI_VERSION);
-    if (d->n_nodes > C2RT_MAX_NODES) return fail(C2RT_ERR_LIMIT, "too many nodes (%u > %d)", d->n_nodes, C2RT_MAX_NODES);
-    if (d->n_geoms > C2RT_MAX_GEOMS) return fail(C2RT_ERR_LIMIT, "too many geometries (%u > %d)", d->n_geoms, C2RT_MAX_GEOMS);
-    if (d->n_shaders > C2RT_MAX_SHADERS) return fail(C2RT_ERR_LIMIT, "too many shaders (%u > %d)", d->n_shaders, C2RT_MAX_SHADERS);
-    if (d->n_textures > C2RT_MAX_TEXTURES) return fail(C2RT_ERR_LIMIT, "too many textures (%u > %d)", d->n_textures, C2RT_MAX_TEXTURES);
+    if (d->n_nodes > C2RT_MAX_NODES_GLOBAL) return fail(C2RT_ERR_LIMIT, "too many nodes (%u > %d)", d->n_nodes, C2RT_MAX_NODES_GLOBAL);
+    if (d->n_geoms > C2RT_MAX_GEOMS_GLOBAL) return fail(C2RT_ERR_LIMIT, "too many geometries (%u > %d)", d->n_geoms, C2RT_MAX_GEOMS_GLOBAL);
+    if (d->n_shaders > C2RT_MAX_SHADERS_GLOBAL) return fail(C2RT_ERR_LIMIT, "too many shaders (%u > %d)", d->n_shaders, C2RT_MAX_SHADERS_GLOBAL);
+    if (d->n_textures > C2RT_MAX_TEXTURES_GLOBAL) return fail(C2RT_ERR_LIMIT, "too many textures (%u > %d)", d->n_textures, C2RT_MAX_TEXTURES_GLOBAL);
     if (d->n_lights > C2RT_MAX_LIGHTS) return fail(C2RT_ERR_LIMIT, "too many lights (%u > %d)", d->n_lights, C2RT_MAX_LIGHTS);
+    // a scene beyond the constant block keeps its records in global memory (C2RT_FORCE_GLOBAL=1: test hook, any scene does)
+    const char* force_big = getenv("C2RT_FORCE_GLOBAL");
+    s->big = d->n_nodes > C2RT_MAX_NODES || d->n_geoms > C2RT_MAX_GEOMS || d->n_shaders > C2RT_MAX_SHADERS ||
+             d->n_textures > C2RT_MAX_TEXTURES || (force_big && force_big[0] == '1');
     if (d->n_nodes && !(d->node_geom && d->node_shader && d->node_transform && d->node_inverse && d->node_inverse_t && d->node_offset))
         return fail(C2RT_ERR_INVALID_ARG, "node arrays missing");
     if (d->n_geoms && !(d->geom_type && d->geom_params && d->geom_left && d->geom_right))
@@ -411,11 +421,17 @@ int validate_and_build(const c2rt_scene_desc* d, c2rt_scene* s) {
 
     DevScene& h = s->host;
     memset(&h, 0, sizeof h);
+    DevNode zn; DevGeom zg; DevShader zs; DevTex zt;
+    memset(&zn, 0, sizeof zn); memset(&zg, 0, sizeof zg); memset(&zs, 0, sizeof zs); memset(&zt, 0, sizeof zt);
+    s->nodes.assign(d->n_nodes, zn);
+    s->geoms.assign(d->n_geoms, zg);
+    s->shaders.assign(d->n_shaders, zs);
+    s->textures.assign(d->n_textures, zt);
     h.n_nodes = d->n_nodes; h.n_geoms = d->n_geoms; h.n_shaders = d->n_shaders; h.n_textures = d->n_textures; h.n_lights = d->n_lights;
 
     for (uint32_t i = 0; i < d->n_geoms; i++) {
         int t = d->geom_type[i];
-        DevGeom& g = h.geoms[i];
+        DevGeom& g = s->geoms[i];
         g.type = t; g.left = -1; g.right = -1;
         memcpy(g.p, d->geom_params + 4 * i, 4 * sizeof(double));
         if (t < C2RT_GEOM_PLANE || t > C2RT_GEOM_CSG_DIFF) return fail(C2RT_ERR_INVALID_ARG, "geometry %u: unknown type %d", i, t);
@@ -424,7 +440,7 @@ int validate_and_build(const c2rt_scene_desc* d, c2rt_scene* s) {
             if (l < 0 || r < 0 || l >= (int)i || r >= (int)i)
                 return fail(C2RT_ERR_INVALID_ARG, "geometry %u: CSG children must be earlier geometries (left %d, right %d)", i, l, r);
             g.left = l; g.right = r;
-            const int dl = abs(h.geoms[l].pad), dr = abs(h.geoms[r].pad);
+            const int dl = abs(s->geoms[l].pad), dr = abs(s->geoms[r].pad);
             g.pad = 1 + (dl > dr ? dl : dr);
             if (g.pad > 3)
                 return fail(C2RT_ERR_UNSUPPORTED, "geometry %u: CSG nesting deeper than 3 levels is not supported", i);
@@ -437,7 +453,7 @@ int validate_and_build(const c2rt_scene_desc* d, c2rt_scene* s) {
     s->quad_offset.assign(d->n_textures + 6, -1);
     s->pal_offset.assign(d->n_textures + 6, -1);
     for (uint32_t i = 0; i < d->n_textures; i++) {
-        DevTex& t = h.textures[i];
+        DevTex& t = s->textures[i];
         t.type = d->tex_type[i];
         if (t.type < C2RT_TEX_CHECKER || t.type > C2RT_TEX_BITMAP) return fail(C2RT_ERR_INVALID_ARG, "texture %u: unknown type %d", i, t.type);
         memcpy(t.c, d->tex_colors + 18 * i, 18 * sizeof(float));
@@ -467,7 +483,7 @@ int validate_and_build(const c2rt_scene_desc* d, c2rt_scene* s) {
             build_bitmap(s, t, d->texels + 3 * off, (int)d->n_textures + f);
         }
     for (uint32_t i = 0; i < d->n_shaders; i++) {
-        DevShader& sh = h.shaders[i];
+        DevShader& sh = s->shaders[i];
         sh.type = d->shader_type[i];
         if (sh.type != C2RT_SHADER_LAMBERT && sh.type != C2RT_SHADER_PHONG) return fail(C2RT_ERR_INVALID_ARG, "shader %u: unknown type %d", i, sh.type);
         sh.tex = d->shader_texture[i];
@@ -488,7 +504,7 @@ int validate_and_build(const c2rt_scene_desc* d, c2rt_scene* s) {
         for (int k = 0; k < 3; k++) L.posf[k] = (float)L.pos[k];
     }
     for (uint32_t i = 0; i < d->n_nodes; i++) {
-        DevNode& nd = h.nodes[i];
+        DevNode& nd = s->nodes[i];
         nd.geom = d->node_geom[i];
         nd.shader = d->node_shader[i];
         if (nd.geom < 0 || nd.geom >= (int)d->n_geoms) return fail(C2RT_ERR_INVALID_ARG, "node %u: geometry index %d out of range", i, nd.geom);
@@ -541,7 +557,7 @@ int validate_and_build(const c2rt_scene_desc* d, c2rt_scene* s) {
         // diagonal scale (Node "scale", zaphod.sdl): such a plane is the world plane y = y0 * sy + off.y, its
         // object-space uv (geometry.d:54-55) are the world offsets times 1/sx, 1/sz
         nd.kind = KIND_GENERIC;
-        const DevGeom& g = h.geoms[nd.geom];
+        const DevGeom& g = s->geoms[nd.geom];
         nd.wp[1] = 1.0; nd.wp[2] = 1.0;
         if (g.type == C2RT_GEOM_PLANE && std::isnan(g.p[1])) {   // bounded planes (limit set) keep the generic path
             bool diag = nd.M[0] > 0 && nd.M[4] > 0 && nd.M[8] > 0;
@@ -563,47 +579,56 @@ int validate_and_build(const c2rt_scene_desc* d, c2rt_scene* s) {
     }
     s->mode = 0;
     for (uint32_t i = 0; i < d->n_nodes; i++) {
-        if (!(h.nodes[i].flags & NODE_UNBOUNDED)) s->mode |= 1;   // MODE_BOUNDED
-        if (h.nodes[i].kind == KIND_GENERIC) s->mode |= 2;        // MODE_GENERIC
-        const DevGeom& ng = h.geoms[h.nodes[i].geom];
+        if (!(s->nodes[i].flags & NODE_UNBOUNDED)) s->mode |= 1;   // MODE_BOUNDED
+        if (s->nodes[i].kind == KIND_GENERIC) s->mode |= 2;        // MODE_GENERIC
+        const DevGeom& ng = s->geoms[s->nodes[i].geom];
         if (ng.type >= C2RT_GEOM_CSG_UNION && ng.pad != 1) s->mode |= 4 | 2 | 1;  // MODE_NESTED (implies the generic, bounded kernel)
     }
     // MODE_SOLO: exactly one node, a world-space plane, and exactly one light.  The node's shader and that shader's
     // texture are swapped into record 0 so the kernel addresses every scene constant statically.
     const char* no_solo = getenv("C2RT_NO_SOLO");   // test hook: keep such scenes on the general plane-only kernel
-    if (s->mode == 0 && h.n_nodes == 1 && h.n_lights == 1 && h.nodes[0].kind == KIND_PLANE_W && !(no_solo && no_solo[0] == '1')) {
-        const int si = h.nodes[0].shader;
-        std::swap(h.shaders[0], h.shaders[si]);
-        h.nodes[0].shader = 0;
-        const int ti = h.shaders[0].tex;
+    if (!s->big && s->mode == 0 && h.n_nodes == 1 && h.n_lights == 1 && s->nodes[0].kind == KIND_PLANE_W && !(no_solo && no_solo[0] == '1')) {
+        const int si = s->nodes[0].shader;
+        std::swap(s->shaders[0], s->shaders[si]);
+        s->nodes[0].shader = 0;
+        const int ti = s->shaders[0].tex;
         if (ti >= 0) {
-            std::swap(h.textures[0], h.textures[ti]);
+            std::swap(s->textures[0], s->textures[ti]);
             std::swap(s->tex_offset[0], s->tex_offset[ti]);
             std::swap(s->quad_offset[0], s->quad_offset[ti]);
             std::swap(s->pal_offset[0], s->pal_offset[ti]);
             for (int k = 0; k < h.n_shaders; k++) {
-                if (h.shaders[k].tex == 0) h.shaders[k].tex = ti;
-                else if (h.shaders[k].tex == ti) h.shaders[k].tex = 0;
+                if (s->shaders[k].tex == 0) s->shaders[k].tex = ti;
+                else if (s->shaders[k].tex == ti) s->shaders[k].tex = 0;
             }
         }
-        s->mode = MODE_SOLO | ((h.shaders[0].tex >= 0 ? 1 + h.textures[0].type : 0) << MODE_TEX_SHIFT) |
-                  (h.shaders[0].type == C2RT_SHADER_PHONG ? MODE_PHONG : 0);
+        s->mode = MODE_SOLO | ((s->shaders[0].tex >= 0 ? 1 + s->textures[0].type : 0) << MODE_TEX_SHIFT) |
+                  (s->shaders[0].type == C2RT_SHADER_PHONG ? MODE_PHONG : 0);
     }
+    if (s->big) s->mode = (s->mode & MODE_NESTED) | MODE_BOUNDED | MODE_GENERIC | MODE_BIG;   // the general kernels only
     return C2RT_OK;
 }
 
 int upload_to_devices(c2rt_scene* s) {
     s->n_dev = g_ctx.n;
-    for (int i = 0; i < C2RT_MAX_GPUS; i++) { s->d_texels[i] = nullptr; s->d_bounds[i] = nullptr; s->d_quads[i] = nullptr; s->d_palettes[i] = nullptr; }
+    for (int i = 0; i < C2RT_MAX_GPUS; i++) {
+        s->d_texels[i] = nullptr; s->d_bounds[i] = nullptr; s->d_quads[i] = nullptr; s->d_palettes[i] = nullptr;
+        for (int k = 0; k < 4; k++) s->d_records[i][k] = nullptr;
+    }
     std::vector<float4> bounds((size_t)std::max(1, s->host.n_nodes));
     for (int k = 0; k < s->host.n_nodes; k++) {
-        const DevNode& nd = s->host.nodes[k];
+        const DevNode& nd = s->nodes[k];
         bounds[k] = (nd.flags & NODE_UNBOUNDED) ? make_float4(0.f, 0.f, 0.f, -1.f) : make_float4(nd.bcf[0], nd.bcf[1], nd.bcf[2], nd.brf);
     }
     for (int i = 0; i < g_ctx.n; i++) {
         CU(cudaSetDevice(g_ctx.d[i].dev));
         CU(cudaMalloc(&s->d_bounds[i], bounds.size() * sizeof(float4)));
         CU(cudaMemcpy(s->d_bounds[i], bounds.data(), bounds.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        if (s->big) {   // filled by make_resident (the texture records carry per-device pointers)
+            const size_t bytes[4] = {s->nodes.size() * sizeof(DevNode), s->geoms.size() * sizeof(DevGeom),
+                                     s->shaders.size() * sizeof(DevShader), s->textures.size() * sizeof(DevTex)};
+            for (int k = 0; k < 4; k++) CU(cudaMalloc(&s->d_records[i][k], std::max<size_t>(bytes[k], 16)));
+        }
     }
     for (int i = 0; i < g_ctx.n; i++) {
         CU(cudaSetDevice(g_ctx.d[i].dev));
@@ -635,11 +660,27 @@ int make_resident(c2rt_scene* s, int di, cudaStream_t st) {
     CU(cudaDeviceSynchronize());
     const int n_bmp_slots = s->host.n_textures + (s->host.env_type == C2RT_ENV_CUBEMAP ? 6 : 0);
     for (int t = 0; t < n_bmp_slots; t++) {
-        DevTex& tx = t < s->host.n_textures ? s->host.textures[t] : s->host.env_faces[t - s->host.n_textures];
+        DevTex& tx = t < s->host.n_textures ? s->textures[t] : s->host.env_faces[t - s->host.n_textures];
         const bool bmp = tx.type == C2RT_TEX_BITMAP, pal = bmp && s->quad_offset[t] >= 0;
         tx.texels = (bmp && !pal) ? s->d_texels[di] + s->tex_offset[t] : nullptr;
         tx.quads = pal ? s->d_quads[di] + s->quad_offset[t] : nullptr;
         tx.palette = pal ? s->d_palettes[di] + s->pal_offset[t] : nullptr;
+    }
+    if (s->big) {
+        const void* src[4] = {s->nodes.data(), s->geoms.data(), s->shaders.data(), s->textures.data()};
+        const size_t bytes[4] = {s->nodes.size() * sizeof(DevNode), s->geoms.size() * sizeof(DevGeom),
+                                 s->shaders.size() * sizeof(DevShader), s->textures.size() * sizeof(DevTex)};
+        for (int k = 0; k < 4; k++)
+            if (bytes[k]) CU(cudaMemcpyAsync(s->d_records[di][k], src[k], bytes[k], cudaMemcpyHostToDevice, st));
+        s->host.g_nodes = (const DevNode*)s->d_records[di][0];
+        s->host.g_geoms = (const DevGeom*)s->d_records[di][1];
+        s->host.g_shaders = (const DevShader*)s->d_records[di][2];
+        s->host.g_textures = (const DevTex*)s->d_records[di][3];
+    } else {
+        if (!s->nodes.empty()) memcpy(s->host.nodes, s->nodes.data(), s->nodes.size() * sizeof(DevNode));
+        if (!s->geoms.empty()) memcpy(s->host.geoms, s->geoms.data(), s->geoms.size() * sizeof(DevGeom));
+        if (!s->shaders.empty()) memcpy(s->host.shaders, s->shaders.data(), s->shaders.size() * sizeof(DevShader));
+        if (!s->textures.empty()) memcpy(s->host.textures, s->textures.data(), s->textures.size() * sizeof(DevTex));
     }
     CU(upload_scene(s->host, st));
     CU(cudaStreamSynchronize(st));  // the source is pageable host memory that the next device patches
@@ -654,7 +695,7 @@ int check_frame_args(const c2rt_scene* s, const c2rt_camera* cam, const c2rt_set
     if (cam->frame_width == 0 || cam->frame_height == 0) return fail(C2RT_ERR_INVALID_ARG, "camera frame size is zero (setFrameSize not called)");
     if (set->gi_enabled && !cam->dof)   // renderer.d:256-263: the DOF branch is tested first and ignores GIEnabled
         for (int i = 0; i < s->host.n_nodes; i++)
-            if (s->host.shaders[s->host.nodes[i].shader].type == C2RT_SHADER_PHONG)
+            if (s->shaders[s->nodes[i].shader].type == C2RT_SHADER_PHONG)
                 return fail(C2RT_ERR_UNSUPPORTED, "GIEnabled with a Phong-shaded node: Phong.spawnRay / eval are assert(0) in the reference "
                                                   "(shader.d:252-262), it halts as soon as a path reaches that node");
     if (set->gi_enabled && !cam->dof && s->host.env_type != C2RT_ENV_BLACK)
@@ -862,6 +903,7 @@ void c2rt_scene_destroy(c2rt_scene* s) {
             cudaFree(s->d_bounds[i]);
             cudaFree(s->d_quads[i]);
             cudaFree(s->d_palettes[i]);
+            for (int k = 0; k < 4; k++) cudaFree(s->d_records[i][k]);
         }
         if (g_ctx.d[i].uploaded_scene == s->id) g_ctx.d[i].uploaded_scene = 0;
     }
@@ -1159,7 +1201,7 @@ int c2rt_render_pixel(c2rt_scene* s, const c2rt_camera* cam, const c2rt_settings
     fp.counters = c.d_counters;
     fp.lut = c.d_lut;
     fp.count_rays = 0;
-    CU(launch_pixel(fp, x, y, c.d_pixel, c.stream));
+    CU(launch_pixel(fp, s->mode, x, y, c.d_pixel, c.stream));
     PixelOutHost o;
     if (pixel_out_size() != sizeof o) return fail(C2RT_ERR_CUDA, "internal: PixelOut layout mismatch");
     CU(cudaMemcpyAsync(&o, c.d_pixel, sizeof o, cudaMemcpyDeviceToHost, c.stream));

@@ -37,6 +37,23 @@ __constant__ DevScene c_scene;
 __constant__ double c_tap_x[5] = {0.0, 0.3, 0.6, 0.0, 0.6};  // renderer.d:235-242
 __constant__ double c_tap_y[5] = {0.0, 0.3, 0.0, 0.6, 0.6};
 
+// Scene records.  Scenes that fit the constant block (C2RT_MAX_*) are read from it: every record read in the warp-uniform node
+// walk is a constant-cache broadcast.  Larger scenes (MODE_BIG) keep the same records in global memory (c_scene.g_*): the walk's
+// reads are still one address per warp, served by L1.
+template <bool BIG> __device__ __forceinline__ const DevNode& node_at(int i) {
+    if constexpr (BIG) { __builtin_assume(__isGlobal(c_scene.g_nodes)); return c_scene.g_nodes[i]; } else return c_scene.nodes[i];
+}
+template <bool BIG> __device__ __forceinline__ const DevGeom& geom_at(int i) {
+    if constexpr (BIG) { __builtin_assume(__isGlobal(c_scene.g_geoms)); return c_scene.g_geoms[i]; } else return c_scene.geoms[i];
+}
+template <bool BIG> __device__ __forceinline__ const DevShader& shader_at(int i) {
+    if constexpr (BIG) { __builtin_assume(__isGlobal(c_scene.g_shaders)); return c_scene.g_shaders[i]; } else return c_scene.shaders[i];
+}
+template <bool BIG> __device__ __forceinline__ const DevTex& tex_at(int i) {
+    if constexpr (BIG) { __builtin_assume(__isGlobal(c_scene.g_textures)); return c_scene.g_textures[i]; } else return c_scene.textures[i];
+}
+__host__ __device__ constexpr bool is_big(int mode) { return (mode & MODE_BIG) != 0; }
+
 // Precision plan: FP64 carries everything a pixel DECISION or a texture coordinate
 // depends on — ray direction, hit distances, hit points, plane/cube uv, checker cells, face-forward
 // sign, CSG crossing order.  FP32 carries what is continuous and ends in an FP32 colour anyway —
@@ -352,21 +369,21 @@ __device__ __forceinline__ bool csg_bool(int type, bool l, bool r) {  // geometr
 
 // CsgOp.isInside (geometry.d:334-337).  Depth-1 CSGs (primitive children) need no recursion; nested ones
 // are evaluated by a depth-limited template recursion (NESTED_MAX_DEPTH levels, checked at scene create).
-template <int D>
+template <int D, bool BIG>
 __device__ __forceinline__ bool geom_inside_d(int gi, double x, double y, double z) {
-    const DevGeom& g = c_scene.geoms[gi];
-    if (g.type <= C2RT_GEOM_CUBE) return prim_inside(g, x, y, z);
-    return csg_bool(g.type, geom_inside_d<D - 1>(g.left, x, y, z), geom_inside_d<D - 1>(g.right, x, y, z));
+    const DevGeom& g = geom_at<BIG>(gi);
+    if constexpr (D == 0) return prim_inside(g, x, y, z);
+    else {
+        if (g.type <= C2RT_GEOM_CUBE) return prim_inside(g, x, y, z);
+        return csg_bool(g.type, geom_inside_d<D - 1, BIG>(g.left, x, y, z), geom_inside_d<D - 1, BIG>(g.right, x, y, z));
+    }
 }
-template <>
-__device__ __forceinline__ bool geom_inside_d<0>(int gi, double x, double y, double z) {
-    return prim_inside(c_scene.geoms[gi], x, y, z);
-}
+template <bool BIG>
 __device__ __forceinline__ bool geom_inside(int gi, double x, double y, double z) {
-    const DevGeom& g = c_scene.geoms[gi];
+    const DevGeom& g = geom_at<BIG>(gi);
     if (g.type <= C2RT_GEOM_CUBE) return prim_inside(g, x, y, z);
-    if (g.pad <= 1) return csg_bool(g.type, prim_inside(c_scene.geoms[g.left], x, y, z), prim_inside(c_scene.geoms[g.right], x, y, z));
-    return geom_inside_d<3>(gi, x, y, z);
+    if (g.pad <= 1) return csg_bool(g.type, prim_inside(geom_at<BIG>(g.left), x, y, z), prim_inside(geom_at<BIG>(g.right), x, y, z));
+    return geom_inside_d<3, BIG>(gi, x, y, z);
 }
 
 // ---------------------------------------------------------------- CSG
@@ -466,11 +483,12 @@ __device__ __forceinline__ void cex(double& ka, int& ia, double& kb, int& ib) {
     }
 }
 
+template <bool BIG>
 __device__ __forceinline__ bool isect_csg(int gi, double ox, double oy, double oz, double dx, double dy, double dz, double& dist,
                                           double& px, double& py, double& pz, int& face, int& leaf) {
-    const DevGeom& g = c_scene.geoms[gi];
-    const Crossings L = cross_prim(c_scene.geoms[g.left], ox, oy, oz, dx, dy, dz);
-    const Crossings R = cross_prim(c_scene.geoms[g.right], ox, oy, oz, dx, dy, dz);
+    const DevGeom& g = geom_at<BIG>(gi);
+    const Crossings L = cross_prim(geom_at<BIG>(g.left), ox, oy, oz, dx, dy, dz);
+    const Crossings R = cross_prim(geom_at<BIG>(g.right), ox, oy, oz, dx, dy, dz);
     const int n = L.n + R.n;
     if (n == 0) return false;
     // merged list, left child's crossings first (geometry.d:301-302).  id: bit 1 = right child, bit 0 = second crossing,
@@ -520,7 +538,7 @@ __device__ __forceinline__ bool isect_csg(int gi, double ox, double oy, double o
     face = id >> 2;
     leaf = (id & 2) ? g.right : g.left;
     if (g.type == C2RT_GEOM_CSG_DIFF) {
-        const DevGeom& gr = c_scene.geoms[g.right];   // a primitive: this closed form is only used for CSGs of primitives
+        const DevGeom& gr = geom_at<BIG>(g.right);   // a primitive: this closed form is only used for CSGs of primitives
         bool a = prim_inside(gr, px - dx * 1e-6, py - dy * 1e-6, pz - dz * 1e-6);
         bool b = prim_inside(gr, px + dx * 1e-6, py + dy * 1e-6, pz + dz * 1e-6);
         if (a != b) face |= FACE_FLIP;
@@ -543,18 +561,18 @@ struct LitCrossing {
     int face, leaf;
 };
 
-template <int D>
+template <int D, bool BIG>
 __device__ __noinline__ bool isect_geom_lit(int gi, double ox, double oy, double oz, double dx, double dy, double dz, double& dist,
                                             double& px, double& py, double& pz, int& face, int& leaf);
 
-template <int D>
+template <int D, bool BIG>
 __device__ __forceinline__ int find_all_lit(int gi, double ox, double oy, double oz, double dx, double dy, double dz, LitCrossing* out) {
     double cur = 0;
     int n = 0;
     while (n < NESTED_MAX_CROSSINGS) {  // geometry.d:271-290
         double dist = 1e99, px, py, pz;
         int face = 0, leaf = gi;
-        if (!isect_geom_lit<D - 1>(gi, ox, oy, oz, dx, dy, dz, dist, px, py, pz, face, leaf)) break;
+        if (!isect_geom_lit<D - 1, BIG>(gi, ox, oy, oz, dx, dy, dz, dist, px, py, pz, face, leaf)) break;
         dist += cur;
         cur = dist;
         ox = fma(dx, 1e-6, px); oy = fma(dy, 1e-6, py); oz = fma(dz, 1e-6, pz);
@@ -565,28 +583,20 @@ __device__ __forceinline__ int find_all_lit(int gi, double ox, double oy, double
     return n;
 }
 
-template <>
-__device__ __noinline__ bool isect_geom_lit<0>(int gi, double ox, double oy, double oz, double dx, double dy, double dz, double& dist,
-                                               double& px, double& py, double& pz, int& face, int& leaf) {
-    const DevGeom& g = c_scene.geoms[gi];
-    if (g.type > C2RT_GEOM_CUBE) return false;  // deeper than NESTED_MAX_DEPTH: rejected at scene create
-    leaf = gi;
-    face = 0;
-    return isect_prim(g, ox, oy, oz, dx, dy, dz, dist, px, py, pz, face);
-}
-
-template <int D>
+template <int D, bool BIG>
 __device__ __noinline__ bool isect_geom_lit(int gi, double ox, double oy, double oz, double dx, double dy, double dz, double& dist,
                                             double& px, double& py, double& pz, int& face, int& leaf) {
-    const DevGeom& g = c_scene.geoms[gi];
+    const DevGeom& g = geom_at<BIG>(gi);
     if (g.type <= C2RT_GEOM_CUBE) {
         leaf = gi;
         face = 0;
         return isect_prim(g, ox, oy, oz, dx, dy, dz, dist, px, py, pz, face);
     }
+    if constexpr (D == 0) return false;  // deeper than NESTED_MAX_DEPTH: rejected at scene create
+    else {
     LitCrossing all[2 * NESTED_MAX_CROSSINGS];
-    const int nl = find_all_lit<D>(g.left, ox, oy, oz, dx, dy, dz, all);
-    const int nr = find_all_lit<D>(g.right, ox, oy, oz, dx, dy, dz, all + nl);
+    const int nl = find_all_lit<D, BIG>(g.left, ox, oy, oz, dx, dy, dz, all);
+    const int nr = find_all_lit<D, BIG>(g.right, ox, oy, oz, dx, dy, dz, all + nl);
     const int n = nl + nr;
     // util/array.d:95-111 shell sort, including the `ref` loop index and the gap sequence
     int inc = n / 2;
@@ -614,14 +624,15 @@ __device__ __noinline__ bool isect_geom_lit(int gi, double ox, double oy, double
             face = all[k].face;
             leaf = all[k].leaf;
             if (g.type == C2RT_GEOM_CSG_DIFF) {
-                bool a = geom_inside(g.right, px - dx * 1e-6, py - dy * 1e-6, pz - dz * 1e-6);
-                bool b = geom_inside(g.right, px + dx * 1e-6, py + dy * 1e-6, pz + dz * 1e-6);
+                bool a = geom_inside<BIG>(g.right, px - dx * 1e-6, py - dy * 1e-6, pz - dz * 1e-6);
+                bool b = geom_inside<BIG>(g.right, px + dx * 1e-6, py + dy * 1e-6, pz + dz * 1e-6);
                 if (a != b) face ^= FACE_FLIP;
             }
             return true;
         }
     }
     return false;
+    }
 }
 
 // ---------------------------------------------------------------- node
@@ -653,7 +664,8 @@ __device__ __forceinline__ bool cull(const DevNode& nd, const Ray& r, float tmax
 // Returns true and updates `h` iff the node yields a hit with dist <= h.dist; h.p is in the node's local frame.
 template <int MODE>
 __device__ __forceinline__ bool node_hit(int ni, const DevNode& nd, const Ray& r, HitRec& h) {
-    const DevGeom& g = c_scene.geoms[nd.geom];
+    constexpr bool BIG = is_big(MODE);
+    const DevGeom& g = geom_at<BIG>(nd.geom);
     // (a scene class without MODE_GENERIC holds world-space fast-path nodes only: the object-space code compiles away)
     const bool world = !(MODE & MODE_GENERIC) || nd.kind != KIND_GENERIC;
     const bool plain = world || (nd.flags & NODE_IDENTITY);   // no matrix: at most an offset
@@ -677,8 +689,8 @@ __device__ __forceinline__ bool node_hit(int ni, const DevNode& nd, const Ray& r
     else if (g.type == C2RT_GEOM_SPHERE) hit = isect_sphere(prm, ox, oy, oz, dx, dy, dz, dist, px, py, pz);
     else if (g.type == C2RT_GEOM_CUBE) hit = isect_cube(prm, ox, oy, oz, dx, dy, dz, dist, px, py, pz, face);
     else if (!(MODE & MODE_GENERIC)) hit = false;   // (CSG nodes are KIND_GENERIC)
-    else if ((MODE & MODE_NESTED) && g.pad != 1) hit = isect_geom_lit<NESTED_MAX_DEPTH>(nd.geom, ox, oy, oz, dx, dy, dz, dist, px, py, pz, face, leaf);
-    else hit = isect_csg(nd.geom, ox, oy, oz, dx, dy, dz, dist, px, py, pz, face, leaf);
+    else if ((MODE & MODE_NESTED) && g.pad != 1) hit = isect_geom_lit<NESTED_MAX_DEPTH, BIG>(nd.geom, ox, oy, oz, dx, dy, dz, dist, px, py, pz, face, leaf);
+    else hit = isect_csg<BIG>(nd.geom, ox, oy, oz, dx, dy, dz, dist, px, py, pz, face, leaf);
     if (!hit) return false;
     h.dist = plain ? dist : dist * rcp64(len);
     h.px = px; h.py = py; h.pz = pz;
@@ -710,18 +722,43 @@ __device__ __forceinline__ bool node_exact(int ni, const DevNode& nd, const Ray&
 // (the reference's early return at the first occluder, scene.d:73-75, taken by the whole warp at once).
 static_assert(C2RT_MAX_NODES <= 64, "a node mask of the constant-memory scene block is one 64-bit word");
 constexpr unsigned FULL_WARP = 0xffffffffu;
-typedef unsigned long long NodeMask;
-__device__ __forceinline__ NodeMask all_nodes_mask() {
-    const int n = c_scene.n_nodes;
-    return n >= 64 ? ~0ull : (1ull << n) - 1ull;
+constexpr int WARPS_PER_CTA = BLOCK_THREADS / 32;
+constexpr int BIG_MASK_WORDS = C2RT_MAX_NODES_GLOBAL / 64;
+typedef unsigned long long NodeWord;
+// A warp's node mask.  Constant-block scenes (<= 64 nodes): one 64-bit word in a (uniform) register.  MODE_BIG scenes: one
+// word per 64 nodes in shared memory, a row per warp (`more`), word 0 mirrored in `w0`.
+struct NodeMask {
+    NodeWord w0;
+    NodeWord* more;
+};
+__device__ __forceinline__ NodeWord all_nodes_word(int first) {
+    const int left = c_scene.n_nodes - first;
+    return left >= 64 ? ~0ull : left > 0 ? (1ull << left) - 1ull : 0ull;
 }
-// lane l answers for nodes l and l + 32; two ballots make the 64-bit mask (the second only when the scene has > 32 nodes)
-template <class F>
-__device__ __forceinline__ NodeMask ballot_nodes(F&& reaches) {
+template <bool BIG>
+__device__ __forceinline__ int mask_words() { return BIG ? (c_scene.n_nodes + 63) >> 6 : 1; }
+// lane l answers for nodes 64 k + l and 64 k + 32 + l; two ballots make word k (the second only when needed)
+template <bool BIG, class F>
+__device__ __forceinline__ void ballot_nodes(NodeMask& m, F&& reaches) {
     const int lane = (int)(threadIdx.x & 31u), n = c_scene.n_nodes;
-    NodeMask m = __ballot_sync(FULL_WARP, lane < n && reaches(lane));
-    if (n > 32) m |= (NodeMask)__ballot_sync(FULL_WARP, lane + 32 < n && reaches(lane + 32)) << 32;
-    return m;
+#pragma unroll 1
+    for (int k = 0; k < mask_words<BIG>(); k++) {
+        const int i0 = 64 * k + lane;
+        NodeWord w = __ballot_sync(FULL_WARP, i0 < n && reaches(i0));
+        if (n > 64 * k + 32) w |= (NodeWord)__ballot_sync(FULL_WARP, i0 + 32 < n && reaches(i0 + 32)) << 32;
+        if (BIG) { if (lane == 0) m.more[k] = w; }
+        if (k == 0) m.w0 = w;
+    }
+    if (BIG) __syncwarp();
+}
+template <bool BIG>
+__device__ __forceinline__ void all_nodes_mask(NodeMask& m) {
+    m.w0 = all_nodes_word(0);
+    if (BIG) {
+        const int lane = (int)(threadIdx.x & 31u);
+        for (int k = lane; k < mask_words<BIG>(); k += 32) m.more[k] = all_nodes_word(64 * k);
+        __syncwarp();
+    }
 }
 // warp-wide FP32 min / max in one instruction each (CREDUX, sm_100a), result in a uniform register
 __device__ __forceinline__ float warp_min(float v) {
@@ -741,20 +778,23 @@ __device__ __forceinline__ float warp_max(float v) {
 // stays clear of that capsule cannot occlude any lane.  FP32 with an explicit rounding margin (8e-6 of the magnitudes
 // involved: the arithmetic below loses < 1e-6 of them); the node spheres are already inflated (c2rt_api.cu).
 template <int MODE>
-__device__ __forceinline__ NodeMask shadow_mask(const float4* __restrict__ bounds, bool need, const Ray& r, const DevLight& L, bool& any) {
-    NodeMask m = all_nodes_mask();
-    any = true;
-    if (!(MODE & MODE_BOUNDED)) { any = __any_sync(FULL_WARP, need); return m; }
+__device__ __forceinline__ void shadow_mask(NodeMask& m, const float4* __restrict__ bounds, bool need, const Ray& r, const DevLight& L, bool& any) {
+    constexpr bool BIG = is_big(MODE);
+    bool masked = (MODE & MODE_BOUNDED) != 0;
 #ifdef C2RT_NO_WARP_MASK
-    any = __any_sync(FULL_WARP, need);
-    return m;
-#else
+    masked = false;
+#endif
+    if (!masked) {
+        any = __any_sync(FULL_WARP, need);
+        all_nodes_mask<BIG>(m);
+        return;
+    }
     const float INF = __int_as_float(0x7f800000);
     const float mnx = warp_min(need ? r.fox : INF), mxx = warp_max(need ? r.fox : -INF);
     const float mny = warp_min(need ? r.foy : INF), mxy = warp_max(need ? r.foy : -INF);
     const float mnz = warp_min(need ? r.foz : INF), mxz = warp_max(need ? r.foz : -INF);
     any = mnx <= mxx;
-    if (!any) return m;   // no lane of this warp needs a shadow ray (warp-uniform)
+    if (!any) return;   // no lane of this warp needs a shadow ray (warp-uniform); the caller skips the walk
     const float cx = 0.5f * (mnx + mxx), cy = 0.5f * (mny + mxy), cz = 0.5f * (mnz + mxz);
     const float hx = mxx - cx, hy = mxy - cy, hz = mxz - cz;
     const float rho = sqrtf(dot3f(hx, hy, hz, hx, hy, hz));
@@ -762,7 +802,7 @@ __device__ __forceinline__ NodeMask shadow_mask(const float4* __restrict__ bound
     const float dd = dot3f(dx, dy, dz, dx, dy, dz);
     const float inv_dd = dd > 0.f ? 1.0f / dd : 0.f;
     const float mag = sqrtf(dot3f(cx, cy, cz, cx, cy, cz)) + sqrtf(dd);
-    return ballot_nodes([&](int i) {
+    ballot_nodes<BIG>(m, [&](int i) {
         // per-lane index: the bound comes from GLOBAL memory (one coalesced 16-byte load per lane) — a constant-bank read
         // with 32 different addresses would be replayed 32 times
         const float4 b = __ldg(&bounds[i]);
@@ -773,7 +813,6 @@ __device__ __forceinline__ NodeMask shadow_mask(const float4* __restrict__ bound
         const float reachr = b.w + rho + 8e-6f * (mag + sqrtf(dot3f(b.x, b.y, b.z, b.x, b.y, b.z)) + rho);
         return !(dot3f(qx, qy, qz, qx, qy, qz) > reachr * reachr);   // (a NaN bound keeps the node)
     });
-#endif
 }
 
 // testVisibility for the plane-only scene classes.  Dy = light.y - from.y in FP64 settles almost every plane by sign;
@@ -855,7 +894,7 @@ __device__ __forceinline__ Col bitmap_fetch(const DevTex& t, float x, float y) {
 template <int MODE>
 __device__ __forceinline__ Col sample_texture(int ti, double u, double v) {
     constexpr bool SOLO = (MODE & MODE_SOLO) != 0;
-    const DevTex& t = c_scene.textures[SOLO ? 0 : ti];
+    const DevTex& t = tex_at<is_big(MODE)>(SOLO ? 0 : ti);
     const int type = SOLO ? ((MODE & MODE_TEX_MASK) >> MODE_TEX_SHIFT) - 1 : t.type;
     if (type == C2RT_TEX_CHECKER) {
         int x = cast_int_x86(floor(u * t.d[1]));
@@ -886,7 +925,7 @@ __device__ __forceinline__ Col sample_texture(int ti, double u, double v) {
 // environment.d:7-10 for a miss (renderer.d:366-368): black, or — EXTENSION, no counterpart in the reference (c2rt.h
 // C2RT_ENV_CUBEMAP, oracle/orc_scene.hpp Environment) — the bilinear sample of the cube face the direction's largest component
 // points at.  (dx, dy, dz) need not be unit: only ratios of its components are used.
-__device__ __forceinline__ Col env_lookup(double dx, double dy, double dz) {
+__device__ __noinline__ Col env_lookup(double dx, double dy, double dz) {
     if (c_scene.env_type != C2RT_ENV_CUBEMAP) return mkcol(0.f, 0.f, 0.f);
     const double ax = fabs(dx), ay = fabs(dy), az = fabs(dz);
     int face;
@@ -953,7 +992,7 @@ __device__ __forceinline__ void local_surface(int type, const double* c, const H
 // `ray` == nullptr: hin.p is already complete (debug pixel pick)
 template <int MODE>
 __device__ __forceinline__ void surface_of(const HitRec& hin, const Ray* ray, bool need_uv, Surface& s) {
-    const DevNode& nd = c_scene.nodes[(MODE & MODE_SOLO) ? 0 : hin.node];
+    const DevNode& nd = node_at<is_big(MODE)>((MODE & MODE_SOLO) ? 0 : hin.node);
     HitRec h = hin;
     if (plane_only(MODE)) {   // every node is a world-space plane: normal (0, 1, 0), uv = object-space x, z (geometry.d:49-55)
         if (ray) { h.px = fma(ray->dx, h.dist, ray->ox); h.py = fma(ray->dy, h.dist, ray->oy); h.pz = fma(ray->dz, h.dist, ray->oz); }
@@ -964,7 +1003,7 @@ __device__ __forceinline__ void surface_of(const HitRec& hin, const Ray* ray, bo
         s.nx = 0.f; s.ny = 1.f; s.nz = 0.f;
         return;
     }
-    const DevGeom& g = c_scene.geoms[hin.leaf];
+    const DevGeom& g = geom_at<is_big(MODE)>(hin.leaf);
     if (nd.kind != KIND_GENERIC) {
         // world-space fast path: the hit point is o + d * dist (exactly what the intersector computed), nd.wp the pre-offset parameters
         if (ray) { h.px = fma(ray->dx, h.dist, ray->ox); h.py = fma(ray->dy, h.dist, ray->oy); h.pz = fma(ray->dz, h.dist, ray->oz); }
@@ -1092,14 +1131,19 @@ __device__ __forceinline__ Col shade(const FrameParams& fp, const Ray& ray, cons
 // needs an answer has its occluder: the reference's early return, scene.d:73-75, taken by the whole warp).
 template <int MODE>
 __device__ __forceinline__ Col trace_warp(const FrameParams& fp, const Ray& cam_ray, bool live, unsigned& n_shadow, HitRec* out_hit,
-                                          NodeMask cam_mask) {
+                                          const NodeMask& cam_mask) {
+    constexpr bool BIG = is_big(MODE);
     __shared__ double s_view[3][BLOCK_THREADS];   // FP64 camera-ray direction, parked for Phong lobes sharper than 2048
+    __shared__ NodeWord s_shadow_words[BIG ? WARPS_PER_CTA : 1][BIG ? BIG_MASK_WORDS : 1];   // MODE_BIG: this warp's shadow mask
+    NodeMask smask;
+    smask.w0 = 0;
+    smask.more = BIG ? s_shadow_words[threadIdx.x >> 5] : nullptr;
     Ray r = cam_ray;
     HitRec h;
     h.dist = 1e99;
     h.node = -1;
     float tmaxf = 3.0e38f;   // (not +inf = (float)1e99: ptxas would prove tmaxf == (float)h.dist * k and re-convert it in every iteration)
-    NodeMask mask = cam_mask;
+    bool walk = true;            // (a shadow phase in which no lane of the warp has a ray skips the walk)
     bool want = live, found = false, ray_ready = true;
     double Dx = r.dx, Dy = r.dy, Dz = r.dz, len2 = 1.0;   // shadow phases: light - origin (un-normalised), |D|^2
     // shading state of this lane's hit
@@ -1113,10 +1157,14 @@ __device__ __forceinline__ Col trace_warp(const FrameParams& fp, const Ray& cam_
     for (;;) {
         const bool anyhit = li >= 0;
         // ---- the node walk: warp-uniform over the mask, in scene order; per-lane work predicated
+        const NodeMask& mask = anyhit ? smask : cam_mask;
 #pragma unroll 1
-        for (NodeMask bits = mask; bits; bits &= bits - 1) {
-            const int i = __ffsll((long long)bits) - 1;
-            const DevNode& nd = c_scene.nodes[i];
+        for (int wd = 0; walk && wd < mask_words<BIG>(); wd++) {
+        NodeWord bits = BIG ? mask.more[wd] : mask.w0;
+#pragma unroll 1
+        for (; bits; bits &= bits - 1) {
+            const int i = 64 * wd + __ffsll((long long)bits) - 1;
+            const DevNode& nd = node_at<BIG>(i);
             if (want && !found) {
                 bool skip = false;
                 if (nd.kind == KIND_PLANE_W) {
@@ -1139,7 +1187,8 @@ __device__ __forceinline__ Col trace_warp(const FrameParams& fp, const Ray& cam_
                     }
                 }
             }
-            if (anyhit && __all_sync(FULL_WARP, !want || found)) break;   // every lane that asked has its occluder
+            if (anyhit && __all_sync(FULL_WARP, !want || found)) { walk = false; break; }   // every lane that asked has its occluder
+        }
         }
         if (!anyhit) {
             // ---- the camera ray is traced: complete the hit (per lane)
@@ -1148,7 +1197,7 @@ __device__ __forceinline__ Col trace_warp(const FrameParams& fp, const Ray& cam_
             vx = (float)r.dx; vy = (float)r.dy; vz = (float)r.dz;
             s_view[0][threadIdx.x] = r.dx; s_view[1][threadIdx.x] = r.dy; s_view[2][threadIdx.x] = r.dz;
             if (hit) {
-                const DevShader& sh = c_scene.shaders[c_scene.nodes[h.node].shader];
+                const DevShader& sh = shader_at<BIG>(node_at<BIG>(h.node).shader);
                 const bool has_tex = sh.tex >= 0;
                 Surface s;
                 surface_of<MODE>(h, nullptr, has_tex, s);
@@ -1223,9 +1272,7 @@ __device__ __forceinline__ Col trace_warp(const FrameParams& fp, const Ray& cam_
             r.olen = sqrtf(dot3f(r.fox, r.foy, r.foz, r.fox, r.foy, r.foz));
             tmaxf = l2f * rsf * 1.000001f;
         }
-        bool any;
-        mask = shadow_mask<MODE>(fp.bounds, want, r, L, any);
-        if (!any) mask = 0;   // no lane of this warp has a shadow ray for this light (warp-uniform)
+        shadow_mask<MODE>(smask, fp.bounds, want, r, L, walk);   // walk = false: no lane of this warp has a shadow ray for this light
     }
     if (!hit) return diffuse;   // miss: the environment's colour (environment.d:7-10: black), computed in the camera phase
     return mkcol(fmaf(diffuse.r, lightContrib.r, specular.r), fmaf(diffuse.g, lightContrib.g, specular.g),
@@ -1251,7 +1298,7 @@ __device__ __forceinline__ Col trace(const FrameParams& fp, const Ray& ray, unsi
     return shade<MODE>(fp, ray, h, n_shadow);
 }
 template <int MODE>
-__device__ __forceinline__ Col trace_any(const FrameParams& fp, const Ray& ray, bool live, unsigned& n_shadow, HitRec* out_hit, NodeMask cam) {
+__device__ __forceinline__ Col trace_any(const FrameParams& fp, const Ray& ray, bool live, unsigned& n_shadow, HitRec* out_hit, const NodeMask& cam) {
     if constexpr (plane_only(MODE)) return trace<MODE>(fp, ray, n_shadow, out_hit);
     else return trace_warp<MODE>(fp, ray, live, n_shadow, out_hit, cam);
 }
@@ -1272,7 +1319,7 @@ __device__ __forceinline__ Col combine_stereo(Col left, Col right) {
 template <int MODE>
 __device__ __forceinline__ Col render_sample(const FrameParams& fp, double bx, double by, double bz, double x, double y, uint32_t px,
                                              uint32_t py, uint32_t tap, double jw, double jh, bool live, unsigned& n_primary, unsigned& n_shadow,
-                                             HitRec* out_hit, NodeMask cam) {
+                                             HitRec* out_hit, const NodeMask& cam) {
     Ray r;
     if (!(MODE & MODE_SAMPLING)) {               // renderSampleDefault without stereo (renderer.d:303-306): one ray
         uint32_t draw = 0;
@@ -1366,10 +1413,11 @@ __device__ __forceinline__ bool cone_reaches_node(const FrameParams& fp, const P
     return false;                                    // nearest cone point is the apex, and d > r
 }
 template <int MODE>
-__device__ __forceinline__ NodeMask camera_mask(const FrameParams& fp, uint32_t x0, uint32_t y0) {
-    if (!camera_masked(MODE)) return all_nodes_mask();
+__device__ __forceinline__ void camera_mask(NodeMask& m, const FrameParams& fp, uint32_t x0, uint32_t y0) {
+    constexpr bool BIG = is_big(MODE);
+    if (!camera_masked(MODE)) { all_nodes_mask<BIG>(m); return; }
     const PatchCone c = patch_cone(fp, x0, y0);
-    return ballot_nodes([&](int i) { return cone_reaches_node(fp, c, __ldg(&fp.bounds[i])); });   // (global, not constant: per-lane index)
+    ballot_nodes<BIG>(m, [&](int i) { return cone_reaches_node(fp, c, __ldg(&fp.bounds[i])); });   // (global, not constant: per-lane index)
 }
 
 // ---------------------------------------------------------------- frame kernel
@@ -1393,8 +1441,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS) render_frame_kernel
     const bool active = x < fp.W && y < fp.H;
 
     // nodes this warp's camera rays can reach (lane l tests nodes l, l + 32; warp ballot)
-    NodeMask cam = 0;
-    if constexpr (!plane_only(MODE)) cam = camera_mask<MODE>(fp, x0 + (warp & 1) * PATCH_W, y0 + (warp >> 1) * PATCH_H);
+    __shared__ NodeWord s_cam_words[is_big(MODE) ? WARPS_PER_CTA : 1][is_big(MODE) ? BIG_MASK_WORDS : 1];   // MODE_BIG: a row per warp
+    NodeMask cam;
+    cam.w0 = 0;
+    cam.more = is_big(MODE) ? s_cam_words[warp] : nullptr;
+    if constexpr (!plane_only(MODE)) camera_mask<MODE>(cam, fp, x0 + (warp & 1) * PATCH_W, y0 + (warp >> 1) * PATCH_H);
 
     unsigned n_primary = 0, n_shadow = 0;
     Col c = mkcol(0.f, 0.f, 0.f);
@@ -1490,6 +1541,7 @@ struct PixelOut {
     double dist, p[3], n[3], u, v;
 };
 
+template <bool BIG>
 __global__ void render_pixel_kernel(const FrameParams fp, int x, int y, PixelOut* out) {
     // one warp; lane 0 carries the ray, the other lanes only take part in the warp-wide votes of trace_warp
     const bool live = threadIdx.x == 0;
@@ -1499,8 +1551,12 @@ __global__ void render_pixel_kernel(const FrameParams fp, int x, int y, PixelOut
     h.dist = 1e99;
     double bx, by, bz;
     screen_dir(fp, (double)x, (double)y, bx, by, bz);
-    constexpr int M = MODE_BOUNDED | MODE_GENERIC | MODE_NESTED | MODE_SAMPLING;
-    const NodeMask cam = all_nodes_mask();
+    constexpr int M = MODE_BOUNDED | MODE_GENERIC | MODE_NESTED | MODE_SAMPLING | (BIG ? MODE_BIG : 0);
+    __shared__ NodeWord s_cam_words[BIG ? BIG_MASK_WORDS : 1];
+    NodeMask cam;
+    cam.w0 = 0;
+    cam.more = BIG ? s_cam_words : nullptr;
+    all_nodes_mask<BIG>(cam);
     Col c = render_sample<M>(fp, bx, by, bz, (double)x, (double)y, (uint32_t)x, (uint32_t)y, 0, 1.0, 1.0, live, a, b, &h, cam);
     if (!live) return;
     out->rgb[0] = c.r; out->rgb[1] = c.g; out->rgb[2] = c.b;
@@ -1508,7 +1564,7 @@ __global__ void render_pixel_kernel(const FrameParams fp, int x, int y, PixelOut
     out->dist = h.dist;
     if (h.node >= 0) {
         Surface w;
-        surface_of<MODE_BOUNDED | MODE_GENERIC>(h, nullptr, true, w);
+        surface_of<MODE_BOUNDED | MODE_GENERIC | (BIG ? MODE_BIG : 0)>(h, nullptr, true, w);
         out->p[0] = w.px; out->p[1] = w.py; out->p[2] = w.pz;
         double gx = w.gx, gy = w.gy, gz = w.gz;
         normalize3(gx, gy, gz);
@@ -1613,6 +1669,11 @@ cudaError_t launch_frame(const FrameParams& fp, int mode, uint32_t local_tile_ro
             case 6: launch_solo<2, 1>(fp, sampling, grid, st); break;
             default: launch_solo<3, 1>(fp, sampling, grid, st); break;
         }
+    } else if (mode & MODE_BIG) {
+        // scenes beyond the constant block (records in global memory, multi-word node masks): the general kernels only
+        if (sampling) render_frame_kernel<ALL | MODE_BIG | MODE_SAMPLING, 2><<<grid, BLOCK_THREADS, 0, st>>>(fp);
+        else if (mode & MODE_NESTED) render_frame_kernel<ALL | MODE_BIG, 2><<<grid, BLOCK_THREADS, 0, st>>>(fp);
+        else render_frame_kernel<FULL | MODE_BIG, C2RT_MINBLOCKS_FULL><<<grid, BLOCK_THREADS, 0, st>>>(fp);
     } else if (sampling) {
         // DOF / stereo / prepass-only frames: two general kernels only (the per-sample loop dominates, the scene class matters less)
         if (mode & MODE_NESTED) render_frame_kernel<ALL | MODE_SAMPLING, 2><<<grid, BLOCK_THREADS, 0, st>>>(fp);
@@ -1624,8 +1685,9 @@ cudaError_t launch_frame(const FrameParams& fp, int mode, uint32_t local_tile_ro
     return cudaGetLastError();
 }
 
-cudaError_t launch_pixel(const FrameParams& fp, int x, int y, void* d_out, cudaStream_t st) {
-    render_pixel_kernel<<<1, 32, 0, st>>>(fp, x, y, (PixelOut*)d_out);
+cudaError_t launch_pixel(const FrameParams& fp, int mode, int x, int y, void* d_out, cudaStream_t st) {
+    if (mode & MODE_BIG) render_pixel_kernel<true><<<1, 32, 0, st>>>(fp, x, y, (PixelOut*)d_out);
+    else render_pixel_kernel<false><<<1, 32, 0, st>>>(fp, x, y, (PixelOut*)d_out);
     return cudaGetLastError();
 }
 

@@ -70,6 +70,11 @@ struct DevLight {
 
 struct DevScene {
     int n_nodes, n_geoms, n_shaders, n_textures, n_lights, env_type, pad1, pad2;
+    // MODE_BIG (a scene beyond C2RT_MAX_NODES / GEOMS / SHADERS / TEXTURES): the record arrays live in global memory instead
+    const DevNode* g_nodes;
+    const DevGeom* g_geoms;
+    const DevShader* g_shaders;
+    const DevTex* g_textures;
     DevTex env_faces[6];   // C2RT_ENV_CUBEMAP: +x, -x, +y, -y, +z, -z as bitmap records (render_kernel.cu env_lookup)
     DevNode nodes[C2RT_MAX_NODES];
     DevGeom geoms[C2RT_MAX_GEOMS];
@@ -126,6 +131,9 @@ struct FrameParams {
 //                 (MODE_TEX_SHIFT: 0 none, 1 + C2RT_TEX_*) and shader kind (MODE_PHONG) are compile-time
 constexpr int MODE_BOUNDED = 1, MODE_GENERIC = 2, MODE_NESTED = 4, MODE_SAMPLING = 16;
 constexpr int MODE_SOLO = 32, MODE_TEX_SHIFT = 6, MODE_TEX_MASK = 3 << MODE_TEX_SHIFT, MODE_PHONG = 256;
+//   MODE_BIG      the scene exceeds the constant block: node / geometry / shader / texture records in global memory
+//                 (DevScene::g_*), node masks of one 64-bit word per 64 nodes in shared memory (render_kernel.cu NodeMask)
+constexpr int MODE_BIG = 512;
 // every node is a world-space plane (KIND_PLANE_W): no bounded and no generic node exists
 #ifdef __CUDACC__
 __host__ __device__

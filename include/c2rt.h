@@ -44,7 +44,13 @@ typedef enum c2rt_status {
     C2RT_ERR_LIMIT = -5          /* scene exceeds a compiled-in capacity (C2RT_MAX_*) */
 } c2rt_status;
 
-/* capacities of the on-chip (constant memory) scene block */
+/* Capacities of the on-chip (constant memory) scene block.  A scene within them renders from constant memory; a larger one
+ * (the reference's scene.nodes is unbounded: scene.d:38-51, renderer.d:336-338) keeps its node / geometry / shader / texture
+ * records in global memory, up to the *_GLOBAL limits below; beyond those c2rt_scene_create returns C2RT_ERR_LIMIT. */
+#define C2RT_MAX_NODES_GLOBAL 4096
+#define C2RT_MAX_GEOMS_GLOBAL 16384
+#define C2RT_MAX_SHADERS_GLOBAL 4096
+#define C2RT_MAX_TEXTURES_GLOBAL 1024
 #define C2RT_MAX_NODES 64
 #define C2RT_MAX_GEOMS 128
 #define C2RT_MAX_SHADERS 64

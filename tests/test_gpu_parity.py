@@ -407,13 +407,74 @@ def test_degenerate_scenes(tmp_path):
     assert np.all(c2.HostScene(tmp_path / "empty.sdl").render()[0] == 0)
 
 
+def big_scene_text(n_side, width=160, height=100):
+    """n_side x n_side pieces (spheres, cubes, a CSG of both, every third one scaled) on a checker floor: n_side^2 + 1 nodes."""
+    geoms = ['Plane "floor" { y 0 }', 'Sphere "s" { center 0 0 0; R 4 }', 'Cube "c" { center 0 0 0; side 7 }',
+             'Sphere "cut" { center 2 2 -2; R 3.5 }', 'CsgDiff "d" { left "c"; right "cut" }', 'CsgUnion "u" { left "s"; right "c" }']
+    nodes = ['Node "floor" { geometry "floor"; shader "f" }']
+    k = 0
+    for i in range(n_side):
+        for j in range(n_side):
+            g = ("s", "c", "d", "u")[k % 4]
+            sh = ("a", "b", "p")[k % 3]
+            scale = "scale 1.3 0.8 1.1; " if k % 3 == 0 else ""
+            nodes.append('Node "n%d" { geometry "%s"; shader "%s"; %stranslate %g %g %g }' % (k, g, sh, scale, (i - n_side / 2) * 12.0, 4.0 + (k % 5), (j - n_side / 2) * 12.0))
+            k += 1
+    return ('Scene { GlobalSettings { frameWidth %d; frameHeight %d; ambientLightColor 0.1 0.1 0.12; AAEnabled true; prepassEnabled false }\n'
+            ' Camera { pos 5 %g %g; yaw 8; pitch -32; roll 2; fov 70 }\n'
+            ' Lights { PointLight "l" { pos -150 260 -120; color 1 0.95 0.9; power 70000 }; PointLight "l2" { pos 200 120 150; color 0.4 0.5 0.9; power 30000 } }\n'
+            ' Geometries { %s }\n Textures { Checker "chk" { color1 0.15 0.15 0.2; color2 0.9 0.85 0.8; size 9 } }\n'
+            ' Shaders { Lambert "f" { color 1 1 1; texture "chk" }; Lambert "a" { color 0.8 0.4 0.3 }; Lambert "b" { color 0.3 0.7 0.4 }; Phong "p" { color 0.3 0.4 0.9; exponent 30; strength 0.6 } }\n'
+            ' Nodes { %s } }\n') % (width, height, 9.0 * n_side, -10.0 * n_side, "; ".join(geoms), "; ".join(nodes))
+
+
+def test_scene_beyond_the_constant_block_renders_in_parity(tmp_path):
+    """The reference's scene.nodes is unbounded (scene.d:38-51, renderer.d:336-338).  A scene beyond the constant block (64 nodes)
+    keeps its records in global memory and walks multi-word node masks (MODE_BIG): 257 nodes, in parity with the oracle."""
+    p = tmp_path / "big.sdl"
+    p.write_text(big_scene_text(16))
+    g, o = both(str(p))
+    assert g.info()["nodes"] == 257
+    rgb, argb, st = g.render(argb=True, count_rays=True)
+    ref, ost = o.render()
+    assert_parity(rgb, ref, argb, "257 nodes")
+    assert (st.primary_rays, st.shadow_rays) == (ost.primary_rays, ost.shadow_rays)
+    for (x, y) in [(80, 50), (20, 70), (140, 30), (0, 0)]:   # the pixel pick runs its own (one-warp) kernel
+        c, hit = g.render_pixel(x, y)
+        _, ref_hit = o.render_pixel(x, y)
+        assert hit.node == int(ref_hit[0]), (x, y)
+
+
+@pytest.mark.parametrize("name,size,over", [("lecture5.sdl", (200, 150), {}), ("chessboard.sdl", (240, 135), {}),
+                                            ("../tests/scenes/nested.sdl", None, {}), ("../tests/scenes/quirks.sdl", None, {}),
+                                            ("../tests/scenes/stereo_dof.sdl", None, {}), ("../tests/scenes/sky.sdl", None, {})])
+def test_global_memory_scene_form_equals_constant_block_form(name, size, over, monkeypatch):
+    """C2RT_FORCE_GLOBAL=1 routes a small scene through the MODE_BIG kernels: same frame as the constant-block form."""
+    g, o = both(os.path.join(SC, name), size, **over)
+    const, _, st_c = g.render(seed=3, count_rays=True)
+    monkeypatch.setenv("C2RT_FORCE_GLOBAL", "1")   # read at scene-create time
+    big = c2.HostScene(os.path.join(SC, name))
+    if size:
+        big.set_frame_size(*size)
+    big.override(**over)
+    glob, _, st_g = big.render(seed=3, count_rays=True)
+    ref, ost = o.render(seed=3)
+    assert_parity(glob, ref, what="global-memory form " + name)
+    assert (st_g.primary_rays, st_g.shadow_rays) == (st_c.primary_rays, st_c.shadow_rays) == (ost.primary_rays, ost.shadow_rays)
+    assert np.abs(glob - const).max() < 1e-5
+
+
 def test_capacity_limits_are_errors(tmp_path):
-    nodes = "".join('Node "n%d" { geometry "s"; shader "a"; translate %d 0 0 }; ' % (i, 3 * i) for i in range(65))
+    nodes = "".join('Node "n%d" { geometry "s"; shader "a"; translate %d 0 0 }; ' % (i, 3 * i) for i in range(4097))
     p = tmp_path / "many.sdl"
     p.write_text('Scene { Camera { pos 0 0 -50; fov 60 }\n Geometries { Sphere "s" { R 1 } }\n Shaders { Lambert "a" { color 1 1 1 } }\n Nodes { %s } }' % nodes)
     g = c2.HostScene(p)
     with pytest.raises(c2.C2rtError, match="too many nodes"):
         g.render()
+    lights = "".join('PointLight "l%d" { pos %d 50 0; color 1 1 1; power 100 }; ' % (i, i) for i in range(9))
+    p.write_text('Scene { Camera { pos 0 0 -50; fov 60 }\n Lights { %s } }' % lights)
+    with pytest.raises(c2.C2rtError, match="too many lights"):
+        c2.HostScene(p).render()
 
 
 def test_many_scenes_alive_and_scene_switching():
