@@ -81,7 +81,7 @@ class SceneDesc(C.Structure):
 # every symbol include/c2rt.h declares (tests/test_abi.py checks the library exports them all)
 C_ABI_SYMBOLS = [
     "c2rt_init", "c2rt_shutdown", "c2rt_abi_version", "c2rt_device_count", "c2rt_last_error",
-    "c2rt_scene_create", "c2rt_scene_destroy", "c2rt_render", "c2rt_render_device", "c2rt_read_ray_counters",
+    "c2rt_scene_create", "c2rt_scene_destroy", "c2rt_render", "c2rt_cancel", "c2rt_render_device", "c2rt_read_ray_counters",
     "c2rt_deinterleave", "c2rt_render_pixel", "c2rt_band_rows_owned", "c2rt_rng_u31", "c2rt_srgb_table",
     "c2rt_frame_alloc", "c2rt_frame_free", "c2rt_frame_export", "c2rt_frame_import", "c2rt_frame_unimport", "c2rt_frame_memset", "c2rt_frame_download", "c2rt_pin_host_buffer", "c2rt_unpin_host_buffer", "c2rt_gate",
     "c2rt_measure_fma_peak", "c2rt_selftest_device_pool",
@@ -139,6 +139,12 @@ host_lib.c2rt_host_device_scene.argtypes = [C.c_void_p]
 host_lib.c2rt_host_device_scene.restype = C.c_void_p
 host_lib.c2rt_host_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(Stats)]
 host_lib.c2rt_host_render_pixel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(Hit)]
+host_lib.c2rt_host_camera_rotate.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+host_lib.c2rt_host_camera_rotate.restype = None
+host_lib.c2rt_host_camera_move.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+host_lib.c2rt_host_camera_move.restype = None
+host_lib.c2rt_host_save_bmp.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_size_t]
+host_lib.c2rt_host_save_bmp.restype = C.c_size_t
 host_lib.c2rt_host_scene_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
 host_lib.c2rt_host_scene_info.restype = None
 host_lib.c2rt_host_decode_bmp.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_void_p,
@@ -243,21 +249,44 @@ class HostScene:
             raise C2rtError(-3, host_lib.c2rt_host_last_error().decode())
         return p
 
-    def render(self, argb=False, seed=0, count_rays=False, out=None, out_argb=None):
-        """Renderer(scene, output).renderRT() with HOST buffers -> (rgb[H,W,3] float32, argb[H,W] uint32|None, Stats)."""
+    def render(self, argb=False, seed=0, count_rays=False, out=None, out_argb=None, argb_only=False):
+        """Renderer(scene, output).renderRT() with HOST buffers -> (rgb[H,W,3] float32, argb[H,W] uint32|None, Stats).
+        argb_only: no float frame is written or copied (rgb is None in the result)."""
         w, h = self.frame_size
-        rgb = out if out is not None else np.empty((h, w, 3), np.float32)
-        a = out_argb if out_argb is not None else (np.empty((h, w), np.uint32) if argb else None)
+        rgb = None if argb_only else (out if out is not None else np.empty((h, w, 3), np.float32))
+        a = out_argb if out_argb is not None else (np.empty((h, w), np.uint32) if (argb or argb_only) else None)
         st = Stats()
-        _check_host(host_lib.c2rt_host_render(self._h, rgb.ctypes.data, a.ctypes.data if a is not None else None, seed,
-                                              int(count_rays), C.byref(st)))
+        rc = host_lib.c2rt_host_render(self._h, rgb.ctypes.data if rgb is not None else None, a.ctypes.data if a is not None else None,
+                                       seed, int(count_rays), C.byref(st))
+        self.cancelled = rc == 1   # C2RT_CANCELLED: a c2rt_cancel reached the frame (partial image), not an error
+        if rc != 1:
+            _check_host(rc)
         return rgb, a, st
+
+    def camera_rotate(self, d_yaw, d_roll=0.0, d_pitch=0.0):
+        host_lib.c2rt_host_camera_rotate(self._h, d_yaw, d_roll, d_pitch)
+
+    def camera_move(self, dx, dy, dz):
+        host_lib.c2rt_host_camera_move(self._h, dx, dy, dz)
 
     def render_pixel(self, x, y):
         rgb = (C.c_float * 3)()
         hit = Hit()
         _check_host(host_lib.c2rt_host_render_pixel(self._h, x, y, rgb, C.byref(hit)))
         return np.array(list(rgb), np.float32), hit
+
+
+def save_bmp(argb, pad_rows=False):
+    """saveBmp (imageio/bmp.d:195-237) of a packed uint32 plane [H, W] -> bytes."""
+    a = np.ascontiguousarray(argb, np.uint32)
+    h, w = a.shape
+    out = np.zeros(54 + (w * 3 + 3) // 4 * 4 * h, np.uint8)
+    n = host_lib.c2rt_host_save_bmp(a.ctypes.data, w, h, int(pad_rows), out.ctypes.data, out.size)
+    return out[:n].tobytes()
+
+
+def cancel():
+    _check(lib.c2rt_cancel())
 
 
 def render_device(scene_handle, cam, settings, d_rgb_ptr, d_argb_ptr=None, band=None, stream=None):

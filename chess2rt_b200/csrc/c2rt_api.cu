@@ -72,6 +72,8 @@ struct DeviceCtx {
     uint64_t uploaded_scene = 0;   // id of the scene currently in this device's constant memory
     unsigned long long* d_counters = nullptr;
     uint32_t* d_sync = nullptr;    // [0] CTAs of the current launch that finished (in-kernel completion)
+    int* d_cancel = nullptr;       // raised by c2rt_cancel, cleared at the start of every c2rt_render
+    cudaStream_t cancel_stream = nullptr;
     uint8_t* d_lut = nullptr;
     void* d_pixel = nullptr;
     float* d_rgb = nullptr;
@@ -90,6 +92,7 @@ struct Context {
 
 Context g_ctx;
 std::mutex g_mu;
+std::atomic<bool> g_cancel_requested{false};   // c2rt_cancel -> the c2rt_render in progress (c2rt_cancel takes no lock)
 
 // One host thread per extra device (c2rt_init(N > 1)): c2rt_render hands every device's launch / copy sequence to its
 // own thread, so the ~10 driver calls per device are issued in parallel instead of one after the other (at 1080p the
@@ -188,6 +191,8 @@ void destroy_device(DeviceCtx& c) {
     if (c.e1) cudaEventDestroy(c.e1);
     cudaFree(c.d_counters);
     cudaFree(c.d_sync);
+    cudaFree(c.d_cancel);
+    if (c.cancel_stream) cudaStreamDestroy(c.cancel_stream);
     cudaFree(c.d_lut);
     cudaFree(c.d_pixel);
     cudaFree(c.d_rgb);
@@ -221,6 +226,9 @@ int init_locked(int n_gpus, const int* ids) {
         CU(cudaMemset(c.d_counters, 0, 2 * sizeof(unsigned long long)));
         CU(cudaMalloc(&c.d_sync, 2 * sizeof(uint32_t)));
         CU(cudaMemset(c.d_sync, 0, 2 * sizeof(uint32_t)));
+        CU(cudaMalloc(&c.d_cancel, sizeof(int)));
+        CU(cudaMemset(c.d_cancel, 0, sizeof(int)));
+        CU(cudaStreamCreateWithFlags(&c.cancel_stream, cudaStreamNonBlocking));
         CU(cudaMalloc(&c.d_lut, 4097));
         CU(cudaMemcpy(c.d_lut, g_ctx.lut, 4097, cudaMemcpyHostToDevice));
         CU(cudaMalloc(&c.d_pixel, pixel_out_size()));
@@ -746,6 +754,19 @@ void fill_params(FrameParams& fp, const c2rt_camera* cam, const c2rt_settings* s
     fp.tiles_per_band = 1;
 }
 
+// c2rt_cancel bookkeeping: true iff a cancel was requested since the last call; the device flags are lowered again
+bool take_cancel_request() {
+    if (!g_cancel_requested.exchange(false)) return false;
+    for (int i = 0; i < g_ctx.n; i++) {
+        DeviceCtx& c = g_ctx.d[i];
+        cudaSetDevice(c.dev);
+        cudaStreamSynchronize(c.cancel_stream);
+        cudaMemset(c.d_cancel, 0, sizeof(int));
+    }
+    cudaSetDevice(g_ctx.d[0].dev);
+    return true;
+}
+
 uint32_t local_tile_rows(uint32_t H, uint32_t rank, uint32_t n, uint32_t band_rows) {
     uint32_t rows = c2rt_band_rows_owned(H, rank, n, band_rows);
     return (rows + TILE_H - 1) / TILE_H;
@@ -767,6 +788,7 @@ int render_direct_device(int i, int n, c2rt_scene* s, const c2rt_camera* cam, co
         fp.compact = 1;
         fp.counters = c.d_counters;
         fp.lut = c.d_lut;
+        fp.cancel = c.d_cancel;
         // 2..16 interleaved bands per device (one band per ~256k pixels): each band is one launch + one contiguous
         // D2H copy, so small frames must not be cut into many bands (every launch / copy costs a few host microseconds)
         uint32_t per_dev = (uint32_t)std::min<size_t>(16, std::max<size_t>(2, npx / (size_t)n / 262144));
@@ -775,7 +797,7 @@ int render_direct_device(int i, int n, c2rt_scene* s, const c2rt_camera* cam, co
         fp.tiles_per_band = brows / TILE_H;
         const uint32_t rows_owned = c2rt_band_rows_owned(H, fp.rank, fp.n_ranks, brows);
         const size_t need = (size_t)rows_owned * W;
-        if (c.rgb_cap < need * 3) {
+        if (rgb && c.rgb_cap < need * 3) {
             cudaFree(c.d_rgb);
             c.d_rgb = nullptr; c.rgb_cap = 0;
             CU(cudaMalloc(&c.d_rgb, std::max<size_t>(need, 1) * 3 * sizeof(float)));
@@ -787,7 +809,7 @@ int render_direct_device(int i, int n, c2rt_scene* s, const c2rt_camera* cam, co
             CU(cudaMalloc(&c.d_argb, std::max<size_t>(need, 1) * sizeof(uint32_t)));
             c.argb_cap = need;
         }
-        fp.rgb = c.d_rgb;
+        fp.rgb = rgb ? c.d_rgb : nullptr;
         fp.argb = argb ? c.d_argb : nullptr;
         CU(cudaEventRecord(c.e0, c.stream));
         uint32_t local_row = 0, b = 0;
@@ -803,8 +825,9 @@ int render_direct_device(int i, int n, c2rt_scene* s, const c2rt_camera* cam, co
             launches++;
             CU(cudaEventRecord(c.band_done[b], c.stream));
             CU(cudaStreamWaitEvent(c.copy_stream, c.band_done[b], 0));
-            CU(cudaMemcpyAsync(rgb + (size_t)y0 * W * 3, c.d_rgb + (size_t)local_row * W * 3, (size_t)rows * W * 3 * sizeof(float),
-                               cudaMemcpyDeviceToHost, c.copy_stream));
+            if (rgb)
+                CU(cudaMemcpyAsync(rgb + (size_t)y0 * W * 3, c.d_rgb + (size_t)local_row * W * 3, (size_t)rows * W * 3 * sizeof(float),
+                                   cudaMemcpyDeviceToHost, c.copy_stream));
             if (argb)
                 CU(cudaMemcpyAsync(argb + (size_t)y0 * W, c.d_argb + (size_t)local_row * W, (size_t)rows * W * sizeof(uint32_t),
                                    cudaMemcpyDeviceToHost, c.copy_stream));
@@ -986,7 +1009,7 @@ int c2rt_render(c2rt_scene* s, const c2rt_camera* cam, const c2rt_settings* set,
     auto t0 = std::chrono::steady_clock::now();
     int rc = check_frame_args(s, cam, set);
     if (rc) return rc;
-    if (!rgb) return fail(C2RT_ERR_INVALID_ARG, "rgb is null");
+    if (!rgb && !argb) return fail(C2RT_ERR_INVALID_ARG, "rgb and argb are both null");
     if (set->prepass_only && !set->prepass_enabled) {  // renderer.d:110,129-130: nothing is drawn, the image keeps its contents
         if (stats) memset(stats, 0, sizeof *stats);
         return C2RT_OK;
@@ -995,6 +1018,7 @@ int c2rt_render(c2rt_scene* s, const c2rt_camera* cam, const c2rt_settings* set,
     rc = ensure_init_locked();
     if (rc) return rc;
     if (s->n_dev != g_ctx.n) return fail(C2RT_ERR_INVALID_ARG, "scene was created under a different c2rt_init configuration");
+    take_cancel_request();   // a cancel that arrived while no frame was in progress cancels nothing
     const uint32_t W = set->frame_width, H = set->frame_height;
     const size_t npx = (size_t)W * H;
     const int n = g_ctx.n;
@@ -1003,7 +1027,7 @@ int c2rt_render(c2rt_scene* s, const c2rt_camera* cam, const c2rt_settings* set,
     // root frame
     DeviceCtx& root = g_ctx.d[0];
     CU(cudaSetDevice(root.dev));
-    if (root.rgb_cap < npx * 3) {
+    if (rgb && root.rgb_cap < npx * 3) {
         cudaFree(root.d_rgb);
         root.d_rgb = nullptr; root.rgb_cap = 0;
         CU(cudaMalloc(&root.d_rgb, npx * 3 * sizeof(float)));
@@ -1028,7 +1052,8 @@ int c2rt_render(c2rt_scene* s, const c2rt_camera* cam, const c2rt_settings* set,
         fill_params(fp, cam, set, s, 0);
         fp.counters = c.d_counters;
         fp.lut = c.d_lut;
-        fp.rgb = root.d_rgb;
+        fp.cancel = c.d_cancel;
+        fp.rgb = rgb ? root.d_rgb : nullptr;
         fp.argb = argb ? root.d_argb : nullptr;
         const uint32_t tile_rows = (H + TILE_H - 1) / TILE_H;
         const uint32_t n_chunks = tile_rows >= 32 ? 4 : 1;
@@ -1041,8 +1066,9 @@ int c2rt_render(c2rt_scene* s, const c2rt_camera* cam, const c2rt_settings* set,
             CU(cudaEventRecord(c.chunk_done[k], c.stream));
             CU(cudaStreamWaitEvent(c.copy_stream, c.chunk_done[k], 0));
             const size_t y0 = (size_t)t0 * TILE_H, y1 = std::min<size_t>((size_t)t1 * TILE_H, H);
-            CU(cudaMemcpyAsync(rgb + y0 * W * 3, root.d_rgb + y0 * W * 3, (y1 - y0) * W * 3 * sizeof(float), cudaMemcpyDeviceToHost,
-                               c.copy_stream));
+            if (rgb)
+                CU(cudaMemcpyAsync(rgb + y0 * W * 3, root.d_rgb + y0 * W * 3, (y1 - y0) * W * 3 * sizeof(float), cudaMemcpyDeviceToHost,
+                                   c.copy_stream));
             if (argb)
                 CU(cudaMemcpyAsync(argb + y0 * W, root.d_argb + y0 * W, (y1 - y0) * W * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                                    c.copy_stream));
@@ -1103,16 +1129,17 @@ int c2rt_render(c2rt_scene* s, const c2rt_camera* cam, const c2rt_settings* set,
         fp.tiles_per_band = band_rows / TILE_H;
         fp.counters = c.d_counters;
         fp.lut = c.d_lut;
+        fp.cancel = c.d_cancel;
         const uint32_t rows_owned = c2rt_band_rows_owned(H, fp.rank, fp.n_ranks, band_rows);
         if (i == 0 || c.peer_to_root) {
             // bands land directly in the root frame (peer-mapped stores over NVLink for i > 0)
             fp.compact = 0;
-            fp.rgb = root.d_rgb;
+            fp.rgb = rgb ? root.d_rgb : nullptr;
             fp.argb = argb ? root.d_argb : nullptr;
         } else {
             fp.compact = 1;
             size_t need = (size_t)rows_owned * W;
-            if (c.rgb_cap < need * 3) {
+            if (rgb && c.rgb_cap < need * 3) {
                 cudaFree(c.d_rgb);
                 c.d_rgb = nullptr; c.rgb_cap = 0;
                 CU(cudaMalloc(&c.d_rgb, need * 3 * sizeof(float)));
@@ -1124,7 +1151,7 @@ int c2rt_render(c2rt_scene* s, const c2rt_camera* cam, const c2rt_settings* set,
                 CU(cudaMalloc(&c.d_argb, need * sizeof(uint32_t)));
                 c.argb_cap = need;
             }
-            fp.rgb = c.d_rgb;
+            fp.rgb = rgb ? c.d_rgb : nullptr;
             fp.argb = argb ? c.d_argb : nullptr;
         }
         CU(cudaEventRecord(c.e0, c.stream));
@@ -1136,8 +1163,9 @@ int c2rt_render(c2rt_scene* s, const c2rt_camera* cam, const c2rt_settings* set,
             uint32_t local = 0;
             for (uint32_t y0 = fp.rank * band_rows; y0 < H; y0 += n * band_rows, local += band_rows) {
                 uint32_t rows = (H - y0 < band_rows) ? H - y0 : band_rows;
-                CU(cudaMemcpyPeerAsync(root.d_rgb + (size_t)y0 * W * 3, root.dev, c.d_rgb + (size_t)local * W * 3, c.dev,
-                                       (size_t)rows * W * 3 * sizeof(float), c.stream));
+                if (rgb)
+                    CU(cudaMemcpyPeerAsync(root.d_rgb + (size_t)y0 * W * 3, root.dev, c.d_rgb + (size_t)local * W * 3, c.dev,
+                                           (size_t)rows * W * 3 * sizeof(float), c.stream));
                 if (argb)
                     CU(cudaMemcpyPeerAsync(root.d_argb + (size_t)y0 * W, root.dev, c.d_argb + (size_t)local * W, c.dev,
                                            (size_t)rows * W * sizeof(uint32_t), c.stream));
@@ -1155,7 +1183,7 @@ int c2rt_render(c2rt_scene* s, const c2rt_camera* cam, const c2rt_settings* set,
     }
     CU(cudaSetDevice(root.dev));
     if (!copied) {
-        CU(cudaMemcpyAsync(rgb, root.d_rgb, npx * 3 * sizeof(float), cudaMemcpyDeviceToHost, root.stream));
+        if (rgb) CU(cudaMemcpyAsync(rgb, root.d_rgb, npx * 3 * sizeof(float), cudaMemcpyDeviceToHost, root.stream));
         if (argb) CU(cudaMemcpyAsync(argb, root.d_argb, npx * sizeof(uint32_t), cudaMemcpyDeviceToHost, root.stream));
         CU(cudaStreamSynchronize(root.stream));
     }
@@ -1178,6 +1206,27 @@ int c2rt_render(c2rt_scene* s, const c2rt_camera* cam, const c2rt_settings* set,
         }
         stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
+    if (take_cancel_request()) {
+        g_err = "frame cancelled by c2rt_cancel: the output holds the tiles rendered before the request";
+        return C2RT_CANCELLED;
+    }
+    return C2RT_OK;
+}
+
+int c2rt_cancel(void) {
+    // no lock: c2rt_render holds the library mutex for the whole frame, and this must get through while it runs
+    if (!g_ctx.inited) return fail(C2RT_ERR_NOT_INITIALISED, "c2rt_init has not been called");
+    g_cancel_requested.store(true);
+    static const int one = 1;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    for (int i = 0; i < g_ctx.n; i++) {
+        const DeviceCtx& c = g_ctx.d[i];
+        cudaSetDevice(c.dev);
+        cudaMemcpyAsync(c.d_cancel, &one, sizeof(int), cudaMemcpyHostToDevice, c.cancel_stream);
+    }
+    if (prev >= 0) cudaSetDevice(prev);
+    cudaGetLastError();
     return C2RT_OK;
 }
 

@@ -1439,6 +1439,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS) render_frame_kernel
     const uint32_t ly = (warp >> 1) * 4 + (lane >> 3);
     const uint32_t x = x0 + lx, y = y0 + ly;
     const bool active = x < fp.W && y < fp.H;
+    // c2rt_cancel (renderer.d:93-97,129,147,180: a stop request ends the frame early): a CTA that starts after the flag was
+    // raised leaves its tile as it is.  The load is issued here and consumed below, behind the mask / ray set-up.
+    int cancelled = 0;
+    if (fp.cancel) cancelled = *(const volatile int*)fp.cancel;
 
     // nodes this warp's camera rays can reach (lane l tests nodes l, l + 32; warp ballot)
     __shared__ NodeWord s_cam_words[is_big(MODE) ? WARPS_PER_CTA : 1][is_big(MODE) ? BIG_MASK_WORDS : 1];   // MODE_BIG: a row per warp
@@ -1449,6 +1453,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS) render_frame_kernel
 
     unsigned n_primary = 0, n_shadow = 0;
     Col c = mkcol(0.f, 0.f, 0.f);
+    if (cancelled) return;   // (block-uniform: every thread read the same word)
     if (fp.gi) c = mkcol(fp.gi_fill, fp.gi_fill, fp.gi_fill);   // renderSampleGI: provably black (c2rt_api.cu fill_params)
     else if (active || !plane_only(MODE)) {   // (scene classes with warp masks: every lane runs, lanes off the frame carry no ray)
         // renderer.d:223-251: tap 0 at the pixel corner, then +(.3,.3) (.6,0) (0,.6) (.6,.6); mean of 5 in FP32
@@ -1481,7 +1486,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS) render_frame_kernel
     // output row of this tile row: full frame or compact (only this rank's rows, in order)
     const uint32_t out_y0 = fp.compact ? l * TILE_H : y0;
     const bool full_tile = (x0 + TILE_W <= fp.W) && ((fp.W & 3u) == 0);
-    if (full_tile) {
+    if (!fp.rgb) {
+        // ARGB-only delivery (an interactive host that blits the packed plane): no float frame is written
+    } else if (full_tile) {
         s_rgb[ly][lx * 3 + 0] = c.r;
         s_rgb[ly][lx * 3 + 1] = c.g;
         s_rgb[ly][lx * 3 + 2] = c.b;

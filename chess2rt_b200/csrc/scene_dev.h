@@ -112,7 +112,8 @@ struct FrameParams {
     uint32_t* done_flags;             // in rank 0's memory: [r] = last frame number rank r completed, [n_ranks] = wait time-outs
     uint32_t* done_counter;           // this device: CTAs of the current launch that have finished
     uint32_t frame_no, pad_frame;
-    // outputs
+    const int* cancel;                // device flag raised by c2rt_cancel: CTAs that start after it skip their tile (nullptr: off)
+    // outputs (rgb == nullptr: only the ARGB plane is wanted)
     float* rgb;
     uint32_t* argb;
     unsigned long long* counters;     // [0] primary, [1] shadow

@@ -129,6 +129,20 @@ int c2rt_host_render_pixel(c2rt_host_scene* h, int x, int y, float rgb[3], c2rt_
     }
 }
 
+// camera.d:211-229 rotate / :181-204 move — what the GUI's key handlers call between frames (raytracer_demo.d:268-340)
+void c2rt_host_camera_rotate(c2rt_host_scene* h, double dYaw, double dRoll, double dPitch) { h->scene->camera.rotate(dYaw, dRoll, dPitch); }
+void c2rt_host_camera_move(c2rt_host_scene* h, double dx, double dy, double dz) { h->scene->camera.move(dx, dy, dz); }
+
+// saveBmp (imageio/bmp.d:195-237) of a packed Color.toRGB32 plane; returns the byte count (0 if `cap` is too small)
+size_t c2rt_host_save_bmp(const uint32_t* argb, uint32_t w, uint32_t hgt, int pad_rows, uint8_t* out, size_t cap) {
+    Image<uint32_t> img(w, hgt);
+    memcpy(img.pixels.data(), argb, (size_t)w * hgt * sizeof(uint32_t));
+    std::vector<uint8_t> bytes = saveBmp(img, pad_rows != 0);
+    if (bytes.size() > cap) return 0;
+    memcpy(out, bytes.data(), bytes.size());
+    return bytes.size();
+}
+
 // scene summary for tests: nodes, geoms, shaders, textures, lights, AA, dof, numSamples
 void c2rt_host_scene_info(const c2rt_host_scene* h, int32_t out[8]) {
     const Scene& s = *h->scene;

@@ -4,7 +4,12 @@
 // frames through renderSceneAsync -> libc2rt.so without a window, then writes the image.
 //
 //   chess2rt_headless --file scenes/lecture5.sdl --out out.bmp [--pfm out.pfm] [--width W --height H]
-//                     [--gpus N] [--no-dof] [--no-aa] [--seed S] [--repeat K]
+//                     [--gpus N] [--no-dof] [--no-aa] [--seed S] [--repeat K] [--pad-rows] [--orbit K]
+// --out writes the BMP the reference's Bitmap.saveImage would (bitmap.d:84-103 -> bmp.d:195-237, rows unpadded: only
+// widths with 3 W % 4 == 0 give a file other readers accept); --pad-rows writes the valid file for any width.
+// --orbit K: the interactive loop without a window — K frames, the camera turned by 360 / K degrees of yaw before each
+// (Camera.rotate, camera.d:211-229, what the arrow keys do: raytracer_demo.d:268-340), scene resident on the GPU, only the
+// camera / settings blocks go down and only the packed ARGB plane comes back (what SDL2Gui.draw blits, sdl2_gui.d:139-155).
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -18,14 +23,15 @@ using namespace rt;
 static void usage() {
     fprintf(stderr,
             "usage: chess2rt_headless --file <scene.sdl|scene.json> [--out img.bmp] [--pfm img.pfm]\n"
-            "                         [--width W --height H] [--gpus N] [--no-dof] [--no-aa] [--seed S] [--repeat K]\n");
+            "                         [--width W --height H] [--gpus N] [--no-dof] [--no-aa] [--seed S] [--repeat K]\n"
+            "                         [--pad-rows] [--orbit K]\n");
 }
 
 int main(int argc, char** argv) {
     std::string file, out, pfm;
     uint32_t width = 0, height = 0;
-    int gpus = 1, repeat = 1;
-    bool noDof = false, noAA = false;
+    int gpus = 1, repeat = 1, orbit = 0;
+    bool noDof = false, noAA = false, padRows = false;
     uint64_t seed = 0;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
@@ -44,15 +50,17 @@ int main(int argc, char** argv) {
         else if ((v = val("--gpus"))) gpus = atoi(v);
         else if ((v = val("--seed"))) seed = strtoull(v, nullptr, 0);
         else if ((v = val("--repeat"))) repeat = atoi(v);
+        else if ((v = val("--orbit"))) orbit = atoi(v);
+        else if (a == "--pad-rows") padRows = true;
         else if (a == "--no-dof") noDof = true;
         else if (a == "--no-aa") noAA = true;
         else if (a == "--headless") {}
         else { usage(); return 2; }
     }
-    if (file.empty()) { usage(); return 2; }
+    if (file.empty() || gpus < 1 || repeat < 1 || orbit < 0) { usage(); return 2; }
     try {
+        auto scene = parseSceneFromFile(file);   // (load errors are reported before any device is touched)
         setRenderDevices(gpus);
-        auto scene = parseSceneFromFile(file);
         if (width && height) {
             scene->settings.frameWidth = width;
             scene->settings.frameHeight = height;
@@ -84,8 +92,27 @@ int main(int argc, char** argv) {
                    H, stats.n_gpus, stats.kernel_ms, ms, (stats.primary_rays + stats.shadow_rays) / (stats.kernel_ms * 1e3),
                    (double)stats.primary_rays, (double)stats.shadow_rays);
         }
+        if (orbit > 0) {
+            RenderOptions io = opt;
+            io.countRays = false;
+            io.argbOnly = true;
+            double total_ms = 0, kernel_ms = 0;
+            for (int k = 0; k < orbit; k++) {
+                scene->camera.rotate(360.0 / orbit, 0, 0);
+                std::atomic<bool> isRendering{true}, needsRendering{false};
+                auto t0 = std::chrono::steady_clock::now();
+                scene->beginFrame();
+                Renderer renderer(*scene, screen, &isRendering, &needsRendering);
+                renderer.options = io;
+                renderer.renderRT();
+                total_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+                kernel_ms += renderer.lastStats.kernel_ms;
+            }
+            printf("orbit: %d frames of %ux%u, ARGB-only delivery: %.3f ms per frame end to end (%.1f fps), kernel %.3f ms\n", orbit, W, H,
+                   total_ms / orbit, 1e3 * orbit / total_ms, kernel_ms / orbit);
+        }
         if (!out.empty()) {
-            auto bytes = saveBmp(argb);
+            auto bytes = saveBmp(argb, padRows);
             std::ofstream f(out, std::ios::binary);
             f.write((const char*)bytes.data(), (std::streamsize)bytes.size());
             printf("wrote %s\n", out.c_str());

@@ -53,8 +53,16 @@ void Renderer::renderRT() {
         argb = options.argb->pixels.data();
     }
     static_assert(sizeof(Color) == 3 * sizeof(float), "Color must be three packed floats (color.d:27-35)");
-    int rc = c2rt_render(device(), &cam, &set, reinterpret_cast<float*>(output_.pixels.data()), argb, &lastStats);
-    if (rc != C2RT_OK) raise(rc);
+    if (options.argbOnly && !argb) throw RTException("argbOnly needs RenderOptions::argb");
+    float* rgb = options.argbOnly ? nullptr : reinterpret_cast<float*>(output_.pixels.data());
+    int rc = c2rt_render(device(), &cam, &set, rgb, argb, &lastStats);
+    cancelled = rc == C2RT_CANCELLED;   // a stop request reached the frame in flight: return like the reference's `return end()`
+    if (rc != C2RT_OK && !cancelled) raise(rc);
+}
+
+void requestStop(std::atomic<bool>* isStopRequested) {
+    if (isStopRequested) isStopRequested->store(true);
+    c2rt_cancel();
 }
 
 Color Renderer::renderPixelNoAA(int x, int y) {

@@ -30,6 +30,7 @@ struct RenderOptions {        // knobs the reference does not have
     uint64_t rngSeed = 0;     // seed of the pinned DOF generator
     bool countRays = false;   // fill lastStats.primary_rays / shadow_rays
     Image<uint32_t>* argb = nullptr;  // optional Color.toRGB32 plane produced on the GPU
+    bool argbOnly = false;    // interactive hosts that only blit `argb` (sdl2_gui.d:139-155): the float frame is neither written nor copied
 };
 
 struct Renderer {
@@ -42,6 +43,7 @@ struct Renderer {
     TraceResult lastTracingResult;
     c2rt_stats lastStats{};
     RenderOptions options;
+    bool cancelled = false;                        // the last renderRT ended early on a stop request (the frame is partial)
 
 private:
     const Scene& scene_;
@@ -58,6 +60,11 @@ void renderSceneAsync(Scene& scene, Image<Color>& output, std::atomic<bool>* isR
                       const RenderOptions& options = RenderOptions());
 
 std::tuple<Color, TraceResult> renderPixel(Scene& scene, Image<Color>& output, int x, int y);
+
+// The stop request of the reference (raytracer_demo.d:102-124 sets needsRendering; renderer.d:93-97,129,147,180 polls it between
+// passes) for a frame that is already on the GPU: sets *isStopRequested like the GUI does and tells the backend, which skips
+// every tile that has not started.  Callable from the GUI thread while the render thread is inside renderRT.
+void requestStop(std::atomic<bool>* isStopRequested);
 
 // c2rt_init wrapper: selects the GPUs the next frames are banded over (default: device 0 only).
 void setRenderDevices(int nGpus, const int* deviceIds = nullptr);

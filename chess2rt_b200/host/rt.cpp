@@ -221,11 +221,12 @@ Image<Color> loadBmpImage(const std::vector<uint8_t>& bytes) {
     return img;
 }
 
-// 24-bpp BITMAPINFOHEADER writer (imageio/bmp.d:195-237).  Unlike the reference, scanlines are padded
-// to 4 bytes so that every width yields a valid file.
-std::vector<uint8_t> saveBmp(const Image<uint32_t>& img) {
+// 24-bpp BITMAPINFOHEADER writer (imageio/bmp.d:195-237): fileSize = 14 + 40 + 3 W H, sizeOfPixelArray = fileSize - 54,
+// 72.dpiToPPM = lrint(72 * 100 / 2.54) = 2835 (bmp.d:253), rows from the bottom (foreach_reverse), each pixel the low three
+// little-endian bytes of Color.toRGB32 (b, g, r), rows NOT padded (see rt.hpp).
+std::vector<uint8_t> saveBmp(const Image<uint32_t>& img, bool padRows) {
     const size_t W = img.width, H = img.height;
-    const size_t stride = (W * 3 + 3) / 4 * 4;
+    const size_t stride = padRows ? (W * 3 + 3) / 4 * 4 : W * 3;
     std::vector<uint8_t> out(54 + stride * H, 0);
     auto w32 = [&](size_t o, uint32_t v) { out[o] = v & 0xff; out[o + 1] = (v >> 8) & 0xff; out[o + 2] = (v >> 16) & 0xff; out[o + 3] = (v >> 24) & 0xff; };
     auto w16 = [&](size_t o, uint16_t v) { out[o] = v & 0xff; out[o + 1] = (v >> 8) & 0xff; };

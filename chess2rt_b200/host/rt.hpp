@@ -282,6 +282,9 @@ std::unique_ptr<Scene> parseSceneFromFile(const std::string& filename);
 
 // imageio/bmp.d:31-34 loadBmpImage!Color, :195-237 saveBmp (24 bpp)
 Image<Color> loadBmpImage(const std::vector<uint8_t>& bytes);
-std::vector<uint8_t> saveBmp(const Image<uint32_t>& rgb32);
+// saveBmp writes what the reference writes, byte for byte: 14-byte file header, 40-byte BITMAPINFOHEADER (72 dpi = 2835 px/m),
+// rows bottom-up, b g r per pixel — and, like the reference, NO padding of the rows to 4 bytes, so a width with 3 W % 4 != 0
+// gives a file other readers (and the reference's own loader, bmp.d:136-188) misread.  padRows = true writes the valid file.
+std::vector<uint8_t> saveBmp(const Image<uint32_t>& rgb32, bool padRows = false);
 
 }  // namespace rt

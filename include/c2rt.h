@@ -36,6 +36,7 @@ extern "C" {
 #define C2RT_ABI_VERSION 2
 
 typedef enum c2rt_status {
+    C2RT_CANCELLED = 1,          /* not an error: c2rt_render ended early because c2rt_cancel was called (the frame is partial) */
     C2RT_OK = 0,
     C2RT_ERR_INVALID_ARG = -1,   /* null pointer, bad index, inconsistent sizes */
     C2RT_ERR_UNSUPPORTED = -2,   /* input the path cannot honour (GI on a Phong-shaded scene, CSG nesting beyond the limit) */
@@ -227,6 +228,14 @@ void c2rt_scene_destroy(c2rt_scene* scene);
  * Color.toRGB32 packing (color.d:154-162: r<<16 | g<<8 | b through the sRGB table). */
 int c2rt_render(c2rt_scene* scene, const c2rt_camera* camera, const c2rt_settings* settings,
                 float* rgb, uint32_t* argb, c2rt_stats* stats);
+/* rgb may be NULL when argb is not: ARGB-only delivery for an interactive host that only blits the packed plane
+ * (sdl2_gui.d:139-155) — no float frame is written or copied, a 1080p frame is 8.3 MB over PCIe instead of 33 MB. */
+
+/* Replaces the stop request the reference polls between its passes (renderer.d:93-97,129,147,180): callable from ANY thread
+ * while another thread is inside c2rt_render.  Raises a flag on every device; tiles whose CTA has not started yet are skipped,
+ * tiles in flight finish, and that c2rt_render returns C2RT_CANCELLED with a partially rendered frame (a frame the GUI is about
+ * to replace anyway: raytracer_demo.d:102-124).  A cancel that arrives while no frame is in progress cancels nothing. */
+int c2rt_cancel(void);
 
 /* Same frame, outputs in DEVICE memory of the CURRENT device, launched on `stream`
  * (a cudaStream_t, NULL = default stream) and NOT synchronised.  One process per GPU uses this

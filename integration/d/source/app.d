@@ -1,0 +1,107 @@
+// Reference-side edit of source/app.d (INTEGRATION.md section 6): the headless mode the north star asks for.  Written against
+// the reference checkout; NOT compiled in this repository's image (no D toolchain: SURVEY.md F2) — the tested twin is
+// chess2rt_b200/host/main.cpp (same flags, same flow).  Lines marked `// new` are additions to /root/reference/source/app.d:9-22;
+// everything else is the file as it stands.
+module app;
+
+import gui.rtdemo, gui.guidemo;
+import core.stdc.stdlib : exit;
+import std.getopt : getopt;
+import std.stdio : writeln, writefln;
+import std.typecons : scoped;
+
+void main(string[] args)
+{
+    version(unittest) exit(0);
+
+    string sceneFilePath = "";
+    bool headless = false, noDof = false, noAA = false;          // new
+    string outPath = "";                                         // new
+    uint width = 0, height = 0, gpus = 1, orbit = 0;             // new
+    ulong seed = 0;                                              // new
+
+    getopt(args, "file", &sceneFilePath,
+                 "headless", &headless, "out", &outPath, "width", &width, "height", &height,   // new
+                 "gpus", &gpus, "no-dof", &noDof, "no-aa", &noAA, "seed", &seed, "orbit", &orbit);   // new
+
+    if (headless)                                                // new
+        return runHeadless(sceneFilePath, outPath, width, height, gpus, noDof, noAA, seed, orbit);
+
+    runAppInScope(sceneFilePath);
+
+    debug printDiagnostics();
+
+    writeln("At the end.");
+}
+
+// new: the flow of RTDemo.resetScene + render + takeScreenshot (raytracer_demo.d:145-187, 102-124, 227-238) without a window
+void runHeadless(string scenePath, string outPath, uint width, uint height, uint gpus, bool noDof, bool noAA, ulong seed, uint orbit)
+{
+    import std.datetime.stopwatch : StopWatch, AutoStart;
+    import imageio.image : Image;
+    import rt.sceneloader : parseSceneFromFile;
+    import rt.bitmap : Bitmap;
+    import rt.color : Color;
+    import rt.cuda_backend, rt.flatten, rt.renderer_cuda;
+
+    c2rt_init(cast(int) gpus, null);                             // frames are banded over `gpus` devices from here on
+    scope (exit) c2rt_shutdown();
+
+    auto scene = parseSceneFromFile(scenePath);                  // scene_loader.d:20, unchanged
+    if (width && height)                                         // "as if the scene file had been edited" (camera.d:231-236,254)
+    {
+        scene.settings.frameWidth = width; scene.settings.frameHeight = height;
+        scene.camera.setFrameSize(width, height);
+    }
+    if (noDof) scene.camera.dof = false;
+    if (noAA) scene.settings.AAEnabled = false;
+
+    Image!Color screen;
+    screen.alloc(scene.settings.frameWidth, scene.settings.frameHeight);       // raytracer_demo.d:181-182
+    c2rt_pin_host_buffer(screen.pixels.ptr, screen.pixels.length * Color.sizeof);
+    scope (exit) c2rt_unpin_host_buffer(screen.pixels.ptr);
+
+    auto sw = StopWatch(AutoStart.yes);
+    renderSceneSync(scene, screen, seed);                        // renderSceneAsync's body without the spawn (renderer_cuda.d)
+    writefln("%sx%s on %s GPU(s): %s ms end to end", screen.w, screen.h, gpus, sw.peek.total!"usecs" / 1000.0);
+
+    if (orbit)                                                   // the interactive loop without a window: camera-only updates
+    {
+        sw.reset();
+        foreach (k; 0 .. orbit)
+        {
+            scene.camera.rotate(360.0 / orbit, 0, 0);            // camera.d:211-229, what the arrow keys do
+            renderSceneSync(scene, screen, seed);
+        }
+        writefln("orbit: %s frames, %s ms per frame", orbit, sw.peek.total!"usecs" / 1000.0 / orbit);
+    }
+
+    if (outPath.length)
+        (const Bitmap(screen)).saveImage(outPath);               // bitmap.d:84-103 -> bmp.d:195-237 (rows unpadded)
+}
+
+void runAppInScope(string filePath)
+{
+    import std.variant : Variant;
+
+    // auto app = scoped!(GuiDemo!uint)(800, 600, "Test GUI");
+    auto app = scoped!RTDemo();
+
+    bool normalQuit = app.run(Variant(filePath));
+
+    if (normalQuit)
+        writeln("User requested shutdown and the application is closing normally.");
+    else
+        writeln("Something bad happened during shutdown!");
+
+    writeln("Close to the end...");
+}
+
+void printDiagnostics()
+{
+    import rt.shader;
+
+    //writeln(Lambert.shadeFunc.callsCount);
+    //writeln(Lambert.spawnRayFunc.callsCount);
+    //writeln(Lambert.evalFunc.callsCount);
+}

@@ -5,12 +5,13 @@ module rt.cuda_backend;
 
 extern (C) @nogc nothrow:
 
-enum C2RT_ABI_VERSION = 1;
-enum : int { C2RT_OK = 0, C2RT_ERR_INVALID_ARG = -1, C2RT_ERR_UNSUPPORTED = -2, C2RT_ERR_CUDA = -3,
+enum C2RT_ABI_VERSION = 2;
+enum : int { C2RT_CANCELLED = 1, C2RT_OK = 0, C2RT_ERR_INVALID_ARG = -1, C2RT_ERR_UNSUPPORTED = -2, C2RT_ERR_CUDA = -3,
              C2RT_ERR_NOT_INITIALISED = -4, C2RT_ERR_LIMIT = -5 }
 enum : int { C2RT_GEOM_PLANE, C2RT_GEOM_SPHERE, C2RT_GEOM_CUBE, C2RT_GEOM_CSG_UNION, C2RT_GEOM_CSG_INTER, C2RT_GEOM_CSG_DIFF }
 enum : int { C2RT_SHADER_LAMBERT, C2RT_SHADER_PHONG }
 enum : int { C2RT_TEX_CHECKER, C2RT_TEX_PROCEDURE2, C2RT_TEX_BITMAP }
+enum : int { C2RT_ENV_BLACK, C2RT_ENV_CUBEMAP }      // CUBEMAP: extension, environment.d has the black stub only
 
 struct c2rt_scene_desc
 {
@@ -24,6 +25,9 @@ struct c2rt_scene_desc
                      const(int)* tex_width, tex_height; const(ulong)* tex_texel_offset;
                      const(float)* texels; ulong n_texels;
     uint n_lights;   const(double)* light_pos; const(float)* light_color, light_power;
+    int env_type, env_reserved;                       // C2RT_ENV_*
+    int[6] env_face_width, env_face_height;           // +x, -x, +y, -y, +z, -z
+    ulong[6] env_face_texel_offset;                   // into `texels`
 }
 
 struct c2rt_camera
@@ -56,6 +60,7 @@ int  c2rt_scene_create(const(c2rt_scene_desc)* desc, c2rt_scene** out_);
 void c2rt_scene_destroy(c2rt_scene* scene);
 int  c2rt_render(c2rt_scene* scene, const(c2rt_camera)* cam, const(c2rt_settings)* set,
                  float* rgb, uint* argb, c2rt_stats* stats);
+int  c2rt_cancel();                                  // any thread, while another one is inside c2rt_render
 int  c2rt_render_pixel(c2rt_scene* scene, const(c2rt_camera)* cam, const(c2rt_settings)* set,
                        int x, int y, float* rgb, c2rt_hit* hit);
 int  c2rt_pin_host_buffer(void* ptr, size_t bytes);

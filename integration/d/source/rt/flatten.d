@@ -14,6 +14,7 @@ struct FlatScene
     int[] shaderType, shaderTex; float[] shaderColor, shaderStrength; double[] shaderExponent;
     int[] texType, texW, texH; float[] texColors; double[] texParams; ulong[] texOffset; float[] texels;
     double[] lightPos; float[] lightColor, lightPower;
+    int envType = C2RT_ENV_BLACK; int[6] envW, envH; ulong[6] envOffset;
 
     c2rt_scene_desc desc() const
     {
@@ -33,6 +34,7 @@ struct FlatScene
         d.texels = texels.ptr; d.n_texels = texels.length / 3;
         d.n_lights = cast(uint) lightPower.length;
         d.light_pos = lightPos.ptr; d.light_color = lightColor.ptr; d.light_power = lightPower.ptr;
+        d.env_type = envType; d.env_face_width = envW; d.env_face_height = envH; d.env_face_texel_offset = envOffset;
         return d;
     }
 }
@@ -87,6 +89,16 @@ FlatScene flatten(const Scene s)
     {
         auto pl = cast(const PointLight) l;            // the only Light subclass (light.d:52)
         f.lightPos ~= pl.pos.v[]; f.lightColor ~= pl.lightColor.components[]; f.lightPower ~= pl.lightPower;
+    }
+    // cubemap-environment extension (INTEGRATION.md section 8): Environment gains `Bitmap[6] faces; bool cubemap`
+    if (s.environment.cubemap)
+    {
+        f.envType = C2RT_ENV_CUBEMAP;
+        foreach (k, ref face; s.environment.faces)
+        {
+            f.envW[k] = cast(int) face.width; f.envH[k] = cast(int) face.height; f.envOffset[k] = f.texels.length / 3;
+            foreach (px; face.data.pixels) f.texels ~= px.components[];
+        }
     }
     foreach (n; s.nodes)
     {

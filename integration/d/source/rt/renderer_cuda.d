@@ -38,8 +38,28 @@ void renderSceneAsync(Scene scene, Image!Color output, shared(bool)* isRendering
         auto set = flattenSettings(sc.settings);
         // Image!Color.pixels is a tightly packed float[3] array, row-major, top row first (imageio/image.d:18-54)
         auto rc = c2rt_render(deviceScene(sc), &cam, &set, cast(float*) img.pixels.ptr, null, null);
-        if (rc != C2RT_OK) stderr.writeln("c2rt_render: ", c2rt_last_error().fromStringz);
+        // C2RT_CANCELLED: a stop request (requestStop below) reached the frame in flight — the reference's `return end()`
+        if (rc != C2RT_OK && rc != C2RT_CANCELLED) stderr.writeln("c2rt_render: ", c2rt_last_error().fromStringz);
     }, cast(shared) scene, cast(shared) output, isRendering, needsRendering);
+}
+
+// new: the synchronous form app.d's headless mode uses (same body as the spawned delegate above)
+void renderSceneSync(Scene scene, Image!Color output, ulong seed = 0)
+{
+    scene.beginFrame();
+    auto cam = flattenCamera(scene.camera);
+    auto set = flattenSettings(scene.settings, seed);
+    enforce!RTException(c2rt_render(deviceScene(scene), &cam, &set, cast(float*) output.pixels.ptr, null, null) == C2RT_OK,
+                        c2rt_last_error().fromStringz.idup);
+}
+
+// new: what RTDemo calls where it sets `needsRendering = true` while a frame is being rendered (raytracer_demo.d:85-124,268-340),
+// so that the stop request the reference polls between passes (renderer.d:93-97,129,147,180) also reaches a frame already on
+// the GPU: tiles that have not started are skipped and c2rt_render returns C2RT_CANCELLED.
+void requestStop(shared(bool)* needsRendering)
+{
+    if (needsRendering !is null) (*needsRendering).atomicStore(true);
+    c2rt_cancel();
 }
 
 auto renderPixel(Scene scene, Image!Color output, int x, int y)

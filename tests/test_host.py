@@ -84,7 +84,8 @@ def test_loader_and_flattener_lecture5():
 def test_cubemap_environment_extension_is_loaded_and_flattened(tmp_path):
     """Environment { folder ... } (EXTENSION; the reference's Environment reads no keys, environment.d:12-14): six faces loaded
     with the BitmapTexture gamma rule and appended to the flat texel array; scenes without it keep C2RT_ENV_BLACK."""
-    d = c2.HostScene(os.path.join(SC, "lecture5.sdl")).desc().contents
+    plain = c2.HostScene(os.path.join(SC, "lecture5.sdl"))
+    d = plain.desc().contents
     assert d.env_type == 0 and d.n_texels == 256 * 256 + 800 * 400
     s = c2.HostScene(os.path.join(ROOT, "tests", "scenes", "sky.sdl"))
     d = s.desc().contents
@@ -100,6 +101,53 @@ def test_cubemap_environment_extension_is_loaded_and_flattened(tmp_path):
     p.write_text('Scene { Environment { folder "nowhere" } }')
     with pytest.raises(c2.C2rtError):
         c2.HostScene(p)
+
+
+def test_save_bmp_is_the_reference_layout():
+    """imageio/bmp.d:195-237 by hand for a 3x2 image: 14-byte file header (fileSize = 54 + 3 W H, offset 54), BITMAPINFOHEADER
+    (40, W, H, 1 plane, 24 bpp, BI_RGB, size = fileSize - 54, 72 dpi = lrint(7200 / 2.54) = 2835 px/m twice, 0, 0), then the rows
+    from the BOTTOM one up, each pixel the low three little-endian bytes of Color.toRGB32 (b, g, r) — and no row padding
+    (3 * 3 = 9 bytes per row), which makes the reference's own loader (bmp.d:136-188, padded rows) misread such a file."""
+    import struct
+    argb = np.array([[0x00112233, 0x00445566, 0x00778899], [0x00AABBCC, 0x00DDEEFF, 0x00010203]], np.uint32)
+    got = api.save_bmp(argb)
+    head = struct.pack("<2sIHHI", b"BM", 54 + 18, 0, 0, 54) + struct.pack("<IiiHHIIiiII", 40, 3, 2, 1, 24, 0, 18, 2835, 2835, 0, 0)
+    rows = bytes([0xCC, 0xBB, 0xAA, 0xFF, 0xEE, 0xDD, 0x03, 0x02, 0x01]) + bytes([0x33, 0x22, 0x11, 0x66, 0x55, 0x44, 0x99, 0x88, 0x77])
+    assert got == head + rows
+    # --pad-rows: the valid file; PIL and the host's own decoder read the pixels back
+    from io import BytesIO
+    from PIL import Image
+    padded = api.save_bmp(argb, pad_rows=True)
+    assert len(padded) == 54 + 2 * 12
+    img = np.asarray(Image.open(BytesIO(padded)).convert("RGB")).astype(np.uint32)
+    np.testing.assert_array_equal((img[..., 0] << 16) | (img[..., 1] << 8) | img[..., 2], argb)
+    w, h = C.c_uint32(), C.c_uint32()
+    out = np.zeros(6, np.uint32)
+    blob = np.frombuffer(padded, np.uint8)
+    assert api.host_lib.c2rt_host_decode_bmp(blob.ctypes.data, blob.size, C.byref(w), C.byref(h), out.ctypes.data, 6) == 0
+    np.testing.assert_array_equal(out.reshape(2, 3), argb)
+    # widths with 3 W % 4 == 0 need no padding: both forms coincide
+    a4 = np.arange(8, dtype=np.uint32).reshape(2, 4) * 0x010203
+    assert api.save_bmp(a4) == api.save_bmp(a4, pad_rows=True)
+
+
+def test_headless_command_line(tmp_path):
+    """chess2rt_headless (host/main.cpp, the C++ twin of integration/d/source/app.d): usage errors exit 2, load errors exit 1 with
+    the reference's message, and without a GPU a render fails loudly (no CPU fallback) instead of writing an image."""
+    exe = os.path.join(ROOT, "chess2rt_b200", "chess2rt_headless")
+    run = lambda *a: subprocess.run([exe, *a], capture_output=True, text=True, timeout=300)
+    r = run()
+    assert r.returncode == 2 and "usage:" in r.stderr
+    assert run("--file").returncode == 2 and run("--bogus", "1").returncode == 2
+    assert run("--file", os.path.join(SC, "lecture4.sdl"), "--gpus", "0").returncode == 2
+    r = run("--file", str(tmp_path / "missing.sdl"))
+    assert r.returncode == 1 and "Scene file not found" in r.stderr
+    out = tmp_path / "x.bmp"
+    r = run("--headless", "--file=" + os.path.join(SC, "lecture4.sdl"), "--width", "64", "--height", "48", "--out", str(out))
+    if HAS_GPU:
+        assert r.returncode == 0 and out.exists() and out.stat().st_size == 54 + 64 * 48 * 3
+    else:
+        assert r.returncode == 1 and "CUDA" in r.stderr and not out.exists()
 
 
 def test_settings_block_carries_the_gi_fields(tmp_path):
