@@ -557,6 +557,26 @@ def main():
         # the waiting ranks must not sit in an NCCL barrier: its kernel would time-slice with rank 0's work on their GPU
         dist.barrier(group=cpu_group)
     e2e_ms_mean = sum(e2e_ms) / len(e2e_ms)
+
+    # ---- the interactive loop: the camera turns before every frame (Camera.rotate, what the arrow keys
+    # do), the scene stays resident, only the camera / settings blocks go down and only the packed ARGB plane comes back
+    interactive = None
+    if world == 1:
+        import numpy as np
+        argb_pinned = torch.empty((H, W), dtype=torch.int32, pin_memory=True)
+        a_np = argb_pinned.numpy().view(np.uint32)
+        ts = []
+        for i in range(args.warmup + args.steps):
+            scene.camera_rotate(0.5)
+            t0 = time.perf_counter()
+            scene.render(seed=RNG_SEED, out_argb=a_np, argb_only=True)
+            t1 = time.perf_counter()
+            if i >= args.warmup:
+                ts.append((t1 - t0) * 1e3)
+        scene.camera_rotate(-0.5 * (args.warmup + args.steps))
+        interactive = {"ms_per_frame": sum(ts) / len(ts), "frames_per_s": 1e3 * len(ts) / sum(ts), "d2h_bytes_per_frame": W * H * 4,
+                       "h2d_bytes_per_frame": C_sizeof_frame_blocks(api),
+                       "how": "camera yaw changed before every frame; c2rt_render with rgb == NULL (ARGB-only delivery into a pinned plane)"}
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
@@ -609,6 +629,7 @@ def main():
             "scaling_targets": scaling_targets,
             "multi_gpu_frame_check": frame_check,
             "nvlink": ingest,
+            "interactive": interactive,
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1

@@ -92,6 +92,18 @@ int main(int argc, char** argv) {
                    H, stats.n_gpus, stats.kernel_ms, ms, (stats.primary_rays + stats.shadow_rays) / (stats.kernel_ms * 1e3),
                    (double)stats.primary_rays, (double)stats.shadow_rays);
         }
+        if (!out.empty()) {
+            auto bytes = saveBmp(argb, padRows);
+            std::ofstream f(out, std::ios::binary);
+            f.write((const char*)bytes.data(), (std::streamsize)bytes.size());
+            printf("wrote %s\n", out.c_str());
+        }
+        if (!pfm.empty()) {  // float RGB, bottom row first (PFM convention), little endian
+            std::ofstream f(pfm, std::ios::binary);
+            f << "PF\n" << W << " " << H << "\n-1.0\n";
+            for (uint32_t y = H; y-- > 0;) f.write((const char*)&screen.pixels[(size_t)W * y], (std::streamsize)W * sizeof(Color));
+            printf("wrote %s\n", pfm.c_str());
+        }
         if (orbit > 0) {
             RenderOptions io = opt;
             io.countRays = false;
@@ -111,20 +123,8 @@ int main(int argc, char** argv) {
             printf("orbit: %d frames of %ux%u, ARGB-only delivery: %.3f ms per frame end to end (%.1f fps), kernel %.3f ms\n", orbit, W, H,
                    total_ms / orbit, 1e3 * orbit / total_ms, kernel_ms / orbit);
         }
-        if (!out.empty()) {
-            auto bytes = saveBmp(argb, padRows);
-            std::ofstream f(out, std::ios::binary);
-            f.write((const char*)bytes.data(), (std::streamsize)bytes.size());
-            printf("wrote %s\n", out.c_str());
-        }
         c2rt_unpin_host_buffer(screen.pixels.data());
         c2rt_unpin_host_buffer(argb.pixels.data());
-        if (!pfm.empty()) {  // float RGB, bottom row first (PFM convention), little endian
-            std::ofstream f(pfm, std::ios::binary);
-            f << "PF\n" << W << " " << H << "\n-1.0\n";
-            for (uint32_t y = H; y-- > 0;) f.write((const char*)&screen.pixels[(size_t)W * y], (std::streamsize)W * sizeof(Color));
-            printf("wrote %s\n", pfm.c_str());
-        }
     } catch (const std::exception& e) {
         fprintf(stderr, "error: %s\n", e.what());
         return 1;

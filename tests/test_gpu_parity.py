@@ -491,6 +491,75 @@ def test_many_scenes_alive_and_scene_switching():
             assert_parity(g.render()[0], ref)
 
 
+def test_argb_only_delivery():
+    """c2rt_render with rgb == NULL: the interactive host's frame (only the packed plane SDL2Gui.draw blits comes back)."""
+    g = c2.HostScene(os.path.join(SC, "lecture5.sdl"))
+    g.set_frame_size(333, 217)
+    rgb, argb, _ = g.render(argb=True)
+    none, only, st = g.render(argb_only=True)
+    assert none is None and st.launches >= 1
+    np.testing.assert_array_equal(only, argb)
+    np.testing.assert_array_equal(only, pack_rgb32(rgb))
+    cam, stt = g.frame_blocks()
+    assert api.lib.c2rt_render(g.device_scene(), C.byref(cam), C.byref(stt), None, None, None) == -1   # both planes NULL
+
+
+def test_cancel_stops_a_frame_in_flight():
+    """c2rt_cancel from another thread (the reference polls its stop flag between passes: renderer.d:93-97,129,147,180): tiles that
+    have not started are skipped, c2rt_render reports C2RT_CANCELLED, and the next frame is complete again."""
+    import threading
+    import time
+    g = c2.HostScene(os.path.join(SC, "zaphod.sdl"))      # DOF, 125 rays per pixel: ~16 ms of kernel at 4K
+    g.set_frame_size(3840, 2160)
+    buf = np.empty((2160, 3840, 3), np.float32)
+    _, _, full = g.render(seed=1, out=buf)
+    assert not g.cancelled
+    reference = buf.copy()
+    api.cancel()                                           # no frame in progress: cancels nothing
+    _, _, st = g.render(seed=1, out=buf)
+    assert not g.cancelled
+    np.testing.assert_array_equal(buf, reference)
+    started = threading.Event()
+    res = {}
+
+    def worker():
+        started.set()
+        res["st"] = g.render(seed=1, out=buf)[2]
+
+    t = threading.Thread(target=worker)
+    t.start()
+    started.wait()
+    time.sleep(0.004)
+    api.cancel()
+    t.join()
+    assert g.cancelled
+    assert res["st"].kernel_ms < 0.85 * full.kernel_ms, (res["st"].kernel_ms, full.kernel_ms)
+    _, _, st = g.render(seed=1, out=buf)                   # the flag does not outlive the cancelled frame
+    assert not g.cancelled
+    np.testing.assert_array_equal(buf, reference)
+
+
+def test_headless_end_to_end_and_orbit(tmp_path):
+    """chess2rt_headless: the image files hold the frame the library renders (BMP through saveBmp's reference layout, PFM floats),
+    and --orbit runs the camera-move loop with ARGB-only delivery."""
+    import subprocess
+    exe = os.path.join(ROOT, "chess2rt_b200", "chess2rt_headless")
+    bmp, pfm = tmp_path / "o.bmp", tmp_path / "o.pfm"
+    r = subprocess.run([exe, "--headless", "--file", os.path.join(SC, "lecture5.sdl"), "--width", "200", "--height", "120", "--out", str(bmp),
+                        "--pfm", str(pfm), "--orbit", "6"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "orbit: 6 frames of 200x120, ARGB-only delivery" in r.stdout
+    g = c2.HostScene(os.path.join(SC, "lecture5.sdl"))
+    g.set_frame_size(200, 120)
+    rgb, argb, _ = g.render(argb=True)
+    assert bmp.read_bytes() == api.save_bmp(argb)
+    raw = pfm.read_bytes()
+    head = b"PF\n200 120\n-1.0\n"
+    assert raw.startswith(head)
+    got = np.frombuffer(raw[len(head):], np.float32).reshape(120, 200, 3)[::-1]
+    np.testing.assert_array_equal(got, rgb)
+
+
 def test_fma_peak_microbenchmarks_are_sane():
     tf32, mhz = c2.measure_fma_peak(False)
     tf64, _ = c2.measure_fma_peak(True)

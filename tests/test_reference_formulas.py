@@ -61,13 +61,13 @@ def write_scene(tmp_path, name):
     return str(p)
 
 
-def check(name, rgb, node, dist, p, n, uv):
+def check(name, rgb, node, dist, p, n, uv, uv_atol=1e-11):
     _, _, e_dist, e_p, e_n, e_uv, e_rgb = CASES[name]
     assert node == 0, name
     np.testing.assert_allclose(dist, e_dist, rtol=1e-12, err_msg=name)
     np.testing.assert_allclose(p, e_p, rtol=0, atol=1e-11, err_msg=name)
     np.testing.assert_allclose(n, e_n, rtol=0, atol=1e-12, err_msg=name)
-    np.testing.assert_allclose(uv, e_uv, rtol=0, atol=1e-11, err_msg=name)
+    np.testing.assert_allclose(uv, e_uv, rtol=0, atol=uv_atol, err_msg=name)
     np.testing.assert_allclose(rgb, e_rgb, rtol=0, atol=2e-6, err_msg=name)   # FP32 colour arithmetic (color.d:27-35)
 
 
@@ -98,7 +98,8 @@ def test_gpu_reproduces_hand_derived_hits(name, tmp_path):
     g = c2.HostScene(write_scene(tmp_path, name))
     x, y = CASES[name][1]
     rgb, hit = g.render_pixel(x, y)
-    check(name, rgb, hit.node, hit.dist, list(hit.p), list(hit.normal), [hit.u, hit.v])
+    # (sphere uv is the one FP32 quantity of the hit record on the GPU: atan2f on the FP64 difference vector)
+    check(name, rgb, hit.node, hit.dist, list(hit.p), list(hit.normal), [hit.u, hit.v], uv_atol=1e-6)
     frame, _, _ = g.render()
     np.testing.assert_allclose(frame[y, x], CASES[name][6], rtol=0, atol=2e-6)
 
