@@ -293,18 +293,20 @@ __device__ __forceinline__ bool isect_plane_u(double y, double ox, double oy, do
     return true;
 }
 
+// geometry.d:92-125.  Every ray that reaches a geometry is unit (camera.d:144,172; scene.d:66-71; node.d:31-34 re-normalises in
+// object space), so the reference's A = dot(d, d) is 1 to 2 ulp: the quadratic is solved in the half-b form
+// t = -b -+ sqrt(b^2 - c), b = H . d, c = H . H - R^2 — the same roots as (-B -+ sqrt(B^2 - 4 A C)) / 2A to ~4e-16 relative,
+// without the division and with a third fewer FP64 instructions.
 __device__ __forceinline__ bool isect_sphere(const double* p, double ox, double oy, double oz, double dx, double dy, double dz,
                                              double& dist, double& px, double& py, double& pz) {
     double hx = ox - p[0], hy = oy - p[1], hz = oz - p[2];
-    double A = dot3(dx, dy, dz, dx, dy, dz);
-    double B = 2 * dot3(hx, hy, hz, dx, dy, dz);
-    double C = dot3(hx, hy, hz, hx, hy, hz) - p[3] * p[3];
-    double D = fma(B, B, -4 * A * C);
+    double b = dot3(hx, hy, hz, dx, dy, dz);
+    double c = fma(-p[3], p[3], dot3(hx, hy, hz, hx, hy, hz));
+    double D = fma(b, b, -c);
     if (D < 0) return false;
     double sq = D > 0 ? D * rsqrt64(D) : 0.0;
-    double inv2a = rcp64(2 * A);
-    double sol = (-B - sq) * inv2a;
-    if (sol < 0) sol = (-B + sq) * inv2a;
+    double sol = -b - sq;
+    if (sol < 0) sol = sq - b;
     if (sol < 0) return false;
     if (sol > dist) return false;
     dist = sol;
@@ -404,14 +406,12 @@ __device__ __forceinline__ Crossings cross_sphere(const double* p, double ox, do
     Crossings c;
     c.n = 0; c.f0 = 0; c.f1 = 0; c.d0 = 0; c.d1 = 0;
     double hx = ox - p[0], hy = oy - p[1], hz = oz - p[2];
-    double A = dot3(dx, dy, dz, dx, dy, dz);
-    double B = 2 * dot3(hx, hy, hz, dx, dy, dz);
-    double C = dot3(hx, hy, hz, hx, hy, hz) - p[3] * p[3];
-    double D = fma(B, B, -4 * A * C);
+    double b = dot3(hx, hy, hz, dx, dy, dz);          // half-b form for a unit direction (see isect_sphere)
+    double cc = fma(-p[3], p[3], dot3(hx, hy, hz, hx, hy, hz));
+    double D = fma(b, b, -cc);
     if (D < 0) return c;
     double sq = D > 0 ? D * rsqrt64(D) : 0.0;
-    double inv2a = rcp64(2 * A);
-    double x2 = (-B - sq) * inv2a, x1 = (-B + sq) * inv2a;
+    double x2 = -b - sq, x1 = sq - b;
     if (x2 >= 0) {
         c.d0 = x2;
         c.n = 1;
@@ -800,8 +800,8 @@ __device__ __forceinline__ void shadow_mask(NodeMask& m, const float4* __restric
     const float rho = sqrtf(dot3f(hx, hy, hz, hx, hy, hz));
     const float dx = L.posf[0] - cx, dy = L.posf[1] - cy, dz = L.posf[2] - cz;   // capsule axis: box centre -> light
     const float dd = dot3f(dx, dy, dz, dx, dy, dz);
-    const float inv_dd = dd > 0.f ? 1.0f / dd : 0.f;
-    const float mag = sqrtf(dot3f(cx, cy, cz, cx, cy, cz)) + sqrtf(dd);
+    const float inv_dd = dd > 0.f ? __fdividef(1.0f, dd) : 0.f;   // (approximate: t only picks the point of the axis; the margin covers it)
+    const float mag = fabsf(cx) + fabsf(cy) + fabsf(cz) + fabsf(dx) + fabsf(dy) + fabsf(dz);   // L1 >= L2: a cheaper, larger margin
     ballot_nodes<BIG>(m, [&](int i) {
         // per-lane index: the bound comes from GLOBAL memory (one coalesced 16-byte load per lane) — a constant-bank read
         // with 32 different addresses would be replayed 32 times
@@ -810,7 +810,7 @@ __device__ __forceinline__ void shadow_mask(NodeMask& m, const float4* __restric
         const float ax = b.x - cx, ay = b.y - cy, az = b.z - cz;
         const float t = fminf(fmaxf(dot3f(ax, ay, az, dx, dy, dz) * inv_dd, 0.f), 1.f);
         const float qx = fmaf(-t, dx, ax), qy = fmaf(-t, dy, ay), qz = fmaf(-t, dz, az);
-        const float reachr = b.w + rho + 8e-6f * (mag + sqrtf(dot3f(b.x, b.y, b.z, b.x, b.y, b.z)) + rho);
+        const float reachr = b.w + rho + 8e-6f * (mag + fabsf(b.x) + fabsf(b.y) + fabsf(b.z) + rho);
         return !(dot3f(qx, qy, qz, qx, qy, qz) > reachr * reachr);   // (a NaN bound keeps the node)
     });
 }
@@ -1138,20 +1138,25 @@ __device__ __forceinline__ Col trace_warp(const FrameParams& fp, const Ray& cam_
     NodeMask smask;
     smask.w0 = 0;
     smask.more = BIG ? s_shadow_words[threadIdx.x >> 5] : nullptr;
+    // Register diet (the walk below holds the CSG test's working set; whatever is only needed before or after it is parked in
+    // shared memory or recomputed): the FP64 view direction and the surface colour live in s_view / s_diffuse, the shader is
+    // kept as an index, the light vector D = L - origin is recomputed where it is needed instead of being carried.
+    __shared__ float s_diffuse[3][BLOCK_THREADS];
     Ray r = cam_ray;
     HitRec h;
     h.dist = 1e99;
     h.node = -1;
     float tmaxf = 3.0e38f;   // (not +inf = (float)1e99: ptxas would prove tmaxf == (float)h.dist * k and re-convert it in every iteration)
-    bool walk = true;            // (a shadow phase in which no lane of the warp has a ray skips the walk)
+    float rsf = 0.f;         // shadow phases: 1 / |D| in FP32
+    bool walk = true;        // (a shadow phase in which no lane of the warp has a ray skips the walk)
     bool want = live, found = false, ray_ready = true;
-    double Dx = r.dx, Dy = r.dy, Dz = r.dz, len2 = 1.0;   // shadow phases: light - origin (un-normalised), |D|^2
     // shading state of this lane's hit
-    bool hit = false, phong = false;
-    float Nx = 0.f, Ny = 0.f, Nz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f, strength = 0.f;
-    double exponent = 1.0;
-    Col diffuse = mkcol(0.f, 0.f, 0.f), specular = mkcol(0.f, 0.f, 0.f);
+    bool hit = false;
+    int shi = -1;            // shader record of the hit
+    float Nx = 0.f, Ny = 0.f, Nz = 0.f;
+    Col specular = mkcol(0.f, 0.f, 0.f);
     Col lightContrib = mkcol(fp.ambient[0], fp.ambient[1], fp.ambient[2]);
+    s_diffuse[0][threadIdx.x] = 0.f; s_diffuse[1][threadIdx.x] = 0.f; s_diffuse[2][threadIdx.x] = 0.f;
     const int nl = c_scene.n_lights;
     int li = -1;
     for (;;) {
@@ -1170,12 +1175,16 @@ __device__ __forceinline__ Col trace_warp(const FrameParams& fp, const Ray& cam_
                 if (nd.kind == KIND_PLANE_W) {
                     // implied by geometry.d:35-36 (dir.y has the sign of D.y): the common "above the floor, looking / lit from above" case
                     const double y = nd.wp[0];
-                    skip = (r.oy > y && Dy >= 0) || (r.oy < y && Dy <= 0);
+                    const double sy = anyhit ? c_scene.lights[li].pos[1] - r.oy : r.dy;
+                    skip = (r.oy > y && sy >= 0) || (r.oy < y && sy <= 0);
                 } else if ((MODE & MODE_BOUNDED) && !(nd.flags & NODE_UNBOUNDED)) {
                     skip = cull(nd, r, tmaxf);
                 }
                 if (!skip) {
                     if (!ray_ready) {   // the FP64 normalisation of a shadow ray (scene.d:66-71), only once a node survives
+                        const DevLight& L = c_scene.lights[li];
+                        const double Dx = L.pos[0] - r.ox, Dy = L.pos[1] - r.oy, Dz = L.pos[2] - r.oz;
+                        const double len2 = dot3(Dx, Dy, Dz, Dx, Dy, Dz);
                         const double inv = rsqrt64(len2);
                         r.dx = Dx * inv; r.dy = Dy * inv; r.dz = Dz * inv;
                         h.dist = len2 * inv;
@@ -1194,32 +1203,36 @@ __device__ __forceinline__ Col trace_warp(const FrameParams& fp, const Ray& cam_
             // ---- the camera ray is traced: complete the hit (per lane)
             if (out_hit) *out_hit = h;
             hit = live && h.node >= 0;
-            vx = (float)r.dx; vy = (float)r.dy; vz = (float)r.dz;
             s_view[0][threadIdx.x] = r.dx; s_view[1][threadIdx.x] = r.dy; s_view[2][threadIdx.x] = r.dz;
             if (hit) {
-                const DevShader& sh = shader_at<BIG>(node_at<BIG>(h.node).shader);
+                shi = node_at<BIG>(h.node).shader;
+                const DevShader& sh = shader_at<BIG>(shi);
                 const bool has_tex = sh.tex >= 0;
                 Surface s;
                 surface_of<MODE>(h, nullptr, has_tex, s);
                 // faceforward (imported_types.d:69-73): the sign decision in FP64, the vector itself in FP32
                 Nx = s.nx; Ny = s.ny; Nz = s.nz;
                 if (!(dot3(r.dx, r.dy, r.dz, s.gx, s.gy, s.gz) < 0)) { Nx = -Nx; Ny = -Ny; Nz = -Nz; }
-                diffuse = has_tex ? sample_texture<MODE>(sh.tex, s.u, s.v) : mkcol(sh.color[0], sh.color[1], sh.color[2]);
-                phong = sh.type == C2RT_SHADER_PHONG;
-                strength = sh.strength;
-                exponent = sh.exponent;
+                const Col diffuse = has_tex ? sample_texture<MODE>(sh.tex, s.u, s.v) : mkcol(sh.color[0], sh.color[1], sh.color[2]);
+                s_diffuse[0][threadIdx.x] = diffuse.r; s_diffuse[1][threadIdx.x] = diffuse.g; s_diffuse[2][threadIdx.x] = diffuse.b;
                 // shadow-ray origin p + N * 1e-6 (shader.d:88,219)
                 r.ox = s.px + (double)Nx * 1e-6; r.oy = s.py + (double)Ny * 1e-6; r.oz = s.pz + (double)Nz * 1e-6;
             } else if (live) {
-                diffuse = env_lookup(r.dx, r.dy, r.dz);   // a miss: renderer.d:366-368 (black unless the cubemap extension is on)
+                const Col env = env_lookup(r.dx, r.dy, r.dz);   // a miss: renderer.d:366-368 (black unless the cubemap extension is on)
+                s_diffuse[0][threadIdx.x] = env.r; s_diffuse[1][threadIdx.x] = env.g; s_diffuse[2][threadIdx.x] = env.b;
             }
         } else if (want && !found) {
             // ---- light li is visible from this lane's hit: lighting in FP32 (the reference narrows every factor to float
             // before it touches a Color: SURVEY.md App. C.1)
             const DevLight& L = c_scene.lights[li];
-            const float fDx = (float)Dx, fDy = (float)Dy, fDz = (float)Dz, d2 = (float)len2;
-            const float rs = rsqrtf(d2);
-            const float lx = fDx * rs, ly = fDy * rs, lz = fDz * rs;
+            float lx, ly, lz, rs;
+            if (MODE & MODE_BOUNDED) {   // (float)D * rsqrtf((float)|D|^2): the cull's FP32 direction is exactly that
+                lx = r.fdx; ly = r.fdy; lz = r.fdz; rs = rsf;
+            } else {
+                const double Dx = L.pos[0] - r.ox, Dy = L.pos[1] - r.oy, Dz = L.pos[2] - r.oz;
+                rs = rsqrtf((float)dot3(Dx, Dy, Dz, Dx, Dy, Dz));
+                lx = (float)Dx * rs; ly = (float)Dy * rs; lz = (float)Dz * rs;
+            }
             const float inv_d2 = rs * rs;
             const float cosTheta = dot3f(lx, ly, lz, Nx, Ny, Nz);
             const float br = L.color[0] * inv_d2, bg = L.color[1] * inv_d2, bb = L.color[2] * inv_d2;
@@ -1228,17 +1241,18 @@ __device__ __forceinline__ Col trace_warp(const FrameParams& fp, const Ray& cam_
                 lightContrib.g = fmaf(bg, cosTheta, lightContrib.g);
                 lightContrib.b = fmaf(bb, cosTheta, lightContrib.b);
             }
-            if (phong) {
+            const DevShader& sh = shader_at<BIG>(shi);
+            if (sh.type == C2RT_SHADER_PHONG) {
                 float pw;
-                if (exponent <= 2048.0) {
+                if (sh.exponent <= 2048.0) {
                     // reflect(-lightDir, N) . (-ray.dir)  (imported_types.d:62-67, shader.d:235-239)
                     const float k = 2.f * cosTheta;
                     const float rx = fmaf(k, Nx, -lx), ry = fmaf(k, Ny, -ly), rz = fmaf(k, Nz, -lz);
-                    const float cosGamma = -dot3f(rx, ry, rz, vx, vy, vz);
-                    pw = cosGamma > 0 ? powf(cosGamma, (float)exponent) : 0.f;
+                    const float cosGamma = -dot3f(rx, ry, rz, (float)s_view[0][threadIdx.x], (float)s_view[1][threadIdx.x], (float)s_view[2][threadIdx.x]);
+                    pw = cosGamma > 0 ? powf(cosGamma, (float)sh.exponent) : 0.f;
                 } else {
                     // very sharp lobes amplify FP32 rounding of cosGamma by `exponent`: keep FP64 here
-                    double ldx = Dx, ldy = Dy, ldz = Dz;
+                    double ldx = L.pos[0] - r.ox, ldy = L.pos[1] - r.oy, ldz = L.pos[2] - r.oz;
                     normalize3(ldx, ldy, ldz);
                     double nx = Nx, ny = Ny, nz = Nz;
                     normalize3(nx, ny, nz);
@@ -1246,9 +1260,9 @@ __device__ __forceinline__ Col trace_warp(const FrameParams& fp, const Ray& cam_
                     double rx = k * nx - ldx, ry = k * ny - ldy, rz = k * nz - ldz;
                     normalize3(rx, ry, rz);
                     double cg = -dot3(rx, ry, rz, s_view[0][threadIdx.x], s_view[1][threadIdx.x], s_view[2][threadIdx.x]);
-                    pw = cg > 0 ? (float)pow(cg, exponent) : 0.f;
+                    pw = cg > 0 ? (float)pow(cg, sh.exponent) : 0.f;
                 }
-                const float w = pw * strength;
+                const float w = pw * sh.strength;
                 specular.r = fmaf(br, w, specular.r);
                 specular.g = fmaf(bg, w, specular.g);
                 specular.b = fmaf(bb, w, specular.b);
@@ -1262,11 +1276,10 @@ __device__ __forceinline__ Col trace_warp(const FrameParams& fp, const Ray& cam_
         found = false;
         ray_ready = false;
         n_shadow += hit;
-        Dx = L.pos[0] - r.ox; Dy = L.pos[1] - r.oy; Dz = L.pos[2] - r.oz;
-        len2 = dot3(Dx, Dy, Dz, Dx, Dy, Dz);
         if (MODE & MODE_BOUNDED) {   // FP32 shadow of the ray for the conservative cull
-            const float l2f = (float)len2;
-            const float rsf = rsqrtf(l2f);
+            const double Dx = L.pos[0] - r.ox, Dy = L.pos[1] - r.oy, Dz = L.pos[2] - r.oz;
+            const float l2f = (float)dot3(Dx, Dy, Dz, Dx, Dy, Dz);
+            rsf = rsqrtf(l2f);
             r.fox = cvt_keep(r.ox); r.foy = cvt_keep(r.oy); r.foz = cvt_keep(r.oz);
             r.fdx = cvt_keep(Dx) * rsf; r.fdy = cvt_keep(Dy) * rsf; r.fdz = cvt_keep(Dz) * rsf;
             r.olen = sqrtf(dot3f(r.fox, r.foy, r.foz, r.fox, r.foy, r.foz));
@@ -1274,9 +1287,9 @@ __device__ __forceinline__ Col trace_warp(const FrameParams& fp, const Ray& cam_
         }
         shadow_mask<MODE>(smask, fp.bounds, want, r, L, walk);   // walk = false: no lane of this warp has a shadow ray for this light
     }
-    if (!hit) return diffuse;   // miss: the environment's colour (environment.d:7-10: black), computed in the camera phase
-    return mkcol(fmaf(diffuse.r, lightContrib.r, specular.r), fmaf(diffuse.g, lightContrib.g, specular.g),
-                 fmaf(diffuse.b, lightContrib.b, specular.b));
+    const float dr = s_diffuse[0][threadIdx.x], dg = s_diffuse[1][threadIdx.x], db = s_diffuse[2][threadIdx.x];
+    if (!hit) return mkcol(dr, dg, db);   // miss: the environment's colour (environment.d:7-10: black), computed in the camera phase
+    return mkcol(fmaf(dr, lightContrib.r, specular.r), fmaf(dg, lightContrib.g, specular.g), fmaf(db, lightContrib.b, specular.b));
 }
 
 // renderer.d:325-376 for the plane-only scene classes (per lane; only lanes with a ray call it)
@@ -1424,6 +1437,7 @@ __device__ __forceinline__ void camera_mask(NodeMask& m, const FrameParams& fp, 
 template <int MODE, int MIN_BLOCKS>
 __global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS) render_frame_kernel(const FrameParams fp) {
     __shared__ __align__(16) float s_rgb[TILE_H][TILE_W * 3];
+    __shared__ double s_base[plane_only(MODE) ? 1 : 3][plane_only(MODE) ? 1 : BLOCK_THREADS];
 
     // tile -> rows: local tile l of this rank belongs to its band (l / tiles_per_band), which is
     // global band (band_local * n_ranks + rank)
@@ -1475,8 +1489,14 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS) render_frame_kernel
         const double xd = (double)sx, yd = (double)sy;
         double bx, by, bz;
         screen_dir(fp, xd, yd, bx, by, bz);
+        if constexpr (!plane_only(MODE)) {   // the pixel's base direction waits in shared memory while a tap is traced (register diet)
+            s_base[0][threadIdx.x] = bx; s_base[1][threadIdx.x] = by; s_base[2][threadIdx.x] = bz;
+        }
 #pragma unroll 1
         for (int s = 0; s < taps; s++) {
+            if constexpr (!plane_only(MODE)) {
+                bx = ((volatile double*)s_base[0])[threadIdx.x]; by = ((volatile double*)s_base[1])[threadIdx.x]; bz = ((volatile double*)s_base[2])[threadIdx.x];
+            }
             Col t = render_sample<MODE>(fp, bx, by, bz, xd, yd, sx, sy, s, jw, jh, active, n_primary, n_shadow, nullptr, cam);
             c.r += t.r; c.g += t.g; c.b += t.b;
         }
