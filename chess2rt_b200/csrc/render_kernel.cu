@@ -89,6 +89,12 @@ __device__ __forceinline__ double dot3(double ax, double ay, double az, double b
 __device__ __forceinline__ float dot3f(float ax, float ay, float az, float bx, float by, float bz) {
     return fmaf(az, bz, fmaf(ay, by, ax * bx));
 }
+// sqrt(a) from the SFU, nudged up: an upper bound (to ~1e-6) for quantities that only feed conservative margins / radii
+__device__ __forceinline__ float sqrt_up(float a) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r * 1.000002f;
+}
 // 1/a and 1/sqrt(a) in FP64: hardware seed (MUFU.RCP64H / MUFU.RSQ64H, ~20 bits) + two Newton steps
 __device__ __forceinline__ double rcp64(double a) {
     double y;
@@ -720,43 +726,46 @@ __device__ __forceinline__ bool node_exact(int ni, const DevNode& nd, const Ray&
 // geometry.d:43,111,214, are untouched).  The walk is warp-uniform — same node for all lanes, per-lane work predicated —
 // and a shadow walk is left through __all_sync as soon as every lane that needs an answer has found an occluder
 // (the reference's early return at the first occluder, scene.d:73-75, taken by the whole warp at once).
-static_assert(C2RT_MAX_NODES <= 64, "a node mask of the constant-memory scene block is one 64-bit word");
+static_assert(C2RT_MAX_NODES <= 64, "a node mask of the constant-memory scene block is two 32-bit words");
 constexpr unsigned FULL_WARP = 0xffffffffu;
 constexpr int WARPS_PER_CTA = BLOCK_THREADS / 32;
-constexpr int BIG_MASK_WORDS = C2RT_MAX_NODES_GLOBAL / 64;
-typedef unsigned long long NodeWord;
-// A warp's node mask.  Constant-block scenes (<= 64 nodes): one 64-bit word in a (uniform) register.  MODE_BIG scenes: one
-// word per 64 nodes in shared memory, a row per warp (`more`), word 0 mirrored in `w0`.
+constexpr int BIG_MASK_WORDS = C2RT_MAX_NODES_GLOBAL / 32;
+typedef uint32_t NodeWord;
+// A warp's node mask: one bit per node, 32 nodes per word (one ballot each).  Constant-block scenes (<= 64 nodes): two words in
+// (uniform) registers.  MODE_BIG scenes: the words live in shared memory, a row per warp (`more`).
 struct NodeMask {
-    NodeWord w0;
+    NodeWord w0, w1;
     NodeWord* more;
 };
 __device__ __forceinline__ NodeWord all_nodes_word(int first) {
     const int left = c_scene.n_nodes - first;
-    return left >= 64 ? ~0ull : left > 0 ? (1ull << left) - 1ull : 0ull;
+    return left >= 32 ? 0xffffffffu : left > 0 ? (1u << left) - 1u : 0u;
 }
+__device__ __forceinline__ int mask_words() { return (c_scene.n_nodes + 31) >> 5; }
 template <bool BIG>
-__device__ __forceinline__ int mask_words() { return BIG ? (c_scene.n_nodes + 63) >> 6 : 1; }
-// lane l answers for nodes 64 k + l and 64 k + 32 + l; two ballots make word k (the second only when needed)
+__device__ __forceinline__ NodeWord mask_word(const NodeMask& m, int k) { return BIG ? m.more[k] : (k ? m.w1 : m.w0); }
+// lane l answers for node 32 k + l; one ballot makes word k
 template <bool BIG, class F>
 __device__ __forceinline__ void ballot_nodes(NodeMask& m, F&& reaches) {
     const int lane = (int)(threadIdx.x & 31u), n = c_scene.n_nodes;
+    m.w0 = 0; m.w1 = 0;
 #pragma unroll 1
-    for (int k = 0; k < mask_words<BIG>(); k++) {
-        const int i0 = 64 * k + lane;
-        NodeWord w = __ballot_sync(FULL_WARP, i0 < n && reaches(i0));
-        if (n > 64 * k + 32) w |= (NodeWord)__ballot_sync(FULL_WARP, i0 + 32 < n && reaches(i0 + 32)) << 32;
+    for (int k = 0; k < mask_words(); k++) {
+        const int i = 32 * k + lane;
+        const NodeWord w = __ballot_sync(FULL_WARP, i < n && reaches(i));
         if (BIG) { if (lane == 0) m.more[k] = w; }
-        if (k == 0) m.w0 = w;
+        else if (k == 0) m.w0 = w;
+        else m.w1 = w;
     }
     if (BIG) __syncwarp();
 }
 template <bool BIG>
 __device__ __forceinline__ void all_nodes_mask(NodeMask& m) {
     m.w0 = all_nodes_word(0);
+    m.w1 = all_nodes_word(32);
     if (BIG) {
         const int lane = (int)(threadIdx.x & 31u);
-        for (int k = lane; k < mask_words<BIG>(); k += 32) m.more[k] = all_nodes_word(64 * k);
+        for (int k = lane; k < mask_words(); k += 32) m.more[k] = all_nodes_word(32 * k);
         __syncwarp();
     }
 }
@@ -797,7 +806,7 @@ __device__ __forceinline__ void shadow_mask(NodeMask& m, const float4* __restric
     if (!any) return;   // no lane of this warp needs a shadow ray (warp-uniform); the caller skips the walk
     const float cx = 0.5f * (mnx + mxx), cy = 0.5f * (mny + mxy), cz = 0.5f * (mnz + mxz);
     const float hx = mxx - cx, hy = mxy - cy, hz = mxz - cz;
-    const float rho = sqrtf(dot3f(hx, hy, hz, hx, hy, hz));
+    const float rho = sqrt_up(dot3f(hx, hy, hz, hx, hy, hz));
     const float dx = L.posf[0] - cx, dy = L.posf[1] - cy, dz = L.posf[2] - cz;   // capsule axis: box centre -> light
     const float dd = dot3f(dx, dy, dz, dx, dy, dz);
     const float inv_dd = dd > 0.f ? __fdividef(1.0f, dd) : 0.f;   // (approximate: t only picks the point of the axis; the margin covers it)
@@ -1136,7 +1145,7 @@ __device__ __forceinline__ Col trace_warp(const FrameParams& fp, const Ray& cam_
     __shared__ double s_view[3][BLOCK_THREADS];   // FP64 camera-ray direction, parked for Phong lobes sharper than 2048
     __shared__ NodeWord s_shadow_words[BIG ? WARPS_PER_CTA : 1][BIG ? BIG_MASK_WORDS : 1];   // MODE_BIG: this warp's shadow mask
     NodeMask smask;
-    smask.w0 = 0;
+    smask.w0 = 0; smask.w1 = 0;
     smask.more = BIG ? s_shadow_words[threadIdx.x >> 5] : nullptr;
     // Register diet (the walk below holds the CSG test's working set; whatever is only needed before or after it is parked in
     // shared memory or recomputed): the FP64 view direction and the surface colour live in s_view / s_diffuse, the shader is
@@ -1156,33 +1165,32 @@ __device__ __forceinline__ Col trace_warp(const FrameParams& fp, const Ray& cam_
     float Nx = 0.f, Ny = 0.f, Nz = 0.f;
     Col specular = mkcol(0.f, 0.f, 0.f);
     Col lightContrib = mkcol(fp.ambient[0], fp.ambient[1], fp.ambient[2]);
-    s_diffuse[0][threadIdx.x] = 0.f; s_diffuse[1][threadIdx.x] = 0.f; s_diffuse[2][threadIdx.x] = 0.f;
-    const int nl = c_scene.n_lights;
+    double sy = r.dy;        // the ray's vertical direction up to a positive factor (planes are first settled by its sign)
+    const int nl = c_scene.n_lit;   // lights with intensity != 0 (shader.d:88,219), listed at scene create
     int li = -1;
     for (;;) {
         const bool anyhit = li >= 0;
         // ---- the node walk: warp-uniform over the mask, in scene order; per-lane work predicated
         const NodeMask& mask = anyhit ? smask : cam_mask;
 #pragma unroll 1
-        for (int wd = 0; walk && wd < mask_words<BIG>(); wd++) {
-        NodeWord bits = BIG ? mask.more[wd] : mask.w0;
+        for (int wd = 0; walk && wd < mask_words(); wd++) {
+        NodeWord bits = mask_word<BIG>(mask, wd);
 #pragma unroll 1
         for (; bits; bits &= bits - 1) {
-            const int i = 64 * wd + __ffsll((long long)bits) - 1;
+            const int i = 32 * wd + __ffs((int)bits) - 1;
             const DevNode& nd = node_at<BIG>(i);
             if (want && !found) {
                 bool skip = false;
                 if (nd.kind == KIND_PLANE_W) {
                     // implied by geometry.d:35-36 (dir.y has the sign of D.y): the common "above the floor, looking / lit from above" case
                     const double y = nd.wp[0];
-                    const double sy = anyhit ? c_scene.lights[li].pos[1] - r.oy : r.dy;
                     skip = (r.oy > y && sy >= 0) || (r.oy < y && sy <= 0);
                 } else if ((MODE & MODE_BOUNDED) && !(nd.flags & NODE_UNBOUNDED)) {
                     skip = cull(nd, r, tmaxf);
                 }
                 if (!skip) {
                     if (!ray_ready) {   // the FP64 normalisation of a shadow ray (scene.d:66-71), only once a node survives
-                        const DevLight& L = c_scene.lights[li];
+                        const DevLight& L = c_scene.lights[c_scene.lit[li]];
                         const double Dx = L.pos[0] - r.ox, Dy = L.pos[1] - r.oy, Dz = L.pos[2] - r.oz;
                         const double len2 = dot3(Dx, Dy, Dz, Dx, Dy, Dz);
                         const double inv = rsqrt64(len2);
@@ -1224,7 +1232,7 @@ __device__ __forceinline__ Col trace_warp(const FrameParams& fp, const Ray& cam_
         } else if (want && !found) {
             // ---- light li is visible from this lane's hit: lighting in FP32 (the reference narrows every factor to float
             // before it touches a Color: SURVEY.md App. C.1)
-            const DevLight& L = c_scene.lights[li];
+            const DevLight& L = c_scene.lights[c_scene.lit[li]];
             float lx, ly, lz, rs;
             if (MODE & MODE_BOUNDED) {   // (float)D * rsqrtf((float)|D|^2): the cull's FP32 direction is exactly that
                 lx = r.fdx; ly = r.fdy; lz = r.fdz; rs = rsf;
@@ -1269,20 +1277,20 @@ __device__ __forceinline__ Col trace_warp(const FrameParams& fp, const Ray& cam_
             }
         }
         // ---- next lit light (one sample per PointLight, light.d:56-59: avg / numSamples is a division by 1.0f)
-        do li++; while (li < nl && !c_scene.lights[li].lit);
-        if (li >= nl) break;
-        const DevLight& L = c_scene.lights[li];
+        if (++li >= nl) break;
+        const DevLight& L = c_scene.lights[c_scene.lit[li]];
         want = hit;
         found = false;
         ray_ready = false;
         n_shadow += hit;
+        sy = L.pos[1] - r.oy;
         if (MODE & MODE_BOUNDED) {   // FP32 shadow of the ray for the conservative cull
-            const double Dx = L.pos[0] - r.ox, Dy = L.pos[1] - r.oy, Dz = L.pos[2] - r.oz;
-            const float l2f = (float)dot3(Dx, Dy, Dz, Dx, Dy, Dz);
+            const double Dx = L.pos[0] - r.ox, Dz = L.pos[2] - r.oz;
+            const float l2f = (float)dot3(Dx, sy, Dz, Dx, sy, Dz);
             rsf = rsqrtf(l2f);
             r.fox = cvt_keep(r.ox); r.foy = cvt_keep(r.oy); r.foz = cvt_keep(r.oz);
-            r.fdx = cvt_keep(Dx) * rsf; r.fdy = cvt_keep(Dy) * rsf; r.fdz = cvt_keep(Dz) * rsf;
-            r.olen = sqrtf(dot3f(r.fox, r.foy, r.foz, r.fox, r.foy, r.foz));
+            r.fdx = cvt_keep(Dx) * rsf; r.fdy = cvt_keep(sy) * rsf; r.fdz = cvt_keep(Dz) * rsf;
+            r.olen = sqrt_up(dot3f(r.fox, r.foy, r.foz, r.fox, r.foy, r.foz));   // (only feeds the cull's rounding margins)
             tmaxf = l2f * rsf * 1.000001f;
         }
         shadow_mask<MODE>(smask, fp.bounds, want, r, L, walk);   // walk = false: no lane of this warp has a shadow ray for this light
@@ -1461,7 +1469,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS) render_frame_kernel
     // nodes this warp's camera rays can reach (lane l tests nodes l, l + 32; warp ballot)
     __shared__ NodeWord s_cam_words[is_big(MODE) ? WARPS_PER_CTA : 1][is_big(MODE) ? BIG_MASK_WORDS : 1];   // MODE_BIG: a row per warp
     NodeMask cam;
-    cam.w0 = 0;
+    cam.w0 = 0; cam.w1 = 0;
     cam.more = is_big(MODE) ? s_cam_words[warp] : nullptr;
     if constexpr (!plane_only(MODE)) camera_mask<MODE>(cam, fp, x0 + (warp & 1) * PATCH_W, y0 + (warp >> 1) * PATCH_H);
 
@@ -1581,7 +1589,7 @@ __global__ void render_pixel_kernel(const FrameParams fp, int x, int y, PixelOut
     constexpr int M = MODE_BOUNDED | MODE_GENERIC | MODE_NESTED | MODE_SAMPLING | (BIG ? MODE_BIG : 0);
     __shared__ NodeWord s_cam_words[BIG ? BIG_MASK_WORDS : 1];
     NodeMask cam;
-    cam.w0 = 0;
+    cam.w0 = 0; cam.w1 = 0;
     cam.more = BIG ? s_cam_words : nullptr;
     all_nodes_mask<BIG>(cam);
     Col c = render_sample<M>(fp, bx, by, bz, (double)x, (double)y, (uint32_t)x, (uint32_t)y, 0, 1.0, 1.0, live, a, b, &h, cam);

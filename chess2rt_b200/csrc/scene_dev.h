@@ -69,7 +69,8 @@ struct DevLight {
 };
 
 struct DevScene {
-    int n_nodes, n_geoms, n_shaders, n_textures, n_lights, env_type, pad1, pad2;
+    int n_nodes, n_geoms, n_shaders, n_textures, n_lights, env_type, n_lit, pad2;
+    int lit[C2RT_MAX_LIGHTS];   // indices of the lights with intensity != 0, in scene order (the others shoot no shadow ray: shader.d:88,219)
     // MODE_BIG (a scene beyond C2RT_MAX_NODES / GEOMS / SHADERS / TEXTURES): the record arrays live in global memory instead
     const DevNode* g_nodes;
     const DevGeom* g_geoms;

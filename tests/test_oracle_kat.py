@@ -355,18 +355,18 @@ def test_shadow_capsule_keeps_every_node_a_shadow_ray_can_touch():
         mn, mx = o32.min(axis=0), o32.max(axis=0)
         c = f32(0.5) * (mn + mx)
         hdiag = mx - c
-        rho = np.sqrt(np.dot(hdiag, hdiag), dtype=f32)
+        rho = np.sqrt(np.dot(hdiag, hdiag), dtype=f32) * f32(1.000002)   # sqrt_up
         d = light.astype(f32) - c
         dd = np.dot(d, d)
         inv_dd = f32(1.0) / dd if dd > 0 else f32(0)
-        mag = np.sqrt(np.dot(c, c), dtype=f32) + np.sqrt(dd, dtype=f32)
+        mag = np.abs(c).sum(dtype=f32) + np.abs(d).sum(dtype=f32)          # L1 norms: cheaper, larger margins
         for k in range(40):
             b = centres[k].astype(f32)
             r = f32(radii[k])
             a = b - c
             t = np.clip(np.dot(a, d) * inv_dd, f32(0), f32(1))
             q = a - t * d
-            reachr = r + rho + f32(8e-6) * (mag + np.sqrt(np.dot(b, b), dtype=f32) + rho)
+            reachr = r + rho + f32(8e-6) * (mag + np.abs(b).sum(dtype=f32) + rho)
             keep = not (np.dot(q, q) > reachr * reachr)
             # exact side, FP64: does any segment come within the sphere?
             touches = False
