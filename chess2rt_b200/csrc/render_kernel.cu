@@ -494,6 +494,9 @@ __device__ __forceinline__ bool isect_csg(int gi, double ox, double oy, double o
                                           double& px, double& py, double& pz, int& face, int& leaf) {
     const DevGeom& g = geom_at<BIG>(gi);
     const Crossings L = cross_prim(geom_at<BIG>(g.left), ox, oy, oz, dx, dy, dz);
+    // inter / diff need the ray inside the LEFT child at the reported crossing (geometry.d:371-374,399-402); with no left
+    // crossing inL stays false along the whole walk (L.n & 1 == 0), so nothing is reported: skip the right child
+    if (g.type != C2RT_GEOM_CSG_UNION && L.n == 0) return false;
     const Crossings R = cross_prim(geom_at<BIG>(g.right), ox, oy, oz, dx, dy, dz);
     const int n = L.n + R.n;
     if (n == 0) return false;
@@ -1457,8 +1460,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS) render_frame_kernel
     const uint32_t x0 = blockIdx.x * TILE_W;
     // 4 warps, each an 8x4 pixel patch
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t lx = (warp & 1) * 8 + (lane & 7);
-    const uint32_t ly = (warp >> 1) * 4 + (lane >> 3);
+    constexpr uint32_t WARPS_X = TILE_W / 8;
+    const uint32_t lx = (warp % WARPS_X) * 8 + (lane & 7);
+    const uint32_t ly = (warp / WARPS_X) * 4 + (lane >> 3);
     const uint32_t x = x0 + lx, y = y0 + ly;
     const bool active = x < fp.W && y < fp.H;
     // c2rt_cancel (renderer.d:93-97,129,147,180: a stop request ends the frame early): a CTA that starts after the flag was
@@ -1471,7 +1475,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS) render_frame_kernel
     NodeMask cam;
     cam.w0 = 0; cam.w1 = 0;
     cam.more = is_big(MODE) ? s_cam_words[warp] : nullptr;
-    if constexpr (!plane_only(MODE)) camera_mask<MODE>(cam, fp, x0 + (warp & 1) * PATCH_W, y0 + (warp >> 1) * PATCH_H);
+    if constexpr (!plane_only(MODE)) camera_mask<MODE>(cam, fp, x0 + (warp % WARPS_X) * PATCH_W, y0 + (warp / WARPS_X) * PATCH_H);
 
     unsigned n_primary = 0, n_shadow = 0;
     Col c = mkcol(0.f, 0.f, 0.f);

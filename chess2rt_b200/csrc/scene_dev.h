@@ -156,8 +156,17 @@ constexpr bool camera_masked(int mode) {
 #endif
 }
 
-constexpr int TILE_W = 16;
-constexpr int TILE_H = 8;
+// CTA tile: 4 warps of 8x4 pixels each.  16x8 (2x2 warps) by default; -DC2RT_TILE_W=32 -DC2RT_TILE_H=4 lays the warps side by
+// side (384 contiguous bytes per tile row instead of 192: tuning aid for the NVLink band stores, profiles/r2_tile_shape.log)
+#ifndef C2RT_TILE_W
+#define C2RT_TILE_W 16
+#endif
+#ifndef C2RT_TILE_H
+#define C2RT_TILE_H 8
+#endif
+constexpr int TILE_W = C2RT_TILE_W;
+constexpr int TILE_H = C2RT_TILE_H;
+static_assert(TILE_W % 8 == 0 && TILE_H % 4 == 0 && TILE_W * TILE_H == 128, "a CTA tile is four 8x4 warp patches");
 constexpr int BLOCK_THREADS = TILE_W * TILE_H;
 
 }  // namespace c2rt

@@ -389,3 +389,94 @@ def test_json_and_sdl_forms_of_every_object_type_agree(tmp_path):
     ca, _ = ha.frame_blocks()
     cb, _ = hb.frame_blocks()
     assert bytes(ca) == bytes(cb)
+
+
+# ---------------------------------------------------------------- the loader against an independent reader
+SDL_FILES = ["scenes/lecture4.sdl", "scenes/lecture4-proc-texture.sdl", "scenes/lecture5.sdl", "scenes/zaphod.sdl",
+             "scenes/chessboard.sdl", "tests/scenes/quirks.sdl", "tests/scenes/nested.sdl", "tests/scenes/sky.sdl"]
+GEOM_TYPES = {"Plane": 0, "Sphere": 1, "Cube": 2, "CsgUnion": 3, "CsgInter": 4, "CsgDiff": 5}
+
+
+def _vec(v):
+    return list(v) if isinstance(v, (list, tuple)) else [v]
+
+
+@pytest.mark.parametrize("path", SDL_FILES)
+def test_loader_agrees_with_an_independent_sdl_reader(path):
+    """host/scene_text.hpp parses the scene text for the host loader AND for the oracle, so a parse bug would be common-mode.
+    tests/sdl_reader.py is a second, independent reader (Python, no shared code): every value it finds in the file must be the
+    value the loader + flattener hand to the backend (indices for names, offsets / diagonal matrices for translate / scale)."""
+    import sdl_reader as R
+    scene = R.parse(open(os.path.join(ROOT, path)).read())[0]
+    assert scene[0] == "Scene"
+    host = c2.HostScene(os.path.join(ROOT, path))
+    d = host.desc().contents
+    cam, st = host.frame_blocks()
+    sect = lambda n: (R.child(scene, n) or (n, [], []))[2]
+    geoms, shaders, textures, lights, nodes = sect("Geometries"), sect("Shaders"), sect("Textures"), sect("Lights"), sect("Nodes")
+    assert (d.n_geoms, d.n_shaders, d.n_textures, d.n_lights, d.n_nodes) == (len(geoms), len(shaders), len(textures), len(lights), len(nodes))
+    gname = {R.obj_name(g): i for i, g in enumerate(geoms)}
+    sname = {R.obj_name(s): i for i, s in enumerate(shaders)}
+    tname = {R.obj_name(t): i for i, t in enumerate(textures)}
+    for i, g in enumerate(geoms):
+        assert d.geom_type[i] == GEOM_TYPES[g[0]], (path, i)
+        p = [d.geom_params[4 * i + k] for k in range(4)]
+        if g[0] == "Plane" and R.prop(g, "y") is not None:
+            assert p[0] == float(R.prop(g, "y"))
+        if g[0] in ("Sphere", "Cube"):
+            if R.prop(g, "center") is not None:
+                assert p[:3] == [float(x) for x in R.prop(g, "center")]
+            key = "R" if g[0] == "Sphere" else "side"
+            if R.prop(g, key) is not None:
+                assert p[3] == float(R.prop(g, key))
+        if g[0].startswith("Csg"):
+            assert (d.geom_left[i], d.geom_right[i]) == (gname[R.prop(g, "left")], gname[R.prop(g, "right")])
+    for i, s in enumerate(shaders):
+        assert d.shader_type[i] == {"Lambert": 0, "Phong": 1}[s[0]]
+        if R.prop(s, "color") is not None:
+            np.testing.assert_array_equal([d.shader_color[3 * i + k] for k in range(3)], np.float32(R.prop(s, "color")))
+        assert d.shader_texture[i] == (tname[R.prop(s, "texture")] if R.prop(s, "texture") is not None else -1)
+        if s[0] == "Phong" and R.prop(s, "exponent") is not None:
+            assert d.shader_exponent[i] == float(R.prop(s, "exponent"))
+    for i, l in enumerate(lights):
+        if R.prop(l, "pos") is not None:
+            assert [d.light_pos[3 * i + k] for k in range(3)] == [float(x) for x in R.prop(l, "pos")]
+        if R.prop(l, "power") is not None:
+            assert d.light_power[i] == np.float32(R.prop(l, "power"))
+        if R.prop(l, "color") is not None:
+            np.testing.assert_array_equal([d.light_color[3 * i + k] for k in range(3)], np.float32(R.prop(l, "color")))
+    for i, n in enumerate(nodes):
+        assert d.node_geom[i] == gname[R.prop(n, "geometry")] and d.node_shader[i] == sname[R.prop(n, "shader")]
+        off = [float(x) for x in R.prop(n, "translate", [0, 0, 0])]
+        assert [d.node_offset[3 * i + k] for k in range(3)] == off
+        diag = np.ones(3)
+        for key in ("scale", "rotate"):   # node.d:89-90: `rotate` is applied as a second scale
+            if R.prop(n, key) is not None:
+                diag = diag * np.array([float(x) for x in R.prop(n, key)])
+        M = np.array([d.node_transform[9 * i + k] for k in range(9)]).reshape(3, 3)
+        np.testing.assert_allclose(M, np.diag(diag), rtol=1e-15)
+    c = R.child(scene, "Camera")
+    if c is not None and R.prop(c, "pos") is not None:
+        assert list(cam.pos) == [float(x) for x in R.prop(c, "pos")]
+    if c is not None and R.prop(c, "dof") is not None:
+        assert bool(cam.dof) == R.prop(c, "dof")
+    gs = R.child(scene, "GlobalSettings")
+    if gs is not None:
+        assert (st.frame_width, st.frame_height) == (R.prop(gs, "frameWidth", 640), R.prop(gs, "frameHeight", 480))
+        if R.prop(gs, "ambientLightColor") is not None:
+            np.testing.assert_array_equal(list(st.ambient_light), np.float32(R.prop(gs, "ambientLightColor")))
+        if R.prop(gs, "AAEnabled") is not None:
+            assert bool(st.aa_enabled) == R.prop(gs, "AAEnabled")
+
+
+def test_json_loader_agrees_with_python_json():
+    import json as pyjson
+    j = pyjson.load(open(os.path.join(SC, "lecture4.json")))
+    host = c2.HostScene(os.path.join(SC, "lecture4.json"))
+    d = host.desc().contents
+    cam, st = host.frame_blocks()
+    assert list(cam.pos) == [float(x) for x in j["Camera"]["pos"]]
+    assert (st.frame_width, st.frame_height, bool(st.aa_enabled)) == (j["GlobalSettings"]["frameWidth"], j["GlobalSettings"]["frameHeight"], j["GlobalSettings"]["AAEnabled"])
+    assert d.n_lights == len(j["Lights"]) and d.n_nodes == len(j["Nodes"]) and d.n_geoms == len(j["Geometries"])
+    L = j["Lights"][0]
+    assert [d.light_pos[k] for k in range(3)] == [float(x) for x in L["pos"]] and d.light_power[0] == np.float32(L["power"])
