@@ -875,21 +875,33 @@ __device__ __forceinline__ float sin_rev(double u, double f) {
     return __sinf(x * 6.2831853f);
 }
 
+// MODE_SOLO kernels compiled for a bitmap texture stage its 4 KB palette (if it has one) in shared memory once per CTA: the
+// palette read depends on the index-quad load, and a shared-memory read is the shorter second hop (C3: the zaphod page)
+__host__ __device__ constexpr bool solo_bitmap(int mode) {
+    return (mode & MODE_SOLO) && ((mode & MODE_TEX_MASK) >> MODE_TEX_SHIFT) == 1 + C2RT_TEX_BITMAP;
+}
+__shared__ float4 s_solo_palette[256];
+
 // Bitmap.getFilteredPixel (bitmap.d:48-63): bilinear fetch at float texel coordinates (x, y), wrapping at the edges;
 // out-of-range coordinates (incl. NaN) give NamedColors.red
-__device__ __forceinline__ Col bitmap_fetch(const DevTex& t, float x, float y) {
+// `spal`: the texture's palette staged in shared memory (MODE_SOLO bitmap kernels, render_frame_kernel), or nullptr
+__device__ __forceinline__ Col bitmap_fetch(const DevTex& t, float x, float y, const float4* spal = nullptr) {
     if (!(x >= 0.f) || !(y >= 0.f) || !(x < (float)t.w) || !(y < (float)t.h))   // (t.w, t.h are integers: x < w <=> (size_t)x < w)
         return mkcol(1.f, 0.f, 0.f);
     int tx = (int)x, ty = (int)y;
     int txn = tx + 1 == t.w ? 0 : tx + 1, tyn = ty + 1 == t.h ? 0 : ty + 1;
     float p = x - (float)tx, q = y - (float)ty;
     float4 a, b, c, d;
-    if (t.quads) {   // palette form (scene_dev.h DevTex): one 4-byte load, then the 4 KB palette (L1-resident)
+    if (t.quads) {   // palette form (scene_dev.h DevTex): one 4-byte load, then the 4 KB palette (shared memory or L1)
         const uint32_t k = __ldg(&t.quads[(size_t)ty * t.w + tx]);
-        a = __ldg(&t.palette[k & 255u]);
-        b = __ldg(&t.palette[(k >> 8) & 255u]);
-        c = __ldg(&t.palette[(k >> 16) & 255u]);
-        d = __ldg(&t.palette[k >> 24]);
+        if (spal) {
+            a = spal[k & 255u]; b = spal[(k >> 8) & 255u]; c = spal[(k >> 16) & 255u]; d = spal[k >> 24];
+        } else {
+            a = __ldg(&t.palette[k & 255u]);
+            b = __ldg(&t.palette[(k >> 8) & 255u]);
+            c = __ldg(&t.palette[(k >> 16) & 255u]);
+            d = __ldg(&t.palette[k >> 24]);
+        }
     } else {
         a = __ldg(&t.texels[(size_t)ty * t.w + tx]);
         b = __ldg(&t.texels[(size_t)ty * t.w + txn]);
@@ -931,7 +943,7 @@ __device__ __forceinline__ Col sample_texture(int ti, double u, double v) {
     v *= t.d[0];
     u = u - floor(u);
     v = v - floor(v);
-    return bitmap_fetch(t, (float)u * (float)t.w, (float)v * (float)t.h);
+    return bitmap_fetch(t, (float)u * (float)t.w, (float)v * (float)t.h, solo_bitmap(MODE) ? s_solo_palette : nullptr);
 }
 
 // environment.d:7-10 for a miss (renderer.d:366-368): black, or — EXTENSION, no counterpart in the reference (c2rt.h
@@ -1465,6 +1477,14 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS) render_frame_kernel
     const uint32_t ly = (warp / WARPS_X) * 4 + (lane >> 3);
     const uint32_t x = x0 + lx, y = y0 + ly;
     const bool active = x < fp.W && y < fp.H;
+    if constexpr (solo_bitmap(MODE)) {   // stage the palette (bitmap_fetch); textures without one never read it
+        const DevTex& t = c_scene.textures[0];
+        if (t.quads) {
+            s_solo_palette[threadIdx.x] = __ldg(&t.palette[threadIdx.x]);
+            s_solo_palette[threadIdx.x + BLOCK_THREADS] = __ldg(&t.palette[threadIdx.x + BLOCK_THREADS]);
+        }
+        __syncthreads();
+    }
     // c2rt_cancel (renderer.d:93-97,129,147,180: a stop request ends the frame early): a CTA that starts after the flag was
     // raised leaves its tile as it is.  The load is issued here and consumed below, behind the mask / ray set-up.
     int cancelled = 0;
@@ -1680,6 +1700,9 @@ cudaError_t upload_scene(const DevScene& s, cudaStream_t st) {
 #ifndef C2RT_MINBLOCKS_SOLO
 #define C2RT_MINBLOCKS_SOLO 7
 #endif
+#ifndef C2RT_MINBLOCKS_NESTED
+#define C2RT_MINBLOCKS_NESTED 2
+#endif
 #ifndef C2RT_MINBLOCKS_SOLO_SAMPLING
 #define C2RT_MINBLOCKS_SOLO_SAMPLING 6
 #endif
@@ -1710,14 +1733,14 @@ cudaError_t launch_frame(const FrameParams& fp, int mode, uint32_t local_tile_ro
         }
     } else if (mode & MODE_BIG) {
         // scenes beyond the constant block (records in global memory, multi-word node masks): the general kernels only
-        if (sampling) render_frame_kernel<ALL | MODE_BIG | MODE_SAMPLING, 2><<<grid, BLOCK_THREADS, 0, st>>>(fp);
-        else if (mode & MODE_NESTED) render_frame_kernel<ALL | MODE_BIG, 2><<<grid, BLOCK_THREADS, 0, st>>>(fp);
+        if (sampling) render_frame_kernel<ALL | MODE_BIG | MODE_SAMPLING, C2RT_MINBLOCKS_NESTED><<<grid, BLOCK_THREADS, 0, st>>>(fp);
+        else if (mode & MODE_NESTED) render_frame_kernel<ALL | MODE_BIG, C2RT_MINBLOCKS_NESTED><<<grid, BLOCK_THREADS, 0, st>>>(fp);
         else render_frame_kernel<FULL | MODE_BIG, C2RT_MINBLOCKS_FULL><<<grid, BLOCK_THREADS, 0, st>>>(fp);
     } else if (sampling) {
         // DOF / stereo / prepass-only frames: two general kernels only (the per-sample loop dominates, the scene class matters less)
-        if (mode & MODE_NESTED) render_frame_kernel<ALL | MODE_SAMPLING, 2><<<grid, BLOCK_THREADS, 0, st>>>(fp);
+        if (mode & MODE_NESTED) render_frame_kernel<ALL | MODE_SAMPLING, C2RT_MINBLOCKS_NESTED><<<grid, BLOCK_THREADS, 0, st>>>(fp);
         else render_frame_kernel<FULL | MODE_SAMPLING, C2RT_MINBLOCKS_SAMPLING><<<grid, BLOCK_THREADS, 0, st>>>(fp);
-    } else if (mode & MODE_NESTED) render_frame_kernel<ALL, 2><<<grid, BLOCK_THREADS, 0, st>>>(fp);
+    } else if (mode & MODE_NESTED) render_frame_kernel<ALL, C2RT_MINBLOCKS_NESTED><<<grid, BLOCK_THREADS, 0, st>>>(fp);
     else if (mode & MODE_GENERIC) render_frame_kernel<FULL, C2RT_MINBLOCKS_FULL><<<grid, BLOCK_THREADS, 0, st>>>(fp);
     else if (mode & MODE_BOUNDED) render_frame_kernel<MODE_BOUNDED, C2RT_MINBLOCKS_BOUNDED><<<grid, BLOCK_THREADS, 0, st>>>(fp);
     else render_frame_kernel<0, C2RT_MINBLOCKS_SIMPLE><<<grid, BLOCK_THREADS, 0, st>>>(fp);

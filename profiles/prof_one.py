@@ -2,7 +2,7 @@
 nothing else launched), prints the mean kernel time, and gives ncu a clean launch list:
   ncu --set full --import-source on --clock-control none -k regex:render_frame --launch-skip 2 --launch-count 1 \
       -o gpurun_out/prof python profiles/prof_one.py c4 3
-usage: python profiles/prof_one.py <workload> [frames]"""
+usage: python profiles/prof_one.py <workload | path/to/scene.sdl@WxH> [frames]"""
 import os
 import sys
 
@@ -17,7 +17,11 @@ from bench import RNG_SEED, WORKLOADS  # noqa: E402
 def main():
     name = sys.argv[1]
     frames = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-    path, W, H, over = WORKLOADS[name]
+    if "@" in name:   # an arbitrary scene file at a given size
+        f, size = name.split("@")
+        path, (W, H), over = f, tuple(int(v) for v in size.split("x")), {}
+    else:
+        path, W, H, over = WORKLOADS[name]
     c2.init(1, [0])
     scene = c2.HostScene(os.path.join(ROOT, path))
     scene.set_frame_size(W, H)
