@@ -23,6 +23,9 @@ def _ctx():
 FAR_HIT = 1e5      # a camera-ray hit farther than this: the reference's own formulation (upLeft holds the camera position,
                    # which is subtracted again) is ill-conditioned to ~1e-9 relative there
 TIE_GAP = 1e-9     # two candidates / crossings / an occluder and the light / a checker edge closer than this (relative)
+OVERBRIGHT = 256.0  # a channel hundreds of times over the displayable range (a light a hair above the surface): FP32 itself
+                    # resolves such a value to ~1e-4 (one ulp of 1581 is 1.2e-4), the 8-bit pixel saturates at 255 either way;
+                    # there the two FP32 colour pipelines are held to 4e-6 RELATIVE (~32 ulp) instead of 1e-3 absolute
 SHIFT_EPS = 1e-7   # a pixel whose ORACLE colour moves by > 1e-3 when its samples shift by 1e-7 pixel sits on a
                    # discontinuity of the reference image (silhouette, grazing hit, coincident surfaces)
 
@@ -37,7 +40,11 @@ def assert_every_outlier_is_classified(o, rgb, ref, seed, what):
     classes = {}
     for y, x in zip(ys.tolist(), xs.tolist()):
         d = o.pixel_diag(x, y, seed=seed, eps=SHIFT_EPS)
-        if d["max_dist"] > FAR_HIT:
+        g64, r64 = rgb[y, x].astype(np.float64), ref[y, x].astype(np.float64)
+        bad = np.abs(g64 - r64) > 1e-3
+        if np.all(np.abs(r64[bad]) > OVERBRIGHT) and np.all(np.abs(g64[bad] - r64[bad]) <= 4e-6 * np.abs(r64[bad])):
+            cls = "overbright"
+        elif d["max_dist"] > FAR_HIT:
             cls = "far_hit"
         elif d["min_gap"] < TIE_GAP:
             cls = "tie"
@@ -71,7 +78,7 @@ def test_random_scene_matches_oracle(seed, tmp_path):
     assert ost.csg_max_crossings <= 8
 
 
-@pytest.mark.parametrize("seed", list(range(32)))
+@pytest.mark.parametrize("seed", list(range(32)) + [212])   # 212: found by tests/fuzz_extended.py (an over-bright pixel, 1581 +- 1.5e-3)
 def test_random_plane_scene_matches_oracle(seed, tmp_path):
     """The MODE_SOLO and plane-only kernel classes (un-normalised camera rays, sign-test shadowing among planes)."""
     path = tmp_path / f"planes{seed}.sdl"
