@@ -510,6 +510,7 @@ int validate_and_build(const c2rt_scene_desc* d, c2rt_scene* s) {
         float intensity = (L.color[0] + L.color[1] + L.color[2]) / 3;  // color.d:141-144
         L.lit = intensity != 0;
         for (int k = 0; k < 3; k++) L.posf[k] = (float)L.pos[k];
+        L.near2 = (float)(0.0576 * (L.pos[0] * L.pos[0] + L.pos[1] * L.pos[1] + L.pos[2] * L.pos[2]));
         if (L.lit) h.lit[h.n_lit++] = (int)i;
     }
     for (uint32_t i = 0; i < d->n_nodes; i++) {

@@ -1096,6 +1096,13 @@ __device__ __forceinline__ Col shade(const FrameParams& fp, const Ray& ray, cons
             if (occluded_planes<MODE>(fx, fy, fz, L, Dy)) continue;
             fDx = L.posf[0] - (float)fx; fDy = (float)Dy; fDz = L.posf[2] - (float)fz;
             d2 = dot3f(fDx, fDy, fDz, fDx, fDy, fDz);
+            if (d2 < L.near2) {
+                // the hit point is close to the light compared with the light's distance from the origin: the FP32
+                // difference above cancels (relative error ~6e-8 (|L| + |p|) / |D|) exactly where 1 / d2 makes the pixel
+                // hundreds of times over-bright — take the horizontal part from the FP64 difference there
+                fDx = (float)(L.pos[0] - fx); fDz = (float)(L.pos[2] - fz);
+                d2 = dot3f(fDx, fDy, fDz, fDx, fDy, fDz);
+            }
         } else {
             Dx = Dy = Dz = 0; fDx = fDy = fDz = 0.f; d2 = 1.f;   // (not instantiated: see the static_assert)
         }

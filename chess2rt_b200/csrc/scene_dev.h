@@ -65,7 +65,7 @@ struct DevLight {
     float color[3];   // lightColor * lightPower, the FP32 product of light.d:11-14
     int lit;          // color.intensity() != 0 (shader.d:88,219)
     float posf[3];    // FP32 copy of pos (plane-only scene classes take the horizontal light vector in FP32)
-    int pad;
+    float near2;      // (0.24 |pos|)^2: closer than this to the light, that FP32 difference cancels and FP64 is used (render_kernel.cu shade)
 };
 
 struct DevScene {
