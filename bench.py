@@ -314,6 +314,11 @@ def main():
                 self.flags_ptr = self.peer_frame_ptr + H * W * 12
                 self.band = api.Band(rank, world, BAND_ROWS, 0, self.flags_ptr, 0, 0)
                 self.out_ptr = self.peer_frame_ptr
+                if os.environ.get("C2RT_DIAG_LOCAL_PEER_STORES") == "1" and rank != 0:
+                    # DIAGNOSTIC ONLY (the gathered frame is then wrong and verify() is skipped): peers store their bands into a
+                    # local frame instead of rank 0's, everything else unchanged — what do the NVLink stores cost the peer kernels?
+                    self.local_frame = torch.empty((H, W, 3), dtype=torch.float32, device="cuda")
+                    self.out_ptr = self.local_frame.data_ptr()
                 self.frame_no = 0
                 dist.barrier()   # c2rt_frame_alloc zero-fills: the flags start at 0 before any rank signals
             else:
@@ -431,6 +436,8 @@ def main():
             previous frame left there."""
             if world == 1:
                 return None
+            if os.environ.get("C2RT_DIAG_LOCAL_PEER_STORES") == "1":
+                return "SKIPPED (C2RT_DIAG_LOCAL_PEER_STORES=1: diagnostic run, the frame is not gathered)"
             import ctypes as C
             cur = torch.cuda.current_stream().cuda_stream
             if self.mode == "p2p" and rank == 0:
@@ -438,16 +445,20 @@ def main():
             elif self.mode == "nccl" and rank == 0:
                 self.frame.fill_(float("nan"))
             self.step()   # (p2p: the gate inside keeps the peers' stores behind rank 0's memset)
+            W, H = self.W, self.H
+            got = None
+            if self.mode == "p2p" and rank == 0:
+                # the copy-out is enqueued straight behind rank 0's render kernel, BEFORE any host barrier: the end of that kernel
+                # alone must mean that every peer's band has arrived
+                got = torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True)
+                api._check(api.lib.c2rt_frame_download(got.data_ptr(), self.peer_frame_ptr, H * W * 12, cur))
             barrier()
             n_to = self.timeouts()
             if rank != 0:
                 return None
-            W, H = self.W, self.H
             alone = torch.empty((H, W, 3), dtype=torch.float32, device="cuda")
             c2.render_device(self.handle, self.cam, self.st, alone.data_ptr(), None, None, cur)
             if self.mode == "p2p":
-                got = torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True)
-                api._check(api.lib.c2rt_frame_download(got.data_ptr(), self.peer_frame_ptr, H * W * 12, cur))
                 torch.cuda.synchronize()
                 same = bool(torch.equal(got, alone.cpu()))
             else:
