@@ -132,7 +132,7 @@ def test_save_bmp_is_the_reference_layout():
 
 
 def test_headless_command_line(tmp_path):
-    """chess2rt_headless (host/main.cpp, the C++ twin of integration/d/source/app.d): usage errors exit 2, load errors exit 1 with
+    """chess2rt_headless (host/main.cpp, the C++ twin of integration/d/source/app_headless.d): usage errors exit 2, load errors exit 1 with
     the reference's message, and without a GPU a render fails loudly (no CPU fallback) instead of writing an image."""
     exe = os.path.join(ROOT, "chess2rt_b200", "chess2rt_headless")
     run = lambda *a: subprocess.run([exe, *a], capture_output=True, text=True, timeout=300)
