@@ -467,8 +467,22 @@ int validate_and_build(const c2rt_scene_desc* d, c2rt_scene* s) {
         memcpy(t.c, d->tex_colors + 18 * i, 18 * sizeof(float));
         memcpy(t.d, d->tex_params + 6 * i, 6 * sizeof(double));
         if (t.type == C2RT_TEX_CHECKER) t.d[1] = 1.0 / t.d[0];
-        if (t.type == C2RT_TEX_PROCEDURE2)   // frequencies in revolutions per unit (render_kernel.cu sin_rev)
-            for (int k = 0; k < 6; k++) t.d[k] /= 6.283185307179586476925;
+        if (t.type == C2RT_TEX_PROCEDURE2) {
+            // frequencies in 2^-32 revolutions per unit (render_kernel.cu sin_phase / sin_rev), and the |u|, |v| up to which every
+            // phase stays below 2^18 revolutions, as the high word of a double (compared against the coordinate's high word)
+            for (int a = 0; a < 2; a++) {
+                double fmax = 0.0;
+                for (int k = 0; k < 3; k++) {
+                    double& f = t.d[3 * a + k];
+                    f = f / 6.283185307179586476925 * 4294967296.0;
+                    fmax = std::isfinite(f) ? std::max(fmax, std::fabs(f)) : INFINITY;
+                }
+                const double lim = fmax > 0 ? 262144.0 * 4294967296.0 / fmax : INFINITY;   // (fmax = inf: 0, always the two-step path)
+                uint64_t bits;
+                memcpy(&bits, &lim, 8);
+                (a ? t.h : t.w) = (int)(uint32_t)(bits >> 32);
+            }
+        }
         if (t.type == C2RT_TEX_BITMAP) {
             t.w = d->tex_width[i]; t.h = d->tex_height[i];
             if (t.w <= 0 || t.h <= 0) return fail(C2RT_ERR_INVALID_ARG, "texture %u: empty bitmap", i);
@@ -754,6 +768,22 @@ void fill_params(FrameParams& fp, const c2rt_camera* cam, const c2rt_settings* s
     fp.prepass_bucket = set->prepass_only ? (set->bucket_size ? set->bucket_size : 48u) : 0u;
     fp.n_ranks = 1;
     fp.tiles_per_band = 1;
+    if (s->mode & MODE_SOLO) {   // render_kernel.cu isect_plane_solo
+        const double y = s->nodes[0].wp[0];
+        fp.solo_side = cam->pos[1] > y ? 1 : cam->pos[1] < y ? -1 : 0;
+        fp.solo_sign = fp.solo_side > 0 ? 0x80000000u : 0u;
+        fp.solo_h = cam->pos[1] - y;
+        // |d|^2 is convex in the screen position: its maximum over the sampled rectangle (pixel corners + the AA offsets, one
+        // pixel of margin) is at a corner
+        double dmax2 = 0.0;
+        for (int c = 0; c < 4; c++) {
+            const double sx = (c & 1) ? ((double)fp.W + 1.0) * fp.inv_w : -fp.inv_w, sy = (c & 2) ? ((double)fp.H + 1.0) * fp.inv_h : -fp.inv_h;
+            double l2 = 0.0;
+            for (int k = 0; k < 3; k++) { const double v = fp.ul_rel[k] + fp.du[k] * sx + fp.dv[k] * sy; l2 += v * v; }
+            dmax2 = std::max(dmax2, l2);
+        }
+        fp.graze_dy2 = std::isfinite(dmax2) ? 1e-18 * dmax2 * (1.0 + 1e-6) : INFINITY;
+    }
 }
 
 // c2rt_cancel bookkeeping: true iff a cancel was requested since the last call; the device flags are lowered again

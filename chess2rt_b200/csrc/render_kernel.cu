@@ -268,7 +268,9 @@ __device__ __forceinline__ void gen_ray(const FrameParams& fp, double vx, double
         if (MODE & MODE_BOUNDED) set_shadow<MODE>(fp, r);
         if (!UNNORM) normalize3(r.dx, r.dy, r.dz);
     }
-    if (UNNORM) r.l2 = dot3(r.dx, r.dy, r.dz, r.dx, r.dy, r.dz);
+    // |d|^2 of an un-normalised camera ray: read by the general plane test and by Phong lobes; the one-plane kernels without
+    // sampling form it only where they need it (isect_plane_solo)
+    if (UNNORM && (!(MODE & MODE_SOLO) || (MODE & (MODE_SAMPLING | MODE_PHONG)))) r.l2 = dot3(r.dx, r.dy, r.dz, r.dx, r.dy, r.dz);
 }
 
 // ---------------------------------------------------------------- primitives
@@ -707,6 +709,24 @@ __device__ __forceinline__ bool node_hit(int ni, const DevNode& nd, const Ray& r
     return true;
 }
 
+// MODE_SOLO frames without DOF / stereo: every camera ray starts at the camera position, so which side of the scene's one plane
+// it starts on and its height above it are frame constants (c2rt_api.cu fill_params: fp.solo_sign, fp.solo_h), and
+// geometry.d:35-36 reduces to the SIGN BIT of d.y (an integer test on its high word) plus the grazing test
+// d.y^2 < 1e-18 |d|^2 — which cannot hold while d.y^2 >= fp.graze_dy2 = 1e-18 max|d|^2 over the frame's rays, so |d|^2 is only
+// formed for the (practically absent) rays below that: out of line, or the compiler hoists the dot product above the test.
+// (d.y = -0.0 / +0.0 pass the sign test on the "wrong" side and are rejected as grazing, like the reference rejects them.)
+__device__ __noinline__ bool grazing_exact(double dx, double dy, double dz) { return dy * dy < 1e-18 * dot3(dx, dy, dz, dx, dy, dz); }
+__device__ __forceinline__ bool isect_plane_solo(const FrameParams& fp, double dx, double dy, double dz, double& dist) {
+    if ((int)((unsigned)__double2hiint(dy) ^ fp.solo_sign) < 0) return false;   // d.y points away from the plane
+    if (dy * dy < fp.graze_dy2) {
+        if (grazing_exact(dx, dy, dz)) return false;
+    }
+    const double mult = fp.solo_h * rcp64(-dy);
+    if (mult > dist) return false;
+    dist = mult;
+    return true;
+}
+
 // Plane-only scene classes: no bounded and no generic node exists, i.e. every node is a world-space plane.
 // CAMERA_RAY: `r` comes from gen_ray (un-normalised there); shadow rays are always unit.  The hit point is o + d * dist,
 // computed for the winning hit only (surface_of).
@@ -875,6 +895,17 @@ __device__ __forceinline__ float sin_rev(double u, double f) {
     return __sinf(x * 6.2831853f);
 }
 
+// The same sine with the range reduction in ONE FP64 instruction: F = f * 2^32 (DevTex.d holds that), so fma(u, F, 1.5 * 2^52)
+// leaves round(u f 2^32) mod 2^32 — the phase as a 32-bit fraction of a revolution, wrap-around included — in the low mantissa
+// word.  Its top 23 bits become the mantissa of a float in [1, 2) (whole revolutions do not matter to a sine): the same 2^-23
+// revolution granularity as sin_rev, with one DFMA where sin_rev spends two DFMA and a DADD.  Valid while |u f| < 2^19
+// revolutions (DevTex.w / .h hold the |u| / |v| that keep it under 2^18, as the high word of a double); sample_texture falls back
+// to sin_rev beyond.
+__device__ __forceinline__ float sin_phase(double u, double F) {
+    const unsigned p = (unsigned)__double2loint(fma(u, F, 6755399441055744.0));
+    return __sinf(__uint_as_float((p >> 9) | 0x3f800000u) * 6.2831853f);
+}
+
 // MODE_SOLO kernels compiled for a bitmap texture stage its 4 KB palette (if it has one) in shared memory once per CTA: the
 // palette read depends on the index-quad load, and a shared-memory read is the shorter second hop (C3: the zaphod page)
 __host__ __device__ constexpr bool solo_bitmap(int mode) {
@@ -927,14 +958,25 @@ __device__ __forceinline__ Col sample_texture(int ti, double u, double v) {
         return white ? mkcol(t.c[3], t.c[4], t.c[5]) : mkcol(t.c[0], t.c[1], t.c[2]);
     }
     if (type == C2RT_TEX_PROCEDURE2) {
-        Col res = mkcol(0.f, 0.f, 0.f);
+        // six sines (texture.d:82-83)
+        float su[3], sv[3];
+        const bool near_u = ((unsigned)__double2hiint(u) & 0x7fffffffu) < (unsigned)t.w;
+        const bool near_v = ((unsigned)__double2hiint(v) & 0x7fffffffu) < (unsigned)t.h;
+        if (near_u && near_v) {
 #pragma unroll
-        for (int i = 0; i < 3; i++) {
-            float su = sin_rev(u, t.d[i]);
-            float sv = sin_rev(v, t.d[3 + i]);
-            res.r += t.c[3 * i + 0] * su + t.c[9 + 3 * i + 0] * sv;
-            res.g += t.c[3 * i + 1] * su + t.c[9 + 3 * i + 1] * sv;
-            res.b += t.c[3 * i + 2] * su + t.c[9 + 3 * i + 2] * sv;
+            for (int i = 0; i < 3; i++) { su[i] = sin_phase(u, t.d[i]); sv[i] = sin_phase(v, t.d[3 + i]); }
+        } else {   // beyond 2^18 revolutions (a far horizon, or NaN): the two-step reduction
+            const double R = 2.3283064365386962890625e-10;   // 2^-32, exact
+#pragma unroll
+            for (int i = 0; i < 3; i++) { su[i] = sin_rev(u, t.d[i] * R); sv[i] = sin_rev(v, t.d[3 + i] * R); }
+        }
+        // (the sum starts from its first term, not from 0.f + term: the same value unless the term is -0)
+        Col res = mkcol(t.c[0] * su[0] + t.c[9] * sv[0], t.c[1] * su[0] + t.c[10] * sv[0], t.c[2] * su[0] + t.c[11] * sv[0]);
+#pragma unroll
+        for (int i = 1; i < 3; i++) {
+            res.r += t.c[3 * i + 0] * su[i] + t.c[9 + 3 * i + 0] * sv[i];
+            res.g += t.c[3 * i + 1] * su[i] + t.c[9 + 3 * i + 1] * sv[i];
+            res.b += t.c[3 * i + 2] * su[i] + t.c[9 + 3 * i + 2] * sv[i];
         }
         return res;
     }
@@ -1071,7 +1113,9 @@ __device__ __forceinline__ Col shade(const FrameParams& fp, const Ray& ray, cons
     // faceforward (imported_types.d:69-73): the sign decision in FP64, the vector itself in FP32
     float Nx = s.nx, Ny = s.ny, Nz = s.nz;
     // (plane-only scene classes: the geometric normal is (0, 1, 0), the dot product is ray.dy)
-    const bool facing = plane_only(MODE) ? ray.dy < 0 : dot3(ray.dx, ray.dy, ray.dz, s.gx, s.gy, s.gz) < 0;
+    // (a fixed camera off the scene's one plane only hits it with d.y pointing at it: the sign is the camera's side)
+    const bool facing = (SOLO && !(MODE & MODE_SAMPLING) && fp.solo_side) ? fp.solo_side > 0
+                        : plane_only(MODE) ? ray.dy < 0 : dot3(ray.dx, ray.dy, ray.dz, s.gx, s.gy, s.gz) < 0;
     if (!facing) { Nx = -Nx; Ny = -Ny; Nz = -Nz; }
     Col diffuse = has_tex ? sample_texture<MODE>(sh.tex, s.u, s.v) : mkcol(sh.color[0], sh.color[1], sh.color[2]);
     Col lightContrib = mkcol(fp.ambient[0], fp.ambient[1], fp.ambient[2]);
@@ -1328,7 +1372,13 @@ __device__ __forceinline__ Col trace(const FrameParams& fp, const Ray& ray, unsi
     HitRec h;
     h.dist = 1e99;
     h.node = -1;
-    if (MODE & MODE_SOLO) node_exact<MODE, true>(0, c_scene.nodes[0], ray, h);
+    if constexpr ((MODE & MODE_SOLO) && !(MODE & MODE_SAMPLING)) {
+        // (fp.solo_side == 0: the camera lies in the plane — the general test decides)
+        const bool hit = fp.solo_side ? isect_plane_solo(fp, ray.dx, ray.dy, ray.dz, h.dist)
+                                      : isect_plane_u(c_scene.nodes[0].wp[0], ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz,
+                                                      dot3(ray.dx, ray.dy, ray.dz, ray.dx, ray.dy, ray.dz), h.dist);
+        if (hit) { h.node = 0; h.leaf = c_scene.nodes[0].geom; h.face = 0; }
+    } else if (MODE & MODE_SOLO) node_exact<MODE, true>(0, c_scene.nodes[0], ray, h);
     else {
 #pragma unroll 1
         for (int i = 0; i < c_scene.n_nodes; i++) node_exact<MODE, true>(i, c_scene.nodes[i], ray, h);
@@ -1472,9 +1522,12 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS) render_frame_kernel
     // tile -> rows: local tile l of this rank belongs to its band (l / tiles_per_band), which is
     // global band (band_local * n_ranks + rank)
     const uint32_t l = blockIdx.y + fp.tile_row0;
-    const uint32_t band_local = l / fp.tiles_per_band;
-    const uint32_t within = l - band_local * fp.tiles_per_band;
-    const uint32_t tile_row = (band_local * fp.n_ranks + fp.rank) * fp.tiles_per_band + within;
+    uint32_t tile_row = l;   // one rank owns every band
+    if (fp.n_ranks > 1) {
+        const uint32_t band_local = l / fp.tiles_per_band;
+        const uint32_t within = l - band_local * fp.tiles_per_band;
+        tile_row = (band_local * fp.n_ranks + fp.rank) * fp.tiles_per_band + within;
+    }
     const uint32_t y0 = tile_row * TILE_H;
     const uint32_t x0 = blockIdx.x * TILE_W;
     // 4 warps, each an 8x4 pixel patch

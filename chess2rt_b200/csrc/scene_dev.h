@@ -48,8 +48,10 @@ struct DevShader {
 };
 
 struct DevTex {
-    double d[6];      // checker: size, 1/size | procedure2: freqU[3] / 2pi, freqV[3] / 2pi | bitmap: scaling
+    double d[6];      // checker: size, 1/size | procedure2: freqU[3], freqV[3] in 2^-32 revolutions per unit (freq / 2pi * 2^32) | bitmap: scaling
     float c[18];      // checker: color1, color2 | procedure2: colorU[3][3], colorV[3][3]
+    // bitmap: width, height | procedure2: w / h = high word of the |u| / |v| below which every phase stays under 2^19 revolutions
+    // (render_kernel.cu sin_phase)
     int type, w, h, pad;
     const float4* texels;    // bitmap, general form: one float4 per texel (post-gamma values, exactly the host's Image!Color)
     // bitmap with <= 256 distinct texel colours (every 8-bit-palette BMP; the load-time gamma maps equal inputs to equal
@@ -113,6 +115,12 @@ struct FrameParams {
     uint32_t* done_flags;             // in rank 0's memory: [r] = last frame number rank r completed, [n_ranks] = wait time-outs
     uint32_t* done_counter;           // this device: CTAs of the current launch that have finished
     uint32_t frame_no, pad_frame;
+    // MODE_SOLO frames without DOF / stereo (render_kernel.cu isect_plane_solo): side of the plane the camera is on (+1 above,
+    // -1 below, 0 in it), the sign bit a ray's d.y must NOT have xor'ed in (0x80000000 above the plane: d.y must be negative),
+    // the camera's height above the plane (pos.y - y), and 1e-18 max|d|^2 over the frame's un-normalised camera rays
+    int solo_side;
+    uint32_t solo_sign;
+    double solo_h, graze_dy2;
     const int* cancel;                // device flag raised by c2rt_cancel: CTAs that start after it skip their tile (nullptr: off)
     // outputs (rgb == nullptr: only the ARGB plane is wanted)
     float* rgb;

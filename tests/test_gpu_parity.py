@@ -60,6 +60,10 @@ CASES = [
     ("../tests/scenes/sky_plane.sdl", None, {}),    # the same on the one-plane scene class (MODE_SOLO kernels), assumedGamma 1.8
     ("../tests/scenes/sky.sdl", (97, 61), {"aa": 0}),
     ("zaphod-sky.sdl", (215, 143), {"num_samples": 4}),   # configs[3] "with cubemap skybox": DOF over the page, sky behind the camera
+    ("../tests/scenes/proc_far.sdl", None, {}),       # Procedure2: fast one-step sine reduction and its far-distance fallback in one frame, shared sines
+    ("../tests/scenes/proc_far.sdl", None, {"aa": 0}),
+    ("../tests/scenes/proc_below.sdl", None, {}),     # one-plane class from below the plane, Phong lobe, three equal frequencies
+    ("../tests/scenes/proc_inplane.sdl", None, {}),   # camera in the plane: the fixed-side shortcut must stand aside
 ]
 
 
