@@ -769,12 +769,12 @@ void fill_params(FrameParams& fp, const c2rt_camera* cam, const c2rt_settings* s
     fp.n_ranks = 1;
     fp.tiles_per_band = 1;
     if (s->mode & MODE_SOLO) {   // render_kernel.cu isect_plane_solo
-        const double y = s->nodes[0].wp[0];
-        fp.solo_side = cam->pos[1] > y ? 1 : cam->pos[1] < y ? -1 : 0;
+        const double y = s->nodes[0].wp[0], h = cam->pos[1] - y, ly = s->host.lights[0].pos[1];
+        fp.solo_side = h > 0 ? 1 : h < 0 ? -1 : 0;
         fp.solo_sign = fp.solo_side > 0 ? 0x80000000u : 0u;
-        fp.solo_h = cam->pos[1] - y;
+        fp.solo_h = h;
         // |d|^2 is convex in the screen position: its maximum over the sampled rectangle (pixel corners + the AA offsets, one
-        // pixel of margin) is at a corner
+        // pixel of margin) is at a corner; its minimum is at least the squared distance of the screen's plane from the camera
         double dmax2 = 0.0;
         for (int c = 0; c < 4; c++) {
             const double sx = (c & 1) ? ((double)fp.W + 1.0) * fp.inv_w : -fp.inv_w, sy = (c & 2) ? ((double)fp.H + 1.0) * fp.inv_h : -fp.inv_h;
@@ -782,7 +782,16 @@ void fill_params(FrameParams& fp, const c2rt_camera* cam, const c2rt_settings* s
             for (int k = 0; k < 3; k++) { const double v = fp.ul_rel[k] + fp.du[k] * sx + fp.dv[k] * sy; l2 += v * v; }
             dmax2 = std::max(dmax2, l2);
         }
-        fp.graze_dy2 = std::isfinite(dmax2) ? 1e-18 * dmax2 * (1.0 + 1e-6) : INFINITY;
+        fp.graze_dy2 = 1e-18 * dmax2 * (1.0 + 1e-6);
+        const double n[3] = {fp.du[1] * fp.dv[2] - fp.du[2] * fp.dv[1], fp.du[2] * fp.dv[0] - fp.du[0] * fp.dv[2], fp.du[0] * fp.dv[1] - fp.du[1] * fp.dv[0]};
+        const double nl = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+        const double dmin = nl > 0 ? std::fabs(fp.ul_rel[0] * n[0] + fp.ul_rel[1] * n[1] + fp.ul_rel[2] * n[2]) / nl : 0.0;
+        // regular: the rounding of the hit point's y (|h| 1e-15 + an ulp of y) and of the shadow-ray origin cannot reach the
+        // 1e-6 offset, the light is on the camera's side by more than 1e-5, distances stay far below 1e99
+        const double mag = std::fabs(h) + std::fabs(y) + std::fabs(cam->pos[1]) + std::fabs(ly);
+        const char* no_fast = getenv("C2RT_NO_SOLO_FAST");   // test hook: every one-plane frame on the general sampling kernel
+        fp.solo_fast = fp.solo_side != 0 && std::isfinite(dmax2) && std::isfinite(mag) && mag < 1e6 && (double)fp.solo_side * (ly - y) > 1e-5 &&
+                       dmin > 1e-6 && dmax2 < 1e12 && !(no_fast && no_fast[0] == '1');
     }
 }
 

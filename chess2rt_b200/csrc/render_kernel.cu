@@ -95,6 +95,13 @@ __device__ __forceinline__ float sqrt_up(float a) {
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
     return r * 1.000002f;
 }
+// 1/sqrt(a) in FP32: MUFU.RSQ as rsqrtf issues it, without rsqrtf's rescaling of denormal inputs (three more instructions per
+// call; the arguments here are squared lengths of non-degenerate vectors).  Identical result for every normal input.
+__device__ __forceinline__ float rsqrt_fast(float a) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
+}
 // 1/a and 1/sqrt(a) in FP64: hardware seed (MUFU.RCP64H / MUFU.RSQ64H, ~20 bits) + two Newton steps
 __device__ __forceinline__ double rcp64(double a) {
     double y;
@@ -158,7 +165,7 @@ __device__ __forceinline__ void set_shadow(const FrameParams& fp, Ray& r) {
         r.olen = fp.posf_len;
     }
     const float vx = (float)r.dx, vy = (float)r.dy, vz = (float)r.dz;
-    const float inv = rsqrtf(dot3f(vx, vy, vz, vx, vy, vz));
+    const float inv = rsqrt_fast(dot3f(vx, vy, vz, vx, vy, vz));
     r.fdx = vx * inv; r.fdy = vy * inv; r.fdz = vz * inv;
 }
 
@@ -709,23 +716,28 @@ __device__ __forceinline__ bool node_hit(int ni, const DevNode& nd, const Ray& r
     return true;
 }
 
-// MODE_SOLO frames without DOF / stereo: every camera ray starts at the camera position, so which side of the scene's one plane
-// it starts on and its height above it are frame constants (c2rt_api.cu fill_params: fp.solo_sign, fp.solo_h), and
-// geometry.d:35-36 reduces to the SIGN BIT of d.y (an integer test on its high word) plus the grazing test
-// d.y^2 < 1e-18 |d|^2 — which cannot hold while d.y^2 >= fp.graze_dy2 = 1e-18 max|d|^2 over the frame's rays, so |d|^2 is only
-// formed for the (practically absent) rays below that: out of line, or the compiler hoists the dot product above the test.
-// (d.y = -0.0 / +0.0 pass the sign test on the "wrong" side and are rejected as grazing, like the reference rejects them.)
+// MODE_SOLO frames without DOF / stereo whose geometry is REGULAR (fp.solo_fast, decided per frame by c2rt_api.cu fill_params;
+// every other frame of the scene class runs on the general sampling kernel): every camera ray starts at the camera position,
+// off the scene's one plane, so
+//  * which side of the plane it starts on and its height above it are frame constants (fp.solo_sign, fp.solo_h), and
+//    geometry.d:35-36 reduces to the SIGN BIT of d.y (an integer test on its high word) plus the grazing test
+//    d.y^2 < 1e-18 |d|^2 — which cannot hold while d.y^2 >= fp.graze_dy2 = 1e-18 max|d|^2 over the frame's rays, so |d|^2 is
+//    only formed for the (practically absent) rays below that: out of line, or the compiler hoists the dot product above
+//    the test.  (d.y = -0.0 / +0.0 pass the sign test on the "wrong" side and are rejected as grazing, like the reference does.)
+//  * the hit distance |h| / |d.y| <= |h| 1e9 / min|d| stays far below the initial 1e99 (geometry.d:39 never rejects);
+//  * every hit faces the camera's side (faceforward, imported_types.d:69-73), the shadow-ray origin p + N 1e-6 lies strictly
+//    on that side of the plane, and so does the light, by more than 1e-5: geometry.d:35-36 rejects the shadow ray by side
+//    and sign, testVisibility (scene.d:62-78) finds nothing — the one plane cannot shadow itself.
 __device__ __noinline__ bool grazing_exact(double dx, double dy, double dz) { return dy * dy < 1e-18 * dot3(dx, dy, dz, dx, dy, dz); }
 __device__ __forceinline__ bool isect_plane_solo(const FrameParams& fp, double dx, double dy, double dz, double& dist) {
     if ((int)((unsigned)__double2hiint(dy) ^ fp.solo_sign) < 0) return false;   // d.y points away from the plane
     if (dy * dy < fp.graze_dy2) {
         if (grazing_exact(dx, dy, dz)) return false;
     }
-    const double mult = fp.solo_h * rcp64(-dy);
-    if (mult > dist) return false;
-    dist = mult;
+    dist = fp.solo_h * rcp64(-dy);
     return true;
 }
+__host__ __device__ constexpr bool solo_fast(int mode) { return (mode & MODE_SOLO) && !(mode & MODE_SAMPLING); }
 
 // Plane-only scene classes: no bounded and no generic node exists, i.e. every node is a world-space plane.
 // CAMERA_RAY: `r` comes from gen_ray (un-normalised there); shadow rays are always unit.  The hit point is o + d * dist,
@@ -1097,7 +1109,7 @@ __device__ __forceinline__ void surface_of(const HitRec& hin, const Ray* ray, bo
         return;
     }
     float fx = (float)s.gx, fy = (float)s.gy, fz = (float)s.gz;
-    float inv = rsqrtf(dot3f(fx, fy, fz, fx, fy, fz));
+    float inv = rsqrt_fast(dot3f(fx, fy, fz, fx, fy, fz));
     s.nx = fx * inv; s.ny = fy * inv; s.nz = fz * inv;
 }
 
@@ -1114,7 +1126,7 @@ __device__ __forceinline__ Col shade(const FrameParams& fp, const Ray& ray, cons
     float Nx = s.nx, Ny = s.ny, Nz = s.nz;
     // (plane-only scene classes: the geometric normal is (0, 1, 0), the dot product is ray.dy)
     // (a fixed camera off the scene's one plane only hits it with d.y pointing at it: the sign is the camera's side)
-    const bool facing = (SOLO && !(MODE & MODE_SAMPLING) && fp.solo_side) ? fp.solo_side > 0
+    const bool facing = solo_fast(MODE) ? fp.solo_side > 0
                         : plane_only(MODE) ? ray.dy < 0 : dot3(ray.dx, ray.dy, ray.dz, s.gx, s.gy, s.gz) < 0;
     if (!facing) { Nx = -Nx; Ny = -Ny; Nz = -Nz; }
     Col diffuse = has_tex ? sample_texture<MODE>(sh.tex, s.u, s.v) : mkcol(sh.color[0], sh.color[1], sh.color[2]);
@@ -1137,7 +1149,9 @@ __device__ __forceinline__ Col shade(const FrameParams& fp, const Ray& ray, cons
         if (plane_only(MODE)) {
             // among planes only the sign of D.y decides visibility: D.y in FP64, the rest of the light vector in FP32
             Dy = L.pos[1] - fy;
-            if (occluded_planes<MODE>(fx, fy, fz, L, Dy)) continue;
+            if constexpr (!solo_fast(MODE)) {   // (regular one-plane frames: the plane cannot shadow itself, see isect_plane_solo)
+                if (occluded_planes<MODE>(fx, fy, fz, L, Dy)) continue;
+            }
             fDx = L.posf[0] - (float)fx; fDy = (float)Dy; fDz = L.posf[2] - (float)fz;
             d2 = dot3f(fDx, fDy, fDz, fDx, fDy, fDz);
             if (d2 < L.near2) {
@@ -1151,7 +1165,7 @@ __device__ __forceinline__ Col shade(const FrameParams& fp, const Ray& ray, cons
             Dx = Dy = Dz = 0; fDx = fDy = fDz = 0.f; d2 = 1.f;   // (not instantiated: see the static_assert)
         }
         // lighting in FP32 (the reference narrows every factor to float before it touches a Color: SURVEY.md App. C.1)
-        const float rs = rsqrtf(d2);
+        const float rs = rsqrt_fast(d2);
         const float lx = fDx * rs, ly = fDy * rs, lz = fDz * rs;
         const float inv_d2 = rs * rs;
         const float cosTheta = plane_only(MODE) ? (facing ? ly : -ly) : dot3f(lx, ly, lz, Nx, Ny, Nz);
@@ -1169,7 +1183,7 @@ __device__ __forceinline__ Col shade(const FrameParams& fp, const Ray& ray, cons
                 const float rx = fmaf(k, Nx, -lx), ry = fmaf(k, Ny, -ly), rz = fmaf(k, Nz, -lz);
                 float vx = (float)ray.dx, vy = (float)ray.dy, vz = (float)ray.dz;
                 if (plane_only(MODE)) {   // un-normalised camera ray (gen_ray)
-                    const float iv = rsqrtf((float)ray.l2);
+                    const float iv = rsqrt_fast((float)ray.l2);
                     vx *= iv; vy *= iv; vz *= iv;
                 }
                 const float cosGamma = -dot3f(rx, ry, rz, vx, vy, vz);
@@ -1304,7 +1318,7 @@ __device__ __forceinline__ Col trace_warp(const FrameParams& fp, const Ray& cam_
                 lx = r.fdx; ly = r.fdy; lz = r.fdz; rs = rsf;
             } else {
                 const double Dx = L.pos[0] - r.ox, Dy = L.pos[1] - r.oy, Dz = L.pos[2] - r.oz;
-                rs = rsqrtf((float)dot3(Dx, Dy, Dz, Dx, Dy, Dz));
+                rs = rsqrt_fast((float)dot3(Dx, Dy, Dz, Dx, Dy, Dz));
                 lx = (float)Dx * rs; ly = (float)Dy * rs; lz = (float)Dz * rs;
             }
             const float inv_d2 = rs * rs;
@@ -1353,7 +1367,7 @@ __device__ __forceinline__ Col trace_warp(const FrameParams& fp, const Ray& cam_
         if (MODE & MODE_BOUNDED) {   // FP32 shadow of the ray for the conservative cull
             const double Dx = L.pos[0] - r.ox, Dz = L.pos[2] - r.oz;
             const float l2f = (float)dot3(Dx, sy, Dz, Dx, sy, Dz);
-            rsf = rsqrtf(l2f);
+            rsf = rsqrt_fast(l2f);
             r.fox = cvt_keep(r.ox); r.foy = cvt_keep(r.oy); r.foz = cvt_keep(r.oz);
             r.fdx = cvt_keep(Dx) * rsf; r.fdy = cvt_keep(sy) * rsf; r.fdz = cvt_keep(Dz) * rsf;
             r.olen = sqrt_up(dot3f(r.fox, r.foy, r.foz, r.fox, r.foy, r.foz));   // (only feeds the cull's rounding margins)
@@ -1372,12 +1386,8 @@ __device__ __forceinline__ Col trace(const FrameParams& fp, const Ray& ray, unsi
     HitRec h;
     h.dist = 1e99;
     h.node = -1;
-    if constexpr ((MODE & MODE_SOLO) && !(MODE & MODE_SAMPLING)) {
-        // (fp.solo_side == 0: the camera lies in the plane — the general test decides)
-        const bool hit = fp.solo_side ? isect_plane_solo(fp, ray.dx, ray.dy, ray.dz, h.dist)
-                                      : isect_plane_u(c_scene.nodes[0].wp[0], ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz,
-                                                      dot3(ray.dx, ray.dy, ray.dz, ray.dx, ray.dy, ray.dz), h.dist);
-        if (hit) { h.node = 0; h.leaf = c_scene.nodes[0].geom; h.face = 0; }
+    if constexpr (solo_fast(MODE)) {
+        if (isect_plane_solo(fp, ray.dx, ray.dy, ray.dz, h.dist)) { h.node = 0; h.leaf = c_scene.nodes[0].geom; h.face = 0; }
     } else if (MODE & MODE_SOLO) node_exact<MODE, true>(0, c_scene.nodes[0], ray, h);
     else {
 #pragma unroll 1
@@ -1779,7 +1789,8 @@ cudaError_t launch_frame(const FrameParams& fp, int mode, uint32_t local_tile_ro
     if (local_tile_rows == 0) return cudaSuccess;
     dim3 grid((fp.W + TILE_W - 1) / TILE_W, local_tile_rows);
     constexpr int FULL = MODE_BOUNDED | MODE_GENERIC, ALL = FULL | MODE_NESTED;
-    const bool sampling = fp.dof || fp.stereo_sep != 0 || fp.prepass_bucket;
+    // (one-plane scenes: a frame whose geometry is not regular — fill_params — runs on the general sampling kernel too)
+    const bool sampling = fp.dof || fp.stereo_sep != 0 || fp.prepass_bucket || ((mode & MODE_SOLO) && !fp.solo_fast);
     if (mode & MODE_SOLO) {
         switch (((mode & MODE_TEX_MASK) >> MODE_TEX_SHIFT) | ((mode & MODE_PHONG) ? 4 : 0)) {
             case 0: launch_solo<0, 0>(fp, sampling, grid, st); break;

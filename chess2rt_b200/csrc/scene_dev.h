@@ -115,11 +115,13 @@ struct FrameParams {
     uint32_t* done_flags;             // in rank 0's memory: [r] = last frame number rank r completed, [n_ranks] = wait time-outs
     uint32_t* done_counter;           // this device: CTAs of the current launch that have finished
     uint32_t frame_no, pad_frame;
-    // MODE_SOLO frames without DOF / stereo (render_kernel.cu isect_plane_solo): side of the plane the camera is on (+1 above,
-    // -1 below, 0 in it), the sign bit a ray's d.y must NOT have xor'ed in (0x80000000 above the plane: d.y must be negative),
-    // the camera's height above the plane (pos.y - y), and 1e-18 max|d|^2 over the frame's un-normalised camera rays
-    int solo_side;
-    uint32_t solo_sign;
+    // MODE_SOLO frames without DOF / stereo (render_kernel.cu isect_plane_solo): solo_fast = the frame is regular (camera off
+    // the plane, light on the camera's side, moderate magnitudes: c2rt_api.cu fill_params) and runs on the kernels that use the
+    // constants below; side of the plane the camera is on (+1 above, -1 below), the sign bit a ray's d.y must NOT have xor'ed
+    // in (0x80000000 above the plane: d.y must be negative), the camera's height above the plane (pos.y - y), and
+    // 1e-18 max|d|^2 over the frame's un-normalised camera rays
+    int solo_fast, solo_side;
+    uint32_t solo_sign, pad_solo;
     double solo_h, graze_dy2;
     const int* cancel;                // device flag raised by c2rt_cancel: CTAs that start after it skip their tile (nullptr: off)
     // outputs (rgb == nullptr: only the ARGB plane is wanted)

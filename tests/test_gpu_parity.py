@@ -172,6 +172,27 @@ def test_palette_quad_bitmaps_equal_float4_texels(name, size, over, monkeypatch)
     assert pal.max() > 0.05
 
 
+@pytest.mark.parametrize("name,size", [("lecture4-proc-texture.sdl", (333, 187)), ("lecture4.sdl", None), ("../tests/scenes/proc_below.sdl", None),
+                                       ("../tests/scenes/proc_far.sdl", None), ("../tests/scenes/sky_plane.sdl", None),
+                                       ("zaphod.sdl", (161, 107))])
+def test_regular_one_plane_frames_equal_the_general_kernel(name, size, monkeypatch):
+    """One-plane frames with a fixed camera off the plane and the light on its side run on kernels that take the camera's
+    side, its height and 'the plane cannot shadow itself' as frame constants (render_kernel.cu isect_plane_solo, c2rt_api.cu
+    fill_params).  Those are shortcuts, not approximations: the frame must be BIT-identical to the one the general kernel of
+    the scene class renders (C2RT_NO_SOLO_FAST=1, read per frame), ray counts included."""
+    g = c2.HostScene(os.path.join(SC, name))
+    if size:
+        g.set_frame_size(*size)
+    g.override(dof=0)
+    fast, fast_a, st_fast = g.render(argb=True, seed=5, count_rays=True)
+    monkeypatch.setenv("C2RT_NO_SOLO_FAST", "1")
+    gen, gen_a, st_gen = g.render(argb=True, seed=5, count_rays=True)
+    np.testing.assert_array_equal(fast, gen)
+    np.testing.assert_array_equal(fast_a, gen_a)
+    assert (st_fast.primary_rays, st_fast.shadow_rays) == (st_gen.primary_rays, st_gen.shadow_rays)
+    assert fast.max() > 0.05
+
+
 def test_cubemap_extension_is_inert_where_no_ray_misses_and_refuses_gi(tmp_path):
     """zaphod-sky.sdl = zaphod.sdl + the cubemap environment: its camera looks down at the page, no ray misses, so the frame is
     bit-identical to zaphod.sdl's.  GI frames are only built for the reference's black environment: refused with a cubemap."""
