@@ -752,6 +752,7 @@ void fill_params(FrameParams& fp, const c2rt_camera* cam, const c2rt_settings* s
         for (int k = 0; k < 3; k++) fp.tap_d[t][k] = fp.du[k] * (kx[t] * fp.inv_w) + fp.dv[k] * (ky[t] * fp.inv_h);
     fp.focal_plane_dist = cam->focal_plane_dist;
     fp.disc_multiplier = cam->disc_multiplier;
+    fp.disc_multiplier_f = (float)cam->disc_multiplier;
     fp.stereo_sep = cam->stereo_separation;
     fp.seed = set->rng_seed;
     fp.W = set->frame_width;
@@ -773,25 +774,48 @@ void fill_params(FrameParams& fp, const c2rt_camera* cam, const c2rt_settings* s
         fp.solo_side = h > 0 ? 1 : h < 0 ? -1 : 0;
         fp.solo_sign = fp.solo_side > 0 ? 0x80000000u : 0u;
         fp.solo_h = h;
-        // |d|^2 is convex in the screen position: its maximum over the sampled rectangle (pixel corners + the AA offsets, one
-        // pixel of margin) is at a corner; its minimum is at least the squared distance of the screen's plane from the camera
+        // |d|^2 of the un-normalised pinhole direction is convex in the screen position: its maximum over the sampled rectangle
+        // (pixel corners + the AA offsets + DOF's one-pixel jitter, one more pixel of margin) is at a corner; its minimum is at
+        // least the squared distance of the screen's plane from the camera
         double dmax2 = 0.0;
         for (int c = 0; c < 4; c++) {
-            const double sx = (c & 1) ? ((double)fp.W + 1.0) * fp.inv_w : -fp.inv_w, sy = (c & 2) ? ((double)fp.H + 1.0) * fp.inv_h : -fp.inv_h;
+            const double sx = (c & 1) ? ((double)fp.W + 2.0) * fp.inv_w : -fp.inv_w, sy = (c & 2) ? ((double)fp.H + 2.0) * fp.inv_h : -fp.inv_h;
             double l2 = 0.0;
             for (int k = 0; k < 3; k++) { const double v = fp.ul_rel[k] + fp.du[k] * sx + fp.dv[k] * sy; l2 += v * v; }
             dmax2 = std::max(dmax2, l2);
         }
-        fp.graze_dy2 = 1e-18 * dmax2 * (1.0 + 1e-6);
         const double n[3] = {fp.du[1] * fp.dv[2] - fp.du[2] * fp.dv[1], fp.du[2] * fp.dv[0] - fp.du[0] * fp.dv[2], fp.du[0] * fp.dv[1] - fp.du[1] * fp.dv[0]};
         const double nl = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
         const double dmin = nl > 0 ? std::fabs(fp.ul_rel[0] * n[0] + fp.ul_rel[1] * n[1] + fp.ul_rel[2] * n[2]) / nl : 0.0;
+        // DOF / stereo move the ray origin inside the lens: by at most `lens` in any direction, `lens_y` in height; a DOF ray
+        // runs from there to the focal point, at most focalPlaneDist |d| / (d . front) from the camera position (camera.d:154-173)
+        double lens = std::fabs(cam->stereo_separation), lens_y = std::fabs(cam->stereo_separation * cam->right_dir[1]);
+        double front_min = 1e300;   // min over the corners of d . front (linear in the screen position)
+        for (int c = 0; c < 4; c++) {
+            const double sx = (c & 1) ? ((double)fp.W + 2.0) * fp.inv_w : -fp.inv_w, sy = (c & 2) ? ((double)fp.H + 2.0) * fp.inv_h : -fp.inv_h;
+            double f = 0.0;
+            for (int k = 0; k < 3; k++) f += (fp.ul_rel[k] + fp.du[k] * sx + fp.dv[k] * sy) * cam->front_dir[k];
+            front_min = std::min(front_min, f);
+        }
+        double dray2 = dmax2;
+        bool lens_ok = true;
+        if (cam->dof) {
+            const double dm = std::fabs(cam->disc_multiplier) * (1.0 + 1e-6);
+            lens += 2.0 * dm;
+            lens_y += dm * (std::fabs(cam->right_dir[1]) + std::fabs(cam->up_dir[1]));
+            lens_ok = front_min > 1e-6 && std::isfinite(cam->focal_plane_dist);
+            const double reach = lens_ok ? std::fabs(cam->focal_plane_dist) * std::sqrt(dmax2) / front_min + lens : 0.0;
+            dray2 = reach * reach;
+        }
+        fp.graze_dy2 = 1e-18 * dray2 * (1.0 + 1e-6);
         // regular: the rounding of the hit point's y (|h| 1e-15 + an ulp of y) and of the shadow-ray origin cannot reach the
-        // 1e-6 offset, the light is on the camera's side by more than 1e-5, distances stay far below 1e99
-        const double mag = std::fabs(h) + std::fabs(y) + std::fabs(cam->pos[1]) + std::fabs(ly);
-        const char* no_fast = getenv("C2RT_NO_SOLO_FAST");   // test hook: every one-plane frame on the general sampling kernel
-        fp.solo_fast = fp.solo_side != 0 && std::isfinite(dmax2) && std::isfinite(mag) && mag < 1e6 && (double)fp.solo_side * (ly - y) > 1e-5 &&
-                       dmin > 1e-6 && dmax2 < 1e12 && !(no_fast && no_fast[0] == '1');
+        // 1e-6 offset, the whole lens is on one side of the plane and the light on the same side by more than 1e-5, distances stay
+        // far below 1e99; preview frames (prepassOnly: jitter over whole blocks) are left to the general path
+        const double mag = std::fabs(h) + std::fabs(y) + std::fabs(cam->pos[1]) + std::fabs(ly) + lens;
+        const char* no_fast = getenv("C2RT_NO_SOLO_FAST");   // test hook: every one-plane frame on the general path
+        fp.solo_fast = fp.solo_side != 0 && lens_ok && std::isfinite(dray2) && std::isfinite(mag) && mag < 1e6 && dray2 < 1e12 &&
+                       std::fabs(h) > lens_y + 1e-5 && (double)fp.solo_side * (ly - y) > 1e-5 && dmin > 1e-6 &&
+                       !set->prepass_only && !(no_fast && no_fast[0] == '1');
     }
 }
 

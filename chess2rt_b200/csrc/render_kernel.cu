@@ -264,7 +264,11 @@ __device__ __forceinline__ void gen_ray(const FrameParams& fp, double vx, double
         double u2 = uniform01(fp, px, py, tap, sample, draw);
         double rad = u2 > 0 ? u2 * rsqrt64(u2) : 0.0;
         double sa, ca;
-        sincos_rev(u1, sa, ca);  // lens position: kept in FP64 (it moves the ray origin by up to discMultiplier)
+        // lens position: kept in FP64.  It moves the ray origin by up to discMultiplier and so every texture coordinate of the
+        // sample; an FP32 lens sample (measured: C3 14.9 -> 12.4 ms) shifts them by ~1e-7 of a texel, which is invisible
+        // except where the reference's own image is discontinuous — bitmap.d:48-63 returns red when float(u) rounds up to 1.0 —
+        // and one such sample in 8 M moved a zaphod pixel by 3e-3
+        sincos_rev(u1, sa, ca);
         double ddx = sa * rad * fp.disc_multiplier;
         double ddy = ca * rad * fp.disc_multiplier;
         r.ox = fp.pos[0] + ddx * fp.right_dir[0] + ddy * fp.up_dir[0];
@@ -729,15 +733,24 @@ __device__ __forceinline__ bool node_hit(int ni, const DevNode& nd, const Ray& r
 //    on that side of the plane, and so does the light, by more than 1e-5: geometry.d:35-36 rejects the shadow ray by side
 //    and sign, testVisibility (scene.d:62-78) finds nothing — the one plane cannot shadow itself.
 __device__ __noinline__ bool grazing_exact(double dx, double dy, double dz) { return dy * dy < 1e-18 * dot3(dx, dy, dz, dx, dy, dz); }
-__device__ __forceinline__ bool isect_plane_solo(const FrameParams& fp, double dx, double dy, double dz, double& dist) {
+// `h`: the ray origin's height above the plane (fp.solo_h for a fixed camera; per ray under DOF / stereo, where fill_params has
+// checked the whole lens against the same conditions)
+__device__ __forceinline__ bool isect_plane_solo(const FrameParams& fp, double h, double dx, double dy, double dz, double& dist) {
     if ((int)((unsigned)__double2hiint(dy) ^ fp.solo_sign) < 0) return false;   // d.y points away from the plane
     if (dy * dy < fp.graze_dy2) {
         if (grazing_exact(dx, dy, dz)) return false;
     }
-    dist = fp.solo_h * rcp64(-dy);
+    dist = h * rcp64(-dy);
     return true;
 }
+// the kernels without the sampling loop only run regular frames; the sampling kernels run both kinds (fp.solo_fast, warp-uniform)
 __host__ __device__ constexpr bool solo_fast(int mode) { return (mode & MODE_SOLO) && !(mode & MODE_SAMPLING); }
+template <int MODE>
+__device__ __forceinline__ bool solo_regular(const FrameParams& fp) {
+    if constexpr (solo_fast(MODE)) return true;
+    else if constexpr ((MODE & MODE_SOLO) != 0) return fp.solo_fast != 0;
+    else return false;
+}
 
 // Plane-only scene classes: no bounded and no generic node exists, i.e. every node is a world-space plane.
 // CAMERA_RAY: `r` comes from gen_ray (un-normalised there); shadow rays are always unit.  The hit point is o + d * dist,
@@ -1126,7 +1139,8 @@ __device__ __forceinline__ Col shade(const FrameParams& fp, const Ray& ray, cons
     float Nx = s.nx, Ny = s.ny, Nz = s.nz;
     // (plane-only scene classes: the geometric normal is (0, 1, 0), the dot product is ray.dy)
     // (a fixed camera off the scene's one plane only hits it with d.y pointing at it: the sign is the camera's side)
-    const bool facing = solo_fast(MODE) ? fp.solo_side > 0
+    const bool regular = solo_regular<MODE>(fp);
+    const bool facing = regular ? fp.solo_side > 0
                         : plane_only(MODE) ? ray.dy < 0 : dot3(ray.dx, ray.dy, ray.dz, s.gx, s.gy, s.gz) < 0;
     if (!facing) { Nx = -Nx; Ny = -Ny; Nz = -Nz; }
     Col diffuse = has_tex ? sample_texture<MODE>(sh.tex, s.u, s.v) : mkcol(sh.color[0], sh.color[1], sh.color[2]);
@@ -1150,7 +1164,7 @@ __device__ __forceinline__ Col shade(const FrameParams& fp, const Ray& ray, cons
             // among planes only the sign of D.y decides visibility: D.y in FP64, the rest of the light vector in FP32
             Dy = L.pos[1] - fy;
             if constexpr (!solo_fast(MODE)) {   // (regular one-plane frames: the plane cannot shadow itself, see isect_plane_solo)
-                if (occluded_planes<MODE>(fx, fy, fz, L, Dy)) continue;
+                if (!regular && occluded_planes<MODE>(fx, fy, fz, L, Dy)) continue;
             }
             fDx = L.posf[0] - (float)fx; fDy = (float)Dy; fDz = L.posf[2] - (float)fz;
             d2 = dot3f(fDx, fDy, fDz, fDx, fDy, fDz);
@@ -1387,9 +1401,12 @@ __device__ __forceinline__ Col trace(const FrameParams& fp, const Ray& ray, unsi
     h.dist = 1e99;
     h.node = -1;
     if constexpr (solo_fast(MODE)) {
-        if (isect_plane_solo(fp, ray.dx, ray.dy, ray.dz, h.dist)) { h.node = 0; h.leaf = c_scene.nodes[0].geom; h.face = 0; }
-    } else if (MODE & MODE_SOLO) node_exact<MODE, true>(0, c_scene.nodes[0], ray, h);
-    else {
+        if (isect_plane_solo(fp, fp.solo_h, ray.dx, ray.dy, ray.dz, h.dist)) { h.node = 0; h.leaf = c_scene.nodes[0].geom; h.face = 0; }
+    } else if constexpr ((MODE & MODE_SOLO) != 0) {
+        if (fp.solo_fast) {
+            if (isect_plane_solo(fp, ray.oy - c_scene.nodes[0].wp[0], ray.dx, ray.dy, ray.dz, h.dist)) { h.node = 0; h.leaf = c_scene.nodes[0].geom; h.face = 0; }
+        } else node_exact<MODE, true>(0, c_scene.nodes[0], ray, h);
+    } else {
 #pragma unroll 1
         for (int i = 0; i < c_scene.n_nodes; i++) node_exact<MODE, true>(i, c_scene.nodes[i], ray, h);
     }

@@ -95,6 +95,7 @@ struct FrameParams {
     double inv_w, inv_h;
     double tap_d[5][3];               // ray-direction offset of AA tap k: du * kx/W + dv * ky/H (renderer.d:235-247)
     double focal_plane_dist, disc_multiplier;
+    float disc_multiplier_f, pad_disc;   // FP32 copy (the lens sample, render_kernel.cu gen_ray)
     double stereo_sep;                // camera.stereoSeparation (0 = off)
     unsigned long long seed;
     uint32_t W, H;                    // output size
@@ -115,11 +116,11 @@ struct FrameParams {
     uint32_t* done_flags;             // in rank 0's memory: [r] = last frame number rank r completed, [n_ranks] = wait time-outs
     uint32_t* done_counter;           // this device: CTAs of the current launch that have finished
     uint32_t frame_no, pad_frame;
-    // MODE_SOLO frames without DOF / stereo (render_kernel.cu isect_plane_solo): solo_fast = the frame is regular (camera off
-    // the plane, light on the camera's side, moderate magnitudes: c2rt_api.cu fill_params) and runs on the kernels that use the
-    // constants below; side of the plane the camera is on (+1 above, -1 below), the sign bit a ray's d.y must NOT have xor'ed
-    // in (0x80000000 above the plane: d.y must be negative), the camera's height above the plane (pos.y - y), and
-    // 1e-18 max|d|^2 over the frame's un-normalised camera rays
+    // MODE_SOLO frames (render_kernel.cu isect_plane_solo): solo_fast = the frame is regular (camera — the whole lens under
+    // DOF / stereo — off the plane, light on the camera's side, moderate magnitudes: c2rt_api.cu fill_params); the kernels
+    // without the sampling loop only run such frames, the sampling kernels branch on it.  Then: side of the plane the camera is
+    // on (+1 above, -1 below), the sign bit a ray's d.y must NOT have xor'ed in (0x80000000 above the plane: d.y must be
+    // negative), the camera position's height above the plane (pos.y - y), and 1e-18 max|d|^2 over the frame's camera rays
     int solo_fast, solo_side;
     uint32_t solo_sign, pad_solo;
     double solo_h, graze_dy2;

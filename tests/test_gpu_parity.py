@@ -172,10 +172,11 @@ def test_palette_quad_bitmaps_equal_float4_texels(name, size, over, monkeypatch)
     assert pal.max() > 0.05
 
 
-@pytest.mark.parametrize("name,size", [("lecture4-proc-texture.sdl", (333, 187)), ("lecture4.sdl", None), ("../tests/scenes/proc_below.sdl", None),
-                                       ("../tests/scenes/proc_far.sdl", None), ("../tests/scenes/sky_plane.sdl", None),
-                                       ("zaphod.sdl", (161, 107))])
-def test_regular_one_plane_frames_equal_the_general_kernel(name, size, monkeypatch):
+@pytest.mark.parametrize("name,size,over", [("lecture4-proc-texture.sdl", (333, 187), {}), ("lecture4.sdl", None, {}),
+                                            ("../tests/scenes/proc_below.sdl", None, {}), ("../tests/scenes/proc_far.sdl", None, {}),
+                                            ("../tests/scenes/sky_plane.sdl", None, {}), ("zaphod.sdl", (161, 107), {"dof": 0}),
+                                            ("zaphod.sdl", (161, 107), {"num_samples": 3})])   # DOF: the whole lens is checked
+def test_regular_one_plane_frames_equal_the_general_kernel(name, size, over, monkeypatch):
     """One-plane frames with a fixed camera off the plane and the light on its side run on kernels that take the camera's
     side, its height and 'the plane cannot shadow itself' as frame constants (render_kernel.cu isect_plane_solo, c2rt_api.cu
     fill_params).  Those are shortcuts, not approximations: the frame must be BIT-identical to the one the general kernel of
@@ -183,7 +184,7 @@ def test_regular_one_plane_frames_equal_the_general_kernel(name, size, monkeypat
     g = c2.HostScene(os.path.join(SC, name))
     if size:
         g.set_frame_size(*size)
-    g.override(dof=0)
+    g.override(**over)
     fast, fast_a, st_fast = g.render(argb=True, seed=5, count_rays=True)
     monkeypatch.setenv("C2RT_NO_SOLO_FAST", "1")
     gen, gen_a, st_gen = g.render(argb=True, seed=5, count_rays=True)
