@@ -191,41 +191,64 @@ __device__ __forceinline__ double uniform01(const FrameParams& fp, uint32_t px, 
     return r * (1.0 / 2147483647.0);
 }
 
-// sin(2 pi u), cos(2 pi u) for u in [0, 1] in FP64 (|err| < 3e-16): quadrant by the 2^52 rounding trick, then the
-// classic degree-13 / degree-14 minimax kernels on |t| <= pi/4.  Replaces sincos(u * 2 pi) of camera.d:260-263, whose
-// library form spends most of its ~75 instructions on argument ranges a unit-interval input cannot reach.
-// (coefficients in constant memory: a DFMA takes them as c[bank][imm] operands; FP64 literals would each cost two UMOVs)
-__constant__ double c_sincos[14] = {
-    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06, -1.98412698298579493134e-04,
-    8.33333333332248946124e-03, -1.66666666666666324348e-01,
-    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07, 2.48015872894767294178e-05,
-    -1.38888888888741095749e-03, 4.16666666666666019037e-02,
-    6.283185307179586476925, 6755399441055744.0};
+// sin(2 pi u), cos(2 pi u) for u in [0, 1] in FP64 (|err| < 4e-16): u = k / 64 + r with |r| <= 1 / 128 by the 2^52 rounding
+// trick, the rotation by k / 64 of a revolution from a 64-entry table (correctly rounded, global memory: the index differs per
+// lane, the 1 KB stays in L1), and short Taylor kernels on |t| = |2 pi r| <= 0.0491 (first neglected terms: t^11 / 11! and
+// t^10 / 10!, < 1e-19).  Replaces sincos(u * 2 pi) of camera.d:260-263 — whose library form spends most of its ~75 instructions
+// on argument ranges a unit-interval input cannot reach — with 19 FP64 instructions (round 1's quadrant form: 24 + 20 selects).
+__device__ const double2 c_rot64[64] = {
+    {1.0, 0.0}, {0.9951847266721969, 0.0980171403295606},
+    {0.9807852804032304, 0.19509032201612828}, {0.9569403357322088, 0.2902846772544624},
+    {0.9238795325112867, 0.3826834323650898}, {0.881921264348355, 0.47139673682599764},
+    {0.8314696123025452, 0.5555702330196022}, {0.773010453362737, 0.6343932841636455},
+    {0.7071067811865476, 0.7071067811865476}, {0.6343932841636455, 0.773010453362737},
+    {0.5555702330196022, 0.8314696123025452}, {0.47139673682599764, 0.881921264348355},
+    {0.3826834323650898, 0.9238795325112867}, {0.2902846772544624, 0.9569403357322088},
+    {0.19509032201612828, 0.9807852804032304}, {0.0980171403295606, 0.9951847266721969},
+    {0.0, 1.0}, {-0.0980171403295606, 0.9951847266721969},
+    {-0.19509032201612828, 0.9807852804032304}, {-0.2902846772544624, 0.9569403357322088},
+    {-0.3826834323650898, 0.9238795325112867}, {-0.47139673682599764, 0.881921264348355},
+    {-0.5555702330196022, 0.8314696123025452}, {-0.6343932841636455, 0.773010453362737},
+    {-0.7071067811865476, 0.7071067811865476}, {-0.773010453362737, 0.6343932841636455},
+    {-0.8314696123025452, 0.5555702330196022}, {-0.881921264348355, 0.47139673682599764},
+    {-0.9238795325112867, 0.3826834323650898}, {-0.9569403357322088, 0.2902846772544624},
+    {-0.9807852804032304, 0.19509032201612828}, {-0.9951847266721969, 0.0980171403295606},
+    {-1.0, 0.0}, {-0.9951847266721969, -0.0980171403295606},
+    {-0.9807852804032304, -0.19509032201612828}, {-0.9569403357322088, -0.2902846772544624},
+    {-0.9238795325112867, -0.3826834323650898}, {-0.881921264348355, -0.47139673682599764},
+    {-0.8314696123025452, -0.5555702330196022}, {-0.773010453362737, -0.6343932841636455},
+    {-0.7071067811865476, -0.7071067811865476}, {-0.6343932841636455, -0.773010453362737},
+    {-0.5555702330196022, -0.8314696123025452}, {-0.47139673682599764, -0.881921264348355},
+    {-0.3826834323650898, -0.9238795325112867}, {-0.2902846772544624, -0.9569403357322088},
+    {-0.19509032201612828, -0.9807852804032304}, {-0.0980171403295606, -0.9951847266721969},
+    {0.0, -1.0}, {0.0980171403295606, -0.9951847266721969},
+    {0.19509032201612828, -0.9807852804032304}, {0.2902846772544624, -0.9569403357322088},
+    {0.3826834323650898, -0.9238795325112867}, {0.47139673682599764, -0.881921264348355},
+    {0.5555702330196022, -0.8314696123025452}, {0.6343932841636455, -0.773010453362737},
+    {0.7071067811865476, -0.7071067811865476}, {0.773010453362737, -0.6343932841636455},
+    {0.8314696123025452, -0.5555702330196022}, {0.881921264348355, -0.47139673682599764},
+    {0.9238795325112867, -0.3826834323650898}, {0.9569403357322088, -0.2902846772544624},
+    {0.9807852804032304, -0.19509032201612828}, {0.9951847266721969, -0.0980171403295606},
+};
 __device__ __forceinline__ void sincos_rev(double u, double& s, double& c) {
-    const double MAGIC = c_sincos[13];                  // 1.5 * 2^52
-    const double qm = fma(u, 4.0, MAGIC);               // nearest integer to 4u in the low mantissa bits
-    const int q = __double2loint(qm);
-    const double r = fma(qm - MAGIC, -0.25, u);         // exact: u - q/4 in [-1/8, 1/8]
-    const double t = r * c_sincos[12];
+    const double MAGIC = 6755399441055744.0;            // 1.5 * 2^52
+    const double qm = fma(u, 64.0, MAGIC);              // nearest integer to 64 u in the low mantissa bits
+    const double2 R = __ldg(&c_rot64[__double2loint(qm) & 63]);   // (cos, sin) of k / 64 revolutions; k = 64 is k = 0
+    const double r = fma(qm - MAGIC, -0.015625, u);     // exact: u - k / 64 in [-1/128, 1/128]
+    const double t = r * 6.283185307179586476925;
     const double z = t * t;
-    double ps = c_sincos[0];
-    ps = fma(ps, z, c_sincos[1]);
-    ps = fma(ps, z, c_sincos[2]);
-    ps = fma(ps, z, c_sincos[3]);
-    ps = fma(ps, z, c_sincos[4]);
-    ps = fma(ps, z, c_sincos[5]);
+    double ps = 2.75573192239858906525573e-6;           // 1/9!
+    ps = fma(ps, z, -1.98412698412698412698413e-4);     // -1/7!
+    ps = fma(ps, z, 8.33333333333333333333333e-3);      // 1/5!
+    ps = fma(ps, z, -1.66666666666666666666667e-1);     // -1/3!
     const double st = fma(t * z, ps, t);
-    double pc = c_sincos[6];
-    pc = fma(pc, z, c_sincos[7]);
-    pc = fma(pc, z, c_sincos[8]);
-    pc = fma(pc, z, c_sincos[9]);
-    pc = fma(pc, z, c_sincos[10]);
-    pc = fma(pc, z, c_sincos[11]);
-    const double ct = fma(z * z, pc, fma(z, -0.5, 1.0));
-    // quadrant q mod 4: (s, c), (c, -s), (-s, -c), (-c, s)
-    const double a = (q & 1) ? ct : st, b = (q & 1) ? st : ct;
-    s = (q & 2) ? -a : a;
-    c = ((q + 1) & 2) ? -b : b;
+    double pc = 2.48015873015873015873016e-5;           // 1/8!
+    pc = fma(pc, z, -1.38888888888888888888889e-3);     // -1/6!
+    pc = fma(pc, z, 4.16666666666666666666667e-2);      // 1/4!
+    pc = fma(pc, z, -0.5);
+    const double ct = fma(pc, z, 1.0);
+    s = fma(R.x, st, R.y * ct);
+    c = fma(-R.y, st, R.x * ct);
 }
 
 // ---------------------------------------------------------------- camera
@@ -1488,6 +1511,15 @@ __device__ __forceinline__ uint32_t pack_rgb32(const uint8_t* lut, Col c) {  // 
     return lut8(lut, c.b) | (lut8(lut, c.g) << 8) | (lut8(lut, c.r) << 16);
 }
 
+// x / 5.f, correctly rounded, for the mean of the five AA taps (renderer.d:249): the fast path of the IEEE division — refined
+// reciprocal y, q = x y, one residual correction — written out, without its range check and out-of-line slow path (a colour sum
+// is never near the ends of the FP32 range; 0 stays 0).  y = 0.2f + 0.2f (1 - 5 * 0.2f) in FP32 is 0.2f itself.
+__device__ __forceinline__ float div5(float x) {
+    const float y = fmaf(fmaf(0.2f, -5.f, 1.f), 0.2f, 0.2f);
+    const float q = x * y;
+    return fmaf(y, fmaf(q, -5.f, x), q);
+}
+
 // ---------------------------------------------------------------- per-warp camera-ray node mask
 // Which nodes can a camera ray of this warp's 8x4 pixel patch reach?  All those rays start at the camera position and pass
 // through the screen rectangle [x0, x0+8] x [y0, y0+4] (pixel corners plus the AA tap offsets <= 0.6), so they lie in the
@@ -1619,7 +1651,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, MIN_BLOCKS) render_frame_kernel
             Col t = render_sample<MODE>(fp, bx, by, bz, xd, yd, sx, sy, s, jw, jh, active, n_primary, n_shadow, nullptr, cam);
             c.r += t.r; c.g += t.g; c.b += t.b;
         }
-        if (taps == 5) { c.r = c.r / 5.f; c.g = c.g / 5.f; c.b = c.b / 5.f; }  // accum / 5 (renderer.d:249)
+        if (taps == 5) { c.r = div5(c.r); c.g = div5(c.g); c.b = div5(c.b); }  // accum / 5 (renderer.d:249)
     }
 
     // output row of this tile row: full frame or compact (only this rank's rows, in order)
