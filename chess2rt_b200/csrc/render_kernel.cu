@@ -230,22 +230,27 @@ __device__ const double2 c_rot64[64] = {
     {0.9238795325112867, -0.3826834323650898}, {0.9569403357322088, -0.2902846772544624},
     {0.9807852804032304, -0.19509032201612828}, {0.9951847266721969, -0.0980171403295606},
 };
+// (coefficients in constant memory: a DFMA takes them as c[bank][imm] operands; FP64 literals would each cost two moves)
+__constant__ double c_sincos[12] = {
+    2.75573192239858906525573e-6, -1.98412698412698412698413e-4, 8.33333333333333333333333e-3, -1.66666666666666666666667e-1,   // 1/9! -1/7! 1/5! -1/3!
+    2.48015873015873015873016e-5, -1.38888888888888888888889e-3, 4.16666666666666666666667e-2, -0.5,                            // 1/8! -1/6! 1/4! -1/2!
+    6.283185307179586476925, 6755399441055744.0, -0.015625, 64.0};
 __device__ __forceinline__ void sincos_rev(double u, double& s, double& c) {
-    const double MAGIC = 6755399441055744.0;            // 1.5 * 2^52
-    const double qm = fma(u, 64.0, MAGIC);              // nearest integer to 64 u in the low mantissa bits
+    const double MAGIC = c_sincos[9];                   // 1.5 * 2^52
+    const double qm = fma(u, c_sincos[11], MAGIC);      // nearest integer to 64 u in the low mantissa bits
     const double2 R = __ldg(&c_rot64[__double2loint(qm) & 63]);   // (cos, sin) of k / 64 revolutions; k = 64 is k = 0
-    const double r = fma(qm - MAGIC, -0.015625, u);     // exact: u - k / 64 in [-1/128, 1/128]
-    const double t = r * 6.283185307179586476925;
+    const double r = fma(qm - MAGIC, c_sincos[10], u);  // exact: u - k / 64 in [-1/128, 1/128]
+    const double t = r * c_sincos[8];
     const double z = t * t;
-    double ps = 2.75573192239858906525573e-6;           // 1/9!
-    ps = fma(ps, z, -1.98412698412698412698413e-4);     // -1/7!
-    ps = fma(ps, z, 8.33333333333333333333333e-3);      // 1/5!
-    ps = fma(ps, z, -1.66666666666666666666667e-1);     // -1/3!
+    double ps = c_sincos[0];
+    ps = fma(ps, z, c_sincos[1]);
+    ps = fma(ps, z, c_sincos[2]);
+    ps = fma(ps, z, c_sincos[3]);
     const double st = fma(t * z, ps, t);
-    double pc = 2.48015873015873015873016e-5;           // 1/8!
-    pc = fma(pc, z, -1.38888888888888888888889e-3);     // -1/6!
-    pc = fma(pc, z, 4.16666666666666666666667e-2);      // 1/4!
-    pc = fma(pc, z, -0.5);
+    double pc = c_sincos[4];
+    pc = fma(pc, z, c_sincos[5]);
+    pc = fma(pc, z, c_sincos[6]);
+    pc = fma(pc, z, c_sincos[7]);
     const double ct = fma(pc, z, 1.0);
     s = fma(R.x, st, R.y * ct);
     c = fma(-R.y, st, R.x * ct);
