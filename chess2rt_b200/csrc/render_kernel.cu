@@ -61,6 +61,21 @@ __host__ __device__ constexpr bool is_big(int mode) { return (mode & MODE_BIG) !
 // sin after an FP64 range reduction, sphere uv.  Divisions and square roots in FP64 use the
 // MUFU seed + Newton steps below instead of the IEEE library sequences (|rel err| < 4e-16).
 
+// FP64 literals of the node walk as constant-bank operands: a DSETP / DFMA / DADD reads c[bank][imm] directly, whereas a literal
+// whose low word is not zero is first assembled in a register pair by two moves at every use
+__constant__ double c_lit[4] = {1e-9, 1e-6, 1e300, 1e99};
+#ifdef C2RT_LITERAL_IMMEDIATES
+#define K_1EM9 1e-9
+#define K_1EM6 1e-6
+#define K_1E300 1e300
+#define K_1E99 1e99
+#else
+#define K_1EM9 c_lit[0]
+#define K_1EM6 c_lit[1]
+#define K_1E300 c_lit[2]
+#define K_1E99 c_lit[3]
+#endif
+
 struct Ray {
     double ox, oy, oz, dx, dy, dz;   // d is unit (to ~1e-16) — except camera rays of the plane-only scene classes, see l2
     double l2;                       // plane-only scene classes: camera rays keep the UN-normalised direction, l2 = |d|^2 (gen_ray)
@@ -317,7 +332,7 @@ __device__ __forceinline__ void gen_ray(const FrameParams& fp, double vx, double
 // (o, d) is the ray in the primitive's frame, p[] the primitive's parameters in that frame.
 __device__ __forceinline__ bool isect_plane(double y, double limit, double ox, double oy, double oz, double dx, double dy, double dz,
                                             double& dist, double& px, double& py, double& pz) {
-    if ((oy > y && dy > -1e-9) || (oy < y && dy < 1e-9)) return false;
+    if ((oy > y && dy > -K_1EM9) || (oy < y && dy < K_1EM9)) return false;
     double mult = (oy - y) * rcp64(-dy);
     if (mult > dist) return false;
     double x = fma(dx, mult, ox), yy = fma(dy, mult, oy), z = fma(dz, mult, oz);
@@ -364,7 +379,7 @@ __device__ __forceinline__ bool isect_sphere(const double* p, double ox, double 
 // one axis pass of geometry.d:199-235; (a) is the slab axis, (b, c) the in-face axes
 __device__ __forceinline__ bool cube_pass(double oa, double ob, double oc, double da, double db, double dc, double ca, double cb,
                                           double cc, double half, double& dist, double& pa, double& pb, double& pc, int& side_out) {
-    if (fabs(da) < 1e-9) return false;
+    if (fabs(da) < K_1EM9) return false;
     bool found = false;
     const double inv = rcp64(-da);
 #pragma unroll
@@ -463,7 +478,7 @@ __device__ __forceinline__ Crossings cross_sphere(const double* p, double ox, do
         c.d0 = x2;
         c.n = 1;
         // restart 1e-6 past the entry: the far root is found iff it is still ahead
-        double rest = x1 - x2 - 1e-6;
+        double rest = x1 - x2 - K_1EM6;
         if (rest >= 0) { c.d1 = x2 + rest; c.n = 2; }
     } else if (x1 >= 0) {
         c.d0 = x1;
@@ -477,14 +492,14 @@ __device__ __forceinline__ Crossings cross_cube(const double* p, double ox, doub
     Crossings c;
     c.n = 0; c.f0 = 0; c.f1 = 0; c.d0 = 0; c.d1 = 0;
     const double half = p[3] * 0.5;
-    double tin = -1e300, tout = 1e300;
+    double tin = -K_1E300, tout = K_1E300;
     int fin = 0, fout = 0;
     bool miss = false;
     // pass order of geometry.d:172-191: Y (code 0), X (code 2), Z (code 4)
     const double o3[3] = {oy, ox, oz}, d3[3] = {dy, dx, dz}, c3[3] = {p[1], p[0], p[2]};
 #pragma unroll
     for (int a = 0; a < 3; a++) {
-        if (fabs(d3[a]) < 1e-9) {
+        if (fabs(d3[a]) < K_1EM9) {
             // geometry.d:201-202 skips the pass; the other passes' in-face bounds still reject an origin outside this slab
             if (o3[a] < c3[a] - half || o3[a] > c3[a] + half) miss = true;
         } else {
@@ -500,7 +515,7 @@ __device__ __forceinline__ Crossings cross_cube(const double* p, double ox, doub
     if (miss || tin > tout || tout < 0) return c;
     if (tin >= 0) {
         c.d0 = tin; c.f0 = fin; c.n = 1;
-        double rest = tout - tin - 1e-6;
+        double rest = tout - tin - K_1EM6;
         if (rest >= 0) { c.d1 = tin + rest; c.f1 = fout; c.n = 2; }
     } else {
         c.d0 = tout; c.f0 = fout; c.n = 1;
@@ -511,7 +526,7 @@ __device__ __forceinline__ Crossings cross_cube(const double* p, double ox, doub
 __device__ __forceinline__ Crossings cross_plane(const double* p, double ox, double oy, double oz, double dx, double dy, double dz) {
     Crossings c;
     c.n = 0; c.f0 = 0; c.f1 = 0; c.d0 = 0; c.d1 = 0;
-    double dist = 1e99, px, py, pz;
+    double dist = K_1E99, px, py, pz;
     if (isect_plane(p[0], p[1], ox, oy, oz, dx, dy, dz, dist, px, py, pz)) { c.d0 = dist; c.n = 1; }
     return c;
 }
@@ -583,14 +598,14 @@ __device__ __forceinline__ bool isect_csg(int gi, double ox, double oy, double o
     if (id < 0) return false;
     if (kd > dist) return false;
     dist = kd;
-    const double tt = (id & 1) ? kd + 1e-6 : kd;   // true parameter of the crossing point
+    const double tt = (id & 1) ? kd + K_1EM6 : kd;   // true parameter of the crossing point
     px = fma(dx, tt, ox); py = fma(dy, tt, oy); pz = fma(dz, tt, oz);
     face = id >> 2;
     leaf = (id & 2) ? g.right : g.left;
     if (g.type == C2RT_GEOM_CSG_DIFF) {
         const DevGeom& gr = geom_at<BIG>(g.right);   // a primitive: this closed form is only used for CSGs of primitives
-        bool a = prim_inside(gr, px - dx * 1e-6, py - dy * 1e-6, pz - dz * 1e-6);
-        bool b = prim_inside(gr, px + dx * 1e-6, py + dy * 1e-6, pz + dz * 1e-6);
+        bool a = prim_inside(gr, px - dx * K_1EM6, py - dy * K_1EM6, pz - dz * K_1EM6);
+        bool b = prim_inside(gr, px + dx * K_1EM6, py + dy * K_1EM6, pz + dz * K_1EM6);
         if (a != b) face |= FACE_FLIP;
     }
     return true;
@@ -1275,7 +1290,7 @@ __device__ __forceinline__ Col trace_warp(const FrameParams& fp, const Ray& cam_
     __shared__ float s_diffuse[3][BLOCK_THREADS];
     Ray r = cam_ray;
     HitRec h;
-    h.dist = 1e99;
+    h.dist = K_1E99;
     h.node = -1;
     float tmaxf = 3.0e38f;   // (not +inf = (float)1e99: ptxas would prove tmaxf == (float)h.dist * k and re-convert it in every iteration)
     float rsf = 0.f;         // shadow phases: 1 / |D| in FP32
@@ -1346,7 +1361,7 @@ __device__ __forceinline__ Col trace_warp(const FrameParams& fp, const Ray& cam_
                 const Col diffuse = has_tex ? sample_texture<MODE>(sh.tex, s.u, s.v) : mkcol(sh.color[0], sh.color[1], sh.color[2]);
                 s_diffuse[0][threadIdx.x] = diffuse.r; s_diffuse[1][threadIdx.x] = diffuse.g; s_diffuse[2][threadIdx.x] = diffuse.b;
                 // shadow-ray origin p + N * 1e-6 (shader.d:88,219)
-                r.ox = s.px + (double)Nx * 1e-6; r.oy = s.py + (double)Ny * 1e-6; r.oz = s.pz + (double)Nz * 1e-6;
+                r.ox = s.px + (double)Nx * K_1EM6; r.oy = s.py + (double)Ny * K_1EM6; r.oz = s.pz + (double)Nz * K_1EM6;
             } else if (live) {
                 const Col env = env_lookup(r.dx, r.dy, r.dz);   // a miss: renderer.d:366-368 (black unless the cubemap extension is on)
                 s_diffuse[0][threadIdx.x] = env.r; s_diffuse[1][threadIdx.x] = env.g; s_diffuse[2][threadIdx.x] = env.b;
