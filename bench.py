@@ -19,6 +19,9 @@ scaling is "strong".
              chess2rt_b200/workloads.json) / mean kernel time (CUDA events)
   cpu_baseline  the CPU oracle (C++ restatement of the reference: the D reference cannot be built in
              this image) timed on the box's host cores on the same frame
+  parity     (N = 1, with the CPU leg) the frame the e2e leg delivered against the oracle: max |diff|, pixels over 1e-3, share
+             of 8-bit pixels off by > 1 LSB, a diff image under gpurun_out/ when that directory exists; the run fails above the
+             bar.  Each scaling target carries the same check on 96 rows of its frame
   scaling_targets  BASELINE.json configs[2..4] (lecture5 4K, zaphod 4K DOF, chessboard 8K) measured in the same run
              at the same N: ms per frame, efficiency against rank 0 rendering the frame alone, frame check
 `--impl reference` times that CPU implementation alone with the same metric/config.
@@ -171,6 +174,45 @@ def cpu_rows_seconds(path, w, h, over, threads, rows):
         _, st = s.render_rows(y0, min(h, y0 + 8), threads=threads, seed=RNG_SEED)
         sec += st.seconds; rays += st.primary_rays + st.shadow_rays; done += min(h, y0 + 8) - y0
     return sec, rays, done
+
+
+def oracle_parity(path, w, h, over, gpu_rows, rows=None, diff_path=None):
+    """Parity check alongside timing (untimed, rank 0, N = 1, part of the CPU leg): the frame the product
+    path rendered for this workload against the CPU oracle — max |diff|, pixels over 1e-3, share of 8-bit pixels off by more than
+    1 LSB; the run FAILS above the bar.  `gpu_rows(y0, y1)` returns rows [y0, y1) of the GPU frame as a numpy array.
+    rows=None: the whole frame; otherwise `rows` rows in windows of 8 spread over the frame (bounded CPU time for 4K / 8K frames).
+    diff_path: the per-pixel max |diff| as an 8-bit PGM, 255 = 1e-3 (whole-frame checks only)."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_binding import OracleScene, parity_report
+    o = OracleScene(os.path.join(ROOT, path))
+    o.set_frame_size(w, h)
+    o.override(**over)
+    threads = os.cpu_count() or 1
+    if rows is None:
+        wins = [(0, h)]
+    else:
+        n_win = max(1, rows // 8)
+        wins = sorted({min(h - 8, (h // n_win) * i) // 8 * 8 for i in range(n_win)})
+        wins = [(y0, min(h, y0 + 8)) for y0 in wins]
+    got, ref = [], []
+    for y0, y1 in wins:
+        r, _ = o.render_rows(y0, y1, threads=threads, seed=RNG_SEED)
+        ref.append(r)
+        got.append(np.asarray(gpu_rows(y0, y1), dtype=np.float32))
+    got, ref = np.concatenate(got), np.concatenate(ref)
+    rep = parity_report(got, ref)
+    rep["sample"] = "whole frame" if rows is None else "%d rows (windows of 8 rows spread over the frame)" % got.shape[0]
+    rep["bar"] = "0 px over 1e-3 absolute; <= 0.1 % of 8-bit pixels off by more than 1 LSB"
+    rep["pass"] = rep["px_over_1e-3"] == 0 and rep["frac_over_1lsb"] <= 1e-3
+    if diff_path and rows is None:
+        d = np.abs(got.astype(np.float64) - ref.astype(np.float64)).max(axis=-1)
+        img = np.clip(d / 1e-3 * 255.0, 0, 255).astype(np.uint8)
+        with open(diff_path, "wb") as f:
+            f.write(b"P5\n%d %d\n255\n" % (w, h))
+            f.write(img.tobytes())
+        rep["diff_image"] = os.path.relpath(diff_path, ROOT) + " (max |diff| per pixel, 255 = 1e-3)"
+    return rep
 
 
 def run_reference(args, rank, world):
@@ -523,13 +565,19 @@ def main():
             ms_1 = rn.time_alone(k) if world > 1 else ms_n
             cal_n = load_calibration().get(name) or {}
             ex_n = executed_fractions(name, ms_1, peaks) if rank == 0 else None
+            par_n = None
+            if world == 1 and not args.no_cpu_baseline:
+                pth_n, w_n, h_n, over_n = WORKLOADS[name]
+                par_n = oracle_parity(pth_n, w_n, h_n, over_n, lambda y0, y1: rn.frame[y0:y1].cpu().numpy(), rows=96)
+                if not par_n["pass"]:
+                    raise SystemExit(f"{name}: the timed frame is not in parity with the oracle: {par_n}")
             scaling_targets.append({
                 "workload": workload_label(name), "n_gpus": world, "ms_per_step": ms_n, "ms_per_step_1gpu_same_run": ms_1,
                 "efficiency": ms_1 / (world * ms_n), "value": (pn + sn) / (ms_n * 1e-3) / 1e6, "unit": "Mrays/s",
                 "frames_per_s": 1e3 / ms_n, "steps": k, "gather": rn.mode, "frame_check": check_n,
                 "algorithmic_flops_per_frame": cal_n.get("flops"),
                 "achieved_tflops_per_gpu": (cal_n["flops"] / world / (ms_n * 1e-3) / 1e12) if cal_n.get("flops") else None,
-                "executed_1gpu": ex_n})
+                "executed_1gpu": ex_n, "parity": par_n})
             rn.close()
 
     # ---- e2e: public host API, HOST buffers, copies inside the timed region ------------------------
@@ -655,6 +703,13 @@ def main():
             # one thread beside it (comparable with the reference's published single-thread numbers, perf-results.md:21):
             # 96 rows spread over the frame, scaled
             s1, r1, done1 = cpu_rows_seconds(path, W, H, over, 1, rows=96)
+            # parity of the timed workload alongside its timing: the frame the e2e leg just delivered through the public host API
+            # against the oracle (whole frame up to 4K without DOF, else 128 rows)
+            diff_path = os.path.join(ROOT, "gpurun_out", "bench_parity_diff_%s.pgm" % args.workload) if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else None
+            whole = W * H <= 3840 * 2160 and args.workload not in ("c3", "c3_nosky")
+            line["parity"] = oracle_parity(path, W, H, over, lambda y0, y1: pinned.numpy()[y0:y1], rows=None if whole else 128, diff_path=diff_path)
+            if not line["parity"]["pass"]:
+                raise SystemExit("the timed frame is not in parity with the oracle: %s" % line["parity"])
             line["cpu_baseline"] = {"value": rays / sec / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
                                     "sample": sample, "frames_per_s": 1.0 / sec,
                                     "single_thread": {"value": r1 / s1 / 1e6, "unit": "Mrays/s", "cores": 1, "frames_per_s": done1 / (s1 * H),
