@@ -12,7 +12,7 @@ KEYS = [
     'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active',
     'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
     'smsp__thread_inst_executed_per_inst_executed.ratio', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
-    'FBSP.TriageCompute.dram__throughput.avg.pct_of_peak_sustained_elapsed',
+    'dram__bytes.sum.per_second', 'dram__cycles_active.avg.pct_of_peak_sustained_elapsed',
     'lts__t_sector_hit_rate.pct', 'sass__inst_executed_local_loads', 'sass__inst_executed_local_stores',
     'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
     'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
