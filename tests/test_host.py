@@ -480,3 +480,31 @@ def test_json_loader_agrees_with_python_json():
     assert d.n_lights == len(j["Lights"]) and d.n_nodes == len(j["Nodes"]) and d.n_geoms == len(j["Geometries"])
     L = j["Lights"][0]
     assert [d.light_pos[k] for k in range(3)] == [float(x) for x in L["pos"]] and d.light_power[0] == np.float32(L["power"])
+
+
+def test_bench_parity_check_passes_the_oracle_and_fails_a_wrong_frame(tmp_path):
+    """bench.py's parity check alongside timing, exercised on the CPU: fed the oracle's own rows it
+    passes with a zero report, fed a frame with one pixel off by 2e-3 it reports that pixel and does not pass; the row windows
+    cover the frame and the diff image is written for whole-frame checks."""
+    import bench
+    from oracle_binding import OracleScene
+    path, w, h = "scenes/lecture4.sdl", 96, 64
+    o = OracleScene(os.path.join(ROOT, path))
+    o.set_frame_size(w, h)
+    ref, _ = o.render(threads=2, seed=bench.RNG_SEED)
+    diff = tmp_path / "diff.pgm"
+    rep = bench.oracle_parity(path, w, h, {}, lambda y0, y1: ref[y0:y1], rows=None, diff_path=str(diff))
+    assert rep["pass"] and rep["max_abs"] == 0.0 and rep["n"] == w * h and rep["sample"] == "whole frame"
+    assert diff.read_bytes().startswith(b"P5\n96 64\n255\n") and len(diff.read_bytes()) == len(b"P5\n96 64\n255\n") + w * h
+    bad = ref.copy()
+    bad[40, 10, 1] += 2e-3
+    asked = []
+
+    def rows(y0, y1):
+        asked.append((y0, y1))
+        return bad[y0:y1]
+    rep = bench.oracle_parity(path, w, h, {}, rows, rows=64)
+    assert asked == [(8 * i, 8 * i + 8) for i in range(8)]          # 64 rows = the whole 64-row frame in windows of 8
+    assert not rep["pass"] and rep["px_over_1e-3"] == 1 and abs(rep["max_abs"] - 2e-3) < 1e-6
+    rep = bench.oracle_parity(path, w, h, {}, lambda y0, y1: bad[y0:y1], rows=16)   # two windows, rows 0-7 and 32-39: the bad pixel is outside
+    assert rep["pass"] and rep["n"] == 16 * w
