@@ -1843,7 +1843,7 @@ cudaError_t upload_scene(const DevScene& s, cudaStream_t st) {
 #define C2RT_MINBLOCKS_NESTED 2
 #endif
 #ifndef C2RT_MINBLOCKS_SOLO_SAMPLING
-#define C2RT_MINBLOCKS_SOLO_SAMPLING 6
+#define C2RT_MINBLOCKS_SOLO_SAMPLING 7   // 71 registers, no spills: C3 14.30 -> 13.74 ms (5: 15.37, 6: 14.30, 8: 13.88; profiles/r2_s2_experiments.log)
 #endif
 
 // MODE_SOLO scene classes: texture kind x shader kind, each with and without the DOF / stereo sampling loop
