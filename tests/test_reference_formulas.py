@@ -183,3 +183,94 @@ def test_node_transform_inverse_and_transpose_are_consistent():
             MiT = np.array([d.node_inverse_t[9 * i + k] for k in range(9)]).reshape(3, 3)
             np.testing.assert_allclose(M @ Mi, np.eye(3), atol=1e-15)
             np.testing.assert_array_equal(MiT, Mi.T)
+
+
+# ---------------------------------------------------------------- shading and textures, derived by hand
+# Same 4x4 frame and camera.  Pixel (3, 3): target - pos = upLeft + (upRight - upLeft) 3/4 + (downLeft - upLeft) 3/4 - pos = (s/2, -s/2, 1),
+# s = 1/sqrt(2); on the plane y = 0 the ray from (0, 5, 0) arrives at t with 5 = t (s/2)/len, i.e. p = (5, 0, 5 / (s/2)) = (5, 0, 10 sqrt 2)
+# whatever the length: (u, v) = (p.x, p.z) = (5, 10 sqrt 2) (geometry.d:49-55).  The light sits 10 above p: |L - p|^2 = 100, lightDir = N =
+# (0, 1, 0), cosTheta = 1, baseLight = color * power / 100 = 0.5 (shader.d:67-105,197-250; light.d:11-14), so lightContrib = ambient 0.1 + 0.5 = 0.6.
+V2 = 10 * S2
+SHADE_HEAD = """Scene {{
+  GlobalSettings {{ frameWidth 4; frameHeight 4; ambientLightColor 0.1 0.1 0.1; AAEnabled false; prepassEnabled false }}
+  Camera {{ pos 0 5 0; yaw 0; pitch 0; roll 0; fov 90 }}
+  Lights {{ PointLight "l" {{ pos 5 10 %.17g; color 1 1 1; power 50 }} }}
+  Geometries {{ Plane "g" {{ y 0 }} }}
+  Textures {{ {textures} }}
+  Shaders {{ {shader} }}
+  Nodes {{ Node "n" {{ geometry "g"; shader "s" }} }}
+}}
+""" % V2
+
+_Q = float(np.float32(np.float32(V2 * 0.1 - 1.0) * np.float32(2)))   # bitmap case: ty = float(v') * height, v' = frac(0.1 * 10 sqrt 2)
+
+SHADE_CASES = {
+    # shader.d:197-250 Phong: R = reflect(-lightDir, N) = (0, -1, 0) - 2 (-1) (0, 1, 0) = (0, 1, 0) (imported_types.d:62-67);
+    # -ray.dir = -(s/2, -s/2, 1) / sqrt(1.25): cosGamma = (s/2) / sqrt(1.25) = sqrt(0.1); specular = baseLight * cosGamma^2 * strength
+    # = 0.5 * 0.1 * 0.5 = 0.025; colour = diffuse * 0.6 + 0.025
+    "phong": (dict(textures="", shader='Phong "s" { color 1 0.5 0.25; exponent 2; strength 0.5 }'),
+              (0.6 + 0.025, 0.3 + 0.025, 0.15 + 0.025)),
+    # texture.d:36-54 Checker, size 5: x = floor(5 / 5) = 1, y = floor(14.142 / 5) = 2, (1 + 2) % 2 = 1 -> color2; size 4: x = 1, y = 3 -> 0 -> color1
+    "checker_color2": (dict(textures='Checker "t" { color1 0.2 0.4 0.6; color2 1 0.9 0.8; size 5 }', shader='Lambert "s" { color 1 1 1; texture "t" }'),
+                       (0.6 * 1.0, 0.6 * 0.9, 0.6 * 0.8)),
+    "checker_color1": (dict(textures='Checker "t" { color1 0.2 0.4 0.6; color2 1 0.9 0.8; size 4 }', shader='Lambert "s" { color 1 1 1; texture "t" }'),
+                       (0.6 * 0.2, 0.6 * 0.4, 0.6 * 0.6)),
+    # texture.d:77-86 Procedure2: sum_i colorU[i] sin(u freqU[i]) + colorV[i] sin(v freqV[i]) at (u, v) = (5, 10 sqrt 2)
+    "procedure2": (dict(textures='Procedure2 "t" { freqU 0.1 0.2 0.3; freqV 0.1 0.2 0.3; '
+                                 'colorU { color 1 0 0; color 0 1 0; color 0 0 1 }; colorV { color 0.5 0.5 0.5; color 0.25 0 0; color 0 0 0.125 } }',
+                        shader='Lambert "s" { color 1 1 1; texture "t" }'),
+                   tuple(0.6 * c for c in (
+                       math.sin(0.5) + 0.5 * math.sin(0.1 * V2) + 0.25 * math.sin(0.2 * V2),
+                       math.sin(1.0) + 0.5 * math.sin(0.1 * V2),
+                       math.sin(1.5) + 0.5 * math.sin(0.1 * V2) + 0.125 * math.sin(0.3 * V2)))),
+    # texture.d:116-126 + bitmap.d:48-63 BitmapTexture, scaling 0.1, assumedGamma 1 (no remap, texture.d:137-141), on the 2x2 bitmap written by
+    # _write_bmp (top row red, green; bottom row blue, white): u' = frac(0.5) = 0.5 -> tx = 1.0, tx_next = (1 + 1) % 2 = 0, p = 0;
+    # v' = frac(1.41421...) -> ty = float(v') * 2 = 0.828427..., ty = 0, ty_next = 1, q = 0.828427...;
+    # colour = data[1, 0] (1 - q) + data[1, 1] q = green (1 - q) + white q = (q, 1, q)
+    "bitmap": (dict(textures='BitmapTexture "t" { file "t.bmp"; scaling 0.1; assumedGamma 1 }', shader='Lambert "s" { color 1 1 1; texture "t" }'),
+               (0.6 * _Q, 0.6, 0.6 * _Q)),
+}
+
+
+def _write_bmp(path):
+    """2x2, 24 bpp, BITMAPINFOHEADER; rows bottom-up (imageio/bmp.d:130-150), pixels B, G, R, rows padded to 4 bytes."""
+    import struct
+    rows = bytes([255, 0, 0, 255, 255, 255, 0, 0]) + bytes([0, 0, 255, 0, 255, 0, 0, 0])   # bottom: blue, white; top: red, green
+    hdr = b"BM" + struct.pack("<IHHI", 54 + len(rows), 0, 0, 54) + struct.pack("<IiiHHIIiiII", 40, 2, 2, 1, 24, 0, len(rows), 2835, 2835, 0, 0)
+    open(path, "wb").write(hdr + rows)
+
+
+def write_shade_scene(tmp_path, name):
+    _write_bmp(str(tmp_path / "t.bmp"))
+    p = tmp_path / (name + ".sdl")
+    p.write_text(SHADE_HEAD.format(**SHADE_CASES[name][0]))
+    return str(p)
+
+
+@pytest.mark.parametrize("name", sorted(SHADE_CASES))
+def test_oracle_reproduces_hand_derived_shading(name, tmp_path):
+    from oracle_binding import OracleScene
+    o = OracleScene(write_shade_scene(tmp_path, name))
+    rgb, hit = o.render_pixel(3, 3)
+    assert int(hit[0]) == 0
+    np.testing.assert_allclose(hit[2:5], (5.0, 0.0, V2), rtol=0, atol=1e-11)
+    np.testing.assert_allclose(hit[8:10], (5.0, V2), rtol=0, atol=1e-11)
+    np.testing.assert_allclose(rgb, SHADE_CASES[name][1], rtol=0, atol=2e-6, err_msg=name)
+    frame, _ = o.render()
+    np.testing.assert_allclose(frame[3, 3], SHADE_CASES[name][1], rtol=0, atol=2e-6, err_msg=name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(SHADE_CASES))
+def test_gpu_reproduces_hand_derived_shading(name, tmp_path):
+    import chess2rt_b200 as c2
+    c2.init(1, [0])
+    g = c2.HostScene(write_shade_scene(tmp_path, name))
+    rgb, hit = g.render_pixel(3, 3)
+    assert hit.node == 0
+    np.testing.assert_allclose(list(hit.p), (5.0, 0.0, V2), rtol=0, atol=1e-11)
+    # (Procedure2: six SFU sines of a phase kept to 2^-23 revolution, each good to ~1e-6: DESIGN.md section 4.2)
+    atol = 1e-5 if name == "procedure2" else 3e-6
+    np.testing.assert_allclose(rgb, SHADE_CASES[name][1], rtol=0, atol=atol, err_msg=name)
+    frame, _, _ = g.render()   # one plane, one light: the MODE_SOLO kernels (Procedure2 through sin_phase, the bitmap through its palette quads)
+    np.testing.assert_allclose(frame[3, 3], SHADE_CASES[name][1], rtol=0, atol=atol, err_msg=name)
