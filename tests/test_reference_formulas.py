@@ -274,3 +274,89 @@ def test_gpu_reproduces_hand_derived_shading(name, tmp_path):
     np.testing.assert_allclose(rgb, SHADE_CASES[name][1], rtol=0, atol=atol, err_msg=name)
     frame, _, _ = g.render()   # one plane, one light: the MODE_SOLO kernels (Procedure2 through sin_phase, the bitmap through its palette quads)
     np.testing.assert_allclose(frame[3, 3], SHADE_CASES[name][1], rtol=0, atol=atol, err_msg=name)
+
+
+# ---------------------------------------------------------------- a whole (tiny) frame, restated independently in Python
+# A third implementation, written from the D sources alone and sharing nothing with oracle/ or the CUDA path: camera.d:84-117,139-146
+# (corners, screen ray), renderer.d:223-251 (corner sample + the four AA taps, accum / 5), geometry.d:30-59 (plane), texture.d:36-54
+# (checker), shader.d:67-105 (Lambert, faceforward, shadow-ray origin p + N 1e-6), scene.d:62-78 (visibility), light.d:11-14
+# (color * power), color.d:122-132 (FP32 colour arithmetic).  4x4 frame, fov 90, camera (0, 5, 0) looking down +z: rows 0 and 1 miss,
+# row 2 sits ON the horizon (its corner sample misses, some of its AA taps hit the plane far away), row 3 hits.
+FRAME_SCENE = """Scene {
+  GlobalSettings { frameWidth 4; frameHeight 4; ambientLightColor 0.1 0.2 0.3; AAEnabled true; prepassEnabled false }
+  Camera { pos 0 5 0; yaw 0; pitch 0; roll 0; fov 90 }
+  Lights { PointLight "l" { pos 1 10 12; color 1 0.9 0.8; power 300 } }
+  Geometries { Plane "g" { y 0 } }
+  Textures { Checker "t" { color1 0.2 0.4 0.6; color2 1 0.9 0.8; size 3 } }
+  Shaders { Lambert "s" { color 1 1 1; texture "t" } }
+  Nodes { Node "n" { geometry "g"; shader "s" } }
+}
+"""
+
+
+def python_frame():
+    f32 = np.float32
+    W = H = 4
+    pos = np.array([0.0, 5.0, 0.0])
+    light = np.array([1.0, 10.0, 12.0])
+    light_color = np.array([f32(1) * f32(300), f32(0.9) * f32(300), f32(0.8) * f32(300)], dtype=f32)   # light.d:11-14
+    ambient = np.array([0.1, 0.2, 0.3], dtype=f32)
+    c1, c2 = np.array([0.2, 0.4, 0.6], dtype=f32), np.array([1, 0.9, 0.8], dtype=f32)
+    # camera.d:84-100
+    x, y = -(W / H), 1.0
+    len_xy = math.hypot(x, y)
+    scaling = math.tan(math.radians(90.0 / 2)) / len_xy
+    x, y = x * scaling, y * scaling
+    up_left, up_right, down_left = np.array([x, y, 1.0]) + pos, np.array([-x, y, 1.0]) + pos, np.array([x, -y, 1.0]) + pos
+
+    def sample(sx, sy):
+        target = up_left + (up_right - up_left) * (sx / W) + (down_left - up_left) * (sy / H)    # camera.d:139-146
+        d = target - pos
+        d = d / math.sqrt(d @ d)
+        if d[1] > -1e-9:                                                                           # geometry.d:35 (origin above the plane)
+            return np.zeros(3, f32)                                                                # environment.d:7-10
+        t = (pos[1] - 0.0) / -d[1]
+        p = pos + d * t
+        n = np.array([0.0, 1.0, 0.0])                                                              # faceforward: d . n < 0
+        cx, cz = int(math.floor(p[0] / 3.0)), int(math.floor(p[2] / 3.0))                          # texture.d:47-48
+        white = int(math.fmod(cx + cz, 2))                                                         # :50, D's % truncates: -1 is true as well
+        diffuse = c2 if white else c1
+        contrib = ambient.copy()
+        frm = p + n * 1e-6
+        # scene.d:62-78: the only node is the plane; from is above it and the light higher still: dir.y > -1e-9 -> no hit -> visible
+        assert frm[1] > 0 and light[1] > frm[1]
+        ld = light - p
+        dist2 = ld @ ld
+        cos_theta = (ld / math.sqrt(dist2)) @ n
+        if cos_theta > 0:
+            contrib = contrib + (light_color / f32(dist2)) * f32(cos_theta)                        # shader.d:97, FP32 Color ops
+        return (diffuse * contrib).astype(f32)
+
+    img = np.zeros((H, W, 3), f32)
+    for py in range(H):
+        for px in range(W):
+            acc = sample(px, py)
+            for kx, ky in ((0.3, 0.3), (0.6, 0.0), (0.0, 0.6), (0.6, 0.6)):                        # renderer.d:235-247
+                acc = acc + sample(px + kx, py + ky)
+            img[py, px] = acc / f32(5)
+    return img
+
+
+def test_oracle_matches_the_independent_python_frame(tmp_path):
+    from oracle_binding import OracleScene
+    p = tmp_path / "frame.sdl"
+    p.write_text(FRAME_SCENE)
+    want = python_frame()
+    assert (want[:2] == 0).all() and (want[2] > 0).any() and (want[2] < want[3].max()).all() and (want[3] > 0).all()
+    got, _ = OracleScene(str(p)).render()
+    np.testing.assert_allclose(got, want, rtol=0, atol=2e-6)
+
+
+@pytest.mark.gpu
+def test_gpu_matches_the_independent_python_frame(tmp_path):
+    import chess2rt_b200 as c2
+    c2.init(1, [0])
+    p = tmp_path / "frame.sdl"
+    p.write_text(FRAME_SCENE)
+    got, _, _ = c2.HostScene(str(p)).render()
+    np.testing.assert_allclose(got, python_frame(), rtol=0, atol=3e-6)
