@@ -360,3 +360,131 @@ def test_gpu_matches_the_independent_python_frame(tmp_path):
     p.write_text(FRAME_SCENE)
     got, _, _ = c2.HostScene(str(p)).render()
     np.testing.assert_allclose(got, python_frame(), rtol=0, atol=3e-6)
+
+
+# ---------------------------------------------------------------- the same, with spheres, shadows, two lights and Phong
+# The independent Python restatement extended by geometry.d:92-125 (sphere: the quadratic as written, closer root first), node.d:23-49
+# (translated node: origin minus offset, identity matrix), renderer.d:325-376 (closest hit over the nodes in scene order),
+# scene.d:62-78 (shadow ray: any node hit closer than the light), shader.d:197-250 (Phong) and imported_types.d:62-73
+# (reflect, faceforward).  8x6 anti-aliased frame of a checkered floor with two spheres, one of them a translated node sharing the
+# other's geometry, lit by two lights: shadows on the floor and on a sphere, highlights, silhouettes, horizon.
+SPHERES_SCENE = """Scene {
+  GlobalSettings { frameWidth 8; frameHeight 6; ambientLightColor 0.05 0.1 0.15; AAEnabled true; prepassEnabled false }
+  Camera { pos 0 6 -4; yaw 0; pitch 0; roll 0; fov 80 }
+  Lights {
+    PointLight "l0" { pos -6 14 4; color 1 0.9 0.8; power 500 }
+    PointLight "l1" { pos 8 9 10; color 0.3 0.5 1; power 400 }
+  }
+  Geometries { Plane "floor" { y 0 }; Sphere "ball" { center 0 3 12; R 3 } }
+  Textures { Checker "t" { color1 0.2 0.4 0.6; color2 1 0.9 0.8; size 2.5 } }
+  Shaders { Lambert "fs" { color 1 1 1; texture "t" }; Phong "bs" { color 0.8 0.3 0.2; exponent 12; strength 0.7 }; Lambert "cs" { color 0.1 0.9 0.4 } }
+  Nodes {
+    Node "n0" { geometry "floor"; shader "fs" }
+    Node "n1" { geometry "ball"; shader "bs" }
+    Node "n2" { geometry "ball"; shader "cs"; translate 5 1 -3 }
+  }
+}
+"""
+
+
+def python_spheres_frame():
+    f32 = np.float32
+    W, H = 8, 6
+    pos = np.array([0.0, 6.0, -4.0])
+    lights = [(np.array([-6.0, 14.0, 4.0]), np.array([f32(1) * f32(500), f32(0.9) * f32(500), f32(0.8) * f32(500)], f32)),
+              (np.array([8.0, 9.0, 10.0]), np.array([f32(0.3) * f32(400), f32(0.5) * f32(400), f32(1) * f32(400)], f32))]
+    ambient = np.array([0.05, 0.1, 0.15], f32)
+    c1, c2 = np.array([0.2, 0.4, 0.6], f32), np.array([1, 0.9, 0.8], f32)
+    centre, R = np.array([0.0, 3.0, 12.0]), 3.0
+    # nodes in scene order: (kind, offset, shader)
+    nodes = [("plane", np.zeros(3), "fs"), ("sphere", np.zeros(3), "bs"), ("sphere", np.array([5.0, 1.0, -3.0]), "cs")]
+    x, y = -(W / H), 1.0
+    scaling = math.tan(math.radians(80.0 / 2)) / math.hypot(x, y)
+    x, y = x * scaling, y * scaling
+    up_left, up_right, down_left = np.array([x, y, 1.0]) + pos, np.array([-x, y, 1.0]) + pos, np.array([x, -y, 1.0]) + pos
+
+    def hit_node(kind, off, o, d, best):
+        """-> (dist, p, normal) or None; (o, d) in world space, d unit; node.d:23-49 with the identity matrix"""
+        o = o - off
+        if kind == "plane":                                           # geometry.d:30-59, y = 0
+            if (o[1] > 0 and d[1] > -1e-9) or (o[1] < 0 and d[1] < 1e-9):
+                return None
+            t = o[1] / -d[1]
+            if t > best:
+                return None
+            return t, o + d * t + off, np.array([0.0, 1.0, 0.0])
+        h = o - centre                                                # geometry.d:92-125
+        a, b, c = d @ d, 2 * (h @ d), h @ h - R * R
+        dscr = b * b - 4 * a * c
+        if dscr < 0:
+            return None
+        x1, x2 = (-b + math.sqrt(dscr)) / (2 * a), (-b - math.sqrt(dscr)) / (2 * a)
+        sol = x2 if x2 >= 0 else x1
+        if sol < 0 or sol > best:
+            return None
+        p = o + d * sol
+        n = p - centre
+        return sol, p + off, n / math.sqrt(n @ n)
+
+    def visible(frm, to):                                             # scene.d:62-78
+        d = to - frm
+        dist = math.sqrt(d @ d)
+        d = d / dist
+        return not any(hit_node(k, off, frm, d, dist) for k, off, _ in nodes)
+
+    def sample(sx, sy):
+        target = up_left + (up_right - up_left) * (sx / W) + (down_left - up_left) * (sy / H)
+        d = target - pos
+        d = d / math.sqrt(d @ d)
+        best, rec = 1e99, None
+        for k, off, sh in nodes:                                      # renderer.d:336-338
+            r = hit_node(k, off, pos, d, best)
+            if r:
+                best, rec = r[0], (r[1], r[2], sh)
+        if rec is None:
+            return np.zeros(3, f32)
+        p, n, sh = rec
+        if not d @ n < 0:                                             # faceforward
+            n = -n
+        if sh == "fs":
+            white = int(math.fmod(int(math.floor(p[0] / 2.5)) + int(math.floor(p[2] / 2.5)), 2))
+            diffuse = c2 if white else c1
+        else:
+            diffuse = np.array([0.8, 0.3, 0.2], f32) if sh == "bs" else np.array([0.1, 0.9, 0.4], f32)
+        contrib, spec = ambient.copy(), np.zeros(3, f32)
+        for lp, lc in lights:
+            if not visible(p + n * 1e-6, lp):
+                continue
+            ld = lp - p
+            dist2 = ld @ ld
+            ld = ld / math.sqrt(dist2)
+            cos_theta = ld @ n
+            base = lc / f32(dist2)
+            if cos_theta > 0:
+                contrib = contrib + base * f32(cos_theta)
+            if sh == "bs":                                            # shader.d:235-241
+                r = -ld - 2 * (-ld @ n) * n
+                r = r / math.sqrt(r @ r)
+                cos_gamma = r @ -d
+                if cos_gamma > 0:
+                    spec = spec + base * f32(cos_gamma ** 12) * f32(0.7)
+        return (diffuse * contrib + spec).astype(f32)
+
+    img = np.zeros((H, W, 3), f32)
+    for py in range(H):
+        for px in range(W):
+            acc = sample(px, py)
+            for kx, ky in ((0.3, 0.3), (0.6, 0.0), (0.0, 0.6), (0.6, 0.6)):
+                acc = acc + sample(px + kx, py + ky)
+            img[py, px] = acc / f32(5)
+    return img
+
+
+def test_oracle_matches_the_independent_python_frame_with_spheres_and_shadows(tmp_path):
+    from oracle_binding import OracleScene
+    p = tmp_path / "spheres.sdl"
+    p.write_text(SPHERES_SCENE)
+    want = python_spheres_frame()
+    got, st = OracleScene(str(p)).render()
+    assert st.shadow_rays < 2 * st.primary_rays and st.shadow_rays > st.primary_rays // 2   # hits, two lights each
+    np.testing.assert_allclose(got, want, rtol=0, atol=3e-6)
