@@ -488,3 +488,234 @@ def test_oracle_matches_the_independent_python_frame_with_spheres_and_shadows(tm
     got, st = OracleScene(str(p)).render()
     assert st.shadow_rays < 2 * st.primary_rays and st.shadow_rays > st.primary_rays // 2   # hits, two lights each
     np.testing.assert_allclose(got, want, rtol=0, atol=3e-6)
+
+
+# ---------------------------------------------------------------- the same, with cubes and CSG
+# The independent Python restatement extended by geometry.d:172-235 (cube: the Y, X, Z side passes through project / unproject,
+# imported_types.d:44-60) and geometry.d:271-402 (CSG: findAllIntersections with its 1e-6 restarts whose offset is never added back,
+# the merged list shell-sorted by util/array.d:95-111 — `foreach (ref i, ...)` with the index moved inside the loop — the walk that
+# flips inL / inR by `current.g is left`, boolOp per class, CsgDiff's normal flip), written from the D text alone.  10x8 frame:
+# a floor, lecture5's cube-minus-sphere, a translated sphere-and-cube intersection, a union of two spheres; one light.
+CSG_SCENE = """Scene {
+  GlobalSettings { frameWidth 10; frameHeight 8; ambientLightColor 0.1 0.1 0.1; AAEnabled true; prepassEnabled false }
+  Camera { pos 0 9 -10; yaw 0; pitch 0; roll 0; fov 85 }
+  Lights { PointLight "l" { pos -7 20 -2; color 1 1 1; power 700 } }
+  Geometries {
+    Plane "floor" { y 0 }
+    Cube "c" { center -4 3 8; side 6 }
+    Sphere "s" { center -4 3 8; R 3.9 }
+    CsgDiff "diff" { left "c"; right "s" }
+    Sphere "s2" { center 0 0 0; R 3 }
+    Cube "c2" { center 0.5 0.5 0; side 4.4 }
+    CsgInter "inter" { left "s2"; right "c2" }
+    Sphere "s3" { center 5 2.5 14; R 2.5 }
+    Sphere "s4" { center 7 4 13; R 2 }
+    CsgUnion "union" { left "s3"; right "s4" }
+  }
+  Shaders { Lambert "f" { color 0.7 0.7 0.7 }; Lambert "a" { color 0.9 0.6 0.1 }; Lambert "b" { color 0.2 0.6 0.9 }; Lambert "u" { color 0.4 0.9 0.3 } }
+  Nodes {
+    Node "n0" { geometry "floor"; shader "f" }
+    Node "n1" { geometry "diff"; shader "a" }
+    Node "n2" { geometry "inter"; shader "b"; translate 4 3 5 }
+    Node "n3" { geometry "union"; shader "u" }
+  }
+}
+"""
+
+
+class _Hit:
+    def __init__(self, dist, p, n, g):
+        self.dist, self.p, self.n, self.g = dist, p, n, g
+
+
+class _Plane:
+    def inside(self, p):
+        return False
+
+    def isect(self, o, d, best):
+        if (o[1] > 0 and d[1] > -1e-9) or (o[1] < 0 and d[1] < 1e-9):
+            return None
+        t = o[1] / -d[1]
+        if t > best:
+            return None
+        return _Hit(t, o + d * t, np.array([0.0, 1.0, 0.0]), self)
+
+
+class _Sphere:
+    def __init__(self, c, r):
+        self.c, self.r = np.array(c, float), r
+
+    def inside(self, p):
+        v = self.c - p
+        return v @ v < self.r * self.r
+
+    def isect(self, o, d, best):
+        h = o - self.c
+        a, b, c = d @ d, 2 * (h @ d), h @ h - self.r * self.r
+        dscr = b * b - 4 * a * c
+        if dscr < 0:
+            return None
+        x1, x2 = (-b + math.sqrt(dscr)) / (2 * a), (-b - math.sqrt(dscr)) / (2 * a)
+        sol = x2 if x2 >= 0 else x1
+        if sol < 0 or sol > best:
+            return None
+        p = o + d * sol
+        n = p - self.c
+        return _Hit(sol, p, n / math.sqrt(n @ n), self)
+
+
+class _Cube:
+    def __init__(self, c, side):
+        self.c, self.side = np.array(c, float), side
+
+    def inside(self, p):
+        return bool((np.abs(p - self.c) <= self.side * 0.5).all())
+
+    def _side(self, o, d, c, best):
+        """intersectCubeSide on (o, d, c) in the pass's frame -> (dist, p, normal) in that frame or None"""
+        if abs(d[1]) < 1e-9:
+            return None
+        half, found = self.side * 0.5, None
+        for s in (-1, 1):
+            mult = (o[1] - (c[1] + s * half)) / -d[1]
+            if mult < 0 or mult > best:
+                continue
+            p = o + d * mult
+            if p[0] < c[0] - half or p[0] > c[0] + half or p[2] < c[2] - half or p[2] > c[2] + half:
+                continue
+            best, found = mult, (mult, p, np.array([0.0, float(s), 0.0]))
+        return found
+
+    def isect(self, o, d, best):
+        res = None
+        for perm in ((0, 1, 2), (1, 0, 2), (0, 2, 1)):       # Y sides; X sides (swap x, y); Z sides (swap y, z): each permutation is its own inverse
+            idx = list(perm)
+            r = self._side(o[idx], d[idx], self.c[idx], best)
+            if r:
+                best = r[0]
+                res = _Hit(r[0], r[1][idx], r[2][idx], self)
+        return res
+
+
+class _Csg:
+    def __init__(self, op, left, right):
+        self.op, self.left, self.right = op, left, right
+
+    def bool_op(self, l, r):
+        return (l or r) if self.op == "union" else (l and r) if self.op == "inter" else (l and not r)
+
+    def inside(self, p):
+        return self.bool_op(self.left.inside(p), self.right.inside(p))
+
+    @staticmethod
+    def _all(geom, o, d):
+        out, cur = [], 0.0
+        while True:
+            h = geom.isect(o, d, 1e99)
+            if h is None:
+                return out
+            h.dist += cur
+            cur = h.dist
+            o = h.p + d * 1e-6
+            out.append(h)
+
+    def isect(self, o, d, best):
+        ld, rd = self._all(self.left, o, d), self._all(self.right, o, d)
+        arr = ld + rd
+        n, inc = len(arr), len(arr) // 2
+        while inc:                                              # util/array.d:95-111
+            i = 0
+            while i < n:
+                elem = arr[i]
+                while i >= inc and arr[i - inc].dist > elem.dist:
+                    arr[i] = arr[i - inc]
+                    i -= inc
+                arr[i] = elem
+                i += 1
+            inc = 1 if inc == 2 else int(inc * 5.0 / 11)
+        in_l, in_r = len(ld) % 2 == 1, len(rd) % 2 == 1
+        for cur in arr:
+            if cur.g is self.left:
+                in_l = not in_l
+            else:
+                in_r = not in_r
+            if self.bool_op(in_l, in_r):
+                if cur.dist > best:
+                    return None
+                hit = _Hit(cur.dist, cur.p, cur.n, cur.g)
+                if self.op == "diff" and self.right.inside(hit.p - d * 1e-6) != self.right.inside(hit.p + d * 1e-6):
+                    hit.n = -hit.n
+                return hit
+        return None
+
+
+def python_csg_frame():
+    f32 = np.float32
+    W, H = 10, 8
+    pos, light = np.array([0.0, 9.0, -10.0]), np.array([-7.0, 20.0, -2.0])
+    lc = np.array([f32(1) * f32(700)] * 3, f32)
+    ambient = np.array([0.1, 0.1, 0.1], f32)
+    diff = _Csg("diff", _Cube((-4, 3, 8), 6), _Sphere((-4, 3, 8), 3.9))
+    inter = _Csg("inter", _Sphere((0, 0, 0), 3), _Cube((0.5, 0.5, 0), 4.4))
+    union = _Csg("union", _Sphere((5, 2.5, 14), 2.5), _Sphere((7, 4, 13), 2))
+    nodes = [(_Plane(), np.zeros(3), (0.7, 0.7, 0.7)), (diff, np.zeros(3), (0.9, 0.6, 0.1)),
+             (inter, np.array([4.0, 3.0, 5.0]), (0.2, 0.6, 0.9)), (union, np.zeros(3), (0.4, 0.9, 0.3))]
+    x, y = -(W / H), 1.0
+    scaling = math.tan(math.radians(85.0 / 2)) / math.hypot(x, y)
+    x, y = x * scaling, y * scaling
+    up_left, up_right, down_left = np.array([x, y, 1.0]) + pos, np.array([-x, y, 1.0]) + pos, np.array([x, -y, 1.0]) + pos
+
+    def node_hit(node, o, d, best):            # node.d:23-49, identity matrix: the ray moves by -offset, the point comes back by +offset
+        g, off, _ = node
+        h = g.isect(o - off, d, best)
+        if h:
+            h.p = h.p + off
+        return h
+
+    def visible(frm, to):
+        d = to - frm
+        dist = math.sqrt(d @ d)
+        d = d / dist
+        return not any(node_hit(nd, frm, d, dist) for nd in nodes)
+
+    def sample(sx, sy):
+        target = up_left + (up_right - up_left) * (sx / W) + (down_left - up_left) * (sy / H)
+        d = target - pos
+        d = d / math.sqrt(d @ d)
+        best, rec = 1e99, None
+        for nd in nodes:
+            h = node_hit(nd, pos, d, best)
+            if h:
+                best, rec = h.dist, (h, nd)
+        if rec is None:
+            return np.zeros(3, f32)
+        h, nd = rec
+        n = h.n if d @ h.n < 0 else -h.n
+        contrib = ambient.copy()
+        if visible(h.p + n * 1e-6, light):
+            ld = light - h.p
+            dist2 = ld @ ld
+            cos_theta = (ld / math.sqrt(dist2)) @ n
+            if cos_theta > 0:
+                contrib = contrib + (lc / f32(dist2)) * f32(cos_theta)
+        return (np.array(nd[2], f32) * contrib).astype(f32)
+
+    img = np.zeros((H, W, 3), f32)
+    for py in range(H):
+        for px in range(W):
+            acc = sample(px, py)
+            for kx, ky in ((0.3, 0.3), (0.6, 0.0), (0.0, 0.6), (0.6, 0.6)):
+                acc = acc + sample(px + kx, py + ky)
+            img[py, px] = acc / f32(5)
+    return img
+
+
+def test_oracle_matches_the_independent_python_frame_with_cubes_and_csg(tmp_path):
+    from oracle_binding import OracleScene
+    p = tmp_path / "csg.sdl"
+    p.write_text(CSG_SCENE)
+    want = python_csg_frame()
+    got, st = OracleScene(str(p)).render()
+    # every CSG node is on screen: its solid colour dominates some pixel (orange, blue, green: largest channel r, b, g well above the floor's grey)
+    assert (want[..., 0] > 1.3 * want[..., 2]).any() and (want[..., 2] > 1.3 * want[..., 0]).any() and (want[..., 1] > 1.3 * want[..., 0]).any()
+    np.testing.assert_allclose(got, want, rtol=0, atol=3e-6)
