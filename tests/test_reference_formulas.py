@@ -366,8 +366,10 @@ def test_gpu_matches_the_independent_python_frame(tmp_path):
 # The independent Python restatement extended by geometry.d:92-125 (sphere: the quadratic as written, closer root first), node.d:23-49
 # (translated node: origin minus offset, identity matrix), renderer.d:325-376 (closest hit over the nodes in scene order),
 # scene.d:62-78 (shadow ray: any node hit closer than the light), shader.d:197-250 (Phong) and imported_types.d:62-73
-# (reflect, faceforward).  8x6 anti-aliased frame of a checkered floor with two spheres, one of them a translated node sharing the
-# other's geometry, lit by two lights: shadows on the floor and on a sphere, highlights, silhouettes, horizon.
+# (reflect, faceforward).  8x6 anti-aliased frame of a checkered floor with three spheres sharing one geometry — one as it is, one a
+# translated node, one scaled: node.d:84-93 applies `scale`, then `rotate` AS A SECOND SCALE (the reference's quirk), so the matrix is
+# diag(1.5 * 1, 0.6 * 2, 1.2 * 0.5) about the object-space origin (transform.d:24-86, imported_types.d:13-20: row vector x matrix) —
+# lit by two lights: shadows on the floor and on a sphere, highlights, silhouettes, horizon.
 SPHERES_SCENE = """Scene {
   GlobalSettings { frameWidth 8; frameHeight 6; ambientLightColor 0.05 0.1 0.15; AAEnabled true; prepassEnabled false }
   Camera { pos 0 6 -4; yaw 0; pitch 0; roll 0; fov 80 }
@@ -382,6 +384,7 @@ SPHERES_SCENE = """Scene {
     Node "n0" { geometry "floor"; shader "fs" }
     Node "n1" { geometry "ball"; shader "bs" }
     Node "n2" { geometry "ball"; shader "cs"; translate 5 1 -3 }
+    Node "n3" { geometry "ball"; shader "cs"; scale 1.5 0.6 1.2; rotate 1 2 0.5; translate -5 -1 3 }
   }
 }
 """
@@ -396,15 +399,25 @@ def python_spheres_frame():
     ambient = np.array([0.05, 0.1, 0.15], f32)
     c1, c2 = np.array([0.2, 0.4, 0.6], f32), np.array([1, 0.9, 0.8], f32)
     centre, R = np.array([0.0, 3.0, 12.0]), 3.0
-    # nodes in scene order: (kind, offset, shader)
-    nodes = [("plane", np.zeros(3), "fs"), ("sphere", np.zeros(3), "bs"), ("sphere", np.array([5.0, 1.0, -3.0]), "cs")]
+    # nodes in scene order: (kind, offset, shader, diagonal of the transform)
+    one = np.ones(3)
+    nodes = [("plane", np.zeros(3), "fs", one), ("sphere", np.zeros(3), "bs", one), ("sphere", np.array([5.0, 1.0, -3.0]), "cs", one),
+             ("sphere", np.array([-5.0, -1.0, 3.0]), "cs", np.array([1.5 * 1.0, 0.6 * 2.0, 1.2 * 0.5]))]
     x, y = -(W / H), 1.0
     scaling = math.tan(math.radians(80.0 / 2)) / math.hypot(x, y)
     x, y = x * scaling, y * scaling
     up_left, up_right, down_left = np.array([x, y, 1.0]) + pos, np.array([-x, y, 1.0]) + pos, np.array([x, -y, 1.0]) + pos
 
-    def hit_node(kind, off, o, d, best):
-        """-> (dist, p, normal) or None; (o, d) in world space, d unit; node.d:23-49 with the identity matrix"""
+    def hit_node(kind, off, o, d, best, scale=one):
+        """-> (dist, p, normal) or None; (o, d) in world space, d unit; node.d:23-49"""
+        if scale is not one:                                          # a diagonal matrix: undoPoint / undoDirection divide, point multiplies,
+            o2, d2 = (o - off) / scale, d / scale                     # normal goes through the transposed inverse (divide again)
+            ln = math.sqrt(d2 @ d2)
+            r = hit_node(kind, np.zeros(3), o2, d2 / ln, best * ln)
+            if r is None:
+                return None
+            n = r[2] / scale
+            return r[0] / ln, r[1] * scale + off, n / math.sqrt(n @ n)
         o = o - off
         if kind == "plane":                                           # geometry.d:30-59, y = 0
             if (o[1] > 0 and d[1] > -1e-9) or (o[1] < 0 and d[1] < 1e-9):
@@ -430,15 +443,15 @@ def python_spheres_frame():
         d = to - frm
         dist = math.sqrt(d @ d)
         d = d / dist
-        return not any(hit_node(k, off, frm, d, dist) for k, off, _ in nodes)
+        return not any(hit_node(k, off, frm, d, dist, sc) for k, off, _, sc in nodes)
 
     def sample(sx, sy):
         target = up_left + (up_right - up_left) * (sx / W) + (down_left - up_left) * (sy / H)
         d = target - pos
         d = d / math.sqrt(d @ d)
         best, rec = 1e99, None
-        for k, off, sh in nodes:                                      # renderer.d:336-338
-            r = hit_node(k, off, pos, d, best)
+        for k, off, sh, sc in nodes:                                  # renderer.d:336-338
+            r = hit_node(k, off, pos, d, best, sc)
             if r:
                 best, rec = r[0], (r[1], r[2], sh)
         if rec is None:
