@@ -732,3 +732,90 @@ def test_oracle_matches_the_independent_python_frame_with_cubes_and_csg(tmp_path
     # every CSG node is on screen: its solid colour dominates some pixel (orange, blue, green: largest channel r, b, g well above the floor's grey)
     assert (want[..., 0] > 1.3 * want[..., 2]).any() and (want[..., 2] > 1.3 * want[..., 0]).any() and (want[..., 1] > 1.3 * want[..., 0]).any()
     np.testing.assert_allclose(got, want, rtol=0, atol=3e-6)
+
+
+# ---------------------------------------------------------------- the same, with depth of field
+# renderer.d:270-287 (renderSampleDof: per sample the pixel jitter x + uniform * dx, y + uniform * dy, then the ray) and camera.d:154-173,
+# 258-269 (focal point T = orig + dir * focalPlaneDist / (dir . front); unitDiscSample: angle = uniform * 2 pi, rad = sqrt(uniform),
+# (sin, cos) * rad * discMultiplier along right / up; dir = normalize(T - orig)), restated in Python.  The reference draws from libc rand();
+# oracle and library draw from the pinned generator c2rt_rng_u31 keyed by (seed, pixel, AA tap, sample, draw), uniform = value / RAND_MAX
+#  — called here through the library's host function, in the order the D code consumes its draws.
+DOF_SCENE = """Scene {
+  GlobalSettings { frameWidth 4; frameHeight 4; ambientLightColor 0.1 0.2 0.3; AAEnabled true; prepassEnabled false }
+  Camera { pos 0 5 0; yaw 0; pitch -30; roll 0; fov 90; dof true; numSamples 3; focalPlaneDist 12; fNumber 8 }
+  Lights { PointLight "l" { pos 1 10 12; color 1 0.9 0.8; power 300 } }
+  Geometries { Plane "g" { y 0 } }
+  Textures { Checker "t" { color1 0.2 0.4 0.6; color2 1 0.9 0.8; size 3 } }
+  Shaders { Lambert "s" { color 1 1 1; texture "t" } }
+  Nodes { Node "n" { geometry "g"; shader "s" } }
+}
+"""
+
+
+def python_dof_frame(seed, cam):
+    """`cam`: pos, upLeft, upRight, downLeft, right, up, front (the camera basis is pinned separately above: rotation conventions)"""
+    import chess2rt_b200 as c2
+    f32 = np.float32
+    W = H = 4
+    pos, up_left, up_right, down_left, right, up, front = [np.array(v, float) for v in cam]
+    light = np.array([1.0, 10.0, 12.0])
+    light_color = np.array([f32(1) * f32(300), f32(0.9) * f32(300), f32(0.8) * f32(300)], dtype=f32)
+    ambient = np.array([0.1, 0.2, 0.3], dtype=f32)
+    c1, c2c = np.array([0.2, 0.4, 0.6], dtype=f32), np.array([1, 0.9, 0.8], dtype=f32)
+    focal, disc, n_samples = 12.0, 10.0 / 8.0, 3
+
+    def shade(o, d):
+        if (o[1] > 0 and d[1] > -1e-9) or (o[1] < 0 and d[1] < 1e-9):
+            return np.zeros(3, f32)
+        t = o[1] / -d[1]
+        p = o + d * t
+        n = np.array([0.0, 1.0, 0.0]) if d[1] < 0 else np.array([0.0, -1.0, 0.0])
+        white = int(math.fmod(int(math.floor(p[0] / 3.0)) + int(math.floor(p[2] / 3.0)), 2))
+        contrib = ambient.copy()
+        frm = p + n * 1e-6
+        sd = light - frm
+        sd = sd / math.sqrt(sd @ sd)
+        if not ((frm[1] > 0 and sd[1] > -1e-9) or (frm[1] < 0 and sd[1] < 1e-9)):   # the plane between the point and the light
+            return ((c2c if white else c1) * contrib).astype(f32)
+        ld = light - p
+        dist2 = ld @ ld
+        cos_theta = (ld / math.sqrt(dist2)) @ n
+        if cos_theta > 0:
+            contrib = contrib + (light_color / f32(dist2)) * f32(cos_theta)
+        return ((c2c if white else c1) * contrib).astype(f32)
+
+    def sample(px, py, tap, kx, ky):
+        avg = np.zeros(3, f32)
+        for i in range(n_samples):
+            u = [c2.rng_u31(seed, px, py, tap, i, k) / 2147483647.0 for k in range(4)]
+            sx, sy = px + kx + u[0] * 1, py + ky + u[1] * 1
+            target = up_left + (up_right - up_left) * (sx / W) + (down_left - up_left) * (sy / H)
+            d = target - pos
+            d = d / math.sqrt(d @ d)
+            T = pos + d * (focal / (d @ front))
+            angle, rad = u[2] * 2 * math.pi, math.sqrt(u[3])
+            o = pos + (math.sin(angle) * rad * disc) * right + (math.cos(angle) * rad * disc) * up
+            d = T - o
+            avg = avg + shade(o, d / math.sqrt(d @ d))
+        return avg / f32(n_samples)
+
+    img = np.zeros((H, W, 3), f32)
+    for py in range(H):
+        for px in range(W):
+            acc = np.zeros(3, f32)
+            for tap, (kx, ky) in enumerate(((0.0, 0.0), (0.3, 0.3), (0.6, 0.0), (0.0, 0.6), (0.6, 0.6))):
+                acc = acc + sample(px, py, tap, kx, ky)
+            img[py, px] = acc / f32(5)
+    return img
+
+
+def test_oracle_matches_the_independent_python_frame_with_depth_of_field(tmp_path):
+    from oracle_binding import OracleScene
+    p = tmp_path / "dof.sdl"
+    p.write_text(DOF_SCENE)
+    o = OracleScene(str(p))
+    got, st = o.render(seed=77)
+    assert st.primary_rays == 4 * 4 * 5 * 3
+    want = python_dof_frame(77, o.camera_vectors())
+    assert (want > 0).any()
+    np.testing.assert_allclose(got, want, rtol=0, atol=3e-6)
