@@ -819,3 +819,111 @@ def test_oracle_matches_the_independent_python_frame_with_depth_of_field(tmp_pat
     want = python_dof_frame(77, o.camera_vectors())
     assert (want > 0).any()
     np.testing.assert_allclose(got, want, rtol=0, atol=3e-6)
+
+
+# ---------------------------------------------------------------- the same, with a bitmap-textured sphere (lecture5's globe)
+# geometry.d:114-120 (sphere uv: u = (pi + atan2(dz, dx)) / 2 pi, v = 1 - (pi/2 + asin(dy / R)) / pi), texture.d:116-141 (BitmapTexture:
+# scaling, wrap to [0, 1), float texel coordinates, assumedGamma 2.2 -> sRGB decompression at load time), bitmap.d:48-63,105-126 (bilinear
+# fetch with wrap; the decompression formula), color.d:60-66 (byte / 255 in FP32), restated in Python; the 8-bpp world.bmp is decoded by
+# PIL, an independent decoder.
+GLOBE_SCENE = """Scene {
+  GlobalSettings { frameWidth 8; frameHeight 6; ambientLightColor 0.2 0.2 0.2; AAEnabled true; prepassEnabled false }
+  Camera { pos 0 3 -9; yaw 0; pitch 0; roll 0; fov 60 }
+  Lights { PointLight "l" { pos -8 12 -10; color 1 1 1; power 400 } }
+  Geometries { Sphere "globe" { center 0.5 3 2; R 4 } }
+  Textures { BitmapTexture "world" { file "%s" } }
+  Shaders { Lambert "s" { color 1 1 1; texture "world" } }
+  Nodes { Node "n" { geometry "globe"; shader "s" } }
+}
+""" % os.path.join(ROOT, "scenes", "world.bmp")
+
+
+def python_globe_frame():
+    from PIL import Image
+    f32 = np.float32
+    W, H = 8, 6
+    tex = np.asarray(Image.open(os.path.join(ROOT, "scenes", "world.bmp")).convert("RGB")).astype(f32) * f32(1.0 / 255.0)   # color.d:60-66
+    lin = np.where(tex <= f32(0.04045), tex / f32(12.92), np.power((tex + f32(0.055)) / f32(1.055), f32(2.4))).astype(f32)   # bitmap.d:115-126
+    lin[tex == 0] = 0
+    lin[tex == 1] = 1
+    th, tw = lin.shape[:2]
+    pos, light = np.array([0.0, 3.0, -9.0]), np.array([-8.0, 12.0, -10.0])
+    lc = np.array([f32(400)] * 3, f32)
+    ambient = np.array([0.2, 0.2, 0.2], f32)
+    centre, R = np.array([0.5, 3.0, 2.0]), 4.0
+    x, y = -(W / H), 1.0
+    scaling = math.tan(math.radians(60.0 / 2)) / math.hypot(x, y)
+    x, y = x * scaling, y * scaling
+    up_left, up_right, down_left = np.array([x, y, 1.0]) + pos, np.array([-x, y, 1.0]) + pos, np.array([x, -y, 1.0]) + pos
+
+    def texel(u, v):
+        u, v = u - math.floor(u), v - math.floor(v)                      # scaling 1 (texture.d:118-122)
+        fx, fy = f32(u) * f32(tw), f32(v) * f32(th)
+        if int(fx) >= tw or int(fy) >= th:
+            return np.array([1, 0, 0], f32)                              # NamedColors.red (bitmap.d:50-51)
+        tx, ty = int(math.floor(fx)), int(math.floor(fy))
+        txn, tyn = (tx + 1) % tw, (ty + 1) % th
+        p, q = fx - f32(tx), fy - f32(ty)
+        one = f32(1)
+        return (lin[ty, tx] * ((one - p) * (one - q)) + lin[ty, txn] * (p * (one - q)) + lin[tyn, tx] * ((one - p) * q) + lin[tyn, txn] * (p * q)).astype(f32)
+
+    def sample(sx, sy):
+        target = up_left + (up_right - up_left) * (sx / W) + (down_left - up_left) * (sy / H)
+        d = target - pos
+        d = d / math.sqrt(d @ d)
+        h = pos - centre
+        a, b, c = d @ d, 2 * (h @ d), h @ h - R * R
+        dscr = b * b - 4 * a * c
+        if dscr < 0:
+            return np.zeros(3, f32)
+        sol = (-b - math.sqrt(dscr)) / (2 * a)
+        if sol < 0:
+            sol = (-b + math.sqrt(dscr)) / (2 * a)
+        if sol < 0:
+            return np.zeros(3, f32)
+        p = pos + d * sol
+        n = (p - centre) / math.sqrt((p - centre) @ (p - centre))
+        angle = math.atan2(p[2] - centre[2], p[0] - centre[0])
+        u = (math.pi + angle) / (2 * math.pi)
+        v = 1.0 - (math.pi / 2 + math.asin((p[1] - centre[1]) / R)) / math.pi
+        if not d @ n < 0:
+            n = -n
+        contrib = ambient.copy()
+        frm = p + n * 1e-6                                               # visible unless the sphere itself is in the way
+        sd = light - frm
+        sdist = math.sqrt(sd @ sd)
+        sd = sd / sdist
+        hh = frm - centre
+        bb, cc = 2 * (hh @ sd), hh @ hh - R * R
+        ds = bb * bb - 4 * cc
+        blocked = False
+        if ds >= 0:
+            s2, s1 = (-bb - math.sqrt(ds)) / 2, (-bb + math.sqrt(ds)) / 2
+            s = s2 if s2 >= 0 else s1
+            blocked = 0 <= s <= sdist
+        if not blocked:
+            ld = light - p
+            dist2 = ld @ ld
+            cos_theta = (ld / math.sqrt(dist2)) @ n
+            if cos_theta > 0:
+                contrib = contrib + (lc / f32(dist2)) * f32(cos_theta)
+        return (texel(u, v) * contrib).astype(f32)
+
+    img = np.zeros((H, W, 3), f32)
+    for py in range(H):
+        for px in range(W):
+            acc = sample(px, py)
+            for kx, ky in ((0.3, 0.3), (0.6, 0.0), (0.0, 0.6), (0.6, 0.6)):
+                acc = acc + sample(px + kx, py + ky)
+            img[py, px] = acc / f32(5)
+    return img
+
+
+def test_oracle_matches_the_independent_python_frame_of_a_textured_globe(tmp_path):
+    from oracle_binding import OracleScene
+    p = tmp_path / "globe.sdl"
+    p.write_text(GLOBE_SCENE)
+    want = python_globe_frame()
+    got, _ = OracleScene(str(p)).render()
+    assert (want > 0.05).mean() > 0.3 and want.std() > 0.02          # the globe fills a good part of the frame, with texture detail
+    np.testing.assert_allclose(got, want, rtol=0, atol=5e-6)
