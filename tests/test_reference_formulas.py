@@ -927,3 +927,71 @@ def test_oracle_matches_the_independent_python_frame_of_a_textured_globe(tmp_pat
     got, _ = OracleScene(str(p)).render()
     assert (want > 0.05).mean() > 0.3 and want.std() > 0.02          # the globe fills a good part of the frame, with texture detail
     np.testing.assert_allclose(got, want, rtol=0, atol=5e-6)
+
+
+# ---------------------------------------------------------------- the same, with the stereo anaglyph
+# renderer.d:303-312 (renderSampleDefault with stereoSeparation != 0: one ray per eye, the origin moved by -/+ stereoSeparation along
+# rightDir, camera.d:148-152), color.d:10-15 (combineStereo: both eyes desaturated to 0.25, left -> red, right -> green and blue) and
+# color.d:76-82,139-142 (adjustSaturation around the mean of the three channels), restated in Python.
+STEREO_SCENE = """Scene {
+  GlobalSettings { frameWidth 4; frameHeight 4; ambientLightColor 0.1 0.2 0.3; AAEnabled true; prepassEnabled false }
+  Camera { pos 0 5 0; yaw 0; pitch -30; roll 0; fov 90; stereoSeparation 1.5 }
+  Lights { PointLight "l" { pos 1 10 12; color 1 0.9 0.8; power 300 } }
+  Geometries { Plane "g" { y 0 } }
+  Textures { Checker "t" { color1 0.2 0.4 0.6; color2 1 0.9 0.8; size 3 } }
+  Shaders { Lambert "s" { color 1 1 1; texture "t" } }
+  Nodes { Node "n" { geometry "g"; shader "s" } }
+}
+"""
+
+
+def python_stereo_frame(cam):
+    f32 = np.float32
+    W = H = 4
+    pos, up_left, up_right, down_left, right, up, front = [np.array(v, float) for v in cam]
+    light = np.array([1.0, 10.0, 12.0])
+    light_color = np.array([f32(1) * f32(300), f32(0.9) * f32(300), f32(0.8) * f32(300)], dtype=f32)
+    ambient = np.array([0.1, 0.2, 0.3], dtype=f32)
+    c1, c2c = np.array([0.2, 0.4, 0.6], dtype=f32), np.array([1, 0.9, 0.8], dtype=f32)
+
+    def shade(o, d):
+        if d[1] > -1e-9:                          # both eyes are above the plane
+            return np.zeros(3, f32)
+        p = o + d * (o[1] / -d[1])
+        white = int(math.fmod(int(math.floor(p[0] / 3.0)) + int(math.floor(p[2] / 3.0)), 2))
+        ld = light - p
+        dist2 = ld @ ld
+        contrib = ambient + (light_color / f32(dist2)) * f32(ld[1] / math.sqrt(dist2))     # light above the plane: visible, cos > 0
+        return ((c2c if white else c1) * contrib).astype(f32)
+
+    def desat(c):
+        mid = (c[0] + c[1] + c[2]) / f32(3)
+        return (c * f32(0.25) + mid * (f32(1) - f32(0.25))).astype(f32)
+
+    def sample(sx, sy):
+        target = up_left + (up_right - up_left) * (sx / W) + (down_left - up_left) * (sy / H)
+        d = target - pos
+        d = d / math.sqrt(d @ d)
+        left, rgt = desat(shade(pos - right * 1.5, d)), desat(shade(pos + right * 1.5, d))
+        return np.array([left[0], rgt[1], rgt[2]], f32)          # left * (1, 0, 0) + right * (0, 1, 1)
+
+    img = np.zeros((H, W, 3), f32)
+    for py in range(H):
+        for px in range(W):
+            acc = sample(px, py)
+            for kx, ky in ((0.3, 0.3), (0.6, 0.0), (0.0, 0.6), (0.6, 0.6)):
+                acc = acc + sample(px + kx, py + ky)
+            img[py, px] = acc / f32(5)
+    return img
+
+
+def test_oracle_matches_the_independent_python_stereo_frame(tmp_path):
+    from oracle_binding import OracleScene
+    p = tmp_path / "stereo.sdl"
+    p.write_text(STEREO_SCENE)
+    o = OracleScene(str(p))
+    got, st = o.render()
+    assert st.primary_rays == 4 * 4 * 5 * 2
+    want = python_stereo_frame(o.camera_vectors())
+    assert (np.abs(want[..., 0] - want[..., 1]) > 1e-3).any()    # the two eyes do see different things
+    np.testing.assert_allclose(got, want, rtol=0, atol=3e-6)
